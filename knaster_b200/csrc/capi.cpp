@@ -1,0 +1,580 @@
+// capi.cpp -- the C ABI (include/knaster_gpu.h) and the plan runtime: device memory, uploads,
+// kernel sequencing.  No torch, no CPU render path: if CUDA is unusable every call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/knaster_gpu.h"
+#include "kernels.h"
+#include "plan.hpp"
+
+namespace kgpu {
+void recompile_group_slots(Group &g, uint32_t sample_rate, const std::vector<std::pair<uint32_t, uint32_t>> &pinned);
+}
+
+using namespace kgpu;
+
+namespace {
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) KGPU_THROW(KGPU_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        size_t want = std::max(n, cap + cap / 2);
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            KGPU_THROW(KGPU_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+        }
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct GroupDev {
+    DevBuf<DevProgram> prog;
+    DevBuf<uint32_t> regs;
+    DevBuf<DevEvent> events;
+    DevBuf<uint32_t> ev_off;
+    DevBuf<DevTap> taps;
+    std::vector<DevTap> host_taps;
+    std::vector<std::pair<uint32_t, uint32_t>> pinned; // (local node, channel) kept live for taps
+    uint32_t rows = 0, row0 = 0;
+    uint32_t chunk = 1;
+    int recipe = -1;
+};
+} // namespace
+
+struct kgpu_plan {
+    HostPlan host;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<GroupDev> gd;
+    DevBuf<float> partials;
+    DevBuf<uint32_t> row_mask;
+    DevBuf<float> out;
+    DevBuf<float> sine;
+    DevBuf<float> tap_out;
+    uint32_t n_rows = 0, n_taps = 0;
+    uint64_t tap_frames = 0;
+    uint64_t frame_clock = 0;
+    bool rendered = false;
+    bool force_interp = false;
+    std::vector<float> last_block;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    uint64_t kernel_launches = 0;
+    std::vector<DevEvent> h_events, h_events_all;
+    std::vector<uint32_t> h_off, h_off_all;
+    DevBuf<DevEvent> d_events_all;
+    DevBuf<uint32_t> d_off_all;
+    uint64_t max_blocks_per_launch = 1024;
+    std::vector<cudaEvent_t> kev;          // per-launch event pairs (profile of the last render call)
+    std::vector<uint8_t> kev_class;        // 0 render kernel, 1 reduce_bus
+    size_t kev_used = 0;
+    bool prepared = false;                 // phase 1 already done for `prepared_blocks`
+    uint64_t prepared_blocks = 0;
+    std::vector<uint64_t> piece_ev, piece_off;
+    std::vector<uint8_t> piece_any;
+    uint64_t last_h2d_bytes = 0;
+};
+
+namespace {
+
+uint32_t pick_chunk(uint32_t block_size) {
+    uint32_t c = 16;
+    while (c > 1 && block_size % c) c >>= 1;
+    return c;
+}
+
+void upload_program(kgpu_plan *p, uint32_t gi) {
+    Group &g = p->host.groups[gi];
+    GroupDev &d = p->gd[gi];
+    d.prog.ensure(1);
+    CUDA_TRY(cudaMemcpyAsync(d.prog.p, &g.prog, sizeof(DevProgram), cudaMemcpyHostToDevice, p->stream));
+}
+
+void layout_rows(kgpu_plan *p) {
+    uint32_t row = 0;
+    std::vector<uint32_t> mask;
+    for (uint32_t gi = 0; gi < p->gd.size(); gi++) {
+        Group &g = p->host.groups[gi];
+        GroupDev &d = p->gd[gi];
+        d.row0 = row;
+        uint32_t units = d.recipe >= 0 ? fused_rows(d.recipe, g.n_voices, g.prog.n_ubus) / std::max(1u, g.prog.n_ubus) : (g.n_voices + 31) / 32;
+        d.rows = units * g.prog.n_ubus;
+        for (uint32_t w = 0; w < units; w++)
+            for (uint32_t u = 0; u < g.prog.n_ubus; u++) mask.push_back(g.prog.ubus_mask[u]);
+        row += d.rows;
+    }
+    p->n_rows = row;
+    p->row_mask.ensure(std::max<size_t>(1, mask.size()));
+    if (!mask.empty()) CUDA_TRY(cudaMemcpyAsync(p->row_mask.p, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+}
+
+void choose_kernels(kgpu_plan *p) {
+    for (uint32_t gi = 0; gi < p->gd.size(); gi++) {
+        Group &g = p->host.groups[gi];
+        GroupDev &d = p->gd[gi];
+        int recipe = p->force_interp ? -1 : match_fused_recipe(g.prog);
+        // a fused kernel can only tap signals that reach the bus (everything else lives in registers)
+        if (recipe >= 0)
+            for (auto &pin : d.pinned) {
+                bool on_bus = false;
+                for (auto &o : g.tpl.outs)
+                    if ((uint32_t)std::get<0>(o) == pin.first && std::get<1>(o) == pin.second) on_bus = true;
+                if (!on_bus) recipe = -1;
+            }
+        d.recipe = recipe;
+        d.chunk = recipe >= 0 ? 1 : pick_chunk(p->host.block_size);
+        g.fused_recipe = recipe;
+        g.kernel_name = recipe >= 0 ? fused_recipe_name(recipe) : "render_interp";
+    }
+    layout_rows(p);
+}
+
+// phase 1 (host): control simulation of the whole range + per-launch device event lists + upload
+void prepare_range(kgpu_plan *p, uint64_t n_blocks, uint64_t bpl, cudaStream_t stream) {
+    const uint32_t bs = p->host.block_size;
+    const uint64_t t_begin = p->frame_clock, t_end = t_begin + n_blocks * bs;
+    p->host.simulate(t_begin, t_end);
+    p->piece_ev.clear(); p->piece_off.clear(); p->piece_any.clear();
+    p->h_events_all.clear();
+    p->h_off_all.clear();
+    for (uint64_t done = 0; done < n_blocks; done += bpl) {
+        const uint64_t nb = std::min(bpl, n_blocks - done);
+        const uint64_t t0 = t_begin + done * bs, t1 = t0 + nb * bs;
+        for (uint32_t gi = 0; gi < p->gd.size(); gi++) {
+            p->host.take_events(gi, t0, t1, p->gd[gi].chunk, p->h_events, p->h_off);
+            p->piece_ev.push_back(p->h_events_all.size());
+            p->piece_off.push_back(p->h_off_all.size());
+            p->piece_any.push_back(!p->h_events.empty());
+            if (!p->h_events.empty()) {
+                p->h_events_all.insert(p->h_events_all.end(), p->h_events.begin(), p->h_events.end());
+                p->h_off_all.insert(p->h_off_all.end(), p->h_off.begin(), p->h_off.end());
+            }
+        }
+    }
+    p->last_h2d_bytes = 0;
+    if (!p->h_events_all.empty()) {
+        p->d_events_all.ensure(p->h_events_all.size());
+        p->d_off_all.ensure(p->h_off_all.size());
+        // pageable source: the runtime stages the copy before returning, the vectors may be reused
+        CUDA_TRY(cudaMemcpyAsync(p->d_events_all.p, p->h_events_all.data(), p->h_events_all.size() * sizeof(DevEvent), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(p->d_off_all.p, p->h_off_all.data(), p->h_off_all.size() * 4, cudaMemcpyHostToDevice, stream));
+        p->last_h2d_bytes = p->h_events_all.size() * sizeof(DevEvent) + p->h_off_all.size() * 4;
+    }
+}
+
+uint64_t blocks_per_launch(kgpu_plan *p) {
+    // bound the partial-sum buffer (rows x frames x 4 B) to ~256 MiB
+    uint64_t max_frames = (256ull << 20) / (4ull * std::max(1u, p->n_rows));
+    uint64_t bpl = std::max<uint64_t>(1, max_frames / p->host.block_size);
+    return std::min<uint64_t>(bpl, p->max_blocks_per_launch);
+}
+
+void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream_t stream) {
+    const uint32_t bs = p->host.block_size, n_out = p->host.n_outputs;
+    p->rendered = true;
+    const uint64_t total_frames = n_blocks * bs;
+    if (p->n_taps) {
+        p->tap_out.ensure((size_t)p->n_taps * total_frames);
+        p->tap_frames = total_frames;
+    }
+    const uint64_t bpl = blocks_per_launch(p);
+    if (!(p->prepared && p->prepared_blocks == n_blocks)) prepare_range(p, n_blocks, bpl, stream);
+    p->prepared = false;
+    p->partials.ensure((size_t)std::max(1u, p->n_rows) * std::min<uint64_t>(bpl, n_blocks) * bs);
+    const uint64_t t_end = p->frame_clock + total_frames;
+
+    // ---- phase 2 (device): back-to-back kernel launches, timed with CUDA events ----
+    if (p->timed) CUDA_TRY(cudaEventRecord(p->ev0, stream));
+    size_t piece = 0;
+    p->kev_used = 0;
+    p->kev_class.clear();
+    auto mark = [&](int cls, bool begin) {
+        if (p->kev_used == p->kev.size()) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            p->kev.push_back(e);
+        }
+        CUDA_TRY(cudaEventRecord(p->kev[p->kev_used++], stream));
+        if (begin) p->kev_class.push_back((uint8_t)cls);
+    };
+    for (uint64_t done = 0; done < n_blocks; done += bpl) {
+        const uint64_t nb = std::min(bpl, n_blocks - done);
+        const uint32_t nf = (uint32_t)(nb * bs);
+        for (uint32_t gi = 0; gi < p->gd.size(); gi++, piece++) {
+            Group &g = p->host.groups[gi];
+            GroupDev &d = p->gd[gi];
+            const DevEvent *d_ev = p->piece_any[piece] ? p->d_events_all.p + p->piece_ev[piece] : nullptr;
+            const uint32_t *d_off = p->piece_any[piece] ? p->d_off_all.p + p->piece_off[piece] : nullptr;
+            mark(0, true);
+            if (d.recipe >= 0) {
+                FusedArgs a{};
+                a.prog = d.prog.p; a.regs = d.regs.p; a.n_voices = g.n_voices; a.events = d_ev; a.ev_off = d_off;
+                a.n_frames = nf; a.partials = p->partials.p; a.row0 = d.row0;
+                a.taps = d.taps.p; a.n_taps = (uint32_t)d.host_taps.size(); a.tap_out = p->tap_out.p;
+                a.tap_stride = total_frames; a.tap_frame0 = done * bs; a.sine_table = p->sine.p;
+                CUDA_TRY(launch_fused(d.recipe, a, stream));
+            } else {
+                InterpArgs a{};
+                a.prog = d.prog.p; a.regs = d.regs.p; a.n_voices = g.n_voices; a.events = d_ev; a.ev_off = d_off;
+                a.n_frames = nf; a.chunk = d.chunk; a.partials = p->partials.p; a.row0 = d.row0;
+                a.taps = d.taps.p; a.n_taps = (uint32_t)d.host_taps.size(); a.tap_out = p->tap_out.p;
+                a.tap_stride = total_frames; a.tap_frame0 = done * bs; a.sine_table = p->sine.p;
+                CUDA_TRY(launch_interp(a, g.prog.n_regs, g.prog.n_slots, stream));
+            }
+            mark(0, false);
+            p->kernel_launches++;
+        }
+        mark(1, true);
+        CUDA_TRY(launch_reduce_bus(p->partials.p, p->row_mask.p, p->n_rows, nf, device_out + (size_t)done * n_out * bs, n_out, bs, stream));
+        mark(1, false);
+        p->kernel_launches++;
+    }
+    p->frame_clock = t_end;
+    if (p->timed) CUDA_TRY(cudaEventRecord(p->ev1, stream));
+}
+
+} // namespace
+
+extern "C" {
+
+const char *kgpu_last_error(void) { return g_err.c_str(); }
+uint32_t kgpu_abi_version(void) { return KGPU_ABI_VERSION; }
+int kgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int kgpu_plan_create(const kgpu_graph_desc *desc, kgpu_plan **out) {
+    if (!desc || !out) return fail(KGPU_ERR_INVALID, "kgpu_plan_create: NULL argument");
+    *out = nullptr;
+    kgpu_plan *p = nullptr;
+    try {
+        p = new kgpu_plan();
+        p->host.build(*desc);
+        p->force_interp = (desc->flags & KGPU_PLAN_FORCE_INTERPRETER) != 0;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            cudaGetLastError();
+            KGPU_THROW(KGPU_ERR_CUDA, "no usable CUDA device: the engine has no CPU fallback");
+        }
+        if (desc->device >= 0) {
+            if (desc->device >= ndev) KGPU_THROW(KGPU_ERR_CUDA, "device %d out of range (%d devices)", desc->device, ndev);
+            CUDA_TRY(cudaSetDevice(desc->device));
+            p->device = desc->device;
+        } else CUDA_TRY(cudaGetDevice(&p->device));
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&p->ev0));
+        CUDA_TRY(cudaEventCreate(&p->ev1));
+        // shared sine table: NonAaWavetable::sine(), wavetable.rs:130-139 (f64 sin, rounded to f32)
+        {
+            std::vector<float> tab(SINE_TABLE_SIZE);
+            for (int i = 0; i < SINE_TABLE_SIZE; i++) tab[i] = (float)std::sin(((double)i / (double)SINE_TABLE_SIZE) * M_PI * 2.0);
+            p->sine.ensure(SINE_TABLE_SIZE);
+            CUDA_TRY(cudaMemcpy(p->sine.p, tab.data(), SINE_TABLE_SIZE * 4, cudaMemcpyHostToDevice));
+        }
+        p->gd.resize(p->host.groups.size());
+        for (uint32_t gi = 0; gi < p->gd.size(); gi++) {
+            Group &g = p->host.groups[gi];
+            GroupDev &d = p->gd[gi];
+            upload_program(p, gi);
+            d.regs.ensure(std::max<size_t>(1, g.init_regs.size()));
+            if (!g.init_regs.empty())
+                CUDA_TRY(cudaMemcpyAsync(d.regs.p, g.init_regs.data(), g.init_regs.size() * 4, cudaMemcpyHostToDevice, p->stream));
+        }
+        choose_kernels(p);
+        p->last_block.assign((size_t)p->host.block_size * p->host.n_outputs, 0.f);
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        *out = p;
+        return KGPU_OK;
+    } catch (const Error &e) {
+        if (p) kgpu_plan_destroy(p);
+        return fail(e.code, e.msg);
+    } catch (const std::exception &e) {
+        if (p) kgpu_plan_destroy(p);
+        return fail(KGPU_ERR_INVALID, std::string("kgpu_plan_create: ") + e.what());
+    }
+}
+
+void kgpu_plan_destroy(kgpu_plan *p) {
+    if (!p) return;
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    for (GroupDev &d : p->gd) {
+        d.prog.release(); d.regs.release(); d.events.release(); d.ev_off.release(); d.taps.release();
+    }
+    p->d_events_all.release(); p->d_off_all.release();
+    p->partials.release(); p->row_mask.release(); p->out.release(); p->sine.release(); p->tap_out.release();
+    for (cudaEvent_t e : p->kev) cudaEventDestroy(e);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int kgpu_plan_push_events(kgpu_plan *p, const kgpu_event *events, size_t n) {
+    if (!p || (n && !events)) return fail(KGPU_ERR_INVALID, "kgpu_plan_push_events: NULL argument");
+    try {
+        p->host.push(events, n, p->frame_clock);
+        return KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
+int kgpu_render_device(kgpu_plan *p, uint64_t n_blocks, float *device_out, void *cuda_stream) {
+    if (!p || !device_out) return fail(KGPU_ERR_INVALID, "kgpu_render_device: NULL argument");
+    try {
+        CUDA_TRY(cudaSetDevice(p->device));
+        p->timed = true;
+        render_range(p, n_blocks, device_out, cuda_stream ? (cudaStream_t)cuda_stream : p->stream);
+        return KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
+int kgpu_render(kgpu_plan *p, uint64_t n_blocks, float *host_out) {
+    if (!p) return fail(KGPU_ERR_INVALID, "kgpu_render: NULL plan");
+    if (n_blocks == 0) return KGPU_OK;
+    try {
+        CUDA_TRY(cudaSetDevice(p->device));
+        const size_t per_block = (size_t)p->host.block_size * p->host.n_outputs;
+        p->out.ensure(per_block * n_blocks);
+        p->timed = true;
+        render_range(p, n_blocks, p->out.p, p->stream);
+        if (host_out) {
+            CUDA_TRY(cudaMemcpyAsync(host_out, p->out.p, per_block * n_blocks * 4, cudaMemcpyDeviceToHost, p->stream));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+            std::memcpy(p->last_block.data(), host_out + per_block * (n_blocks - 1), per_block * 4);
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(p->last_block.data(), p->out.p + per_block * (n_blocks - 1), per_block * 4, cudaMemcpyDeviceToHost, p->stream));
+            CUDA_TRY(cudaStreamSynchronize(p->stream));
+        }
+        return KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
+int kgpu_render_block(kgpu_plan *p) { return kgpu_render(p, 1, nullptr); }
+const float *kgpu_output_block(kgpu_plan *p) { return p ? p->last_block.data() : nullptr; }
+
+int kgpu_plan_synchronize(kgpu_plan *p) {
+    if (!p) return fail(KGPU_ERR_INVALID, "NULL plan");
+    cudaError_t e = cudaStreamSynchronize(p->stream);
+    if (e != cudaSuccess) return fail(KGPU_ERR_CUDA, cudaGetErrorString(e));
+    return KGPU_OK;
+}
+
+uint32_t kgpu_plan_block_size(const kgpu_plan *p) { return p ? p->host.block_size : 0; }
+uint32_t kgpu_plan_outputs(const kgpu_plan *p) { return p ? p->host.n_outputs : 0; }
+uint64_t kgpu_plan_frame_clock(const kgpu_plan *p) { return p ? p->frame_clock : 0; }
+
+int kgpu_plan_add_tap(kgpu_plan *p, uint32_t node, uint32_t channel) {
+    if (!p) return fail(KGPU_ERR_INVALID, "NULL plan");
+    if (p->rendered) return fail(KGPU_ERR_STATE, "kgpu_plan_add_tap must be called before the first render");
+    try {
+        if (node >= p->host.node_ref.size()) KGPU_THROW(KGPU_ERR_INVALID, "tap: NodeNotFound (%u)", node);
+        const NodeRef &nr = p->host.node_ref[node];
+        if (nr.group < 0) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "tap: node %u is a mix-bus Add or is not connected to an output", node);
+        Group &g = p->host.groups[nr.group];
+        GroupDev &d = p->gd[nr.group];
+        if (channel >= g.prog.nodes[nr.local].n_out) KGPU_THROW(KGPU_ERR_INVALID, "tap: OutputOutOfBounds(%u)", channel);
+        CUDA_TRY(cudaSetDevice(p->device));
+        d.pinned.push_back({nr.local, channel});
+        recompile_group_slots(g, p->host.sample_rate, d.pinned); // keep tapped values live
+        upload_program(p, (uint32_t)nr.group);
+        const uint32_t tap = p->n_taps++;
+        d.host_taps.push_back(DevTap{nr.voice, 0, tap, 0});
+        // slots may have moved: refresh every tap of the group
+        for (size_t i = 0; i < d.host_taps.size(); i++) d.host_taps[i].slot = g.slot_of[d.pinned[i].first][d.pinned[i].second];
+        d.taps.ensure(d.host_taps.size());
+        CUDA_TRY(cudaMemcpyAsync(d.taps.p, d.host_taps.data(), d.host_taps.size() * sizeof(DevTap), cudaMemcpyHostToDevice, p->stream));
+        choose_kernels(p);
+        return (int)tap;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
+int kgpu_plan_read_taps(kgpu_plan *p, float *out, uint64_t n_frames) {
+    if (!p || !out) return fail(KGPU_ERR_INVALID, "NULL argument");
+    if (n_frames != p->tap_frames || !p->n_taps) return fail(KGPU_ERR_STATE, "kgpu_plan_read_taps: n_frames must equal the frames of the last render");
+    cudaError_t e = cudaStreamSynchronize(p->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, p->tap_out.p, (size_t)p->n_taps * n_frames * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(KGPU_ERR_CUDA, cudaGetErrorString(e));
+    return KGPU_OK;
+}
+
+int kgpu_plan_get_info(kgpu_plan *p, kgpu_plan_info *info) {
+    if (!p || !info) return fail(KGPU_ERR_INVALID, "NULL argument");
+    std::memset(info, 0, sizeof *info);
+    info->n_groups = (uint32_t)p->host.groups.size();
+    for (size_t gi = 0; gi < p->host.groups.size(); gi++) {
+        const Group &g = p->host.groups[gi];
+        info->n_voices += g.n_voices;
+        info->state_bytes += (uint64_t)g.n_voices * g.prog.n_regs * 4;
+        if (p->gd[gi].recipe >= 0) info->n_fused_groups++;
+    }
+    info->n_mix_nodes = p->host.n_mix_nodes;
+    info->dropped_changes = p->host.dropped_changes;
+    info->ignored_delays = p->host.ignored_delays;
+    info->device_events = p->host.device_events;
+    info->kernel_launches = p->kernel_launches;
+    return KGPU_OK;
+}
+
+const char *kgpu_plan_group_kernel(kgpu_plan *p, uint32_t group) {
+    if (!p || group >= p->host.groups.size()) return "";
+    return p->host.groups[group].kernel_name.c_str();
+}
+
+int kgpu_plan_prepare(kgpu_plan *p, uint64_t n_blocks) {
+    if (!p || n_blocks == 0) return fail(KGPU_ERR_INVALID, "kgpu_plan_prepare: bad argument");
+    try {
+        CUDA_TRY(cudaSetDevice(p->device));
+        prepare_range(p, n_blocks, blocks_per_launch(p), p->stream);
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        p->prepared = true;
+        p->prepared_blocks = n_blocks;
+        return KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
+float kgpu_plan_last_kernel_ms(kgpu_plan *p, uint32_t kernel_class, uint32_t *n_launches) {
+    if (!p) return -1.f;
+    float total = 0.f;
+    uint32_t n = 0;
+    for (size_t i = 0; i < p->kev_class.size(); i++) {
+        if (p->kev_class[i] != kernel_class) continue;
+        if (cudaEventSynchronize(p->kev[2 * i + 1]) != cudaSuccess) return -1.f;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p->kev[2 * i], p->kev[2 * i + 1]) != cudaSuccess) return -1.f;
+        total += ms;
+        n++;
+    }
+    if (n_launches) *n_launches = n;
+    return total;
+}
+
+uint64_t kgpu_plan_last_upload_bytes(kgpu_plan *p) { return p ? p->last_h2d_bytes : 0; }
+
+int kgpu_plan_set_blocks_per_launch(kgpu_plan *p, uint64_t blocks) {
+    if (!p || blocks == 0) return fail(KGPU_ERR_INVALID, "kgpu_plan_set_blocks_per_launch: bad argument");
+    p->max_blocks_per_launch = blocks;
+    return KGPU_OK;
+}
+
+float kgpu_plan_last_render_ms(kgpu_plan *p) {
+    if (!p || !p->timed) return -1.f;
+    if (cudaEventSynchronize(p->ev1) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+} // extern "C"
+
+// ---- host-only debug entry points (csrc/debug.h) ------------------------------------------------
+#include "debug.h"
+extern "C" {
+
+int kgpu_debug_simulate(const kgpu_graph_desc *desc, const kgpu_event *events, size_t n_events, uint64_t n_blocks,
+                        uint64_t blocks_per_call, kgpu_debug_event *out, size_t cap, size_t *n_out, kgpu_debug_node *nodes_out,
+                        kgpu_plan_info *info) {
+    try {
+        HostPlan hp;
+        hp.build(*desc);
+        hp.push(events, n_events, 0);
+        size_t n = 0;
+        const uint64_t bs = hp.block_size;
+        if (blocks_per_call == 0) blocks_per_call = n_blocks;
+        std::vector<DevEvent> ev;
+        std::vector<uint32_t> off;
+        for (uint64_t b = 0; b < n_blocks; b += blocks_per_call) {
+            const uint64_t t0 = b * bs, t1 = std::min(n_blocks, b + blocks_per_call) * bs;
+            hp.simulate(t0, t1);
+            for (uint32_t gi = 0; gi < hp.groups.size(); gi++) {
+                hp.take_events(gi, t0, t1, 1, ev, off);
+                if (ev.empty()) continue;
+                for (uint32_t v = 0; v < hp.groups[gi].n_voices; v++)
+                    for (uint32_t k = off[v]; k < off[v + 1]; k++) {
+                        if (n < cap) out[n] = kgpu_debug_event{gi, v, ev[k].node, ev[k].op, ev[k].reg, ev[k].value, t0 + ev[k].frame};
+                        n++;
+                    }
+            }
+        }
+        if (n_out) *n_out = n;
+        if (nodes_out)
+            for (uint32_t i = 0; i < desc->n_nodes; i++) {
+                const NodeRef &nr = hp.node_ref[i];
+                nodes_out[i] = kgpu_debug_node{nr.group, nr.voice, nr.local,
+                                               nr.group >= 0 ? (uint32_t)hp.groups[nr.group].prog.nodes[nr.local].reg : 0u};
+            }
+        if (info) {
+            std::memset(info, 0, sizeof *info);
+            info->n_groups = (uint32_t)hp.groups.size();
+            for (auto &g : hp.groups) {
+                info->n_voices += g.n_voices;
+                info->state_bytes += (uint64_t)g.n_voices * g.prog.n_regs * 4;
+            }
+            info->n_mix_nodes = hp.n_mix_nodes;
+            info->dropped_changes = hp.dropped_changes;
+            info->ignored_delays = hp.ignored_delays;
+            info->device_events = hp.device_events;
+        }
+        return n > cap ? KGPU_ERR_INVALID : KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
+int kgpu_debug_init_reg(const kgpu_graph_desc *desc, uint32_t node, uint32_t reg_offset, uint32_t *value) {
+    try {
+        HostPlan hp;
+        hp.build(*desc);
+        if (node >= hp.node_ref.size() || hp.node_ref[node].group < 0) return fail(KGPU_ERR_INVALID, "node not in a voice");
+        const NodeRef &nr = hp.node_ref[node];
+        const Group &g = hp.groups[nr.group];
+        uint32_t reg = g.prog.nodes[nr.local].reg + reg_offset;
+        if (reg >= g.prog.n_regs) return fail(KGPU_ERR_INVALID, "register out of range");
+        *value = g.init_regs[(size_t)reg * g.n_voices + nr.voice];
+        return KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+}

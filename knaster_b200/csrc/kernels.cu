@@ -1,0 +1,397 @@
+// kernels.cu -- sm_100a kernels of the batched render engine.
+//
+//   render_interp   generic plan interpreter: one warp = 32 voices of one template, nodes run
+//                   in topological order over 16-frame chunks, node buffers live in shared
+//                   memory (never in HBM), per-voice registers are loaded from / stored to HBM
+//                   once per launch.  This is GraphGen::process_block's task loop
+//                   (graph_gen.rs:196-200) turned inside out: the loop over nodes is
+//                   warp-uniform, the 32 lanes are 32 independent voices.
+//   reduce_bus      deterministic mix-bus reduction of the per-warp partial sums into the
+//                   [block][channel][frame] output layout (graph.rs:850-864 + graph_gen.rs:205-224).
+//   fused kernels   see fused.cuh (register-resident specialisations for known voice shapes).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dev.h"
+#include "kernels.h"
+#include "nodes.cuh"
+
+namespace kgpu {
+
+namespace {
+
+struct LaneEv {
+    const DevEvent *ev;
+    uint32_t cur, end;
+    uint32_t next_frame, next_node;
+    KN_DEV void fetch() {
+        if (cur < end) {
+            next_frame = ev[cur].frame;
+            next_node = ev[cur].node;
+        } else {
+            next_frame = 0xFFFFFFFFu;
+            next_node = 0xFFFFFFFFu;
+        }
+    }
+};
+
+KN_DEV double ld_d(const uint32_t *sreg, uint32_t r) {
+    return __hiloint2double((int)sreg[(r + 1) * 32], (int)sreg[r * 32]);
+}
+KN_DEV void st_d(uint32_t *sreg, uint32_t r, double v) {
+    sreg[r * 32] = (uint32_t)__double2loint(v);
+    sreg[(r + 1) * 32] = (uint32_t)__double2hiint(v);
+}
+
+// apply every event of `node` due at or before `frame` to the lane's registers (in shared memory)
+KN_DEV void apply_events(LaneEv &L, uint32_t node, uint32_t frame, uint32_t *sreg) {
+    while (L.next_node == node && L.next_frame <= frame) {
+        const DevEvent e = L.ev[L.cur];
+        if (e.op == OP_SET) {
+            sreg[e.reg * 32] = e.value;
+        } else if (e.op == OP_ASR_RELEASE) {
+            uint32_t st = sreg[e.reg * 32];
+            float t = __uint_as_float(sreg[(e.reg + 1) * 32]);
+            float sc = __uint_as_float(sreg[(e.reg + 4) * 32]);
+            envasr_release(st, t, sc);
+            sreg[e.reg * 32] = st;
+            sreg[(e.reg + 1) * 32] = __float_as_uint(t);
+            sreg[(e.reg + 4) * 32] = __float_as_uint(sc);
+        } else if (e.op == OP_ENV_STOP) { // envelopes.rs:511-523
+            if (sreg[e.reg * 32]) {
+                uint32_t seg = sreg[(e.reg + 1) * 32];
+                double t = ld_d(sreg, e.reg + 2), from = ld_d(sreg, e.reg + 4);
+                uint32_t sb = e.reg + REGS_ENVELOPE_BASE + REGS_ENVELOPE_PER_SEG * seg;
+                double recip = ld_d(sreg, sb), val = ld_d(sreg, sb + 4);
+                from = __dadd_rn(from, __dmul_rn(__dmul_rn(t, recip), __dsub_rn(val, from)));
+                st_d(sreg, e.reg + 4, from);
+            }
+            sreg[e.reg * 32] = 0;
+        }
+        L.cur++;
+        L.fetch();
+    }
+}
+
+} // namespace
+
+// One CTA = one warp = 32 voices.  Shared memory: registers [n_regs][32] u32, then value slots
+// [n_slots][chunk][32] f32 -- lane-contiguous, so every access is bank-conflict free.
+__global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
+    extern __shared__ uint32_t smem[];
+    const DevProgram *__restrict__ prog = a.prog;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t warp = blockIdx.x;
+    const uint32_t v = warp * 32 + lane;
+    const bool active = v < a.n_voices;
+    const uint32_t n_regs = prog->n_regs, n_nodes = prog->n_nodes;
+    const uint32_t CH = a.chunk;
+    uint32_t *sreg = smem + lane;                              // sreg[r*32]
+    float *sval = reinterpret_cast<float *>(smem + n_regs * 32) + lane; // sval[(slot*CH + f)*32]
+    const float sr = prog->sample_rate;
+    const double sinwt_k = prog->sinwt_k;
+
+    for (uint32_t r = 0; r < n_regs; r++) sreg[r * 32] = active ? a.regs[(size_t)r * a.n_voices + v] : 0u;
+    LaneEv L;
+    L.ev = a.events;
+    L.cur = L.end = 0;
+    if (a.events && active) {
+        L.cur = a.ev_off[v];
+        L.end = a.ev_off[v + 1];
+    }
+    L.fetch();
+
+    for (uint32_t c0 = 0; c0 < a.n_frames; c0 += CH) {
+        const uint32_t nf = min(CH, a.n_frames - c0);
+        for (uint32_t n = 0; n < n_nodes; n++) {
+            const DevNode &dn = prog->nodes[n];
+            const bool evc = __any_sync(0xFFFFFFFFu, L.next_node == n && L.next_frame < c0 + nf);
+            const uint32_t rb = dn.reg;
+            // arithmetic wrapper values
+            float pv[MAX_POST];
+#pragma unroll
+            for (int k = 0; k < MAX_POST; k++) pv[k] = k < dn.n_post ? __uint_as_float(sreg[dn.post_reg[k] * 32]) : 0.f;
+#define EVENTS_AT(f_, STORE_, LOAD_)                                                   \
+    if (evc && L.next_node == n && L.next_frame <= c0 + (f_)) {                        \
+        STORE_;                                                                        \
+        apply_events(L, n, c0 + (f_), sreg);                                           \
+        LOAD_;                                                                         \
+        _Pragma("unroll") for (int k = 0; k < MAX_POST; k++) if (k < dn.n_post)        \
+            pv[k] = __uint_as_float(sreg[dn.post_reg[k] * 32]);                        \
+    }
+#define AR_POST_ROUTES(f_)                                                             \
+    for (int ai = 0; ai < dn.n_ar; ai++)                                               \
+        if (dn.ar_code[ai] >= AR_POST) pv[dn.ar_code[ai] - AR_POST] = sval[(dn.ar_slot[ai] * CH + (f_)) * 32];
+#define EMIT(f_, ch_, y_)                                                              \
+    {                                                                                  \
+        float _y = (y_);                                                               \
+        _Pragma("unroll") for (int k = 0; k < MAX_POST; k++) if (k < dn.n_post)        \
+            _y = post_apply(dn.post_op[k], _y, pv[k]);                                 \
+        sval[(dn.out_slot[ch_] * CH + (f_)) * 32] = _y;                                \
+    }
+            switch (dn.kind) {
+            case DK_SINWT: {
+                uint32_t phase = sreg[rb * 32], off = sreg[(rb + 1) * 32], inc = sreg[(rb + 2) * 32];
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, sreg[rb * 32] = phase, (phase = sreg[rb * 32], off = sreg[(rb + 1) * 32], inc = sreg[(rb + 2) * 32]))
+                    for (int ai = 0; ai < dn.n_ar; ai++) {
+                        float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
+                        if (dn.ar_code[ai] == AR_SINWT_FREQ) inc = kn_sat_u32(__dmul_rn((double)x, sinwt_k));
+                        else if (dn.ar_code[ai] == AR_SINWT_OFFSET) off = kn_sat_u32(__dmul_rn((double)x, 65536.0));
+                        else pv[dn.ar_code[ai] - AR_POST] = x;
+                    }
+                    float y = sinwt_tick(phase, off, inc, a.sine_table);
+                    EMIT(f, 0, y)
+                }
+                sreg[rb * 32] = phase;
+                // audio-rate routes leave their last value in the ugen, like param_apply does
+                if (dn.n_ar) { sreg[(rb + 1) * 32] = off; sreg[(rb + 2) * 32] = inc; }
+                break;
+            }
+            case DK_SINNUM: {
+                float phase = __uint_as_float(sreg[rb * 32]), off = __uint_as_float(sreg[(rb + 1) * 32]),
+                      inc = __uint_as_float(sreg[(rb + 2) * 32]);
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(phase),
+                              (phase = __uint_as_float(sreg[rb * 32]), off = __uint_as_float(sreg[(rb + 1) * 32]),
+                               inc = __uint_as_float(sreg[(rb + 2) * 32])))
+                    for (int ai = 0; ai < dn.n_ar; ai++) {
+                        float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
+                        if (dn.ar_code[ai] == AR_SINNUM_FREQ) inc = x / sr; // osc.rs:240-242
+                        else if (dn.ar_code[ai] == AR_SINNUM_OFFSET) off = x;
+                        else pv[dn.ar_code[ai] - AR_POST] = x;
+                    }
+                    float y = sinnum_tick(phase, off, inc);
+                    EMIT(f, 0, y)
+                }
+                sreg[rb * 32] = __float_as_uint(phase);
+                if (dn.n_ar) { sreg[(rb + 1) * 32] = __float_as_uint(off); sreg[(rb + 2) * 32] = __float_as_uint(inc); }
+                break;
+            }
+            case DK_POLYBLEP: {
+                float t = __uint_as_float(sreg[rb * 32]), dt = __uint_as_float(sreg[(rb + 1) * 32]);
+                uint32_t use_sin = sreg[(rb + 2) * 32];
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(t),
+                              (t = __uint_as_float(sreg[rb * 32]), dt = __uint_as_float(sreg[(rb + 1) * 32]), use_sin = sreg[(rb + 2) * 32]))
+                    for (int ai = 0; ai < dn.n_ar; ai++) {
+                        float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
+                        if (dn.ar_code[ai] == AR_POLYBLEP_FREQ) {
+                            dt = x / sr;
+                            use_sin = (dt * sr >= sr / 4.0f) ? 1u : 0u;
+                        } else pv[dn.ar_code[ai] - AR_POST] = x;
+                    }
+                    float y = polyblep_saw_tick(t, dt, use_sin);
+                    EMIT(f, 0, y)
+                }
+                sreg[rb * 32] = __float_as_uint(t);
+                if (dn.n_ar) { sreg[(rb + 1) * 32] = __float_as_uint(dt); sreg[(rb + 2) * 32] = use_sin; }
+                break;
+            }
+            case DK_SVF: {
+                float ic1, ic2, a1, a2, a3, m0, m1, m2;
+#define SVF_LOAD (ic1 = __uint_as_float(sreg[rb * 32]), ic2 = __uint_as_float(sreg[(rb + 1) * 32]),       \
+                  a1 = __uint_as_float(sreg[(rb + 2) * 32]), a2 = __uint_as_float(sreg[(rb + 3) * 32]),    \
+                  a3 = __uint_as_float(sreg[(rb + 4) * 32]), m0 = __uint_as_float(sreg[(rb + 5) * 32]),    \
+                  m1 = __uint_as_float(sreg[(rb + 6) * 32]), m2 = __uint_as_float(sreg[(rb + 7) * 32]))
+#define SVF_STORE (sreg[rb * 32] = __float_as_uint(ic1), sreg[(rb + 1) * 32] = __float_as_uint(ic2))
+                SVF_LOAD;
+                const int is = dn.in_slot[0];
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, SVF_STORE, SVF_LOAD)
+                    AR_POST_ROUTES(f)
+                    float x = is >= 0 ? sval[(is * CH + f) * 32] : 0.f;
+                    float y = svf_tick(x, ic1, ic2, a1, a2, a3, m0, m1, m2);
+                    EMIT(f, 0, y)
+                }
+                SVF_STORE;
+                break;
+            }
+            case DK_ONEPOLE_LP:
+            case DK_ONEPOLE_HP: {
+                float y1 = __uint_as_float(sreg[rb * 32]), a0 = __uint_as_float(sreg[(rb + 1) * 32]), b1 = __uint_as_float(sreg[(rb + 2) * 32]);
+                const int is = dn.in_slot[0];
+                const bool hp = dn.kind == DK_ONEPOLE_HP;
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(y1),
+                              (y1 = __uint_as_float(sreg[rb * 32]), a0 = __uint_as_float(sreg[(rb + 1) * 32]), b1 = __uint_as_float(sreg[(rb + 2) * 32])))
+                    AR_POST_ROUTES(f)
+                    float x = is >= 0 ? sval[(is * CH + f) * 32] : 0.f;
+                    float y = hp ? onepole_hp_tick(x, y1, a0, b1) : onepole_lp_tick(x, y1, a0, b1);
+                    EMIT(f, 0, y)
+                }
+                sreg[rb * 32] = __float_as_uint(y1);
+                break;
+            }
+            case DK_ENVASR:
+            case DK_ENVAR: {
+                uint32_t st;
+                float t, ar, rr, sc;
+#define ENV_LOAD (st = sreg[rb * 32], t = __uint_as_float(sreg[(rb + 1) * 32]), ar = __uint_as_float(sreg[(rb + 2) * 32]), \
+                  rr = __uint_as_float(sreg[(rb + 3) * 32]), sc = __uint_as_float(sreg[(rb + 4) * 32]))
+#define ENV_STORE (sreg[rb * 32] = st, sreg[(rb + 1) * 32] = __float_as_uint(t), sreg[(rb + 4) * 32] = __float_as_uint(sc))
+                ENV_LOAD;
+                const bool asr = dn.kind == DK_ENVASR;
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, ENV_STORE, ENV_LOAD)
+                    AR_POST_ROUTES(f)
+                    float y = asr ? envasr_tick(st, t, ar, rr, sc) : envar_tick(st, t, ar, rr, sc);
+                    EMIT(f, 0, y)
+                }
+                ENV_STORE;
+                break;
+            }
+            case DK_ENVELOPE: { // envelopes.rs:407-463
+                uint32_t running, seg;
+                double time, from, step;
+#define ENVL_LOAD (running = sreg[rb * 32], seg = sreg[(rb + 1) * 32], time = ld_d(sreg, rb + 2), from = ld_d(sreg, rb + 4), step = ld_d(sreg, rb + 6))
+#define ENVL_STORE (sreg[rb * 32] = running, sreg[(rb + 1) * 32] = seg, st_d(sreg, rb + 2, time), st_d(sreg, rb + 4, from))
+                ENVL_LOAD;
+                const uint32_t n_seg = dn.n_seg;
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, ENVL_STORE, ENVL_LOAD)
+                    AR_POST_ROUTES(f)
+                    float y;
+                    if (!running) {
+                        y = (float)from;
+                    } else {
+                        const uint32_t sb = rb + REGS_ENVELOPE_BASE + REGS_ENVELOPE_PER_SEG * seg;
+                        const double recip = ld_d(sreg, sb), dur = ld_d(sreg, sb + 2), val = ld_d(sreg, sb + 4);
+                        if (time < dur) {
+                            y = (float)__dadd_rn(from, __dmul_rn(__dmul_rn(time, recip), __dsub_rn(val, from)));
+                            time = __dadd_rn(time, step);
+                        } else if (seg + 1 < n_seg) {
+                            from = val;
+                            y = (float)__dadd_rn(from, __dmul_rn(__dmul_rn(time, recip), __dsub_rn(val, from)));
+                            seg = seg + 1;
+                            time = __dadd_rn(__dsub_rn(time, dur), step);
+                        } else {
+                            from = val;
+                            y = (float)from;
+                            if (dn.looping) {
+                                seg = 0;
+                                time = 0.0;
+                            } else running = 0;
+                        }
+                    }
+                    EMIT(f, 0, y)
+                }
+                ENVL_STORE;
+                break;
+            }
+            case DK_MATH: {
+                const uint32_t nch = dn.n_out;
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, (void)0, (void)0)
+                    AR_POST_ROUTES(f)
+                    float ain[MAX_IN];
+#pragma unroll
+                    for (int c = 0; c < MAX_IN; c++) ain[c] = (c < 2 * (int)nch && dn.in_slot[c] >= 0) ? sval[(dn.in_slot[c] * CH + f) * 32] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < MAX_OUT; c++)
+                        if (c < (int)nch) {
+                            float y = math_apply(dn.mode, ain[c], ain[c + nch]);
+                            EMIT(f, c, y)
+                        }
+                }
+                break;
+            }
+            case DK_CONST:
+            case DK_INPLUS: {
+                float val = __uint_as_float(sreg[rb * 32]);
+                const int is = dn.kind == DK_INPLUS ? dn.in_slot[0] : -1;
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, (void)0, val = __uint_as_float(sreg[rb * 32]))
+                    for (int ai = 0; ai < dn.n_ar; ai++) {
+                        float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
+                        if (dn.ar_code[ai] == AR_REG0) val = x;
+                        else pv[dn.ar_code[ai] - AR_POST] = x;
+                    }
+                    float y = val;
+                    if (dn.kind == DK_INPLUS) y = val + (is >= 0 ? sval[(is * CH + f) * 32] : 0.f);
+                    EMIT(f, 0, y)
+                }
+                if (dn.n_ar) sreg[rb * 32] = __float_as_uint(val);
+                break;
+            }
+            default: break;
+            }
+            // an audio-rate route into a wrapper value persists like a param_apply would
+            for (int ai = 0; ai < dn.n_ar; ai++)
+                if (dn.ar_code[ai] >= AR_POST) sreg[dn.post_reg[dn.ar_code[ai] - AR_POST] * 32] = __float_as_uint(pv[dn.ar_code[ai] - AR_POST]);
+            // events due in this chunk but after its last processed frame cannot exist (sorted by chunk)
+        }
+        // mix bus: per-warp partial sums, fixed butterfly order => deterministic
+        for (uint32_t u = 0; u < prog->n_ubus; u++) {
+            const uint32_t slot = prog->ubus_slot[u];
+            float mine = 0.f;
+            for (uint32_t f = 0; f < nf; f++) {
+                float x = active ? sval[(slot * CH + f) * 32] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) x = x + __shfl_xor_sync(0xFFFFFFFFu, x, o);
+                if (lane == (f & 31)) mine = x;
+                if ((f & 31) == 31 || f + 1 == nf) {
+                    const uint32_t fbase = f & ~31u;
+                    if (lane <= (f & 31)) a.partials[(size_t)(a.row0 + warp * prog->n_ubus + u) * a.n_frames + c0 + fbase + lane] = mine;
+                }
+            }
+        }
+        for (uint32_t ti = 0; ti < a.n_taps; ti++) {
+            const DevTap tp = a.taps[ti];
+            if (tp.voice == v)
+                for (uint32_t f = 0; f < nf; f++) a.tap_out[(size_t)tp.tap * a.tap_stride + a.tap_frame0 + c0 + f] = sval[(tp.slot * CH + f) * 32];
+        }
+        __syncwarp();
+    }
+    if (active)
+        for (uint32_t r = 0; r < n_regs; r++) a.regs[(size_t)r * a.n_voices + v] = sreg[r * 32];
+}
+
+// out[block][ch][i] = sum over partial rows feeding ch, rows in index order (deterministic)
+__global__ void reduce_bus(const float *__restrict__ partials, const uint32_t *__restrict__ row_mask, uint32_t n_rows,
+                           uint32_t n_frames, float *__restrict__ out, uint32_t n_out, uint32_t block_size) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_frames) return;
+    float acc[MAX_BUS];
+#pragma unroll
+    for (int c = 0; c < MAX_BUS; c++) acc[c] = 0.f;
+    for (uint32_t r = 0; r < n_rows; r++) {
+        const float x = partials[(size_t)r * n_frames + t];
+        const uint32_t m = row_mask[r];
+#pragma unroll
+        for (int c = 0; c < MAX_BUS; c++)
+            if ((m >> c) & 1u) acc[c] = acc[c] + x;
+    }
+    const uint32_t blk = t / block_size, i = t % block_size;
+#pragma unroll
+    for (int c = 0; c < MAX_BUS; c++)
+        if (c < (int)n_out) out[((size_t)blk * n_out + c) * block_size + i] = acc[c];
+}
+
+// host-callable launchers ---------------------------------------------------------------------
+cudaError_t launch_interp(const InterpArgs &a, uint32_t n_regs, uint32_t n_slots, cudaStream_t stream) {
+    const uint32_t n_warps = (a.n_voices + 31) / 32;
+    const size_t smem = ((size_t)n_regs + (size_t)n_slots * a.chunk) * 32 * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(render_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    render_interp<<<n_warps, 32, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_bus(const float *partials, const uint32_t *row_mask, uint32_t n_rows, uint32_t n_frames, float *out,
+                              uint32_t n_out, uint32_t block_size, cudaStream_t stream) {
+    const uint32_t threads = 128;
+    reduce_bus<<<(n_frames + threads - 1) / threads, threads, 0, stream>>>(partials, row_mask, n_rows, n_frames, out, n_out, block_size);
+    return cudaGetLastError();
+}
+
+#ifndef KGPU_HAVE_FUSED
+int match_fused_recipe(const DevProgram &) { return -1; }
+const char *fused_recipe_name(int) { return "render_interp"; }
+uint32_t fused_rows(int, uint32_t, uint32_t) { return 0; }
+cudaError_t launch_fused(int, const FusedArgs &, cudaStream_t) { return cudaErrorNotSupported; }
+#endif
+
+} // namespace kgpu

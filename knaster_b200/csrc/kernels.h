@@ -1,0 +1,53 @@
+// kernels.h -- launch interface between the plan runtime (capi.cpp) and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dev.h"
+
+namespace kgpu {
+
+struct InterpArgs {
+    const DevProgram *prog; // device
+    uint32_t *regs;         // [n_regs][n_voices]
+    uint32_t n_voices;
+    const DevEvent *events; // device, sorted per voice in processing order; NULL if none this launch
+    const uint32_t *ev_off; // [n_voices+1]
+    uint32_t n_frames;
+    uint32_t chunk;         // frames per interpreter chunk (divides block_size, <= 16)
+    float *partials;        // [rows][n_frames]
+    uint32_t row0;          // first partial row of this group
+    const DevTap *taps;
+    uint32_t n_taps;
+    float *tap_out;         // [n_taps][tap_stride]
+    uint64_t tap_stride;
+    uint64_t tap_frame0;
+    const float *sine_table; // device, 16384 f32 (wavetable.rs:130-139)
+};
+
+cudaError_t launch_interp(const InterpArgs &a, uint32_t n_regs, uint32_t n_slots, cudaStream_t stream);
+cudaError_t launch_reduce_bus(const float *partials, const uint32_t *row_mask, uint32_t n_rows, uint32_t n_frames, float *out,
+                              uint32_t n_out, uint32_t block_size, cudaStream_t stream);
+
+// fused bank kernels (fused.cu)
+struct FusedArgs {
+    const DevProgram *prog;
+    uint32_t *regs;
+    uint32_t n_voices;
+    const DevEvent *events;
+    const uint32_t *ev_off;
+    uint32_t n_frames;
+    float *partials;
+    uint32_t row0;
+    const DevTap *taps;
+    uint32_t n_taps;
+    float *tap_out;
+    uint64_t tap_stride;
+    uint64_t tap_frame0;
+    const float *sine_table;
+};
+// number of partial rows a fused recipe produces for n_voices voices
+uint32_t fused_rows(int recipe, uint32_t n_voices, uint32_t n_ubus);
+cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream);
+
+} // namespace kgpu

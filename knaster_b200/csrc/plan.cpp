@@ -1,0 +1,1147 @@
+// plan.cpp -- graph -> kernel plan compiler and control-rate simulation (host, C++).
+//
+// What knaster does on its control thread at Graph::commit_changes (graph.rs:1707-1726:
+// node order, buffer plan, TaskData) and on its audio thread at the top of every block
+// (graph_gen.rs:111-166,269-305: drain the event ring, apply parameter changes through the
+// wrapper stack) is done here, ahead of time, for a static graph:
+//
+//  * build():    find the mix-bus Add chains (graph.rs:850-864), split the rest into
+//                independent voices, batch isomorphic voices into groups (SoA registers),
+//                lay out registers and value slots (the analogue of buffer_allocator.rs),
+//                run every node's init() (graph.rs:462-475) to get the initial registers.
+//  * simulate(): replay the parameter-change queue through an exact model of the wrapper
+//                stack (WrPreciseTiming / WrSmoothParams / WrArParams / WrMul..) and of every
+//                UGen's setters; all f64 / libm work (tanf, expf, f64 ramps) happens here with
+//                the same libm knaster uses, and the device only sees
+//                "write register r at frame f" events plus three state-dependent triggers.
+//
+// Compiled with -ffp-contract=off: f32 expressions below must round exactly like rustc's.
+#include "plan.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <tuple>
+#include <unordered_map>
+
+namespace kgpu {
+
+std::string format(const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    return buf;
+}
+
+namespace {
+
+constexpr float F_PI = 3.14159265358979323846264338327950288f;
+
+inline uint32_t sat_u32(double v) { // Rust `as u32`
+    if (!(v == v) || v <= 0.0) return 0;
+    if (v >= 4294967295.0) return 4294967295u;
+    return (uint32_t)v;
+}
+inline uint64_t sat_usize(double v) {
+    if (!(v == v) || v <= 0.0) return 0;
+    if (v >= 18446744073709551615.0) return UINT64_MAX;
+    return (uint64_t)v;
+}
+inline uint32_t fbits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+inline void dbits(double d, uint32_t &lo, uint32_t &hi) {
+    uint64_t u;
+    std::memcpy(&u, &d, 8);
+    lo = (uint32_t)u;
+    hi = (uint32_t)(u >> 32);
+}
+
+// ---- static facts about node kinds ------------------------------------------------------
+struct KindInfo {
+    int n_in, n_out, n_params, dev_kind, n_regs;
+};
+KindInfo kind_info(const kgpu_node_desc &d) {
+    switch (d.kind) {
+    case KGPU_SIN_WT: return {0, 1, 3, DK_SINWT, REGS_SINWT};
+    case KGPU_SIN_NUMERIC: return {0, 1, 3, DK_SINNUM, REGS_SINNUM};
+    case KGPU_POLYBLEP: return {0, 1, 3, DK_POLYBLEP, REGS_POLYBLEP};
+    case KGPU_SVF: return {1, 1, 5, DK_SVF, REGS_SVF};
+    case KGPU_ONEPOLE_LPF: return {1, 1, 1, DK_ONEPOLE_LP, REGS_ONEPOLE};
+    case KGPU_ONEPOLE_HPF: return {1, 1, 1, DK_ONEPOLE_HP, REGS_ONEPOLE};
+    case KGPU_ENV_ASR: return {0, 1, 4, DK_ENVASR, REGS_ENV};
+    case KGPU_ENV_AR: return {0, 1, 3, DK_ENVAR, REGS_ENV};
+    case KGPU_ENVELOPE: return {0, 1, 4, DK_ENVELOPE, (int)(REGS_ENVELOPE_BASE + REGS_ENVELOPE_PER_SEG * d.n_segments)};
+    case KGPU_MATH: return {(int)(2 * d.channels), (int)d.channels, 0, DK_MATH, 0};
+    case KGPU_CONSTANT: return {0, 1, 1, DK_CONST, REGS_CONST};
+    case KGPU_TEST_NUM: return {0, 1, 0, DK_CONST, REGS_CONST};
+    case KGPU_TEST_IN_PLUS_PARAM: return {1, 1, 1, DK_INPLUS, REGS_CONST};
+    default: KGPU_THROW(KGPU_ERR_UNSUPPORTED, "unknown ugen kind %u", d.kind);
+    }
+}
+// expected ParameterValue kind per base parameter ('t' = trigger: any value fires)
+const char *param_types(uint32_t kind) {
+    switch (kind) {
+    case KGPU_SIN_WT: case KGPU_SIN_NUMERIC: return "fft";
+    case KGPU_POLYBLEP: return "ffi";
+    case KGPU_SVF: return "fffit";
+    case KGPU_ONEPOLE_LPF: case KGPU_ONEPOLE_HPF: return "f";
+    case KGPU_ENV_ASR: return "fftt";
+    case KGPU_ENV_AR: return "fft";
+    case KGPU_ENVELOPE: return "fitt";
+    case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: return "f";
+    default: return "";
+    }
+}
+bool is_math_wrapper(uint32_t k) { return k >= KGPU_WR_MUL && k <= KGPU_WR_POWI; }
+
+void validate_node(const kgpu_node_desc &d, uint32_t idx) {
+    KindInfo ki = kind_info(d);
+    if (d.kind == KGPU_MATH) {
+        if (d.channels < 1 || d.channels > (uint32_t)MAX_OUT)
+            KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: MathUGen with %u channels (1..%d supported)", idx, d.channels, MAX_OUT);
+        if (d.mode > KGPU_OP_DIV) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: MathUGen Pow is not supported yet", idx);
+    }
+    if (d.kind == KGPU_POLYBLEP && d.mode != 0)
+        KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: PolyBlep waveform %u not supported yet (Sawtooth only)", idx, d.mode);
+    if (d.kind == KGPU_SVF && d.mode > 8) KGPU_THROW(KGPU_ERR_INVALID, "node %u: bad SvfFilterType %u", idx, d.mode);
+    if (d.kind == KGPU_ENVELOPE) {
+        if (d.n_segments < 1 || !d.segments) KGPU_THROW(KGPU_ERR_INVALID, "node %u: Envelope needs >= 1 segment", idx);
+        if (ki.n_regs > MAX_REGS) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: Envelope with %u segments is too large", idx, d.n_segments);
+    }
+    if (d.n_wrappers && !d.wrappers) KGPU_THROW(KGPU_ERR_INVALID, "node %u: wrappers pointer is NULL", idx);
+    int n_post = 0, n_ar = 0, n_smooth = 0, n_precise = 0;
+    for (uint32_t i = 0; i < d.n_wrappers; i++) {
+        uint32_t k = d.wrappers[i].kind;
+        if (k == KGPU_WR_POWF || k == KGPU_WR_POWI) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: WrPowf/WrPowi are not supported yet", idx);
+        if (is_math_wrapper(k)) n_post++;
+        else if (k == KGPU_WR_AR_PARAMS) {
+            n_ar++;
+            if (n_smooth || n_precise)
+                KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: WrArParams outside WrSmoothParams/WrPreciseTiming is not supported "
+                           "(knaster's WrPreciseTiming must be outermost, precise_timing.rs:13)", idx);
+        } else if (k == KGPU_WR_SMOOTH_PARAMS) n_smooth++;
+        else if (k == KGPU_WR_PRECISE_TIMING) {
+            n_precise++;
+            if (d.wrappers[i].capacity == 0 || d.wrappers[i].capacity > 4096) KGPU_THROW(KGPU_ERR_INVALID, "node %u: bad WrPreciseTiming capacity", idx);
+        } else KGPU_THROW(KGPU_ERR_INVALID, "node %u: unknown wrapper kind %u", idx, k);
+    }
+    if (n_post > MAX_POST) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: more than %d arithmetic wrappers", idx, MAX_POST);
+    if (n_ar > 1 || n_smooth > 1 || n_precise > 1) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: duplicate wrapper of one kind", idx);
+}
+
+uint32_t total_params(const kgpu_node_desc &d) {
+    uint32_t n = (uint32_t)kind_info(d).n_params;
+    for (uint32_t i = 0; i < d.n_wrappers; i++)
+        if (d.wrappers[i].kind == KGPU_WR_MUL) n++;
+    return n;
+}
+
+// SvfFilter::set_coeffs, svf.rs:146-242.  out: a1 a2 a3 m0 m1 m2
+void svf_coeffs(uint32_t ty, float cutoff, float q, float gain_db, float sr, float *c) {
+    float g, k, amp;
+    switch (ty) {
+    case 6: // Bell
+        amp = powf(10.0f, gain_db / 40.0f);
+        g = tanf((F_PI * cutoff) / sr) / sqrtf(amp);
+        k = 1.0f / (q * amp);
+        c[0] = 1.0f / (1.0f + g * (g + k)); c[1] = g * c[0]; c[2] = g * c[1];
+        c[3] = 1.0f; c[4] = k * (amp * amp - 1.0f); c[5] = 0.0f;
+        return;
+    case 7: // LowShelf
+        amp = powf(10.0f, gain_db / 40.0f);
+        g = tanf((F_PI * cutoff) / sr) / sqrtf(amp);
+        k = 1.0f / q;
+        c[0] = 1.0f / (1.0f + g * (g + k)); c[1] = g * c[0]; c[2] = g * c[1];
+        c[3] = 1.0f; c[4] = k * (amp - 1.0f); c[5] = amp * amp - 1.0f;
+        return;
+    case 8: // HighShelf
+        amp = powf(10.0f, gain_db / 40.0f);
+        g = tanf((F_PI * cutoff) / sr) * sqrtf(amp);
+        k = 1.0f / q;
+        c[0] = 1.0f / (1.0f + g * (g + k)); c[1] = g * c[0]; c[2] = g * c[1];
+        c[3] = amp * amp; c[4] = k * (1.0f - amp) * amp; c[5] = 1.0f - amp * amp;
+        return;
+    default: break;
+    }
+    g = tanf((F_PI * cutoff) / sr);
+    k = 1.0f / q;
+    c[0] = 1.0f / (1.0f + g * (g + k));
+    c[1] = g * c[0];
+    c[2] = g * c[1];
+    switch (ty) {
+    case 0: c[3] = 0.f; c[4] = 0.f; c[5] = 1.f; break;        // Low
+    case 1: c[3] = 1.f; c[4] = -k; c[5] = -1.f; break;        // High
+    case 2: c[3] = 0.f; c[4] = 1.f; c[5] = 0.f; break;        // Band
+    case 3: c[3] = 1.f; c[4] = -k; c[5] = 0.f; break;         // Notch
+    case 4: c[3] = 1.f; c[4] = -k; c[5] = -2.0f; break;       // Peak
+    default: c[3] = 1.f; c[4] = -2.0f * k; c[5] = 0.f; break; // All
+    }
+}
+
+// ---- control simulation ------------------------------------------------------------------
+struct Sim {
+    HostPlan &P;
+    uint32_t gi;
+    uint32_t voice;
+    uint32_t local;
+    HostNode &hn;
+    void emit(uint64_t frame, uint16_t op, uint32_t reg, uint32_t value) {
+        VoiceEvent ve;
+        ve.voice = voice;
+        ve.frame = frame;
+        ve.seq = P.seq++;
+        ve.ev.frame = 0;
+        ve.ev.node = (uint16_t)local;
+        ve.ev.op = op;
+        ve.ev.reg = reg;
+        ve.ev.value = value;
+        P.out_events[gi].push_back(ve);
+        P.device_events++;
+    }
+    void set_f(uint64_t frame, uint32_t reg, float v) { emit(frame, OP_SET, reg, fbits(v)); }
+    void set_u(uint64_t frame, uint32_t reg, uint32_t v) { emit(frame, OP_SET, reg, v); }
+    void set_d(uint64_t frame, uint32_t reg, double v) {
+        uint32_t lo, hi;
+        dbits(v, lo, hi);
+        emit(frame, OP_SET, reg, lo);
+        emit(frame, OP_SET, reg + 1, hi);
+    }
+};
+
+// the UGen's own param_apply: every #[param] setter of the supported UGens
+void ugen_param_apply(Sim &s, uint32_t param, const PV &v, uint64_t frame) {
+    HostNode &h = s.hn;
+    const float sr = (float)s.P.sample_rate;
+    const uint32_t r = h.reg;
+    switch (h.kind) {
+    case KGPU_SIN_WT: // osc.rs:126-140
+        if (param == 0) {
+            h.f0 = (float)v.f;
+            double k = 16384.0 * 65536.0 * (1.0 / (double)s.P.sample_rate);
+            s.set_u(frame, r + 2, sat_u32((double)h.f0 * k));
+        } else if (param == 1) s.set_u(frame, r + 1, sat_u32(v.f * 65536.0));
+        else if (param == 2) s.set_u(frame, r + 0, 0);
+        break;
+    case KGPU_SIN_NUMERIC: // osc.rs:239-252
+        if (param == 0) s.set_f(frame, r + 2, (float)v.f / sr);
+        else if (param == 1) s.set_f(frame, r + 1, (float)v.f);
+        else if (param == 2) s.set_f(frame, r + 0, 0.0f);
+        break;
+    case KGPU_POLYBLEP: // polyblep.rs:162-184
+        if (param == 0) {
+            h.f0 = (float)v.f;
+            float dt = h.f0 / sr;
+            s.set_f(frame, r + 1, dt);
+            s.set_u(frame, r + 2, (dt * sr >= sr / 4.0f) ? 1u : 0u); // guard of next_sample, polyblep.rs:210
+        } else if (param == 1) s.set_f(frame, r + 3, (float)v.f);
+        else if (param == 2) {
+            if ((int64_t)v.f != 0) s.P.ignored_delays++; // unsupported waveform change: kept as Sawtooth (rejected at push)
+        }
+        break;
+    case KGPU_SVF: { // svf.rs:81-133
+        if (param == 0) h.f0 = (float)v.f;
+        else if (param == 1) h.f1 = (float)v.f;
+        else if (param == 2) h.f2 = (float)v.f;
+        else if (param == 3) h.mode = (uint32_t)(int64_t)v.f;
+        else if (param != 4) break;
+        float c[6];
+        svf_coeffs(h.mode, h.f0, h.f1, h.f2, sr, c);
+        for (int i = 0; i < 6; i++)
+            if (fbits(c[i]) != fbits(h.svf_coef[i])) {
+                h.svf_coef[i] = c[i];
+                s.set_f(frame, r + 2 + i, c[i]);
+            }
+        break;
+    }
+    case KGPU_ONEPOLE_LPF: case KGPU_ONEPOLE_HPF: // onepole.rs:135-139,172-176,35-46
+        if (param == 0) {
+            float f = (float)v.f / sr;
+            float b1 = expf(-2.0f * F_PI * f);
+            s.set_f(frame, r + 2, b1);
+            s.set_f(frame, r + 1, 1.0f - b1);
+        }
+        break;
+    case KGPU_ENV_ASR: case KGPU_ENV_AR: // envelopes.rs:84-133,234-266
+        if (param == 0) {
+            float atk = (float)v.f;
+            if (h.f0 != atk) {
+                h.f0 = atk;
+                s.set_f(frame, r + 2, atk == 0.f ? 1.0f : 1.0f / (atk * sr));
+            }
+        } else if (param == 1) {
+            float rel = (float)v.f;
+            if (h.f1 != rel) {
+                h.f1 = rel;
+                s.set_f(frame, r + 3, rel == 0.f ? 1.0f : 1.0f / (rel * sr));
+            }
+        } else if (h.kind == KGPU_ENV_ASR && param == 2) s.emit(frame, OP_ASR_RELEASE, r, 0);
+        else if ((h.kind == KGPU_ENV_ASR && param == 3) || (h.kind == KGPU_ENV_AR && param == 2))
+            s.set_u(frame, r + 0, ASR_ATTACKING);
+        break;
+    case KGPU_ENVELOPE: // envelopes.rs:476-526
+        if (param == 0) {
+            double ts = (double)(float)v.f;
+            s.set_d(frame, r + 6, ts * (1.0 / (double)s.P.sample_rate));
+        } else if (param == 1) {
+            uint64_t j = sat_usize(v.f);
+            if (j >= h.n_seg) j = h.n_seg - 1;
+            s.set_u(frame, r + 1, (uint32_t)j);
+            s.set_d(frame, r + 2, 0.0);
+            s.set_u(frame, r + 0, 1);
+        } else if (param == 2) {
+            s.set_u(frame, r + 0, 1);
+            s.set_u(frame, r + 1, 0);
+            s.set_d(frame, r + 2, 0.0);
+            s.set_d(frame, r + 4, h.d0);
+        } else if (param == 3) s.emit(frame, OP_ENV_STOP, r, 0);
+        break;
+    case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: // util.rs:45-48
+        if (param == 0) s.set_f(frame, r + 0, (float)v.f);
+        break;
+    default: break;
+    }
+}
+
+void wr_param_apply(Sim &s, int level, uint32_t param, const PV &v, uint64_t frame);
+
+// ParameterSmoothingState::next_value, BlockRate branch (smooth_params.rs:263-300)
+bool smooth_next_value(SmoothState &st, uint64_t block_size, double *out) {
+    if (!st.linear || st.done) return false;
+    double mix = (double)st.frames_elapsed / (double)st.duration_frames;
+    double cur = (st.end_value - st.start_value) * mix + st.start_value;
+    if (st.frames_elapsed == st.duration_frames) st.done = true;
+    else st.frames_elapsed = std::min<uint64_t>(st.frames_elapsed + block_size, st.duration_frames);
+    *out = cur;
+    return true;
+}
+
+void wr_param_apply(Sim &s, int level, uint32_t param, const PV &v, uint64_t frame) {
+    if (level < 0) {
+        if (v.kind == PV::Smoothing) return; // rejected at push time (would panic in knaster)
+        ugen_param_apply(s, param, v, frame);
+        return;
+    }
+    WrapSim &w = s.hn.wr[level];
+    switch (w.kind) {
+    case KGPU_WR_MUL:
+        if (param == w.inner_params) { // wrappers_core/math.rs:92-98
+            if (v.kind == PV::Float) s.set_f(frame, w.reg, (float)v.f);
+            return;
+        }
+        wr_param_apply(s, level - 1, param, v, frame);
+        return;
+    case KGPU_WR_ADD: case KGPU_WR_SUB: case KGPU_WR_VSUB: case KGPU_WR_DIV: case KGPU_WR_VDIV:
+        wr_param_apply(s, level - 1, param, v, frame);
+        return;
+    case KGPU_WR_AR_PARAMS: // audio_rate.rs:70-74
+        if (param < w.ar_bound.size() && w.ar_bound[param]) return;
+        wr_param_apply(s, level - 1, param, v, frame);
+        return;
+    case KGPU_WR_SMOOTH_PARAMS: { // smooth_params.rs:200-244
+        if (param >= w.smooth.size()) return;
+        SmoothState &st = w.smooth[param];
+        if (v.kind == PV::Integer || v.kind == PV::Trigger || v.kind == PV::Bool) {
+            wr_param_apply(s, level - 1, param, v, frame);
+        } else if (v.kind == PV::Float) {
+            if (!st.linear) wr_param_apply(s, level - 1, param, v, frame);
+            else {
+                if (st.done) st.start_value = st.end_value;
+                else {
+                    double mix = (double)st.frames_elapsed / (double)st.duration_frames;
+                    st.start_value = (st.end_value - st.start_value) * mix + st.start_value;
+                }
+                st.end_value = v.f;
+                st.done = false;
+                st.frames_elapsed = 0;
+            }
+        } else if (v.kind == PV::Smoothing) { // set_smoothing, smooth_params.rs:31-102
+            if (v.smoothing == 0) {
+                if (st.linear) {
+                    double mix = (double)st.frames_elapsed / (double)st.duration_frames;
+                    double cur = (st.end_value - st.start_value) * mix + st.start_value;
+                    st = SmoothState{};
+                    st.current_value = cur;
+                }
+            } else {
+                uint64_t dur = sat_usize((double)v.smooth_seconds * (double)s.P.sample_rate);
+                if (!st.linear) {
+                    double cur = st.current_value;
+                    st.linear = true;
+                    st.start_value = cur; st.end_value = cur;
+                    st.duration_frames = dur; st.frames_elapsed = 0; st.done = true;
+                } else if (st.done) {
+                    st.start_value = st.end_value;
+                    st.duration_frames = dur; st.frames_elapsed = 0; st.done = true;
+                } else {
+                    double mix = (double)st.frames_elapsed / (double)st.duration_frames;
+                    st.start_value = (st.end_value - st.start_value) * mix + st.start_value;
+                    st.duration_frames = dur; st.done = true;
+                }
+            }
+        }
+        return;
+    }
+    case KGPU_WR_PRECISE_TIMING: // precise_timing.rs:126-135
+        if (param >= w.next_delay.size()) return; // would index out of bounds in knaster
+        if (w.next_delay[param] == 0) wr_param_apply(s, level - 1, param, v, frame);
+        else if (w.queue.size() < w.capacity) w.queue.push_back(QueuedChange{w.next_delay[param], param, v});
+        else s.P.dropped_changes++;
+        return;
+    default: return;
+    }
+}
+
+// set_delay_within_block_for_param through the wrapper stack
+void wr_set_delay(Sim &s, int level, uint32_t param, uint16_t delay) {
+    for (; level >= 0; level--) {
+        WrapSim &w = s.hn.wr[level];
+        if (w.kind == KGPU_WR_PRECISE_TIMING) { // precise_timing.rs:146-148
+            if (param < w.next_delay.size()) w.next_delay[param] = delay;
+            return;
+        }
+        if (!is_math_wrapper(w.kind)) break; // WrSmoothParams / WrArParams do not forward (trait default)
+    }
+    s.P.ignored_delays++; // ugen.rs:339-341: warning, no effect
+}
+
+// control-side effects of process_block through the wrapper stack for one (partial) block
+void wr_process_block(Sim &s, int level, uint64_t block_start, uint32_t offset, uint32_t frames) {
+    for (; level >= 0; level--) {
+        WrapSim &w = s.hn.wr[level];
+        if (w.kind == KGPU_WR_SMOOTH_PARAMS) { // smooth_params.rs:179-188
+            for (uint32_t j = 0; j < w.smooth.size(); j++) {
+                double v;
+                if (smooth_next_value(w.smooth[j], s.P.block_size, &v)) {
+                    PV pv;
+                    pv.kind = PV::Float;
+                    pv.f = v;
+                    wr_param_apply(s, level - 1, j, pv, block_start + offset);
+                }
+            }
+        } else if (w.kind == KGPU_WR_PRECISE_TIMING) { // precise_timing.rs:65-114
+            uint32_t block_i = 0;
+            size_t change_i = 0;
+            const size_t num = w.queue.size();
+            std::vector<QueuedChange> q;
+            q.swap(w.queue); // next_delay_i = 0 at the end; next_delay[] stays
+            std::vector<uint8_t> some(num, 1);
+            while (true) {
+                uint32_t local_frames = frames - block_i;
+                while (change_i < num) {
+                    if (some[change_i]) {
+                        if ((uint32_t)q[change_i].delay <= block_i + offset) {
+                            wr_param_apply(s, level - 1, q[change_i].param, q[change_i].value, block_start + offset + block_i);
+                            some[change_i] = 0;
+                        } else {
+                            local_frames = std::min(local_frames, (uint32_t)q[change_i].delay - offset - block_i);
+                            break;
+                        }
+                    }
+                    change_i++;
+                }
+                if (block_i >= frames) break;
+                wr_process_block(s, level - 1, block_start, offset + block_i, local_frames);
+                block_i += local_frames;
+            }
+            return;
+        } else if (w.kind == KGPU_WR_AR_PARAMS) {
+            return; // per-frame inner.process(); nothing control-rate inside (validated)
+        }
+    }
+}
+
+bool needs_processing(const HostNode &h) {
+    for (const WrapSim &w : h.wr) {
+        if (w.kind == KGPU_WR_PRECISE_TIMING && !w.queue.empty()) return true;
+        if (w.kind == KGPU_WR_SMOOTH_PARAMS)
+            for (const SmoothState &st : w.smooth)
+                if (st.linear && !st.done) return true;
+    }
+    return false;
+}
+
+uint64_t hash_mix(uint64_t h, uint64_t v) {
+    h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+}
+
+} // namespace
+
+bool TemplateNode::same_shape(const TemplateNode &o) const {
+    if (kind != o.kind || mode != o.mode || channels != o.channels || flags != o.flags || n_segments != o.n_segments) return false;
+    if (wrappers.size() != o.wrappers.size() || in != o.in || par != o.par) return false;
+    for (size_t i = 0; i < wrappers.size(); i++)
+        if (wrappers[i].kind != o.wrappers[i].kind || wrappers[i].capacity != o.wrappers[i].capacity) return false;
+    return true;
+}
+bool Template::same_shape(const Template &o) const {
+    if (nodes.size() != o.nodes.size() || outs != o.outs) return false;
+    for (size_t i = 0; i < nodes.size(); i++)
+        if (!nodes[i].same_shape(o.nodes[i])) return false;
+    return true;
+}
+
+namespace {
+
+uint64_t template_hash(const Template &t) {
+    uint64_t h = 1469598103934665603ULL;
+    for (const TemplateNode &n : t.nodes) {
+        h = hash_mix(h, n.kind | ((uint64_t)n.mode << 8) | ((uint64_t)n.channels << 16) | ((uint64_t)n.flags << 24) | ((uint64_t)n.n_segments << 32));
+        for (auto &w : n.wrappers) h = hash_mix(h, w.kind | ((uint64_t)w.capacity << 8));
+        for (auto &e : n.in) h = hash_mix(h, (uint64_t)(uint32_t)e.first | ((uint64_t)e.second << 32));
+        for (auto &p : n.par) h = hash_mix(h, std::get<0>(p) | ((uint64_t)(uint32_t)std::get<1>(p) << 16) | ((uint64_t)std::get<2>(p) << 40));
+    }
+    for (auto &o : t.outs) h = hash_mix(h, (uint64_t)(uint32_t)std::get<0>(o) | ((uint64_t)std::get<1>(o) << 20) | ((uint64_t)std::get<2>(o) << 40));
+    return h;
+}
+
+// resolve an audio-rate parameter route of a node to a device action
+uint8_t ar_code_for(const TemplateNode &tn, uint32_t param, int ar_level) {
+    // walk inward from the WrArParams wrapper
+    int post_index = 0;
+    for (int l = 0; l < ar_level; l++)
+        if (is_math_wrapper(tn.wrappers[l].kind)) post_index++;
+    uint32_t inner = 0; // parameters of the stack below the AR wrapper
+    {
+        kgpu_node_desc tmp{};
+        tmp.kind = tn.kind;
+        tmp.channels = tn.channels;
+        tmp.n_segments = tn.n_segments;
+        inner = (uint32_t)kind_info(tmp).n_params;
+    }
+    // parameters contributed by WrMul wrappers below the AR level, innermost first
+    uint32_t pcount = inner;
+    int pi = 0;
+    for (int l = 0; l < ar_level; l++) {
+        uint32_t k = tn.wrappers[l].kind;
+        if (is_math_wrapper(k)) {
+            if (k == KGPU_WR_MUL) {
+                if (param == pcount) return (uint8_t)(AR_POST + pi);
+                pcount++;
+            }
+            pi++;
+        }
+    }
+    (void)post_index;
+    if (param >= inner) KGPU_THROW(KGPU_ERR_PARAMETER, "audio-rate route to parameter %u: index out of bounds", param);
+    switch (tn.kind) {
+    case KGPU_SIN_NUMERIC: if (param == 0) return AR_SINNUM_FREQ; if (param == 1) return AR_SINNUM_OFFSET; break;
+    case KGPU_SIN_WT: if (param == 0) return AR_SINWT_FREQ; if (param == 1) return AR_SINWT_OFFSET; break;
+    case KGPU_POLYBLEP: if (param == 0) return AR_POLYBLEP_FREQ; break;
+    case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: if (param == 0) return AR_REG0; break;
+    default: break;
+    }
+    KGPU_THROW(KGPU_ERR_UNSUPPORTED, "audio-rate route to parameter %u of ugen kind %u is not supported yet", param, tn.kind);
+}
+
+// lay out registers + value slots of a template and fill its DevProgram
+void compile_template(Group &g, uint32_t sample_rate, const std::vector<std::pair<uint32_t, uint32_t>> &pinned) {
+    const Template &t = g.tpl;
+    DevProgram &p = g.prog;
+    std::memset(&p, 0, sizeof p);
+    const size_t n = t.nodes.size();
+    if (n > (size_t)MAX_NODES)
+        KGPU_THROW(KGPU_ERR_UNSUPPORTED, "a voice with %zu nodes exceeds the per-voice limit of %d (sources shared between voices "
+                   "merge them into one voice; not supported yet)", n, MAX_NODES);
+    p.n_nodes = (uint32_t)n;
+    p.sample_rate = (float)sample_rate;
+    p.sinwt_k = 16384.0 * 65536.0 * (1.0 / (double)sample_rate);
+    // registers
+    uint32_t reg = 0;
+    std::vector<std::vector<uint16_t>> post_regs(n);
+    for (size_t i = 0; i < n; i++) {
+        const TemplateNode &tn = t.nodes[i];
+        kgpu_node_desc tmp{};
+        tmp.kind = tn.kind; tmp.channels = tn.channels; tmp.n_segments = tn.n_segments;
+        KindInfo ki = kind_info(tmp);
+        DevNode &dn = p.nodes[i];
+        dn.kind = (uint8_t)ki.dev_kind;
+        dn.mode = (uint8_t)tn.mode;
+        dn.n_in = (uint8_t)ki.n_in;
+        dn.n_out = (uint8_t)ki.n_out;
+        dn.reg = (uint16_t)reg;
+        dn.n_seg = (uint16_t)tn.n_segments;
+        dn.looping = (uint8_t)(tn.flags & 1);
+        reg += (uint32_t)ki.n_regs;
+        int ar_level = -1;
+        for (size_t l = 0; l < tn.wrappers.size(); l++) {
+            uint32_t k = tn.wrappers[l].kind;
+            if (is_math_wrapper(k)) {
+                dn.post_op[dn.n_post] = (uint8_t)k; // PO_* == KGPU_WR_* for 1..6
+                dn.post_reg[dn.n_post] = (uint16_t)reg;
+                post_regs[i].push_back((uint16_t)reg);
+                dn.n_post++;
+                reg++;
+            } else if (k == KGPU_WR_AR_PARAMS) ar_level = (int)l;
+        }
+        for (auto &pe : tn.par) {
+            if (ar_level < 0) continue; // no WrArParams: set_ar_param_buffer has no effect (ugen.rs:322-329)
+            if (dn.n_ar >= MAX_AR) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "more than %d audio-rate routes into one node", MAX_AR);
+            dn.ar_code[dn.n_ar] = ar_code_for(tn, std::get<0>(pe), ar_level);
+            dn.ar_slot[dn.n_ar] = -1; // filled below
+            dn.n_ar++;
+        }
+    }
+    if (reg > (uint32_t)MAX_REGS) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "voice needs %u registers (limit %d)", reg, MAX_REGS);
+    p.n_regs = reg;
+    // value slots: liveness-based reuse, the analogue of allocate_node_buffers (graph.rs:1588-1704)
+    std::vector<std::vector<int>> last_use(n);
+    for (size_t i = 0; i < n; i++) last_use[i].assign(p.nodes[i].n_out, -1);
+    const int INF = 1 << 30;
+    for (size_t i = 0; i < n; i++) {
+        for (auto &e : t.nodes[i].in)
+            if (e.first >= 0) last_use[e.first][e.second] = std::max(last_use[e.first][e.second], (int)i);
+        for (auto &pe : t.nodes[i].par) last_use[std::get<1>(pe)][std::get<2>(pe)] = std::max(last_use[std::get<1>(pe)][std::get<2>(pe)], (int)i);
+    }
+    for (auto &o : t.outs) last_use[std::get<0>(o)][std::get<1>(o)] = INF;
+    for (auto &pin : pinned) last_use[pin.first][pin.second] = INF;
+    std::vector<uint16_t> free_slots;
+    uint32_t n_slots = 0;
+    g.slot_of.assign(n, {});
+    for (size_t i = 0; i < n; i++) {
+        DevNode &dn = p.nodes[i];
+        const TemplateNode &tn = t.nodes[i];
+        // inputs (+ release the ones that die here: in-place reuse is safe, every node reads a frame before writing it)
+        std::vector<std::pair<int, uint32_t>> dying;
+        for (int c = 0; c < MAX_IN; c++) dn.in_slot[c] = -1;
+        for (size_t c = 0; c < tn.in.size(); c++) {
+            auto &e = tn.in[c];
+            if (e.first < 0) continue;
+            dn.in_slot[c] = (int16_t)g.slot_of[e.first][e.second];
+            if (last_use[e.first][e.second] == (int)i) dying.push_back(e);
+        }
+        int ai = 0;
+        bool has_ar = false;
+        for (auto &w : tn.wrappers) has_ar |= (w.kind == KGPU_WR_AR_PARAMS);
+        for (auto &pe : tn.par) {
+            int src = std::get<1>(pe);
+            uint32_t ch = std::get<2>(pe);
+            if (has_ar) dn.ar_slot[ai++] = (int16_t)g.slot_of[src][ch];
+            if (last_use[src][ch] == (int)i) dying.push_back({src, ch});
+        }
+        std::sort(dying.begin(), dying.end());
+        dying.erase(std::unique(dying.begin(), dying.end()), dying.end());
+        for (auto &d : dying) free_slots.push_back(g.slot_of[d.first][d.second]);
+        g.slot_of[i].resize(dn.n_out);
+        for (int c = 0; c < dn.n_out; c++) {
+            uint16_t s;
+            if (!free_slots.empty()) {
+                s = free_slots.back();
+                free_slots.pop_back();
+            } else s = (uint16_t)n_slots++;
+            g.slot_of[i][c] = s;
+            dn.out_slot[c] = s;
+        }
+        for (int c = 0; c < dn.n_out; c++)
+            if (last_use[i][c] < 0) free_slots.push_back(g.slot_of[i][c]); // dead output
+    }
+    if (n_slots > (uint32_t)MAX_SLOTS) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "voice needs %u live value slots (limit %d)", n_slots, MAX_SLOTS);
+    p.n_slots = std::max(1u, n_slots);
+    // mix-bus outputs: one partial-sum row per distinct (node, channel), with the set of graph outputs it feeds
+    p.n_ubus = 0;
+    for (auto &o : t.outs) {
+        uint16_t slot = g.slot_of[std::get<0>(o)][std::get<1>(o)];
+        uint32_t u = 0;
+        for (; u < p.n_ubus; u++)
+            if (p.ubus_slot[u] == slot) break;
+        if (u == p.n_ubus) {
+            if (p.n_ubus >= (uint32_t)MAX_BUS) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "voice feeds more than %d distinct bus signals", MAX_BUS);
+            p.ubus_slot[u] = slot;
+            p.ubus_mask[u] = 0;
+            p.n_ubus++;
+        }
+        p.ubus_mask[u] |= 1u << std::get<2>(o);
+    }
+}
+
+} // namespace
+
+void recompile_group_slots(Group &g, uint32_t sample_rate, const std::vector<std::pair<uint32_t, uint32_t>> &pinned) {
+    compile_template(g, sample_rate, pinned);
+}
+
+void HostPlan::build(const kgpu_graph_desc &d) {
+    if (d.abi_version != KGPU_ABI_VERSION) KGPU_THROW(KGPU_ERR_INVALID, "abi_version %u != %u", d.abi_version, KGPU_ABI_VERSION);
+    if (d.sample_rate == 0 || d.block_size == 0) KGPU_THROW(KGPU_ERR_INVALID, "sample_rate and block_size must be non-zero"); // processor.rs:75
+    if (d.block_size > 65535) KGPU_THROW(KGPU_ERR_INVALID, "block_size must fit the u16 in-block delay (graph_gen.rs:292)");
+    if (d.n_outputs < 1 || d.n_outputs > (uint32_t)MAX_BUS) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "n_outputs must be 1..%d", MAX_BUS);
+    if (d.n_inputs != 0) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "graphs with inputs are not supported: render with run_without_inputs()");
+    if ((d.n_nodes && !d.nodes) || (d.n_edges && !d.edges) || (d.n_param_edges && !d.param_edges))
+        KGPU_THROW(KGPU_ERR_INVALID, "NULL array in graph description");
+    sample_rate = d.sample_rate;
+    block_size = d.block_size;
+    n_outputs = d.n_outputs;
+    const uint32_t N = d.n_nodes;
+    for (uint32_t i = 0; i < N; i++) validate_node(d.nodes[i], i);
+
+    // adjacency
+    std::vector<uint32_t> in_off(N + 1, 0);
+    for (uint32_t i = 0; i < N; i++) in_off[i + 1] = in_off[i] + (uint32_t)kind_info(d.nodes[i]).n_in;
+    std::vector<std::pair<int, uint32_t>> in_edges(in_off[N], {-1, 0u});
+    std::vector<std::pair<int, uint32_t>> out_edges(n_outputs, {-1, 0u});
+    std::vector<uint32_t> fanout(N, 0);
+    auto check_src = [&](int32_t src, uint32_t ch, const char *what) {
+        if (src == KGPU_GRAPH) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "%s: graph inputs are not supported", what);
+        if (src < 0 || (uint32_t)src >= N) KGPU_THROW(KGPU_ERR_INVALID, "%s: source node %d not found", what, src);
+        if (ch >= (uint32_t)kind_info(d.nodes[src]).n_out) KGPU_THROW(KGPU_ERR_INVALID, "%s: OutputOutOfBounds(%u)", what, ch);
+    };
+    for (uint32_t e = 0; e < d.n_edges; e++) {
+        const kgpu_edge &ed = d.edges[e];
+        check_src(ed.source_node, ed.source_channel, "edge");
+        if (ed.sink_node == KGPU_GRAPH) {
+            if (ed.sink_channel >= n_outputs) KGPU_THROW(KGPU_ERR_INVALID, "edge: GraphOutputOutOfBounds(%u)", ed.sink_channel);
+            out_edges[ed.sink_channel] = {ed.source_node, ed.source_channel};
+        } else {
+            if (ed.sink_node < 0 || (uint32_t)ed.sink_node >= N) KGPU_THROW(KGPU_ERR_INVALID, "edge: sink node %d not found", ed.sink_node);
+            if (ed.sink_channel >= in_off[ed.sink_node + 1] - in_off[ed.sink_node]) KGPU_THROW(KGPU_ERR_INVALID, "edge: InputOutOfBounds(%u)", ed.sink_channel);
+            in_edges[in_off[ed.sink_node] + ed.sink_channel] = {ed.source_node, ed.source_channel};
+        }
+    }
+    std::vector<std::vector<std::tuple<uint32_t, int, uint32_t>>> par_edges(N);
+    for (uint32_t e = 0; e < d.n_param_edges; e++) {
+        const kgpu_param_edge &pe = d.param_edges[e];
+        check_src(pe.source_node, pe.source_channel, "param edge");
+        if (pe.sink_node < 0 || (uint32_t)pe.sink_node >= N) KGPU_THROW(KGPU_ERR_INVALID, "param edge: sink node %d not found", pe.sink_node);
+        if (pe.param_index >= total_params(d.nodes[pe.sink_node])) KGPU_THROW(KGPU_ERR_PARAMETER, "param edge: ParameterIndexOutOfBounds");
+        par_edges[pe.sink_node].push_back({pe.param_index, pe.source_node, pe.source_channel});
+    }
+    for (auto &e : in_edges)
+        if (e.first >= 0) fanout[e.first]++;
+    for (auto &e : out_edges)
+        if (e.first >= 0) fanout[e.first]++;
+    for (auto &pl : par_edges)
+        for (auto &pe : pl) fanout[std::get<1>(pe)]++;
+
+    // mix-bus Add chains: ((v0+v1)+v2)+... per graph output (graph.rs:850-864)
+    auto is_mix = [&](int node) {
+        const kgpu_node_desc &nd = d.nodes[node];
+        if (nd.kind != KGPU_MATH || nd.mode != KGPU_OP_ADD || nd.channels != 1 || nd.n_wrappers != 0) return false;
+        if (fanout[node] != 1) return false;
+        return in_edges[in_off[node]].first >= 0 && in_edges[in_off[node] + 1].first >= 0;
+    };
+    struct Leaf { int node; uint32_t ch; uint32_t out_ch; };
+    std::vector<Leaf> leaves;
+    std::vector<char> mix_node(N, 0);
+    n_mix_nodes = 0;
+    for (uint32_t oc = 0; oc < n_outputs; oc++) {
+        if (out_edges[oc].first < 0) continue;
+        std::vector<std::pair<int, uint32_t>> stack{out_edges[oc]};
+        while (!stack.empty()) {
+            auto cur = stack.back();
+            stack.pop_back();
+            if (is_mix(cur.first)) {
+                mix_node[cur.first] = 1;
+                n_mix_nodes++;
+                stack.push_back(in_edges[in_off[cur.first] + 1]); // right operand after ...
+                stack.push_back(in_edges[in_off[cur.first]]);     // ... the left one (in-order)
+            } else leaves.push_back({cur.first, cur.second, oc});
+        }
+    }
+    // voices = connected components of the leaves' upstream closures
+    std::vector<int> comp(N, -1);
+    std::vector<int> uf;
+    auto find = [&](int x) {
+        while (uf[x] != x) x = uf[x] = uf[uf[x]];
+        return x;
+    };
+    std::vector<int> stack;
+    for (auto &lf : leaves) {
+        if (comp[lf.node] >= 0) continue;
+        int c = (int)uf.size();
+        uf.push_back(c);
+        comp[lf.node] = c;
+        stack.assign(1, lf.node);
+        while (!stack.empty()) {
+            int nk = stack.back();
+            stack.pop_back();
+            auto visit = [&](int src) {
+                if (src < 0) return;
+                if (mix_node[src]) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %d reads the mix bus: post-mix processing is not supported yet", nk);
+                if (comp[src] < 0) {
+                    comp[src] = c;
+                    stack.push_back(src);
+                } else {
+                    int a = find(comp[src]), b = find(c);
+                    if (a != b) uf[std::max(a, b)] = std::min(a, b);
+                }
+            };
+            for (uint32_t k = in_off[nk]; k < in_off[nk + 1]; k++) visit(in_edges[k].first);
+            for (auto &pe : par_edges[nk]) visit(std::get<1>(pe));
+        }
+    }
+    // per component: leaves in order
+    std::unordered_map<int, std::vector<Leaf>> comp_leaves;
+    std::vector<int> comp_order;
+    for (auto &lf : leaves) {
+        int c = find(comp[lf.node]);
+        auto it = comp_leaves.find(c);
+        if (it == comp_leaves.end()) {
+            comp_order.push_back(c);
+            comp_leaves[c] = {lf};
+        } else it->second.push_back(lf);
+    }
+    node_ref.assign(N, NodeRef{});
+    for (uint32_t i = 0; i < N; i++) node_ref[i].n_params = total_params(d.nodes[i]);
+    std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;
+    std::vector<int> local_of(N, -1);
+    groups.clear();
+    std::vector<std::pair<int, size_t>> dstack;
+    for (int c : comp_order) {
+        // local topological order: post-order DFS from the leaves, inputs in channel order then parameter edges
+        std::vector<uint32_t> order;
+        for (auto &lf : comp_leaves[c]) {
+            if (local_of[lf.node] >= 0) continue;
+            local_of[lf.node] = -2; // on stack / visited marker
+            dstack.assign(1, {lf.node, 0});
+            while (!dstack.empty()) {
+                int nk = dstack.back().first;
+                size_t &cur = dstack.back().second;
+                const size_t ne = in_off[nk + 1] - in_off[nk], np = par_edges[nk].size();
+                bool pushed = false;
+                while (cur < ne + np) {
+                    int src = cur < ne ? in_edges[in_off[nk] + cur].first : std::get<1>(par_edges[nk][cur - ne]);
+                    cur++;
+                    if (src >= 0 && local_of[src] == -1) {
+                        local_of[src] = -2;
+                        dstack.push_back({src, 0});
+                        pushed = true;
+                        break;
+                    } else if (src >= 0 && local_of[src] == -2) {
+                        // visited-but-unfinished on the current DFS path means a cycle
+                        for (auto &st : dstack)
+                            if (st.first == src) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "cycle through node %d: feedback edges are not supported", src);
+                    }
+                }
+                if (!pushed) {
+                    local_of[nk] = (int)order.size();
+                    order.push_back((uint32_t)nk);
+                    dstack.pop_back();
+                }
+            }
+        }
+        Template t;
+        t.nodes.resize(order.size());
+        for (size_t li = 0; li < order.size(); li++) {
+            uint32_t nk = order[li];
+            const kgpu_node_desc &nd = d.nodes[nk];
+            TemplateNode &tn = t.nodes[li];
+            tn.kind = nd.kind; tn.mode = nd.mode; tn.channels = nd.kind == KGPU_MATH ? nd.channels : 1; tn.flags = nd.flags;
+            tn.n_segments = nd.kind == KGPU_ENVELOPE ? nd.n_segments : 0;
+            tn.wrappers.assign(nd.wrappers, nd.wrappers + nd.n_wrappers);
+            for (uint32_t k = in_off[nk]; k < in_off[nk + 1]; k++)
+                tn.in.push_back({in_edges[k].first >= 0 ? local_of[in_edges[k].first] : -1, in_edges[k].second});
+            for (auto &pe : par_edges[nk]) tn.par.push_back({std::get<0>(pe), local_of[std::get<1>(pe)], std::get<2>(pe)});
+        }
+        for (auto &lf : comp_leaves[c]) t.outs.push_back({local_of[lf.node], lf.ch, lf.out_ch});
+        uint64_t h = template_hash(t);
+        int gi = -1;
+        for (uint32_t cand : by_hash[h])
+            if (groups[cand].tpl.same_shape(t)) { gi = (int)cand; break; }
+        if (gi < 0) {
+            gi = (int)groups.size();
+            groups.emplace_back();
+            groups.back().tpl = std::move(t);
+            compile_template(groups.back(), sample_rate, {});
+            by_hash[h].push_back((uint32_t)gi);
+        }
+        Group &g = groups[gi];
+        uint32_t voice = g.n_voices++;
+        g.voice_nodes.push_back(order);
+        for (size_t li = 0; li < order.size(); li++) {
+            node_ref[order[li]].group = gi;
+            node_ref[order[li]].voice = voice;
+            node_ref[order[li]].local = (uint32_t)li;
+        }
+    }
+    // initial registers + control state: Node::init (graph.rs:462-475) of every node of every voice
+    out_events.assign(groups.size(), {});
+    ramp_nodes.assign(groups.size(), {});
+    const float sr = (float)sample_rate;
+    for (Group &g : groups) {
+        const uint32_t V = g.n_voices, nn = (uint32_t)g.tpl.nodes.size();
+        g.init_regs.assign((size_t)g.prog.n_regs * V, 0u);
+        g.host.assign((size_t)V * nn, HostNode{});
+        auto R = [&](uint32_t reg, uint32_t v) -> uint32_t & { return g.init_regs[(size_t)reg * V + v]; };
+        for (uint32_t v = 0; v < V; v++)
+            for (uint32_t li = 0; li < nn; li++) {
+                const kgpu_node_desc &nd = d.nodes[g.voice_nodes[v][li]];
+                const DevNode &dn = g.prog.nodes[li];
+                HostNode &h = g.host[(size_t)v * nn + li];
+                h.kind = (uint8_t)nd.kind;
+                h.dev_kind = dn.kind;
+                h.mode = nd.mode;
+                h.reg = dn.reg;
+                h.n_seg = dn.n_seg;
+                h.base_params = (uint32_t)kind_info(nd).n_params;
+                const uint32_t r = dn.reg;
+                switch (nd.kind) {
+                case KGPU_SIN_WT: { // osc.rs:110-123,142-147
+                    h.f0 = (float)nd.args[0];
+                    R(r + 2, v) = sat_u32((double)h.f0 * g.prog.sinwt_k);
+                    break;
+                }
+                case KGPU_SIN_NUMERIC: { // osc.rs:231-237,253-261
+                    float f = (float)nd.args[0];
+                    R(r + 2, v) = fbits(f / sr);
+                    break;
+                }
+                case KGPU_POLYBLEP: { // polyblep.rs:139-155
+                    h.f0 = (float)nd.args[0];
+                    float dt = 0.f;
+                    if (h.f0 != 0.f) dt = h.f0 / sr;
+                    R(r + 1, v) = fbits(dt);
+                    R(r + 2, v) = (dt * sr >= sr / 4.0f) ? 1u : 0u;
+                    R(r + 3, v) = fbits(0.5f);
+                    R(r + 4, v) = nd.mode;
+                    break;
+                }
+                case KGPU_SVF: { // svf.rs:64-79,134-141
+                    h.f0 = (float)nd.args[0]; h.f1 = (float)nd.args[1]; h.f2 = (float)nd.args[2];
+                    svf_coeffs(h.mode, h.f0, h.f1, h.f2, sr, h.svf_coef);
+                    for (int i = 0; i < 6; i++) R(r + 2 + i, v) = fbits(h.svf_coef[i]);
+                    break;
+                }
+                case KGPU_ONEPOLE_LPF: case KGPU_ONEPOLE_HPF: { // onepole.rs:118-129,157-167,35-46
+                    float freq = nd.kind == KGPU_ONEPOLE_LPF ? (float)nd.args[0] : 0.0f;
+                    float f = freq / sr;
+                    float b1 = expf(-2.0f * F_PI * f);
+                    R(r + 2, v) = fbits(b1);
+                    R(r + 1, v) = fbits(1.0f - b1);
+                    break;
+                }
+                case KGPU_ENV_ASR: case KGPU_ENV_AR: { // envelopes.rs:33-43,135-151
+                    h.f0 = (float)nd.args[0]; h.f1 = (float)nd.args[1];
+                    R(r + 2, v) = fbits(h.f0 == 0.f ? 1.0f : 1.0f / (h.f0 * sr));
+                    R(r + 3, v) = fbits(h.f1 == 0.f ? 1.0f : 1.0f / (h.f1 * sr));
+                    R(r + 4, v) = fbits(1.0f);
+                    break;
+                }
+                case KGPU_ENVELOPE: { // envelopes.rs:372-384,403-405,329-335
+                    h.d0 = nd.args[0];
+                    uint32_t lo, hi;
+                    dbits(nd.args[0], lo, hi);
+                    R(r + 4, v) = lo; R(r + 5, v) = hi;
+                    dbits(nd.args[1] * (1.0 / (double)sample_rate), lo, hi);
+                    R(r + 6, v) = lo; R(r + 7, v) = hi;
+                    for (uint32_t sgi = 0; sgi < nd.n_segments; sgi++) {
+                        double dur = nd.segments[2 * sgi], val = nd.segments[2 * sgi + 1];
+                        uint32_t b = r + REGS_ENVELOPE_BASE + REGS_ENVELOPE_PER_SEG * sgi;
+                        dbits(1.0 / dur, lo, hi); R(b + 0, v) = lo; R(b + 1, v) = hi;
+                        dbits(dur, lo, hi); R(b + 2, v) = lo; R(b + 3, v) = hi;
+                        dbits(val, lo, hi); R(b + 4, v) = lo; R(b + 5, v) = hi;
+                    }
+                    break;
+                }
+                case KGPU_CONSTANT: case KGPU_TEST_NUM: R(r, v) = fbits((float)nd.args[0]); break;
+                default: break;
+                }
+                // wrappers
+                uint32_t inner = h.base_params;
+                int post_i = 0;
+                h.wr.resize(nd.n_wrappers);
+                for (uint32_t l = 0; l < nd.n_wrappers; l++) {
+                    WrapSim &w = h.wr[l];
+                    w.kind = (uint8_t)nd.wrappers[l].kind;
+                    w.capacity = nd.wrappers[l].capacity;
+                    w.inner_params = inner;
+                    if (is_math_wrapper(w.kind)) {
+                        w.reg = dn.post_reg[post_i++];
+                        R(w.reg, v) = fbits((float)nd.wrappers[l].value);
+                        if (w.kind == KGPU_WR_MUL) inner++;
+                    } else if (w.kind == KGPU_WR_SMOOTH_PARAMS) {
+                        w.smooth.assign(inner, SmoothState{});
+                        h.has_smooth = true;
+                    } else if (w.kind == KGPU_WR_PRECISE_TIMING) {
+                        w.next_delay.assign(inner, 0);
+                        h.has_precise = true;
+                    } else if (w.kind == KGPU_WR_AR_PARAMS) {
+                        w.ar_bound.assign(inner, 0);
+                        for (auto &pe : g.tpl.nodes[li].par)
+                            if (std::get<0>(pe) < inner) w.ar_bound[std::get<0>(pe)] = 1;
+                    }
+                }
+            }
+    }
+}
+
+void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
+    // validate everything first so that a failing call queues nothing
+    for (size_t i = 0; i < n; i++) {
+        const kgpu_event &e = evs[i];
+        if (e.node >= node_ref.size()) KGPU_THROW(KGPU_ERR_INVALID, "event %zu: NodeNotFound (%u)", i, e.node);
+        const NodeRef &nr = node_ref[e.node];
+        if (e.param >= nr.n_params) KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: ParameterIndexOutOfBounds (node %u param %u)", i, e.node, e.param);
+        if (e.value_kind > 4 || e.smoothing_kind > 2 || e.time_kind > 2) KGPU_THROW(KGPU_ERR_INVALID, "event %zu: bad enum field", i);
+        if (e.smoothing_kind != 0 && e.smooth_rate != 0)
+            KGPU_THROW(KGPU_ERR_UNSUPPORTED, "event %zu: Rate::AudioRate smoothing is not supported (its branch is unreachable in knaster, "
+                       "smooth_params.rs:140-146)", i);
+        if (nr.group < 0) continue; // unreachable node: knaster would run it, but nothing can hear it
+        const Group &g = groups[nr.group];
+        const HostNode &h = g.host[(size_t)nr.voice * g.tpl.nodes.size() + nr.local];
+        // who consumes the value? walk outermost -> innermost like param_apply does
+        bool wr_mul_target = false, smooth_ok = false;
+        uint32_t p = e.param;
+        for (int l = (int)h.wr.size() - 1; l >= 0; l--) {
+            const WrapSim &w = h.wr[l];
+            if (w.kind == KGPU_WR_MUL && p == w.inner_params) { wr_mul_target = true; break; }
+            if (w.kind == KGPU_WR_SMOOTH_PARAMS && p < w.smooth.size()) smooth_ok = true;
+        }
+        if (e.smoothing_kind != 0 && !smooth_ok)
+            KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: smoothing sent to node %u param %u which has no WrSmoothParams around it "
+                       "(knaster would panic: parameter value is expected to be a float)", i, e.node, e.param);
+        if (e.value_kind != 0) {
+            char want = 'f';
+            if (!wr_mul_target) {
+                const char *types = param_types(h.kind);
+                want = p < std::strlen(types) ? types[p] : 'f';
+            }
+            bool ok = want == 't' || (want == 'f' && e.value_kind == 1) || (want == 'i' && e.value_kind == 3) || (want == 'b' && e.value_kind == 4);
+            if (!ok) KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: wrong value type for node %u param %u", i, e.node, e.param);
+            if (h.kind == KGPU_POLYBLEP && p == 2 && !wr_mul_target && (int64_t)e.value != 0)
+                KGPU_THROW(KGPU_ERR_UNSUPPORTED, "event %zu: PolyBlep waveform %lld not supported yet", i, (long long)e.value);
+            if (h.kind == KGPU_SVF && p == 3 && !wr_mul_target && ((int64_t)e.value < 0 || (int64_t)e.value > 8))
+                KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: bad SvfFilterType", i);
+        }
+    }
+    const uint64_t bs = block_size;
+    for (size_t i = 0; i < n; i++) {
+        const kgpu_event &e = evs[i];
+        if (node_ref[e.node].group < 0) continue;
+        RawEvent r;
+        r.node = e.node;
+        r.param = e.param;
+        if (e.value_kind) {
+            r.value.kind = (PV::Kind)e.value_kind;
+            r.value.f = e.value_kind == 3 ? (double)(int64_t)e.value : e.value;
+        }
+        if (e.smoothing_kind) {
+            r.smoothing.kind = PV::Smoothing;
+            r.smoothing.smoothing = e.smoothing_kind == 2 ? 1 : 0;
+            r.smoothing.smooth_seconds = e.smooth_seconds;
+        }
+        r.timed = e.time_kind != 0;
+        uint64_t samples = (uint64_t)e.seconds * sample_rate + ((uint64_t)e.subsec * sample_rate) / 282240000ull; // time.rs:86-90
+        if (e.time_kind == 1) r.due_frame = samples;                    // scheduling.rs:102-108
+        else if (e.time_kind == 2) r.due_frame = frame_clock + samples; // scheduling.rs:110-119
+        else r.due_frame = frame_clock;
+        if (r.due_frame < frame_clock) r.due_frame = frame_clock;       // late: saturating_sub -> delay 0
+        (void)bs;
+        r.seq = seq++;
+        pending.push_back(r);
+    }
+}
+
+void HostPlan::simulate(uint64_t t0, uint64_t t1) {
+    const uint64_t bs = block_size;
+    const uint64_t b0 = t0 / bs, b1 = t1 / bs;
+    // events that become ready (delay < block_size, graph_gen.rs:283) inside [b0, b1)
+    struct Item { uint64_t key; uint64_t block; uint64_t seq; uint32_t idx; };
+    std::vector<Item> items;
+    std::vector<RawEvent> keep;
+    std::vector<RawEvent> ready;
+    for (RawEvent &r : pending) {
+        uint64_t blk = std::max(r.due_frame / bs, b0);
+        if (blk < b1) ready.push_back(r);
+        else keep.push_back(r);
+    }
+    pending.swap(keep);
+    items.reserve(ready.size());
+    for (uint32_t i = 0; i < ready.size(); i++) {
+        const NodeRef &nr = node_ref[ready[i].node];
+        const Group &g = groups[nr.group];
+        uint64_t hidx = (uint64_t)nr.voice * g.tpl.nodes.size() + nr.local;
+        items.push_back({((uint64_t)nr.group << 40) | hidx, std::max(ready[i].due_frame / bs, b0), ready[i].seq, i});
+    }
+    std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+        if (a.key != b.key) return a.key < b.key;
+        if (a.block != b.block) return a.block < b.block;
+        return a.seq < b.seq;
+    });
+    auto process_node = [&](uint32_t gi, uint64_t hidx, const Item *ev, size_t n) {
+        Group &g = groups[gi];
+        const uint32_t nn = (uint32_t)g.tpl.nodes.size();
+        HostNode &hn = g.host[hidx];
+        Sim s{*this, gi, (uint32_t)(hidx / nn), (uint32_t)(hidx % nn), hn};
+        const int top = (int)hn.wr.size() - 1;
+        size_t ei = 0;
+        uint64_t b = needs_processing(hn) ? b0 : (n ? ev[0].block : b1);
+        while (b < b1) {
+            const uint64_t block_start = b * bs;
+            while (ei < n && ev[ei].block == b) { // apply_parameter_change, graph_gen.rs:269-305
+                const RawEvent &r = ready[ev[ei].idx];
+                uint64_t delay = r.timed && r.due_frame > block_start ? r.due_frame - block_start : 0;
+                if (delay > 0) wr_set_delay(s, top, r.param, (uint16_t)delay);
+                if (r.smoothing.kind != PV::None) wr_param_apply(s, top, r.param, r.smoothing, block_start);
+                if (r.value.kind != PV::None) wr_param_apply(s, top, r.param, r.value, block_start);
+                ei++;
+            }
+            if (needs_processing(hn)) wr_process_block(s, top, block_start, 0, (uint32_t)bs);
+            if (needs_processing(hn)) b++;
+            else if (ei < n) b = ev[ei].block;
+            else break;
+        }
+        return needs_processing(hn);
+    };
+    // nodes with events
+    std::vector<std::vector<uint32_t>> new_ramps(groups.size());
+    std::vector<std::vector<uint8_t>> seen(groups.size());
+    size_t i = 0;
+    while (i < items.size()) {
+        size_t j = i;
+        while (j < items.size() && items[j].key == items[i].key) j++;
+        uint32_t gi = (uint32_t)(items[i].key >> 40);
+        uint64_t hidx = items[i].key & ((1ull << 40) - 1);
+        if (seen[gi].empty()) seen[gi].assign(groups[gi].host.size(), 0);
+        seen[gi][hidx] = 1;
+        if (process_node(gi, hidx, &items[i], j - i)) new_ramps[gi].push_back((uint32_t)hidx);
+        i = j;
+    }
+    // nodes whose ramps are still running from earlier renders
+    for (uint32_t gi = 0; gi < groups.size(); gi++) {
+        for (uint32_t hidx : ramp_nodes[gi]) {
+            if (!seen[gi].empty() && seen[gi][hidx]) continue;
+            if (process_node(gi, hidx, nullptr, 0)) new_ramps[gi].push_back(hidx);
+        }
+        ramp_nodes[gi].swap(new_ramps[gi]);
+    }
+}
+
+void HostPlan::take_events(uint32_t gi, uint64_t t0, uint64_t t1, uint32_t chunk, std::vector<DevEvent> &events,
+                           std::vector<uint32_t> &offsets) {
+    Group &g = groups[gi];
+    std::vector<VoiceEvent> &all = out_events[gi];
+    events.clear();
+    offsets.clear();
+    if (all.empty()) return;
+    std::vector<VoiceEvent> now, later;
+    for (VoiceEvent &ve : all) {
+        if (ve.frame < t1) now.push_back(ve);
+        else later.push_back(ve);
+    }
+    all.swap(later);
+    if (now.empty()) return;
+    for (VoiceEvent &ve : now) ve.ev.frame = (uint32_t)(ve.frame < t0 ? 0 : ve.frame - t0);
+    std::sort(now.begin(), now.end(), [chunk](const VoiceEvent &a, const VoiceEvent &b) {
+        if (a.voice != b.voice) return a.voice < b.voice;
+        uint32_t ca = a.ev.frame / chunk, cb = b.ev.frame / chunk;
+        if (ca != cb) return ca < cb;
+        if (a.ev.node != b.ev.node) return a.ev.node < b.ev.node;
+        if (a.ev.frame != b.ev.frame) return a.ev.frame < b.ev.frame;
+        return a.seq < b.seq;
+    });
+    offsets.assign(g.n_voices + 1, 0);
+    events.resize(now.size());
+    for (size_t i = 0; i < now.size(); i++) {
+        events[i] = now[i].ev;
+        offsets[now[i].voice + 1]++;
+    }
+    for (uint32_t v = 0; v < g.n_voices; v++) offsets[v + 1] += offsets[v];
+}
+
+} // namespace kgpu

@@ -1,0 +1,149 @@
+// plan.hpp -- host side of the engine: graph -> voice templates -> kernel plan, and the
+// control-rate simulation that turns knaster's parameter-change queue into device events.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/knaster_gpu.h"
+#include "dev.h"
+
+namespace kgpu {
+
+struct Error {
+    int code;
+    std::string msg;
+};
+#define KGPU_THROW(code_, ...) throw ::kgpu::Error{(code_), ::kgpu::format(__VA_ARGS__)}
+std::string format(const char *fmt, ...);
+
+// ParameterValue (knaster_core/src/parameters/types.rs:25-37)
+struct PV {
+    enum Kind : uint8_t { None = 0, Float = 1, Trigger = 2, Integer = 3, Bool = 4, Smoothing = 5 } kind = None;
+    double f = 0.0;      // Float / Integer / Bool payload
+    uint8_t smoothing = 0; // Smoothing: 0 ParameterSmoothing::None, 1 Linear
+    float smooth_seconds = 0.f;
+};
+
+// smooth_params.rs:249-261
+struct SmoothState {
+    bool linear = false;
+    double current_value = 0.0;
+    double start_value = 0.0, end_value = 0.0;
+    uint64_t duration_frames = 0, frames_elapsed = 0;
+    bool done = true;
+};
+
+struct QueuedChange { // precise_timing.rs:17
+    uint16_t delay;
+    uint32_t param;
+    PV value;
+};
+
+// control-side state of one wrapper instance
+struct WrapSim {
+    uint8_t kind = 0;        // kgpu_wrapper_kind
+    uint32_t capacity = 0;   // WrPreciseTiming<N>
+    uint16_t reg = 0;        // arithmetic wrappers: register holding the value
+    uint32_t inner_params = 0; // T::Parameters of what it wraps
+    std::vector<SmoothState> smooth;   // WrSmoothParams, one per parameter
+    std::vector<uint16_t> next_delay;  // WrPreciseTiming, sticky (App. B1)
+    std::vector<QueuedChange> queue;   // WrPreciseTiming waiting_changes[0..next_delay_i)
+    std::vector<uint8_t> ar_bound;     // WrArParams: parameter has a buffer (audio_rate.rs:70-74)
+};
+
+// control-side state of one node of one voice: the fields knaster's setters read/write
+struct HostNode {
+    uint8_t kind = 0;        // kgpu_ugen_kind
+    uint8_t dev_kind = 0;
+    uint32_t mode = 0;       // waveform / filter type
+    uint16_t reg = 0;        // register base inside the voice
+    uint16_t n_seg = 0;
+    uint32_t base_params = 0;
+    // SinWt.freq, PolyBlep.freq_in_hz; Svf cutoff,q,gain; EnvAsr attack_seconds,release_seconds
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+    double d0 = 0.0;         // Envelope start_value
+    float svf_coef[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<WrapSim> wr; // innermost first
+    bool has_smooth = false, has_precise = false;
+    bool ramp_active = false;
+    uint32_t ramp_list_pos = 0;
+};
+
+struct TemplateNode {
+    uint32_t kind, mode, channels, flags, n_segments;
+    std::vector<kgpu_wrapper_desc> wrappers; // value ignored for the signature
+    std::vector<std::pair<int, uint32_t>> in;           // per input channel: (local node | -1, channel)
+    std::vector<std::tuple<uint32_t, int, uint32_t>> par; // (param, local source node, channel)
+    bool same_shape(const TemplateNode &o) const;
+};
+
+struct Template {
+    std::vector<TemplateNode> nodes;                         // local topological order
+    std::vector<std::tuple<int, uint32_t, uint32_t>> outs;   // (local node, channel, graph output channel)
+    bool same_shape(const Template &o) const;
+};
+
+struct Group {
+    Template tpl;
+    DevProgram prog;
+    std::vector<std::vector<uint32_t>> voice_nodes; // [voice][local] -> graph node index
+    uint32_t n_voices = 0;
+    std::vector<uint32_t> init_regs;                // [reg][voice]
+    std::vector<HostNode> host;                     // [voice * n_nodes + local]
+    std::vector<std::vector<uint16_t>> slot_of;     // [local][channel] -> value slot
+    int fused_recipe = -1;                          // index into the fused-kernel table, -1 = interpreter
+    std::string kernel_name;
+};
+
+struct NodeRef {
+    int32_t group = -1; // -1: mix-bus Add node or unreachable node
+    uint32_t voice = 0;
+    uint32_t local = 0;
+    uint32_t n_params = 0;
+};
+
+struct RawEvent {
+    uint32_t node, param;
+    PV value;       // kind None if absent
+    PV smoothing;   // kind None if absent
+    uint64_t due_frame; // absolute; events without time: frame clock at push
+    bool timed;     // false: `time: None` (delay 0 by construction)
+    uint64_t seq;
+};
+
+struct VoiceEvent { // a device event tagged with its destination
+    uint32_t voice;
+    uint64_t frame; // absolute
+    uint64_t seq;
+    DevEvent ev;
+};
+
+struct HostPlan {
+    uint32_t sample_rate = 48000, block_size = 64, n_outputs = 2;
+    std::vector<Group> groups;
+    std::vector<NodeRef> node_ref; // per graph node
+    uint32_t n_mix_nodes = 0;
+    uint64_t dropped_changes = 0, ignored_delays = 0, device_events = 0;
+    uint64_t seq = 0;
+    std::vector<RawEvent> pending;                  // not yet simulated
+    std::vector<std::vector<VoiceEvent>> out_events; // per group: simulated, not yet rendered
+    std::vector<std::vector<uint32_t>> ramp_nodes;  // per group: host-node indices with active ramps / queues
+
+    void build(const kgpu_graph_desc &d);
+    // push_events: validate + timestamp (frame_clock = next block to render)
+    void push(const kgpu_event *ev, size_t n, uint64_t frame_clock);
+    // run the control simulation for blocks [t0/bs, t1/bs) and move the resulting device events
+    // (frame in [t0,t1)) of `group` into `out`, sorted per voice in device processing order
+    // (chunk = frames per interpreter chunk, 1 for frame-major fused kernels).
+    void simulate(uint64_t t0, uint64_t t1);
+    void take_events(uint32_t group, uint64_t t0, uint64_t t1, uint32_t chunk, std::vector<DevEvent> &events,
+                     std::vector<uint32_t> &offsets);
+};
+
+// fused-kernel recipes (kernels.cu): returns recipe index or -1
+int match_fused_recipe(const DevProgram &p);
+const char *fused_recipe_name(int recipe);
+
+} // namespace kgpu

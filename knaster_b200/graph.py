@@ -313,15 +313,21 @@ class Graph:
         for node, param, value in changes:
             self.set(node, param, value, time)
 
-    def schedule_bulk(self, nodes, params, value_kinds, values, frames) -> None:
+    def schedule_bulk(self, nodes, params, value_kinds, values, frames, smooth_seconds=None) -> None:
         """Bulk equivalent of many ``Parameter.set_at(value, Seconds::from_samples(frame, sr))``
-        calls, in array order (extension for synthetic voice banks; same event semantics)."""
+        (or ``smooth_at(Linear(s), ..)`` where smooth_seconds is not NaN) calls, in array order
+        (extension for synthetic voice banks; same event semantics)."""
         n = len(nodes)
         arr = np.zeros(n, dtype=EVENT_DTYPE)
         arr["node"] = nodes
         arr["param"] = params
         arr["value_kind"] = value_kinds
         arr["value"] = values
+        if smooth_seconds is not None:
+            ss = np.asarray(smooth_seconds, dtype=np.float32)
+            has = ~np.isnan(ss)
+            arr["smoothing_kind"] = np.where(has, 2, 0)
+            arr["smooth_seconds"] = np.where(has, ss, 0.0)
         fr = np.asarray(frames, dtype=np.uint64)
         sr = np.uint64(self.sample_rate)
         arr["time_kind"] = 1

@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle on the same
+graph + events.  Tolerances are the north star's: bit-exact for integer-phase / pure
+arithmetic paths, max abs error <= 1e-5 for oscillators, <= 1e-4 for IIR filters (the f32
+recurrences are evaluated sequentially in the reference's rounding order, so in practice
+they are far tighter).  The mix bus is summed in a different (tree) order than knaster's
+left fold, so bus comparisons use normalised amplitudes and <= 1e-5."""
+import numpy as np
+import pytest
+
+import knaster_b200 as kn
+from knaster_b200 import banks
+from knaster_b200.graph import Graph
+from knaster_b200.processor import AudioProcessor, AudioProcessorOptions
+from oracle.oracle import OracleProcessor
+
+pytestmark = pytest.mark.gpu
+SR = 48000
+
+
+def both(build, n_blocks, outputs=2, block_size=64, taps=True, force_interpreter=False):
+    """Run `build(graph) -> tap node ids` through the GPU engine and the oracle."""
+    opts = AudioProcessorOptions(block_size=block_size, sample_rate=SR, force_interpreter=force_interpreter)
+    graph, proc = AudioProcessor.new(0, outputs, opts)
+    ids = build(graph)
+    ev = graph.take_events()
+    graph.pending_event_arrays = [ev.copy()] if len(ev) else []
+    if taps:
+        for i in ids:
+            proc.add_tap(i, 0)
+    gpu = proc.render(n_blocks)
+    gpu_taps = proc.read_taps() if (taps and ids) else None
+
+    g2 = Graph(0, outputs, block_size, SR)
+    ids2 = build(g2)
+    g2.take_events()
+    g2.pending_event_arrays = [ev.copy()] if len(ev) else []
+    orc = OracleProcessor(g2, ring_buffer_size=1 << 22)
+    if taps:
+        for i in ids2:
+            orc.add_tap(i, 0)
+    ref, ref_taps = orc.render(n_blocks)
+    return gpu, ref, gpu_taps, ref_taps, proc
+
+
+@pytest.mark.parametrize("force_interp", [False, True])
+def test_readme_sine_bit_identical(force_interp):
+    # configs[0]: SinWt 440 Hz * 0.2 -> stereo, block 64, f32.  Integer phase => bit-identical.
+    gpu, ref, gt, rt, _ = both(banks.readme_sine, 750, force_interpreter=force_interp)
+    assert np.array_equal(gpu, ref)
+    assert np.array_equal(gt, rt)
+    assert np.abs(ref).max() > 0.19
+
+
+def test_run_without_inputs_block_by_block_equals_batched_render():
+    def build(graph):
+        return banks.subtractive_bank(graph, 8, 0.2, n_notes=3)
+
+    opts = AudioProcessorOptions()
+    g1, p1 = AudioProcessor.new(0, 2, opts)
+    build(g1)
+    blocks = []
+    for _ in range(150):
+        p1.run_without_inputs()
+        blocks.append(p1.output_block())
+    g2, p2 = AudioProcessor.new(0, 2, opts)
+    build(g2)
+    batched = p2.render(150)
+    assert np.array_equal(np.stack(blocks), batched)
+    assert p1.frame_clock() == 150 * 64 == p2.frame_clock()
+
+
+def test_reference_graph_tests_on_gpu():
+    # knaster_graph/src/tests/graph_tests.rs:13-47: empty graph -> zeros
+    _g, p = AudioProcessor.new(0, 4, AudioProcessorOptions(block_size=16))
+    p.run_without_inputs()
+    assert not p.output_block().any()
+    # knaster_benchmarks/benches/wrappers_vs_nodes.rs:65-113
+    graph, p = AudioProcessor.new(0, 1, AudioProcessorOptions(block_size=32))
+    with graph.edit() as g:
+        for _ in range(100):
+            g.push(kn.TestNumUGen(2.0).wr_mul(0.5)).to_graph_out()
+    p.run_without_inputs()
+    assert p.output_block()[0, 31] == 100.0
+    graph, p = AudioProcessor.new(0, 1, AudioProcessorOptions(block_size=32))
+    with graph.edit() as g:
+        for _ in range(100):
+            a = g.push(kn.TestNumUGen(2.0))
+            v = g.push(kn.TestNumUGen(0.5))
+            (a * v).to_graph_out()
+    p.run_without_inputs()
+    assert p.output_block()[0, 31] == 100.0
+    # graph_tests.rs:128-160 multichannel_nodes
+    graph, p = AudioProcessor.new(0, 2, AudioProcessorOptions(block_size=16))
+    with graph.edit() as g:
+        v = [g.push(kn.TestNumUGen(x)) for x in (0.125, 1.0, 0.5, 4.125)]
+        m = g.push(kn.MathUGen(2, kn.MathOp.Add))
+        (v[0] | v[1] | v[2] | v[3]).to(m).to_graph_out()
+    p.run_without_inputs()
+    out = p.output_block()
+    assert (out[0, 0], out[1, 0]) == (0.625, 5.125)
+    # graph_edit.rs:2079-2100: parameters set before the first block
+    graph, p = AudioProcessor.new(0, 1, AudioProcessorOptions(block_size=16))
+    with graph.edit() as g:
+        n1 = g.push(kn.TestInPlusParamUGen())
+        g.set(n1, 0, 0.5, kn.Time.asap())
+        n2 = g.push(kn.TestInPlusParamUGen())
+        g.set(n2, 0, 1.25, kn.Time.asap())
+        n3 = g.push(kn.TestInPlusParamUGen())
+        g.set(n3, 0, 0.125, kn.Time.asap())
+        (n1 >> n2 >> n3).to_graph_out()
+    p.run_without_inputs()
+    assert p.output_block()[0, 0] == 0.5 + 1.25 + 0.125
+
+
+def test_precise_timing_golden_vector_through_the_engine():
+    # knaster_core_dsp/src/wrappers_core.rs:167-200, driven by absolute-time events
+    graph, p = AudioProcessor.new(0, 1, AudioProcessorOptions(block_size=16))
+    with graph.edit() as g:
+        n = g.push(kn.TestInPlusParamUGen().precise_timing(10))
+        n.to_graph_out()
+        for d in (5, 6, 8, 9, 10):
+            n.param(0).set_at(float(d), kn.Seconds.from_samples(d, SR))
+    p.run_without_inputs()
+    assert p.output_block()[0].tolist() == [0., 0., 0., 0., 0., 5., 6., 6., 8., 9., 10., 10., 10., 10., 10., 10.]
+
+
+def test_additive_bank_with_smoothing():
+    # configs[1] at reduced size: integer phase + block-rate amplitude ramps => per-voice bit-exact
+    def build(graph):
+        return banks.additive_bank(graph, 96, 1.0)
+
+    gpu, ref, gt, rt, proc = both(build, 750)
+    assert np.array_equal(gt, rt)
+    assert np.abs(gpu - ref).max() <= 1e-5
+    assert np.abs(ref).max() > 1e-3
+    assert proc.info()["n_groups"] == 1
+
+
+@pytest.mark.parametrize("envelope", ["asr", "segments"])
+@pytest.mark.parametrize("force_interp", [False, True])
+def test_subtractive_bank_with_note_events(envelope, force_interp):
+    # configs[2] at reduced size: saw -> SVF lowpass -> envelope -> VCA, sample-accurate events
+    def build(graph):
+        return banks.subtractive_bank(graph, 70, 1.0, envelope=envelope)
+
+    gpu, ref, gt, rt, proc = both(build, 750, force_interpreter=force_interp)
+    assert np.abs(rt).max() > 1e-4
+    assert np.abs(gt - rt).max() <= 1e-4          # IIR budget (sequential evaluation: expect ~0)
+    assert np.abs(gpu - ref).max() <= 1e-5
+    assert proc.info()["dropped_changes"] == 0
+
+
+def test_subtractive_intermediate_nodes_match():
+    # tap every node of a voice (forces the interpreter): oscillators <= 1e-5, filter <= 1e-4
+    ids = {}
+
+    def build(graph):
+        with graph.edit() as g:
+            saw = g.push(kn.PolyBlep(kn.Waveform.Sawtooth, 220.0).precise_timing(8))
+            svf = g.push(kn.SvfFilter(kn.SvfFilterType.Low, 900.0, 4.0, 0.0).precise_timing(8))
+            env = g.push(kn.EnvAsr(0.01, 0.2).precise_timing(8))
+            lp = g.push(kn.OnePoleLpf(2000.0))
+            sig = ((saw >> svf >> lp) * env)
+            sig.to_graph_out()
+            env.param("t_restart").trig_at(kn.Seconds.from_samples(1000, SR))
+            saw.param("freq").set_at(13000.0, kn.Seconds.from_samples(9001, SR))  # >= sr/4: sine guard path
+            saw.param("freq").set_at(330.0, kn.Seconds.from_samples(12345, SR))
+            svf.param("cutoff_freq").set_at(3000.0, kn.Seconds.from_samples(15000, SR))
+            svf.param("q").set_at(0.8, kn.Seconds.from_samples(15001, SR))
+            lp.param("cutoff_freq").set_at(500.0, kn.Seconds.from_samples(20000, SR))
+            env.param("t_release").trig_at(kn.Seconds.from_samples(30000, SR))
+        return [saw.id(), svf.id(), env.id(), lp.id(), sig._outputs[0][0]]
+
+    gpu, ref, gt, rt, _ = both(build, 750, outputs=1)
+    assert np.array_equal(gt[2], rt[2])                    # envelope: pure f32 recurrence
+    assert np.abs(gt[0] - rt[0]).max() <= 1e-5             # oscillator
+    assert np.abs(gt[1] - rt[1]).max() <= 1e-4             # SVF
+    assert np.abs(gt[3] - rt[3]).max() <= 1e-4             # one-pole
+    assert np.abs(gpu - ref).max() <= 1e-4
+    assert np.abs(rt[4]).max() > 0.05
+
+
+@pytest.mark.parametrize("force_interp", [False, True])
+def test_fm_bank_audio_rate_routes(force_interp):
+    # configs[3] at reduced size: SinNumeric -> (*idx + fc) -> SinNumeric.ar_params() freq
+    def build(graph):
+        return banks.fm_bank(graph, 40)
+
+    gpu, ref, gt, rt, _ = both(build, 750, force_interpreter=force_interp)
+    assert np.abs(gt - rt).max() <= 1e-5
+    assert np.abs(gpu - ref).max() <= 1e-5
+    assert np.abs(ref).max() > 1e-2
+
+
+def test_fm_voice_full_scale_over_10_seconds():
+    # the hard case for float-phase parity: a carrier integrates its modulator for 480 000 samples
+    def build(graph):
+        with graph.edit() as g:
+            mod = g.push(kn.SinNumeric(311.0))
+            car = g.push(kn.SinNumeric(207.0).ar_params())
+            car.link("freq", mod * 900.0 + 207.0)
+            car.to_graph_out()
+        return [car.id(), mod.id()]
+
+    gpu, ref, gt, rt, _ = both(build, 7500, outputs=1)
+    assert np.abs(gt[1] - rt[1]).max() <= 1e-5
+    assert np.abs(gt[0] - rt[0]).max() <= 1e-5
+
+
+def test_all_svf_types_and_math_ops():
+    def build(graph):
+        ids = []
+        with graph.edit() as g:
+            for ty in kn.SvfFilterType:
+                saw = g.push(kn.PolyBlep(kn.Waveform.Sawtooth, 100.0 + 30 * int(ty)))
+                f = g.push(kn.SvfFilter(ty, 800.0 + 100 * int(ty), 1.5, 3.0))
+                sig = ((saw >> f) * 0.05 + 0.001 - 0.002) / 2.0
+                sig.to_graph_out()
+                ids.append(sig._outputs[0][0])
+            a = g.push(kn.SinWt(100.0).wr_add(0.5).wr_sub(0.25).wr_v_sub_gen(1.0).wr_div(2.0).wr_v_div_gen(0.1))
+            a.to_graph_out()
+            ids.append(a.id())
+        return ids
+
+    gpu, ref, gt, rt, proc = both(build, 200, outputs=1)
+    assert np.abs(gt - rt).max() <= 1e-4
+    assert np.abs(gpu - ref).max() <= 1e-4
+    assert proc.info()["n_groups"] == 10   # 9 filter types are 9 different voice shapes + the wrapper chain
+
+
+def test_unsupported_graph_fails_loudly_on_gpu_too():
+    graph, p = AudioProcessor.new(0, 1, AudioProcessorOptions())
+    with graph.edit() as g:
+        g.push(kn.PolyBlep(kn.Waveform.Triangle, 100.0)).to_graph_out()
+    from knaster_b200._ffi import KgpuError
+
+    with pytest.raises(KgpuError):
+        p.run_without_inputs()
