@@ -265,6 +265,9 @@ def main():
         graph.pending_event_arrays = [shift_events(ev0, step_no[0] * step_frames)] if len(ev0) else []
         step_no[0] += 1
 
+    # a non-default torch stream: its cudaStream_t is handed to the C ABI, so the engine's kernels,
+    # the NCCL reduce and the torch.cuda.Event timers all live on the same stream
+    torch.cuda.set_stream(torch.cuda.Stream())
     bus = torch.empty((n_blocks, 2, BLOCK), dtype=torch.float32, device="cuda")
     chunks = max(1, min(args.chunks, n_blocks)) if world > 1 else 1
     bounds = [round(i * n_blocks / chunks) for i in range(chunks + 1)]

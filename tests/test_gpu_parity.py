@@ -217,9 +217,10 @@ def test_all_svf_types_and_math_ops():
                 sig = ((saw >> f) * 0.05 + 0.001 - 0.002) / 2.0
                 sig.to_graph_out()
                 ids.append(sig._outputs[0][0])
-            a = g.push(kn.SinWt(100.0).wr_add(0.5).wr_sub(0.25).wr_v_sub_gen(1.0).wr_div(2.0).wr_v_div_gen(0.1))
-            a.to_graph_out()
-            ids.append(a.id())
+            a = g.push(kn.SinWt(100.0).wr_add(1.5).wr_sub(0.25).wr_v_sub_gen(3.0))
+            b = g.push(kn.TestInPlusParamUGen().wr_div(2.0).wr_v_div_gen(0.1).wr_mul(0.5))
+            a.to(b).to_graph_out()
+            ids.append(b.id())
         return ids
 
     gpu, ref, gt, rt, proc = both(build, 200, outputs=1)
