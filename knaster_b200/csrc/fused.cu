@@ -20,7 +20,6 @@ namespace kgpu {
 
 namespace {
 
-constexpr int SUB_WARPS = 4;          // warps per CTA
 constexpr int SUB_TILE = 32;          // frames between mix-bus reductions
 constexpr int SUB_PAD = 33;           // smem row stride (bank-conflict-free transpose)
 
@@ -61,6 +60,7 @@ struct SubVoice {
         default: break; // pulse_width / waveform: not read by the sawtooth path
         }
     }
+    // reference-order evaluation, any parameter values (used on tiles with events / odd dt)
     KN_DEV float tick() {
         const float saw = polyblep_saw_tick(t, dt, use_sin);
         const float y = svf_tick(saw, ic1, ic2, a1, a2, a3, m0, m1, m2);
@@ -69,15 +69,51 @@ struct SubVoice {
     }
 };
 
+// x - trunc(x) for x in [0, 2): trunc(x) is 0 or 1, and x - 1 is exact for x in [1, 2)
+KN_DEV float wrap01(float x) { return x >= 1.0f ? x - 1.0f : x; }
+
+// EnvAsr::next_sample (envelopes.rs:52-81) as straight-line selects: same values, no divergence
+KN_DEV float envasr_tick_sel(uint32_t &st, float &t, float ar, float rr, float sc) {
+    const bool att = st == ASR_ATTACKING, rel = st == ASR_RELEASING;
+    const float cube = ((t * t) * t) * sc;
+    const float out = att ? t : (st == ASR_SUSTAINING ? 1.0f : (rel ? cube : 0.0f));
+    float tn = att ? t + ar : (rel ? t - rr : t);
+    const bool to_sus = att && tn >= 1.0f;
+    const bool to_stop = rel && tn <= 0.0f;
+    st = to_sus ? (uint32_t)ASR_SUSTAINING : (to_stop ? (uint32_t)ASR_STOPPED : st);
+    t = to_stop ? 0.0f : tn;
+    return out;
+}
+
+constexpr int SUB_SUB = 8; // frames per straight-line group
+
+// 8 frames, no events, 0 <= dt < 1 and !use_sin for every lane of the warp: the three
+// recurrences (phase, filter, envelope) are independent chains that ptxas interleaves.
+KN_DEV void sub_group_fast(SubVoice &s, float omd, float *out8) {
+    float saw[SUB_SUB], env[SUB_SUB];
+#pragma unroll
+    for (int k = 0; k < SUB_SUB; k++) {
+        // PolyBlep::saw (polyblep.rs:490-498) with t in [0,1): _t = frac(t + 0.5)
+        const float _t = wrap01(s.t + 0.5f);
+        float y = 2.0f * _t - 1.0f;
+        if (_t < s.dt || _t > omd) y = y - blep(_t, s.dt); // 2 samples per period
+        saw[k] = y;
+        s.t = wrap01(s.t + s.dt); // inc(), polyblep.rs:232-235
+    }
+#pragma unroll
+    for (int k = 0; k < SUB_SUB; k++) env[k] = envasr_tick_sel(s.est, s.et, s.ar, s.rr, s.sc) * s.gain;
+#pragma unroll
+    for (int k = 0; k < SUB_SUB; k++) out8[k] = svf_tick(saw[k], s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * env[k];
+}
+
 template <bool TAPS>
-__global__ void __launch_bounds__(SUB_WARPS * 32) render_sub_asr(FusedArgs a) {
-    __shared__ float stage[SUB_WARPS][SUB_TILE * SUB_PAD];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t gwarp = blockIdx.x * SUB_WARPS + warp;
+__global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
+    __shared__ float st[SUB_TILE * SUB_PAD];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t gwarp = blockIdx.x;
     const uint32_t v = gwarp * 32 + lane;
     const uint32_t V = a.n_voices;
     const bool active = v < V;
-    float *st = stage[warp];
 
     SubVoice s;
     {
@@ -99,37 +135,51 @@ __global__ void __launch_bounds__(SUB_WARPS * 32) render_sub_asr(FusedArgs a) {
             if (a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
 
     float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
+    // the straight-line group needs t in [0,1), 0 <= dt < 1 and the sawtooth branch of next_sample
+    bool fast_ok = __all_sync(0xFFFFFFFFu, !active || (s.dt >= 0.0f && s.dt < 1.0f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin));
+    float omd = 1.0f - s.dt;
     for (uint32_t f0 = 0; f0 < a.n_frames; f0 += SUB_TILE) {
         const uint32_t nf = min((uint32_t)SUB_TILE, a.n_frames - f0);
-        const bool ev_tile = __any_sync(0xFFFFFFFFu, next_frame < f0 + nf);
-        if (!ev_tile && nf == SUB_TILE) {
-#pragma unroll 4
-            for (uint32_t f = 0; f < SUB_TILE; f++) {
-                const float o = s.tick();
-                st[f * SUB_PAD + lane] = active ? o : 0.f;
-                if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + f0 + f] = o;
-            }
-        } else {
-            for (uint32_t f = 0; f < nf; f++) {
-                while (next_frame <= f0 + f) { // events are sorted by (frame, node, arrival)
-                    const DevEvent e = a.events[cur];
-                    if (e.op == OP_SET) s.set(e.reg, e.value);
-                    else if (e.op == OP_ASR_RELEASE) envasr_release(s.est, s.et, s.sc);
-                    cur++;
-                    next_frame = cur < end ? a.events[cur].frame : 0xFFFFFFFFu;
+#pragma unroll 1
+        for (uint32_t g0 = 0; g0 < SUB_TILE; g0 += SUB_SUB) {
+            const uint32_t gf = f0 + g0;
+            const bool ev_group = __any_sync(0xFFFFFFFFu, next_frame < gf + SUB_SUB);
+            if (fast_ok && !ev_group && g0 + SUB_SUB <= nf) {
+                float o[SUB_SUB];
+                sub_group_fast(s, omd, o);
+#pragma unroll
+                for (int k = 0; k < SUB_SUB; k++) {
+                    st[(g0 + k) * SUB_PAD + lane] = active ? o[k] : 0.f;
+                    if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o[k];
                 }
-                const float o = s.tick();
-                st[f * SUB_PAD + lane] = active ? o : 0.f;
-                if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + f0 + f] = o;
+            } else {
+                for (uint32_t k = 0; k < SUB_SUB; k++) {
+                    float o = 0.f;
+                    if (g0 + k < nf) {
+                        while (next_frame <= gf + k) { // events are sorted by (frame, node, arrival)
+                            const DevEvent e = a.events[cur];
+                            if (e.op == OP_SET) s.set(e.reg, e.value);
+                            else if (e.op == OP_ASR_RELEASE) envasr_release(s.est, s.et, s.sc);
+                            cur++;
+                            next_frame = cur < end ? a.events[cur].frame : 0xFFFFFFFFu;
+                        }
+                        o = s.tick();
+                        if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o;
+                    }
+                    st[(g0 + k) * SUB_PAD + lane] = active ? o : 0.f;
+                }
+                if (ev_group) {
+                    omd = 1.0f - s.dt;
+                    fast_ok = __all_sync(0xFFFFFFFFu, !active || (s.dt >= 0.0f && s.dt < 1.0f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin));
+                }
             }
-            for (uint32_t f = nf; f < SUB_TILE; f++) st[f * SUB_PAD + lane] = 0.f;
         }
         __syncwarp();
         // lane l sums frame l over the warp's 32 voices (fixed order => deterministic)
         float acc = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; j++) acc = acc + st[lane * SUB_PAD + j];
-        if (lane < nf && gwarp * 32 < V) prow[f0 + lane] = acc;
+        if (lane < nf) prow[f0 + lane] = acc;
         __syncwarp();
     }
     if (active) {
@@ -183,10 +233,10 @@ uint32_t fused_rows(int recipe, uint32_t n_voices, uint32_t n_ubus) {
 }
 cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream) {
     if (recipe != 0) return cudaErrorNotSupported;
+    // one warp per CTA: 512 warps spread over all 148 SMs (3-4 per SM, one per SM sub-partition)
     const uint32_t n_warps = (a.n_voices + 31) / 32;
-    const uint32_t n_cta = (n_warps + SUB_WARPS - 1) / SUB_WARPS;
-    if (a.n_taps) render_sub_asr<true><<<n_cta, SUB_WARPS * 32, 0, stream>>>(a);
-    else render_sub_asr<false><<<n_cta, SUB_WARPS * 32, 0, stream>>>(a);
+    if (a.n_taps) render_sub_asr<true><<<n_warps, 32, 0, stream>>>(a);
+    else render_sub_asr<false><<<n_warps, 32, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
