@@ -11,7 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "_build", "libknaster_gpu.so")
+LIB_PATH = os.environ.get("KNASTER_GPU_LIB") or os.path.join(CSRC, "_build", "libknaster_gpu.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "knaster_gpu.h")
 
 KGPU_ABI_VERSION = 1

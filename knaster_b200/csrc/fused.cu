@@ -85,25 +85,62 @@ KN_DEV float envasr_tick_sel(uint32_t &st, float &t, float ar, float rr, float s
     return out;
 }
 
-constexpr int SUB_SUB = 8; // frames per straight-line group
+// The refined reciprocal nvcc's IEEE division computes per call (MUFU.RCP + one Newton step).
+// It only depends on the divisor, so it is hoisted: recomputed when dt changes.
+KN_DEV float div_prep(float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    const float e = __fmaf_rn(-d, r, 1.0f);
+    return __fmaf_rn(r, e, r);
+}
+// n / d with rc = div_prep(d): the fast path of nvcc's -prec-div=true sequence (q0 = n*rc,
+// r = n - d*q0, q = q0 + r*rc), which is correctly rounded for operands whose quotient is a
+// normal number -- here |n| < d < 1 and n is 0 or >= 2^-25, so it always is.
+KN_DEV float div_rc(float n, float d, float rc) {
+    const float q0 = __fmul_rn(n, rc);
+    const float r = __fmaf_rn(-d, q0, n);
+    return __fmaf_rn(r, rc, q0);
+}
 
-// 8 frames, no events, 0 <= dt < 1 and !use_sin for every lane of the warp: the three
-// recurrences (phase, filter, envelope) are independent chains that ptxas interleaves.
-KN_DEV void sub_group_fast(SubVoice &s, float omd, float *out8) {
-    float saw[SUB_SUB], env[SUB_SUB];
+// PolyBlep::saw (polyblep.rs:490-498) + blep (polyblep.rs:47-55) for t in [0,1), 0 < dt < 1,
+// as straight-line code: the correction is computed every frame and selected where it applies.
+KN_DEV float saw_eval(float t, float dt, float omd, float rc) {
+    const float _t = wrap01(t + 0.5f);
+    const float y = 2.0f * _t - 1.0f;
+    const bool lo = _t < dt;
+    const bool hi = _t > omd;                    // else-if: only when !lo
+    const float num = lo ? _t : _t - 1.0f;
+    const float q = div_rc(num, dt, rc);
+    const float x = lo ? q - 1.0f : q + 1.0f;
+    const float b = x * x;
+    return lo ? y + b : (hi ? y - b : y);        // y - (-(x*x)) == y + x*x exactly
+}
+
+#ifndef SUB_SUB
+#define SUB_SUB 8 // frames per straight-line group
+#endif
+
+// SUB_SUB frames, no events, fast conditions hold for the lane: the three recurrences (phase,
+// envelope, filter) are independent dependency chains that ptxas interleaves in one basic block.
+KN_DEV void sub_group_fast(SubVoice &s, float omd, float rc, float *out8) {
+    float ph[SUB_SUB], env[SUB_SUB];
 #pragma unroll
     for (int k = 0; k < SUB_SUB; k++) {
-        // PolyBlep::saw (polyblep.rs:490-498) with t in [0,1): _t = frac(t + 0.5)
-        const float _t = wrap01(s.t + 0.5f);
-        float y = 2.0f * _t - 1.0f;
-        if (_t < s.dt || _t > omd) y = y - blep(_t, s.dt); // 2 samples per period
-        saw[k] = y;
+        ph[k] = s.t;
         s.t = wrap01(s.t + s.dt); // inc(), polyblep.rs:232-235
     }
 #pragma unroll
     for (int k = 0; k < SUB_SUB; k++) env[k] = envasr_tick_sel(s.est, s.et, s.ar, s.rr, s.sc) * s.gain;
 #pragma unroll
-    for (int k = 0; k < SUB_SUB; k++) out8[k] = svf_tick(saw[k], s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * env[k];
+    for (int k = 0; k < SUB_SUB; k++) {
+        const float saw = saw_eval(ph[k], s.dt, omd, rc);
+        out8[k] = svf_tick(saw, s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * env[k];
+    }
+}
+
+// per-lane validity of the straight-line formulation
+KN_DEV bool sub_lane_fast(const SubVoice &s) {
+    return s.dt > 0.0f && s.dt < 1.0f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin;
 }
 
 template <bool TAPS>
@@ -135,9 +172,10 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
             if (a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
 
     float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
-    // the straight-line group needs t in [0,1), 0 <= dt < 1 and the sawtooth branch of next_sample
-    bool fast_ok = __all_sync(0xFFFFFFFFu, !active || (s.dt >= 0.0f && s.dt < 1.0f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin));
-    float omd = 1.0f - s.dt;
+    // the straight-line group needs t in [0,1), 0 < dt < 1 and the sawtooth branch of next_sample
+    bool lane_fast = !active || sub_lane_fast(s);
+    bool fast_ok = __all_sync(0xFFFFFFFFu, lane_fast);
+    float omd = 1.0f - s.dt, rc = div_prep(s.dt);
     for (uint32_t f0 = 0; f0 < a.n_frames; f0 += SUB_TILE) {
         const uint32_t nf = min((uint32_t)SUB_TILE, a.n_frames - f0);
 #pragma unroll 1
@@ -146,40 +184,56 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
             const bool ev_group = __any_sync(0xFFFFFFFFu, next_frame < gf + SUB_SUB);
             if (fast_ok && !ev_group && g0 + SUB_SUB <= nf) {
                 float o[SUB_SUB];
-                sub_group_fast(s, omd, o);
+                sub_group_fast(s, omd, rc, o);
 #pragma unroll
                 for (int k = 0; k < SUB_SUB; k++) {
                     st[(g0 + k) * SUB_PAD + lane] = active ? o[k] : 0.f;
                     if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o[k];
                 }
             } else {
+#pragma unroll 1
                 for (uint32_t k = 0; k < SUB_SUB; k++) {
                     float o = 0.f;
                     if (g0 + k < nf) {
-                        while (next_frame <= gf + k) { // events are sorted by (frame, node, arrival)
-                            const DevEvent e = a.events[cur];
-                            if (e.op == OP_SET) s.set(e.reg, e.value);
-                            else if (e.op == OP_ASR_RELEASE) envasr_release(s.est, s.et, s.sc);
-                            cur++;
-                            next_frame = cur < end ? a.events[cur].frame : 0xFFFFFFFFu;
+                        if (next_frame <= gf + k) {
+                            do { // events are sorted by (frame, node, arrival)
+                                const DevEvent e = a.events[cur];
+                                if (e.op == OP_SET) s.set(e.reg, e.value);
+                                else if (e.op == OP_ASR_RELEASE) envasr_release(s.est, s.et, s.sc);
+                                cur++;
+                                next_frame = cur < end ? a.events[cur].frame : 0xFFFFFFFFu;
+                            } while (next_frame <= gf + k);
+                            omd = 1.0f - s.dt;
+                            rc = div_prep(s.dt);
+                            lane_fast = sub_lane_fast(s);
                         }
-                        o = s.tick();
+                        if (lane_fast) {
+                            const float ph = s.t;
+                            s.t = wrap01(s.t + s.dt);
+                            const float e = envasr_tick_sel(s.est, s.et, s.ar, s.rr, s.sc) * s.gain;
+                            o = svf_tick(saw_eval(ph, s.dt, omd, rc), s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * e;
+                        } else {
+                            o = s.tick();
+                            lane_fast = sub_lane_fast(s); // t is back in [0,1) after one generic tick
+                        }
                         if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o;
                     }
                     st[(g0 + k) * SUB_PAD + lane] = active ? o : 0.f;
                 }
-                if (ev_group) {
-                    omd = 1.0f - s.dt;
-                    fast_ok = __all_sync(0xFFFFFFFFu, !active || (s.dt >= 0.0f && s.dt < 1.0f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin));
-                }
+                fast_ok = __all_sync(0xFFFFFFFFu, lane_fast);
             }
         }
         __syncwarp();
         // lane l sums frame l over the warp's 32 voices (fixed order => deterministic)
-        float acc = 0.f;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; j++) acc = acc + st[lane * SUB_PAD + j];
-        if (lane < nf) prow[f0 + lane] = acc;
+        for (int j = 0; j < 32; j += 4) {
+            acc0 = acc0 + st[lane * SUB_PAD + j];
+            acc1 = acc1 + st[lane * SUB_PAD + j + 1];
+            acc2 = acc2 + st[lane * SUB_PAD + j + 2];
+            acc3 = acc3 + st[lane * SUB_PAD + j + 3];
+        }
+        if (lane < nf) prow[f0 + lane] = (acc0 + acc1) + (acc2 + acc3);
         __syncwarp();
     }
     if (active) {
