@@ -3,7 +3,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -87,8 +90,7 @@ struct kgpu_plan {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     uint64_t kernel_launches = 0;
-    std::vector<DevEvent> h_events, h_events_all;
-    std::vector<uint32_t> h_off, h_off_all;
+    HostPlan::CompiledEvents ce;
     DevBuf<DevEvent> d_events_all;
     DevBuf<uint32_t> d_off_all;
     uint64_t max_blocks_per_launch = 1024;
@@ -97,8 +99,7 @@ struct kgpu_plan {
     size_t kev_used = 0;
     bool prepared = false;                 // phase 1 already done for `prepared_blocks`
     uint64_t prepared_blocks = 0;
-    std::vector<uint64_t> piece_ev, piece_off;
-    std::vector<uint8_t> piece_any;
+
     uint64_t last_h2d_bytes = 0;
 };
 
@@ -161,32 +162,20 @@ void choose_kernels(kgpu_plan *p) {
 void prepare_range(kgpu_plan *p, uint64_t n_blocks, uint64_t bpl, cudaStream_t stream) {
     const uint32_t bs = p->host.block_size;
     const uint64_t t_begin = p->frame_clock, t_end = t_begin + n_blocks * bs;
-    p->host.simulate(t_begin, t_end);
-    p->piece_ev.clear(); p->piece_off.clear(); p->piece_any.clear();
-    p->h_events_all.clear();
-    p->h_off_all.clear();
-    for (uint64_t done = 0; done < n_blocks; done += bpl) {
-        const uint64_t nb = std::min(bpl, n_blocks - done);
-        const uint64_t t0 = t_begin + done * bs, t1 = t0 + nb * bs;
-        for (uint32_t gi = 0; gi < p->gd.size(); gi++) {
-            p->host.take_events(gi, t0, t1, p->gd[gi].chunk, p->h_events, p->h_off);
-            p->piece_ev.push_back(p->h_events_all.size());
-            p->piece_off.push_back(p->h_off_all.size());
-            p->piece_any.push_back(!p->h_events.empty());
-            if (!p->h_events.empty()) {
-                p->h_events_all.insert(p->h_events_all.end(), p->h_events.begin(), p->h_events.end());
-                p->h_off_all.insert(p->h_off_all.end(), p->h_off.begin(), p->h_off.end());
-            }
-        }
-    }
+    std::vector<uint64_t> bounds;
+    for (uint64_t done = 0; done < n_blocks; done += bpl) bounds.push_back(t_begin + done * bs);
+    bounds.push_back(t_end);
+    std::vector<uint32_t> chunks;
+    for (GroupDev &d : p->gd) chunks.push_back(d.chunk);
+    p->host.compile_events(bounds, chunks, p->ce);
     p->last_h2d_bytes = 0;
-    if (!p->h_events_all.empty()) {
-        p->d_events_all.ensure(p->h_events_all.size());
-        p->d_off_all.ensure(p->h_off_all.size());
+    if (!p->ce.events.empty()) {
+        p->d_events_all.ensure(p->ce.events.size());
+        p->d_off_all.ensure(p->ce.offsets.size());
         // pageable source: the runtime stages the copy before returning, the vectors may be reused
-        CUDA_TRY(cudaMemcpyAsync(p->d_events_all.p, p->h_events_all.data(), p->h_events_all.size() * sizeof(DevEvent), cudaMemcpyHostToDevice, stream));
-        CUDA_TRY(cudaMemcpyAsync(p->d_off_all.p, p->h_off_all.data(), p->h_off_all.size() * 4, cudaMemcpyHostToDevice, stream));
-        p->last_h2d_bytes = p->h_events_all.size() * sizeof(DevEvent) + p->h_off_all.size() * 4;
+        CUDA_TRY(cudaMemcpyAsync(p->d_events_all.p, p->ce.events.data(), p->ce.events.size() * sizeof(DevEvent), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(p->d_off_all.p, p->ce.offsets.data(), p->ce.offsets.size() * 4, cudaMemcpyHostToDevice, stream));
+        p->last_h2d_bytes = p->ce.events.size() * sizeof(DevEvent) + p->ce.offsets.size() * 4;
     }
 }
 
@@ -231,8 +220,8 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
         for (uint32_t gi = 0; gi < p->gd.size(); gi++, piece++) {
             Group &g = p->host.groups[gi];
             GroupDev &d = p->gd[gi];
-            const DevEvent *d_ev = p->piece_any[piece] ? p->d_events_all.p + p->piece_ev[piece] : nullptr;
-            const uint32_t *d_off = p->piece_any[piece] ? p->d_off_all.p + p->piece_off[piece] : nullptr;
+            const DevEvent *d_ev = p->ce.piece_any[piece] ? p->d_events_all.p + p->ce.piece_ev[piece] : nullptr;
+            const uint32_t *d_off = p->ce.piece_any[piece] ? p->d_off_all.p + p->ce.piece_off[piece] : nullptr;
             mark(0, true);
             if (d.recipe >= 0) {
                 FusedArgs a{};
@@ -517,19 +506,29 @@ int kgpu_debug_simulate(const kgpu_graph_desc *desc, const kgpu_event *events, s
                         kgpu_plan_info *info) {
     try {
         HostPlan hp;
+        const bool timing = getenv("KGPU_TIMING") != nullptr;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        auto t0_ = now();
         hp.build(*desc);
+        auto t1_ = now();
         hp.push(events, n_events, 0);
+        auto t2_ = now();
+        double sim_ms = 0;
         size_t n = 0;
         const uint64_t bs = hp.block_size;
         if (blocks_per_call == 0) blocks_per_call = n_blocks;
-        std::vector<DevEvent> ev;
-        std::vector<uint32_t> off;
+        HostPlan::CompiledEvents ce;
+        std::vector<uint32_t> chunks(hp.groups.size(), 1);
         for (uint64_t b = 0; b < n_blocks; b += blocks_per_call) {
             const uint64_t t0 = b * bs, t1 = std::min(n_blocks, b + blocks_per_call) * bs;
-            hp.simulate(t0, t1);
+            auto a_ = now();
+            hp.compile_events({t0, t1}, chunks, ce);
+            sim_ms += ms(a_, now());
             for (uint32_t gi = 0; gi < hp.groups.size(); gi++) {
-                hp.take_events(gi, t0, t1, 1, ev, off);
-                if (ev.empty()) continue;
+                if (!ce.piece_any[gi]) continue;
+                const DevEvent *ev = ce.events.data() + ce.piece_ev[gi];
+                const uint32_t *off = ce.offsets.data() + ce.piece_off[gi];
                 for (uint32_t v = 0; v < hp.groups[gi].n_voices; v++)
                     for (uint32_t k = off[v]; k < off[v + 1]; k++) {
                         if (n < cap) out[n] = kgpu_debug_event{gi, v, ev[k].node, ev[k].op, ev[k].reg, ev[k].value, t0 + ev[k].frame};
@@ -537,6 +536,7 @@ int kgpu_debug_simulate(const kgpu_graph_desc *desc, const kgpu_event *events, s
                     }
             }
         }
+        if (timing) fprintf(stderr, "[kgpu timing] build %.1f ms, push %.1f ms, compile_events %.1f ms\n", ms(t0_, t1_), ms(t1_, t2_), sim_ms);
         if (n_out) *n_out = n;
         if (nodes_out)
             for (uint32_t i = 0; i < desc->n_nodes; i++) {

@@ -21,7 +21,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <tuple>
 #include <unordered_map>
 
@@ -185,8 +189,17 @@ void svf_coeffs(uint32_t ty, float cutoff, float q, float gain_db, float sr, flo
 }
 
 // ---- control simulation ------------------------------------------------------------------
+// per-thread sink of the control simulation
+struct Sink {
+    std::vector<VoiceEvent> buf; // device events of the voice being processed, one run per node
+    std::vector<uint32_t> run_start; // start of each node's run in buf (frames non-decreasing inside a run)
+    std::vector<VoiceEvent> merged;
+    uint32_t seq = 0;
+    uint64_t dropped = 0, ignored = 0, devev = 0;
+};
 struct Sim {
     HostPlan &P;
+    Sink &out;
     uint32_t gi;
     uint32_t voice;
     uint32_t local;
@@ -195,14 +208,14 @@ struct Sim {
         VoiceEvent ve;
         ve.voice = voice;
         ve.frame = frame;
-        ve.seq = P.seq++;
+        ve.seq = out.seq++;
         ve.ev.frame = 0;
         ve.ev.node = (uint16_t)local;
         ve.ev.op = op;
         ve.ev.reg = reg;
         ve.ev.value = value;
-        P.out_events[gi].push_back(ve);
-        P.device_events++;
+        out.buf.push_back(ve);
+        out.devev++;
     }
     void set_f(uint64_t frame, uint32_t reg, float v) { emit(frame, OP_SET, reg, fbits(v)); }
     void set_u(uint64_t frame, uint32_t reg, uint32_t v) { emit(frame, OP_SET, reg, v); }
@@ -241,7 +254,7 @@ void ugen_param_apply(Sim &s, uint32_t param, const PV &v, uint64_t frame) {
             s.set_u(frame, r + 2, (dt * sr >= sr / 4.0f) ? 1u : 0u); // guard of next_sample, polyblep.rs:210
         } else if (param == 1) s.set_f(frame, r + 3, (float)v.f);
         else if (param == 2) {
-            if ((int64_t)v.f != 0) s.P.ignored_delays++; // unsupported waveform change: kept as Sawtooth (rejected at push)
+            if ((int64_t)v.f != 0) s.out.ignored++; // unsupported waveform change: kept as Sawtooth (rejected at push)
         }
         break;
     case KGPU_SVF: { // svf.rs:81-133
@@ -391,7 +404,7 @@ void wr_param_apply(Sim &s, int level, uint32_t param, const PV &v, uint64_t fra
         if (param >= w.next_delay.size()) return; // would index out of bounds in knaster
         if (w.next_delay[param] == 0) wr_param_apply(s, level - 1, param, v, frame);
         else if (w.queue.size() < w.capacity) w.queue.push_back(QueuedChange{w.next_delay[param], param, v});
-        else s.P.dropped_changes++;
+        else s.out.dropped++;
         return;
     default: return;
     }
@@ -407,7 +420,7 @@ void wr_set_delay(Sim &s, int level, uint32_t param, uint16_t delay) {
         }
         if (!is_math_wrapper(w.kind)) break; // WrSmoothParams / WrArParams do not forward (trait default)
     }
-    s.P.ignored_delays++; // ugen.rs:339-341: warning, no effect
+    s.out.ignored++; // ugen.rs:339-341: warning, no effect
 }
 
 // control-side effects of process_block through the wrapper stack for one (partial) block
@@ -428,9 +441,23 @@ void wr_process_block(Sim &s, int level, uint64_t block_start, uint32_t offset, 
             uint32_t block_i = 0;
             size_t change_i = 0;
             const size_t num = w.queue.size();
-            std::vector<QueuedChange> q;
-            q.swap(w.queue); // next_delay_i = 0 at the end; next_delay[] stays
-            std::vector<uint8_t> some(num, 1);
+            // next_delay_i = 0 at the end; next_delay[] stays.  Small fixed scratch: the queue holds
+            // at most `capacity` entries and nested WrPreciseTiming is rejected at plan time.
+            QueuedChange qbuf[16];
+            std::vector<QueuedChange> qheap;
+            QueuedChange *q = qbuf;
+            if (num > 16) {
+                qheap = w.queue;
+                q = qheap.data();
+            } else std::copy(w.queue.begin(), w.queue.end(), qbuf);
+            w.queue.clear();
+            uint8_t some_buf[16];
+            std::vector<uint8_t> some_heap;
+            uint8_t *some = some_buf;
+            if (num > 16) {
+                some_heap.assign(num, 1);
+                some = some_heap.data();
+            } else std::fill(some_buf, some_buf + 16, (uint8_t)1);
             while (true) {
                 uint32_t local_frames = frames - block_i;
                 while (change_i < num) {
@@ -457,12 +484,10 @@ void wr_process_block(Sim &s, int level, uint64_t block_start, uint32_t offset, 
 }
 
 bool needs_processing(const HostNode &h) {
-    for (const WrapSim &w : h.wr) {
-        if (w.kind == KGPU_WR_PRECISE_TIMING && !w.queue.empty()) return true;
-        if (w.kind == KGPU_WR_SMOOTH_PARAMS)
-            for (const SmoothState &st : w.smooth)
-                if (st.linear && !st.done) return true;
-    }
+    if (h.precise_level >= 0 && !h.wr[h.precise_level].queue.empty()) return true;
+    if (h.smooth_level >= 0)
+        for (const SmoothState &st : h.wr[h.smooth_level].smooth)
+            if (st.linear && !st.done) return true;
     return false;
 }
 
@@ -860,8 +885,6 @@ void HostPlan::build(const kgpu_graph_desc &d) {
         }
     }
     // initial registers + control state: Node::init (graph.rs:462-475) of every node of every voice
-    out_events.assign(groups.size(), {});
-    ramp_nodes.assign(groups.size(), {});
     const float sr = (float)sample_rate;
     for (Group &g : groups) {
         const uint32_t V = g.n_voices, nn = (uint32_t)g.tpl.nodes.size();
@@ -957,9 +980,12 @@ void HostPlan::build(const kgpu_graph_desc &d) {
                     } else if (w.kind == KGPU_WR_SMOOTH_PARAMS) {
                         w.smooth.assign(inner, SmoothState{});
                         h.has_smooth = true;
+                        h.smooth_level = (int8_t)l;
                     } else if (w.kind == KGPU_WR_PRECISE_TIMING) {
                         w.next_delay.assign(inner, 0);
+                        w.queue.reserve(std::min<uint32_t>(w.capacity, 8));
                         h.has_precise = true;
+                        h.precise_level = (int8_t)l;
                     } else if (w.kind == KGPU_WR_AR_PARAMS) {
                         w.ar_bound.assign(inner, 0);
                         for (auto &pe : g.tpl.nodes[li].par)
@@ -970,7 +996,48 @@ void HostPlan::build(const kgpu_graph_desc &d) {
     }
 }
 
+// Validation of an event only depends on (group, node-in-template, parameter): cache it.
+struct ParamRule {
+    char want = 'f';      // expected ParameterValue kind ('t' trigger: anything fires)
+    bool smooth_ok = false;
+    bool polyblep_wave = false, svf_type = false;
+};
+static ParamRule param_rule(const HostNode &h, uint32_t p) {
+    ParamRule r;
+    bool wr_mul_target = false;
+    for (int l = (int)h.wr.size() - 1; l >= 0; l--) { // outermost -> innermost, like param_apply
+        const WrapSim &w = h.wr[l];
+        if (w.kind == KGPU_WR_MUL && p == w.inner_params) { wr_mul_target = true; break; }
+        if (w.kind == KGPU_WR_SMOOTH_PARAMS && p < w.smooth.size()) r.smooth_ok = true;
+    }
+    if (!wr_mul_target) {
+        const char *types = param_types(h.kind);
+        r.want = p < std::strlen(types) ? types[p] : 'f';
+        r.polyblep_wave = h.kind == KGPU_POLYBLEP && p == 2;
+        r.svf_type = h.kind == KGPU_SVF && p == 3;
+    }
+    return r;
+}
+
 void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
+    if (rules.empty()) { // [group][local][param], built from voice 0 of each group
+        rules.resize(groups.size());
+        for (size_t gi = 0; gi < groups.size(); gi++) {
+            const Group &g = groups[gi];
+            const size_t nn = g.tpl.nodes.size();
+            rules[gi].resize(nn);
+            for (size_t li = 0; li < nn; li++) {
+                const HostNode &h = g.host[li];
+                uint32_t np = h.base_params;
+                for (const WrapSim &w : h.wr)
+                    if (w.kind == KGPU_WR_MUL) np++;
+                for (uint32_t p = 0; p < np; p++) {
+                    ParamRule pr = param_rule(h, p);
+                    rules[gi][li].push_back({pr.want, (uint8_t)pr.smooth_ok, (uint8_t)pr.polyblep_wave, (uint8_t)pr.svf_type});
+                }
+            }
+        }
+    }
     // validate everything first so that a failing call queues nothing
     for (size_t i = 0; i < n; i++) {
         const kgpu_event &e = evs[i];
@@ -982,166 +1049,318 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
             KGPU_THROW(KGPU_ERR_UNSUPPORTED, "event %zu: Rate::AudioRate smoothing is not supported (its branch is unreachable in knaster, "
                        "smooth_params.rs:140-146)", i);
         if (nr.group < 0) continue; // unreachable node: knaster would run it, but nothing can hear it
-        const Group &g = groups[nr.group];
-        const HostNode &h = g.host[(size_t)nr.voice * g.tpl.nodes.size() + nr.local];
-        // who consumes the value? walk outermost -> innermost like param_apply does
-        bool wr_mul_target = false, smooth_ok = false;
-        uint32_t p = e.param;
-        for (int l = (int)h.wr.size() - 1; l >= 0; l--) {
-            const WrapSim &w = h.wr[l];
-            if (w.kind == KGPU_WR_MUL && p == w.inner_params) { wr_mul_target = true; break; }
-            if (w.kind == KGPU_WR_SMOOTH_PARAMS && p < w.smooth.size()) smooth_ok = true;
-        }
-        if (e.smoothing_kind != 0 && !smooth_ok)
+        const Rule &r = rules[nr.group][nr.local][e.param];
+        if (e.smoothing_kind != 0 && !r.smooth_ok)
             KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: smoothing sent to node %u param %u which has no WrSmoothParams around it "
                        "(knaster would panic: parameter value is expected to be a float)", i, e.node, e.param);
         if (e.value_kind != 0) {
-            char want = 'f';
-            if (!wr_mul_target) {
-                const char *types = param_types(h.kind);
-                want = p < std::strlen(types) ? types[p] : 'f';
-            }
+            const char want = r.want;
             bool ok = want == 't' || (want == 'f' && e.value_kind == 1) || (want == 'i' && e.value_kind == 3) || (want == 'b' && e.value_kind == 4);
             if (!ok) KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: wrong value type for node %u param %u", i, e.node, e.param);
-            if (h.kind == KGPU_POLYBLEP && p == 2 && !wr_mul_target && (int64_t)e.value != 0)
+            if (r.polyblep_wave && (int64_t)e.value != 0)
                 KGPU_THROW(KGPU_ERR_UNSUPPORTED, "event %zu: PolyBlep waveform %lld not supported yet", i, (long long)e.value);
-            if (h.kind == KGPU_SVF && p == 3 && !wr_mul_target && ((int64_t)e.value < 0 || (int64_t)e.value > 8))
+            if (r.svf_type && ((int64_t)e.value < 0 || (int64_t)e.value > 8))
                 KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: bad SvfFilterType", i);
         }
     }
-    const uint64_t bs = block_size;
+    pending.reserve(pending.size() + n);
     for (size_t i = 0; i < n; i++) {
         const kgpu_event &e = evs[i];
         if (node_ref[e.node].group < 0) continue;
         RawEvent r;
         r.node = e.node;
-        r.param = e.param;
-        if (e.value_kind) {
-            r.value.kind = (PV::Kind)e.value_kind;
-            r.value.f = e.value_kind == 3 ? (double)(int64_t)e.value : e.value;
-        }
-        if (e.smoothing_kind) {
-            r.smoothing.kind = PV::Smoothing;
-            r.smoothing.smoothing = e.smoothing_kind == 2 ? 1 : 0;
-            r.smoothing.smooth_seconds = e.smooth_seconds;
-        }
+        r.param = (uint16_t)e.param;
+        r.value_kind = (uint8_t)e.value_kind;
+        r.smoothing_kind = (uint8_t)e.smoothing_kind;
         r.timed = e.time_kind != 0;
+        r.smooth_seconds = e.smooth_seconds;
+        r.value = e.value_kind == 3 ? (double)(int64_t)e.value : e.value;
         uint64_t samples = (uint64_t)e.seconds * sample_rate + ((uint64_t)e.subsec * sample_rate) / 282240000ull; // time.rs:86-90
         if (e.time_kind == 1) r.due_frame = samples;                    // scheduling.rs:102-108
         else if (e.time_kind == 2) r.due_frame = frame_clock + samples; // scheduling.rs:110-119
         else r.due_frame = frame_clock;
         if (r.due_frame < frame_clock) r.due_frame = frame_clock;       // late: saturating_sub -> delay 0
-        (void)bs;
-        r.seq = seq++;
+        if (!pending.empty() && r.due_frame < pending.back().due_frame) pending_sorted = false;
+        pending_max_due = std::max(pending_max_due, r.due_frame);
         pending.push_back(r);
     }
 }
 
-void HostPlan::simulate(uint64_t t0, uint64_t t1) {
-    const uint64_t bs = block_size;
-    const uint64_t b0 = t0 / bs, b1 = t1 / bs;
-    // events that become ready (delay < block_size, graph_gen.rs:283) inside [b0, b1)
-    struct Item { uint64_t key; uint64_t block; uint64_t seq; uint32_t idx; };
-    std::vector<Item> items;
-    std::vector<RawEvent> keep;
-    std::vector<RawEvent> ready;
-    for (RawEvent &r : pending) {
-        uint64_t blk = std::max(r.due_frame / bs, b0);
-        if (blk < b1) ready.push_back(r);
-        else keep.push_back(r);
+namespace {
+struct PhaseTimer {
+    const char *name;
+    std::chrono::steady_clock::time_point t;
+    explicit PhaseTimer(const char *n) : name(n), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        static const bool on = getenv("KGPU_TIMING") != nullptr;
+        auto n = std::chrono::steady_clock::now();
+        if (on) fprintf(stderr, "[kgpu timing]   %s/%s %.1f ms\n", name, what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
     }
-    pending.swap(keep);
-    items.reserve(ready.size());
-    for (uint32_t i = 0; i < ready.size(); i++) {
-        const NodeRef &nr = node_ref[ready[i].node];
-        const Group &g = groups[nr.group];
-        uint64_t hidx = (uint64_t)nr.voice * g.tpl.nodes.size() + nr.local;
-        items.push_back({((uint64_t)nr.group << 40) | hidx, std::max(ready[i].due_frame / bs, b0), ready[i].seq, i});
-    }
-    std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
-        if (a.key != b.key) return a.key < b.key;
-        if (a.block != b.block) return a.block < b.block;
-        return a.seq < b.seq;
-    });
-    auto process_node = [&](uint32_t gi, uint64_t hidx, const Item *ev, size_t n) {
-        Group &g = groups[gi];
-        const uint32_t nn = (uint32_t)g.tpl.nodes.size();
-        HostNode &hn = g.host[hidx];
-        Sim s{*this, gi, (uint32_t)(hidx / nn), (uint32_t)(hidx % nn), hn};
-        const int top = (int)hn.wr.size() - 1;
-        size_t ei = 0;
-        uint64_t b = needs_processing(hn) ? b0 : (n ? ev[0].block : b1);
-        while (b < b1) {
-            const uint64_t block_start = b * bs;
-            while (ei < n && ev[ei].block == b) { // apply_parameter_change, graph_gen.rs:269-305
-                const RawEvent &r = ready[ev[ei].idx];
-                uint64_t delay = r.timed && r.due_frame > block_start ? r.due_frame - block_start : 0;
-                if (delay > 0) wr_set_delay(s, top, r.param, (uint16_t)delay);
-                if (r.smoothing.kind != PV::None) wr_param_apply(s, top, r.param, r.smoothing, block_start);
-                if (r.value.kind != PV::None) wr_param_apply(s, top, r.param, r.value, block_start);
-                ei++;
-            }
-            if (needs_processing(hn)) wr_process_block(s, top, block_start, 0, (uint32_t)bs);
-            if (needs_processing(hn)) b++;
-            else if (ei < n) b = ev[ei].block;
-            else break;
-        }
-        return needs_processing(hn);
-    };
-    // nodes with events
-    std::vector<std::vector<uint32_t>> new_ramps(groups.size());
-    std::vector<std::vector<uint8_t>> seen(groups.size());
-    size_t i = 0;
-    while (i < items.size()) {
-        size_t j = i;
-        while (j < items.size() && items[j].key == items[i].key) j++;
-        uint32_t gi = (uint32_t)(items[i].key >> 40);
-        uint64_t hidx = items[i].key & ((1ull << 40) - 1);
-        if (seen[gi].empty()) seen[gi].assign(groups[gi].host.size(), 0);
-        seen[gi][hidx] = 1;
-        if (process_node(gi, hidx, &items[i], j - i)) new_ramps[gi].push_back((uint32_t)hidx);
-        i = j;
-    }
-    // nodes whose ramps are still running from earlier renders
-    for (uint32_t gi = 0; gi < groups.size(); gi++) {
-        for (uint32_t hidx : ramp_nodes[gi]) {
-            if (!seen[gi].empty() && seen[gi][hidx]) continue;
-            if (process_node(gi, hidx, nullptr, 0)) new_ramps[gi].push_back(hidx);
-        }
-        ramp_nodes[gi].swap(new_ramps[gi]);
-    }
-}
+};
 
-void HostPlan::take_events(uint32_t gi, uint64_t t0, uint64_t t1, uint32_t chunk, std::vector<DevEvent> &events,
-                           std::vector<uint32_t> &offsets) {
-    Group &g = groups[gi];
-    std::vector<VoiceEvent> &all = out_events[gi];
-    events.clear();
-    offsets.clear();
-    if (all.empty()) return;
-    std::vector<VoiceEvent> now, later;
-    for (VoiceEvent &ve : all) {
-        if (ve.frame < t1) now.push_back(ve);
-        else later.push_back(ve);
+// one node of one voice: replay its ready events block by block (graph_gen.rs:111-166,269-305)
+bool process_node(HostPlan &P, Sink &out, uint32_t gi, uint32_t voice, uint32_t local, const RawEvent *const *ev, size_t n,
+                  uint64_t b0, uint64_t b1) {
+    Group &g = P.groups[gi];
+    const uint64_t bs = P.block_size;
+    HostNode &hn = g.host[(size_t)voice * g.tpl.nodes.size() + local];
+    Sim s{P, out, gi, voice, local, hn};
+    const int top = (int)hn.wr.size() - 1;
+    auto blk = [&](size_t i) { return std::max(ev[i]->due_frame / bs, b0); };
+    size_t ei = 0;
+    uint64_t b = needs_processing(hn) ? b0 : (n ? blk(0) : b1);
+    while (b < b1) {
+        const uint64_t block_start = b * bs;
+        while (ei < n && blk(ei) == b) { // apply_parameter_change, graph_gen.rs:269-305
+            const RawEvent &r = *ev[ei];
+            uint64_t delay = r.timed && r.due_frame > block_start ? r.due_frame - block_start : 0;
+            if (delay > 0) wr_set_delay(s, top, r.param, (uint16_t)delay);
+            if (r.smoothing_kind) {
+                PV pv;
+                pv.kind = PV::Smoothing;
+                pv.smoothing = r.smoothing_kind == 2 ? 1 : 0;
+                pv.smooth_seconds = r.smooth_seconds;
+                wr_param_apply(s, top, r.param, pv, block_start);
+            }
+            if (r.value_kind) {
+                PV pv;
+                pv.kind = (PV::Kind)r.value_kind;
+                pv.f = r.value;
+                wr_param_apply(s, top, r.param, pv, block_start);
+            }
+            ei++;
+        }
+        if (needs_processing(hn)) wr_process_block(s, top, block_start, 0, (uint32_t)bs);
+        if (needs_processing(hn)) b++;
+        else if (ei < n) b = blk(ei);
+        else break;
     }
-    all.swap(later);
-    if (now.empty()) return;
-    for (VoiceEvent &ve : now) ve.ev.frame = (uint32_t)(ve.frame < t0 ? 0 : ve.frame - t0);
-    std::sort(now.begin(), now.end(), [chunk](const VoiceEvent &a, const VoiceEvent &b) {
-        if (a.voice != b.voice) return a.voice < b.voice;
-        uint32_t ca = a.ev.frame / chunk, cb = b.ev.frame / chunk;
-        if (ca != cb) return ca < cb;
-        if (a.ev.node != b.ev.node) return a.ev.node < b.ev.node;
-        if (a.ev.frame != b.ev.frame) return a.ev.frame < b.ev.frame;
-        return a.seq < b.seq;
-    });
-    offsets.assign(g.n_voices + 1, 0);
-    events.resize(now.size());
-    for (size_t i = 0; i < now.size(); i++) {
-        events[i] = now[i].ev;
-        offsets[now[i].voice + 1]++;
+    return needs_processing(hn);
+}
+} // namespace
+
+// The host half of a render call for frames [bounds.front(), bounds.back()), launch L covering
+// [bounds[L], bounds[L+1]): run the control simulation for every voice (voices are independent:
+// the work is spread over host threads), and emit the device events per (launch, group), each
+// voice's events ordered the way its kernel consumes them: (frame / chunk, node, frame, arrival).
+void HostPlan::compile_events(const std::vector<uint64_t> &bounds, const std::vector<uint32_t> &chunk_of_group, CompiledEvents &out) {
+    PhaseTimer pt("compile_events");
+    const uint64_t bs = block_size;
+    const uint64_t t0 = bounds.front(), t1 = bounds.back();
+    const uint64_t b0 = t0 / bs, b1 = t1 / bs;
+    const size_t n_launch = bounds.size() - 1, n_groups = groups.size();
+    out.events.clear();
+    out.offsets.clear();
+    out.piece_ev.assign(n_launch * n_groups, 0);
+    out.piece_off.assign(n_launch * n_groups, 0);
+    out.piece_any.assign(n_launch * n_groups, 0);
+    if (n_launch > 255) KGPU_THROW(KGPU_ERR_INVALID, "too many launches in one render call (%zu)", n_launch);
+    if (voice_base.size() != n_groups + 1) {
+        voice_base.assign(n_groups + 1, 0);
+        for (size_t gi = 0; gi < n_groups; gi++) voice_base[gi + 1] = voice_base[gi] + groups[gi].n_voices;
+        voice_ramps.assign(voice_base.back(), 0);
+        later.assign(n_groups, {});
     }
-    for (uint32_t v = 0; v < g.n_voices; v++) offsets[v + 1] += offsets[v];
+    // ---- ready events: due block < b1 (graph_gen.rs:283: ready iff delay < block_size)
+    size_t n_ready = pending.size();
+    if (pending_max_due / bs >= b1) {
+        if (!pending_sorted) {
+            std::stable_sort(pending.begin(), pending.end(), [](const RawEvent &a, const RawEvent &b) { return a.due_frame < b.due_frame; });
+            pending_sorted = true;
+        }
+        RawEvent probe{};
+        probe.due_frame = b1 * bs;
+        n_ready = std::lower_bound(pending.begin(), pending.end(), probe, [](const RawEvent &a, const RawEvent &b) { return a.due_frame < b.due_frame; }) - pending.begin();
+    }
+    bool any_work = n_ready > 0 || n_active_ramps > 0;
+    for (auto &l : later) any_work |= !l.empty();
+    if (!any_work) return;
+    // bucket by global voice (stable counting sort keeps arrival order inside a voice)
+    const size_t NV = voice_base.back();
+    vcount.assign(NV + 1, 0);
+    for (size_t i = 0; i < n_ready; i++) {
+        const NodeRef &nr = node_ref[pending[i].node];
+        vcount[voice_base[nr.group] + nr.voice + 1]++;
+    }
+    for (size_t v = 0; v < NV; v++) vcount[v + 1] += vcount[v];
+    vorder.resize(n_ready);
+    {
+        vfill.assign(vcount.begin(), vcount.end() - 1);
+        for (size_t i = 0; i < n_ready; i++) {
+            const NodeRef &nr = node_ref[pending[i].node];
+            vorder[vfill[voice_base[nr.group] + nr.voice]++] = (uint32_t)i;
+        }
+    }
+    pt.lap("bucket");
+    for (size_t gi = 0; gi < n_groups; gi++) {
+        Group &g = groups[gi];
+        const uint32_t V = g.n_voices, nn = (uint32_t)g.tpl.nodes.size();
+        const uint32_t chunk = chunk_of_group[gi];
+        // leftovers of the previous call (events at/after its end), bucketed by voice
+        std::vector<VoiceEvent> &lat = later[gi];
+        std::vector<uint32_t> lat_start;
+        if (!lat.empty()) {
+            std::stable_sort(lat.begin(), lat.end(), [](const VoiceEvent &a, const VoiceEvent &b) { return a.voice < b.voice; });
+            lat_start.assign(V + 1, 0);
+            for (auto &ve : lat) lat_start[ve.voice + 1]++;
+            for (uint32_t v = 0; v < V; v++) lat_start[v + 1] += lat_start[v];
+        }
+        struct alignas(256) ThreadOut {
+            std::vector<std::vector<DevEvent>> ev;   // per launch
+            std::vector<std::vector<uint32_t>> cnt;  // per launch, per voice of the range
+            std::vector<VoiceEvent> later;
+            Sink sink;
+            int64_t ramp_delta = 0;
+        };
+        const size_t work = n_ready + lat.size() + n_active_ramps;
+        unsigned T = work > 20000 ? std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u) : 1u;
+        T = std::min<unsigned>(T, std::max(1u, V / 64));
+        if (const char *e = getenv("KGPU_THREADS")) T = std::max(1, atoi(e));
+        std::vector<ThreadOut> touts(T);
+        auto run = [&](unsigned ti) {
+            auto t_start = std::chrono::steady_clock::now();
+            double t_proc = 0, t_sort = 0;
+            ThreadOut &to = touts[ti];
+            const uint32_t v_begin = (uint32_t)((uint64_t)V * ti / T), v_end = (uint32_t)((uint64_t)V * (ti + 1) / T);
+            to.ev.assign(n_launch, {});
+            to.cnt.assign(n_launch, std::vector<uint32_t>(v_end - v_begin, 0));
+            std::vector<const RawEvent *> evp, node_ev;
+            auto key_less = [&](const VoiceEvent &a, const VoiceEvent &b) {
+                const uint64_t fa = a.frame < t0 ? t0 : a.frame, fb = b.frame < t0 ? t0 : b.frame;
+                const uint64_t ca = fa / chunk, cb = fb / chunk;
+                if (ca != cb) return ca < cb;
+                if (a.ev.node != b.ev.node) return a.ev.node < b.ev.node;
+                if (fa != fb) return fa < fb;
+                return a.seq < b.seq;
+            };
+            for (uint32_t v = v_begin; v < v_end; v++) {
+                const size_t gv = voice_base[gi] + v;
+                const uint32_t e0 = vcount[gv], e1 = vcount[gv + 1];
+                const bool has_later = !lat_start.empty() && lat_start[v + 1] > lat_start[v];
+                if (e0 == e1 && !voice_ramps[gv] && !has_later) continue;
+                Sink &sk = to.sink;
+                sk.buf.clear();
+                sk.run_start.clear();
+                sk.seq = 0;
+                sk.run_start.push_back(0);
+                if (has_later)
+                    for (uint32_t k = lat_start[v]; k < lat_start[v + 1]; k++) {
+                        VoiceEvent ve = lat[k];
+                        ve.seq = sk.seq++;
+                        sk.buf.push_back(ve);
+                    }
+                evp.clear();
+                for (uint32_t k = e0; k < e1; k++) evp.push_back(&pending[vorder[k]]);
+                for (uint32_t li = 0; li < nn; li++) {
+                    HostNode &hn = g.host[(size_t)v * nn + li];
+                    node_ev.clear();
+                    for (const RawEvent *r : evp)
+                        if (node_ref[r->node].local == li) node_ev.push_back(r);
+                    if (node_ev.empty() && !hn.ramp_active) continue;
+                    // (due block, arrival) order; arrival order is usually time order already
+                    bool sorted = true;
+                    for (size_t i = 1; i < node_ev.size() && sorted; i++)
+                        sorted = std::max(node_ev[i - 1]->due_frame / bs, b0) <= std::max(node_ev[i]->due_frame / bs, b0);
+                    if (!sorted)
+                        std::stable_sort(node_ev.begin(), node_ev.end(), [&](const RawEvent *x, const RawEvent *y) {
+                            return std::max(x->due_frame / bs, b0) < std::max(y->due_frame / bs, b0);
+                        });
+                    const bool was = hn.ramp_active;
+                    if (sk.run_start.back() != sk.buf.size()) sk.run_start.push_back((uint32_t)sk.buf.size());
+                    
+                    hn.ramp_active = process_node(*this, sk, (uint32_t)gi, v, li, node_ev.data(), node_ev.size(), b0, b1);
+                    
+                    if (hn.ramp_active != was) {
+                        to.ramp_delta += hn.ramp_active ? 1 : -1;
+                        voice_ramps[gv] += hn.ramp_active ? 1 : -1;
+                    }
+                }
+                // order for the device: k-way merge of the per-node runs (each already in time order)
+                
+                sk.run_start.push_back((uint32_t)sk.buf.size());
+                std::vector<VoiceEvent> *bufp = &sk.buf;
+                const size_t n_runs = sk.run_start.size() - 1;
+                if (n_runs > 1 && !std::is_sorted(sk.buf.begin(), sk.buf.end(), key_less)) {
+                    sk.merged.clear();
+                    uint32_t head[MAX_NODES + 2];
+                    if (n_runs > (size_t)MAX_NODES + 1) {
+                        std::sort(sk.buf.begin(), sk.buf.end(), key_less);
+                    } else {
+                        for (size_t r = 0; r < n_runs; r++) head[r] = sk.run_start[r];
+                        for (size_t done_n = 0; done_n < sk.buf.size(); done_n++) {
+                            int best = -1;
+                            for (size_t r = 0; r < n_runs; r++) {
+                                if (head[r] == sk.run_start[r + 1]) continue;
+                                if (best < 0 || key_less(sk.buf[head[r]], sk.buf[head[best]])) best = (int)r;
+                            }
+                            sk.merged.push_back(sk.buf[head[best]++]);
+                        }
+                        bufp = &sk.merged;
+                    }
+                }
+                std::vector<VoiceEvent> &buf = *bufp;
+                for (const VoiceEvent &ve : buf) {
+                    if (ve.frame >= t1) {
+                        to.later.push_back(ve);
+                        continue;
+                    }
+                    size_t L = std::upper_bound(bounds.begin(), bounds.end(), ve.frame) - bounds.begin();
+                    L = L == 0 ? 0 : L - 1; // late events (frame < bounds[0]): first launch, relative frame 0
+                    DevEvent d = ve.ev;
+                    d.frame = (uint32_t)(ve.frame < bounds[L] ? 0 : ve.frame - bounds[L]);
+                    to.ev[L].push_back(d);
+                    to.cnt[L][v - v_begin]++;
+                }
+                
+            }
+            if (getenv("KGPU_TIMING"))
+                fprintf(stderr, "[kgpu timing]     thread %u: %.1f ms (process_node %.1f, sort+split %.1f)\n", ti,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), t_proc, t_sort);
+            (void)t_sort;
+        };
+        if (T == 1) run(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned ti = 0; ti < T; ti++) th.emplace_back(run, ti);
+            for (auto &t : th) t.join();
+        }
+        pt.lap("simulate");
+        // merge thread outputs: per launch, events in voice order + CSR offsets
+        lat.clear();
+        for (ThreadOut &to : touts) {
+            lat.insert(lat.end(), to.later.begin(), to.later.end());
+            dropped_changes += to.sink.dropped;
+            ignored_delays += to.sink.ignored;
+            device_events += to.sink.devev;
+            n_active_ramps = (uint64_t)((int64_t)n_active_ramps + to.ramp_delta);
+        }
+        for (size_t L = 0; L < n_launch; L++) {
+            size_t total = 0;
+            for (ThreadOut &to : touts) total += to.ev[L].size();
+            const size_t pi = L * n_groups + gi;
+            out.piece_ev[pi] = out.events.size();
+            if (!total) continue;
+            out.piece_any[pi] = 1;
+            out.piece_off[pi] = out.offsets.size();
+            out.offsets.reserve(out.offsets.size() + V + 1);
+            uint32_t run_off = 0;
+            for (ThreadOut &to : touts) {
+                out.events.insert(out.events.end(), to.ev[L].begin(), to.ev[L].end());
+                for (uint32_t c : to.cnt[L]) {
+                    out.offsets.push_back(run_off);
+                    run_off += c;
+                }
+            }
+            out.offsets.push_back(run_off);
+        }
+        pt.lap("merge");
+    }
+    pending.erase(pending.begin(), pending.begin() + n_ready);
+    if (pending.empty()) {
+        pending_sorted = true;
+        pending_max_due = 0;
+    }
 }
 
 } // namespace kgpu

@@ -67,6 +67,7 @@ struct HostNode {
     float svf_coef[6] = {0, 0, 0, 0, 0, 0};
     std::vector<WrapSim> wr; // innermost first
     bool has_smooth = false, has_precise = false;
+    int8_t smooth_level = -1, precise_level = -1;
     bool ramp_active = false;
     uint32_t ramp_list_pos = 0;
 };
@@ -104,19 +105,21 @@ struct NodeRef {
     uint32_t n_params = 0;
 };
 
-struct RawEvent {
-    uint32_t node, param;
-    PV value;       // kind None if absent
-    PV smoothing;   // kind None if absent
-    uint64_t due_frame; // absolute; events without time: frame clock at push
-    bool timed;     // false: `time: None` (delay 0 by construction)
-    uint64_t seq;
+struct RawEvent { // 32 bytes
+    uint32_t node;
+    uint16_t param;
+    uint8_t value_kind;     // 0 none, 1 float, 2 trigger, 3 integer, 4 bool
+    uint8_t smoothing_kind; // 0 none, 1 ParameterSmoothing::None, 2 Linear
+    uint8_t timed;          // 0: `time: None` (delay 0 by construction)
+    float smooth_seconds;
+    double value;
+    uint64_t due_frame;     // absolute; events without time: frame clock at push
 };
 
 struct VoiceEvent { // a device event tagged with its destination
     uint32_t voice;
+    uint32_t seq;   // arrival order inside the voice
     uint64_t frame; // absolute
-    uint64_t seq;
     DevEvent ev;
 };
 
@@ -126,20 +129,31 @@ struct HostPlan {
     std::vector<NodeRef> node_ref; // per graph node
     uint32_t n_mix_nodes = 0;
     uint64_t dropped_changes = 0, ignored_delays = 0, device_events = 0;
-    uint64_t seq = 0;
     std::vector<RawEvent> pending;                  // not yet simulated
-    std::vector<std::vector<VoiceEvent>> out_events; // per group: simulated, not yet rendered
-    std::vector<std::vector<uint32_t>> ramp_nodes;  // per group: host-node indices with active ramps / queues
+
+    // caches / scratch of the hot host path (push / compile_events)
+    struct Rule { char want; uint8_t smooth_ok, polyblep_wave, svf_type; };
+    std::vector<std::vector<std::vector<Rule>>> rules;   // [group][local][param]
+    bool pending_sorted = true;
+    uint64_t pending_max_due = 0;
+    uint64_t n_active_ramps = 0;
+    std::vector<uint64_t> voice_base;                    // prefix sum of voices per group
+    std::vector<int32_t> voice_ramps;                    // per global voice: nodes with active ramps / queues
+    std::vector<std::vector<VoiceEvent>> later;          // per group: simulated events at/after the last render's end
+    std::vector<uint32_t> vcount, vfill, vorder;
+
+    struct CompiledEvents {
+        std::vector<DevEvent> events;      // concatenated pieces
+        std::vector<uint32_t> offsets;     // concatenated CSR offset arrays (n_voices+1 each)
+        std::vector<uint64_t> piece_ev, piece_off; // [launch * n_groups + group]
+        std::vector<uint8_t> piece_any;
+    };
 
     void build(const kgpu_graph_desc &d);
     // push_events: validate + timestamp (frame_clock = next block to render)
     void push(const kgpu_event *ev, size_t n, uint64_t frame_clock);
-    // run the control simulation for blocks [t0/bs, t1/bs) and move the resulting device events
-    // (frame in [t0,t1)) of `group` into `out`, sorted per voice in device processing order
-    // (chunk = frames per interpreter chunk, 1 for frame-major fused kernels).
-    void simulate(uint64_t t0, uint64_t t1);
-    void take_events(uint32_t group, uint64_t t0, uint64_t t1, uint32_t chunk, std::vector<DevEvent> &events,
-                     std::vector<uint32_t> &offsets);
+    // host half of a render call, see plan.cpp
+    void compile_events(const std::vector<uint64_t> &bounds, const std::vector<uint32_t> &chunk_of_group, CompiledEvents &out);
 };
 
 // fused-kernel recipes (kernels.cu): returns recipe index or -1
