@@ -248,6 +248,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from knaster_b200.multi_gpu import reduce_bus
     from knaster_b200.processor import AudioProcessor, AudioProcessorOptions
 
     n_blocks = int(round(args.seconds * SR)) // BLOCK
@@ -276,9 +277,7 @@ def main():
         """kernels (+ NCCL reduce of the rank-local bus to rank 0) with inputs already in HBM"""
         cur = torch.cuda.current_stream()
         proc.render_device(n_blocks, bus.data_ptr(), cur.cuda_stream)
-        if world > 1:
-            for c in range(chunks):
-                dist.reduce(bus[bounds[c]:bounds[c + 1]], dst=0)
+        reduce_bus(bus, dst=0, chunks=chunks)
 
     def barrier():
         torch.cuda.synchronize()
