@@ -246,6 +246,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from knaster_b200.multi_gpu import reduce_bus
@@ -355,6 +356,14 @@ def main():
         rows = (args.voices + 31) // 32
         alg_bytes = 2 * state_bytes + (h2d / max(1, kern_launches / args.steps)) + rows * frames_per_launch * 4
         hbm_gbs = alg_bytes / (avg_launch_ms / 1e3) / 1e9
+        traffic = None
+        try:  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this run's launch size
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f)
+            if tj["kernel"] == info["kernels"][0] and tj["voices"] == args.voices:
+                traffic = tj["traffic_bytes_per_launch"] * frames_per_launch / tj["frames_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
         line = {
             "metric": "voice-samples/sec (f32, 48 kHz)", "value": value, "unit": "voice-samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -363,7 +372,7 @@ def main():
             "kernels": info["kernels"],
             "roofline": {
                 "bound": "fp32", "achieved": achieved, "peak": peak_fp32, "unit": "GFLOP/s (un-fused FP32 instr)",
-                "frac": achieved / peak_fp32, "traffic": None,
+                "frac": achieved / peak_fp32, "traffic": traffic,
                 "kernel": info["kernels"][0], "avg_launch_ms": avg_launch_ms, "launches": kern_launches,
                 "flops_per_voice_sample": W,
                 "peak_source": f"{N_SM} SMs x {FP32_LANES} FP32 lanes x sm_max_mhz {sm_max:g} ({peak_src}); no tensor/HBM bound: "
