@@ -499,7 +499,15 @@ float kgpu_plan_last_render_ms(kgpu_plan *p) {
 
 // ---- host-only debug entry points (csrc/debug.h) ------------------------------------------------
 #include "debug.h"
+#include "sinf_glibc.h"
 extern "C" {
+
+int kgpu_debug_sinf(const float *x, float *y, size_t n) {
+    for (size_t i = 0; i < n; i++)
+        if (!kgpu::kn_sinf_glibc(x[i], &y[i])) y[i] = (float)std::sin((double)x[i]);
+    return KGPU_OK;
+}
+
 
 int kgpu_debug_simulate(const kgpu_graph_desc *desc, const kgpu_event *events, size_t n_events, uint64_t n_blocks,
                         uint64_t blocks_per_call, kgpu_debug_event *out, size_t cap, size_t *n_out, kgpu_debug_node *nodes_out,

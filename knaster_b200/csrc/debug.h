@@ -28,6 +28,9 @@ int kgpu_debug_simulate(const kgpu_graph_desc *desc, const kgpu_event *events, s
 /* initial register value of a node register after init() */
 int kgpu_debug_init_reg(const kgpu_graph_desc *desc, uint32_t node, uint32_t reg_offset, uint32_t *value);
 
+/* host instantiation of the device sine (csrc/sinf_glibc.h), for the libm bit-exactness test */
+int kgpu_debug_sinf(const float *x, float *y, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 // rounding order (the f32 phase / envelope recurrences cannot be re-associated).
 //
 //   recipe 0  "render_sub_asr"   PolyBlep(saw) -> SvfFilter -> (* EnvAsr.wr_mul) [MathUGen<Mul>]   (configs[2], [4])
+//   recipe 1  "render_fm2"       (SinNumeric * idx + fc) -> SinNumeric.ar_params() freq, * amp       (configs[3])
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -269,15 +270,151 @@ bool match_sub_asr(const DevProgram &p) {
     return p.ubus_slot[0] == mul.out_slot[0];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// recipe 1 "render_fm2": (SinNumeric mod * idx + fc) -> SinNumeric.ar_params() "freq", * amp  (configs[3])
+// template order: 0 mod, 1 Constant idx, 2 Mul, 3 Constant fc, 4 Add, 5 car, 6 Constant amp, 7 Mul
+enum : uint32_t { F_MPH = 0, F_MOFF = 1, F_MINC = 2, F_IDX = 3, F_FC = 4, F_CPH = 5, F_COFF = 6, F_CINC = 7, F_AMP = 8, FM_NREGS = 9 };
+constexpr int FM_SUB = 4;
+
+struct FmVoice {
+    float mph, moff, minc, idx, fc, cph, coff, cinc, amp;
+    KN_DEV void set(uint32_t reg, uint32_t bits) {
+        const float f = __uint_as_float(bits);
+        switch (reg) {
+        case F_MPH: mph = f; break;
+        case F_MOFF: moff = f; break;
+        case F_MINC: minc = f; break;
+        case F_IDX: idx = f; break;
+        case F_FC: fc = f; break;
+        case F_CPH: cph = f; break;
+        case F_COFF: coff = f; break;
+        case F_CINC: cinc = f; break;
+        case F_AMP: amp = f; break;
+        default: break;
+        }
+    }
+    // one frame in graph order: mod.process, Mul, Add, WrArParams(car): freq(v) then process, Mul
+    KN_DEV float tick(float sr, float rc_sr) {
+        const float m = kn_sinf((mph + moff) * KN_TAU);          // osc.rs:264
+        mph = mph + minc;
+        if (mph > 1.0f) mph = mph - 1.0f;                        // osc.rs:266-268
+        const float v = m * idx + fc;                            // MathUGen<Mul>, MathUGen<Add>
+        // audio_rate.rs:42-57 + osc.rs:240-242: phase_increment = F::new(v as f64) / F::new(sr as f32)
+        cinc = fabsf(v) > 1e-20f ? div_rc(v, sr, rc_sr) : v / sr;
+        const float c = kn_sinf((cph + coff) * KN_TAU);
+        cph = cph + cinc;
+        if (cph > 1.0f) cph = cph - 1.0f;
+        return c * amp;
+    }
+};
+
+template <bool TAPS>
+__global__ void __launch_bounds__(32, 8) render_fm2(FusedArgs a) {
+    __shared__ float st[SUB_TILE * SUB_PAD];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t gwarp = blockIdx.x;
+    const uint32_t v = gwarp * 32 + lane;
+    const uint32_t V = a.n_voices;
+    const bool active = v < V;
+    const float sr = a.prog->sample_rate;
+    const float rc_sr = div_prep(sr);
+
+    FmVoice s;
+#pragma unroll
+    for (int i = 0; i < FM_NREGS; i++) s.set(i, active ? a.regs[(size_t)i * V + v] : 0u);
+    uint32_t cur = 0, end = 0, next_frame = 0xFFFFFFFFu;
+    if (a.events && active) {
+        cur = a.ev_off[v];
+        end = a.ev_off[v + 1];
+        if (cur < end) next_frame = a.events[cur].frame;
+    }
+    int tap_row = -1;
+    if (TAPS)
+        for (uint32_t i = 0; i < a.n_taps; i++)
+            if (a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
+
+    float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
+    for (uint32_t f0 = 0; f0 < a.n_frames; f0 += SUB_TILE) {
+        const uint32_t nf = min((uint32_t)SUB_TILE, a.n_frames - f0);
+#pragma unroll 1
+        for (uint32_t g0 = 0; g0 < SUB_TILE; g0 += FM_SUB) {
+            const uint32_t gf = f0 + g0;
+            const bool ev_group = __any_sync(0xFFFFFFFFu, next_frame < gf + FM_SUB);
+            if (!ev_group && g0 + FM_SUB <= nf) {
+#pragma unroll
+                for (int k = 0; k < FM_SUB; k++) {
+                    const float o = s.tick(sr, rc_sr);
+                    st[(g0 + k) * SUB_PAD + lane] = active ? o : 0.f;
+                    if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o;
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t k = 0; k < FM_SUB; k++) {
+                    float o = 0.f;
+                    if (g0 + k < nf) {
+                        while (next_frame <= gf + k) {
+                            const DevEvent e = a.events[cur];
+                            if (e.op == OP_SET) s.set(e.reg, e.value);
+                            cur++;
+                            next_frame = cur < end ? a.events[cur].frame : 0xFFFFFFFFu;
+                        }
+                        o = s.tick(sr, rc_sr);
+                        if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o;
+                    }
+                    st[(g0 + k) * SUB_PAD + lane] = active ? o : 0.f;
+                }
+            }
+        }
+        __syncwarp();
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            acc0 = acc0 + st[lane * SUB_PAD + j];
+            acc1 = acc1 + st[lane * SUB_PAD + j + 1];
+            acc2 = acc2 + st[lane * SUB_PAD + j + 2];
+            acc3 = acc3 + st[lane * SUB_PAD + j + 3];
+        }
+        if (lane < nf) prow[f0 + lane] = (acc0 + acc1) + (acc2 + acc3);
+        __syncwarp();
+    }
+    if (active) {
+        const float regs_out[FM_NREGS] = {s.mph, s.moff, s.minc, s.idx, s.fc, s.cph, s.coff, s.cinc, s.amp};
+#pragma unroll
+        for (int i = 0; i < FM_NREGS; i++) a.regs[(size_t)i * V + v] = __float_as_uint(regs_out[i]);
+    }
+}
+
+bool match_fm2(const DevProgram &p) {
+    if (p.n_nodes != 8 || p.n_regs != FM_NREGS || p.n_ubus != 1) return false;
+    const DevNode *n = p.nodes;
+    auto plain = [](const DevNode &d) { return d.n_post == 0 && d.n_ar == 0; };
+    if (n[0].kind != DK_SINNUM || !plain(n[0]) || n[0].reg != F_MPH) return false;
+    if (n[1].kind != DK_CONST || !plain(n[1]) || n[1].reg != F_IDX) return false;
+    if (n[2].kind != DK_MATH || n[2].mode != 2 || n[2].n_out != 1 || !plain(n[2])) return false;
+    if (n[2].in_slot[0] != (int)n[0].out_slot[0] || n[2].in_slot[1] != (int)n[1].out_slot[0]) return false;
+    if (n[3].kind != DK_CONST || !plain(n[3]) || n[3].reg != F_FC) return false;
+    if (n[4].kind != DK_MATH || n[4].mode != 0 || n[4].n_out != 1 || !plain(n[4])) return false;
+    if (n[4].in_slot[0] != (int)n[2].out_slot[0] || n[4].in_slot[1] != (int)n[3].out_slot[0]) return false;
+    if (n[5].kind != DK_SINNUM || n[5].n_post || n[5].n_ar != 1 || n[5].ar_code[0] != AR_SINNUM_FREQ || n[5].reg != F_CPH) return false;
+    if (n[5].ar_slot[0] != (int)n[4].out_slot[0]) return false;
+    if (n[6].kind != DK_CONST || !plain(n[6]) || n[6].reg != F_AMP) return false;
+    if (n[7].kind != DK_MATH || n[7].mode != 2 || n[7].n_out != 1 || !plain(n[7])) return false;
+    if (n[7].in_slot[0] != (int)n[5].out_slot[0] || n[7].in_slot[1] != (int)n[6].out_slot[0]) return false;
+    return p.ubus_slot[0] == n[7].out_slot[0];
+}
+
 } // namespace
 
 int match_fused_recipe(const DevProgram &p) {
     if (match_sub_asr(p)) return 0;
+    if (match_fm2(p)) return 1;
     return -1;
 }
 const char *fused_recipe_name(int recipe) {
     switch (recipe) {
     case 0: return "render_sub_asr";
+    case 1: return "render_fm2";
     default: return "render_interp";
     }
 }
@@ -286,6 +423,12 @@ uint32_t fused_rows(int recipe, uint32_t n_voices, uint32_t n_ubus) {
     return ((n_voices + 31) / 32) * n_ubus; // one partial row per warp
 }
 cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream) {
+    if (recipe == 1) {
+        const uint32_t nw = (a.n_voices + 31) / 32;
+        if (a.n_taps) render_fm2<true><<<nw, 32, 0, stream>>>(a);
+        else render_fm2<false><<<nw, 32, 0, stream>>>(a);
+        return cudaGetLastError();
+    }
     if (recipe != 0) return cudaErrorNotSupported;
     // one warp per CTA: 512 warps spread over all 148 SMs (3-4 per SM, one per SM sub-partition)
     const uint32_t n_warps = (a.n_voices + 31) / 32;

@@ -303,3 +303,29 @@ def test_bad_events_are_reported_with_knaster_error_names():
     expect_error(g, _ffi.KGPU_ERR_PARAMETER, ev)        # smoothing without WrSmoothParams
     ev["smoothing_kind"], ev["node"] = 0, 5
     expect_error(g, _ffi.KGPU_ERR_INVALID, ev)          # NodeNotFound
+
+
+def test_sinf_restatement_matches_libm():
+    """csrc/sinf_glibc.h (the device sine, host instantiation) against the libm the oracle links:
+    bit-for-bit over random + structured arguments in the domain SinNumeric / PolyBlep use."""
+    import ctypes.util
+
+    lib = _ffi.lib()
+    lib.kgpu_debug_sinf.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    libm = C.CDLL(ctypes.util.find_library("m"))
+    libm.sinf.restype = C.c_float
+    libm.sinf.argtypes = [C.c_float]
+    rng = np.random.Generator(np.random.PCG64(7))
+    xs = np.concatenate([
+        rng.uniform(0.0, 2.0 * np.pi * 1.5, 400_000),            # (phase + offset) * TAU, phase in [0, 1]
+        rng.uniform(-16.0, 16.0, 200_000),
+        rng.uniform(-119.9, 119.9, 100_000),                     # whole reduce_fast domain
+        np.float32(np.pi / 4) + np.arange(-2000, 2000) * np.float32(1e-7),
+        np.logspace(-14, 0, 5000), [0.0, -0.0, 1e-30, 130.0, -500.0],
+    ]).astype(np.float32)
+    ys = np.empty_like(xs)
+    _ffi.check(lib.kgpu_debug_sinf(xs.ctypes.data, ys.ctypes.data, len(xs)))
+    ref = np.array([libm.sinf(float(x)) for x in xs], dtype=np.float32)
+    inside = np.abs(xs) < 120.0
+    assert np.array_equal(ys[inside].view(np.uint32), ref[inside].view(np.uint32))
+    assert np.abs(ys[~inside] - ref[~inside]).max() <= 1.2e-7   # fallback path: f64 sine rounded once
