@@ -103,27 +103,50 @@ KN_DEV float div_rc(float n, float d, float rc) {
     return __fmaf_rn(r, rc, q0);
 }
 
-// PolyBlep::saw (polyblep.rs:490-498) + blep (polyblep.rs:47-55) for t in [0,1), 0 < dt < 1,
-// as straight-line code: the correction is computed every frame and selected where it applies.
+// PolyBlep::saw (polyblep.rs:490-498) + blep (polyblep.rs:47-55) for t in [0,1), 2^-20 <= dt < 1/4,
+// as 15 straight-line instructions.  Exactness notes (every step rounds like the reference's):
+//   * 2*_t is exact, so fma(2,_t,-1) == (2*_t) - 1;
+//   * c = +1 inside the lower window, -1 inside the upper one, 0 elsewhere; c*b is exact, so
+//     fma(c,b,y) == y + b, y - b or y (y - (-(x*x)) == y + x*x exactly);
+//   * x = q - c gives q - 1 / q + 1 as blep() does; outside the windows x is finite and unused.
 KN_DEV float saw_eval(float t, float dt, float omd, float rc) {
     const float _t = wrap01(t + 0.5f);
-    const float y = 2.0f * _t - 1.0f;
+    const float y = __fmaf_rn(2.0f, _t, -1.0f);
     const bool lo = _t < dt;
-    const bool hi = _t > omd;                    // else-if: only when !lo
-    const float num = lo ? _t : _t - 1.0f;
-    const float q = div_rc(num, dt, rc);
-    const float x = lo ? q - 1.0f : q + 1.0f;
-    const float b = x * x;
-    return lo ? y + b : (hi ? y - b : y);        // y - (-(x*x)) == y + x*x exactly
+    const bool hi = _t > omd;                    // else-if: lo and hi exclude each other for dt < 1/2
+    const float hf = hi ? 1.0f : 0.0f;
+    const float c = lo ? 1.0f : -hf;
+    const float q = div_rc(_t - hf, dt, rc);     // _t - 1 is exact for _t in (1/2, 1)
+    const float x = q - c;
+    return __fmaf_rn(c, x * x, y);
 }
 
 #ifndef SUB_SUB
 #define SUB_SUB 8 // frames per straight-line group
 #endif
 
-// SUB_SUB frames, no events, fast conditions hold for the lane: the three recurrences (phase,
-// envelope, filter) are independent dependency chains that ptxas interleaves in one basic block.
-KN_DEV void sub_group_fast(SubVoice &s, float omd, float rc, float *out8) {
+// envelope registers derived from the state machine, constant while no transition happens
+struct EnvDerived {
+    float delta;   // per-frame increment of t: +attack_rate, -release_rate or 0
+    float cval;    // output of the constant states: Sustaining 1, Stopped 0
+    float hi, lo;  // group pre-check thresholds (t + 9*delta beyond them => a transition may be near)
+    bool att, rel;
+    KN_DEV void derive(uint32_t est, float ar, float rr) {
+        att = est == ASR_ATTACKING;
+        rel = est == ASR_RELEASING;
+        delta = att ? ar : (rel ? -rr : 0.0f);
+        cval = est == ASR_SUSTAINING ? 1.0f : 0.0f;
+        hi = att ? 0.9999f : __int_as_float(0x7f800000);
+        lo = rel ? 0.0001f : __int_as_float(0xff800000);
+    }
+};
+
+// SUB_SUB frames, no events, no envelope transition, fast conditions hold for every lane: the
+// three recurrences (phase, envelope, filter) are independent dependency chains that ptxas
+// interleaves in one basic block.  LP: m0 == 0, m1 == 0, m2 == 1 (lowpass) for every lane, where
+// m0*v0 + m1*v1 + m2*v2 == v2 for finite signals.
+template <bool LP>
+KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc, float *out8) {
     float ph[SUB_SUB], env[SUB_SUB];
 #pragma unroll
     for (int k = 0; k < SUB_SUB; k++) {
@@ -131,17 +154,47 @@ KN_DEV void sub_group_fast(SubVoice &s, float omd, float rc, float *out8) {
         s.t = wrap01(s.t + s.dt); // inc(), polyblep.rs:232-235
     }
 #pragma unroll
-    for (int k = 0; k < SUB_SUB; k++) env[k] = envasr_tick_sel(s.est, s.et, s.ar, s.rr, s.sc) * s.gain;
+    for (int k = 0; k < SUB_SUB; k++) {
+        // EnvAsr::next_sample (envelopes.rs:52-81) with the state fixed over the group
+        const float cube = ((s.et * s.et) * s.et) * s.sc;
+        const float o = d.att ? s.et : (d.rel ? cube : d.cval);
+        s.et = s.et + d.delta;
+        env[k] = o * s.gain;      // WrMul, wrappers_core/math.rs:63-67
+    }
 #pragma unroll
     for (int k = 0; k < SUB_SUB; k++) {
-        const float saw = saw_eval(ph[k], s.dt, omd, rc);
-        out8[k] = svf_tick(saw, s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * env[k];
+        const float v0 = saw_eval(ph[k], s.dt, omd, rc);
+        float y;
+        if (LP) {                 // svf.rs:272-278; 2*v is exact, so fma(2,v,-ic) == 2*v - ic
+            const float v3 = v0 - s.ic2;
+            const float v1 = s.a1 * s.ic1 + s.a2 * v3;
+            const float v2 = (s.ic2 + s.a2 * s.ic1) + s.a3 * v3;
+            s.ic1 = __fmaf_rn(2.0f, v1, -s.ic1);
+            s.ic2 = __fmaf_rn(2.0f, v2, -s.ic2);
+            y = v2;
+        } else {
+            y = svf_tick(v0, s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2);
+        }
+        out8[k] = y * env[k];     // MathUGen<Mul>, math.rs:45-47
     }
 }
 
 // per-lane validity of the straight-line formulation
 KN_DEV bool sub_lane_fast(const SubVoice &s) {
-    return s.dt > 0.0f && s.dt < 1.0f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin;
+    return s.dt >= 9.5367431640625e-7f && s.dt < 0.25f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin;
+}
+KN_DEV bool sub_lane_lp(const SubVoice &s) { return s.m0 == 0.0f && s.m1 == 0.0f && s.m2 == 1.0f; }
+
+// one parameter event (16 B) through the read-only path
+KN_DEV DevEvent ldg_event(const DevEvent *p) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p));
+    DevEvent e;
+    e.frame = q.x;
+    e.node = (uint16_t)(q.y & 0xFFFFu);
+    e.op = (uint16_t)(q.y >> 16);
+    e.reg = q.z;
+    e.value = q.w;
+    return e;
 }
 
 template <bool TAPS>
@@ -154,18 +207,28 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
     const bool active = v < V;
 
     SubVoice s;
-    {
+    if (active) {
         uint32_t r[SUB_NREGS];
 #pragma unroll
-        for (int i = 0; i < SUB_NREGS; i++) r[i] = active ? a.regs[(size_t)i * V + v] : 0u;
+        for (int i = 0; i < SUB_NREGS; i++) r[i] = a.regs[(size_t)i * V + v];
 #pragma unroll
         for (int i = 0; i < SUB_NREGS; i++) s.set(i, r[i]);
+    } else { // idle lane: a silent voice whose arithmetic stays finite (its output is +-0)
+        s.t = 0.f; s.dt = 0.125f; s.use_sin = 0;
+        s.ic1 = s.ic2 = s.a1 = s.a2 = s.a3 = s.m0 = s.m1 = 0.f; s.m2 = 1.f;
+        s.est = ASR_STOPPED; s.et = 0.f; s.ar = s.rr = 1.f; s.sc = 0.f; s.gain = 0.f;
     }
+    // event cursor: `ev` is the next event of this lane, already in registers (loaded one event
+    // ahead so that its latency is never on the critical path of a single-warp scheduler)
     uint32_t cur = 0, end = 0, next_frame = 0xFFFFFFFFu;
+    DevEvent ev = {};
     if (a.events && active) {
         cur = a.ev_off[v];
         end = a.ev_off[v + 1];
-        if (cur < end) next_frame = a.events[cur].frame;
+        if (cur < end) {
+            ev = ldg_event(a.events + cur);
+            next_frame = ev.frame;
+        }
     }
     int tap_row = -1;
     if (TAPS)
@@ -173,40 +236,52 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
             if (a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
 
     float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
-    // the straight-line group needs t in [0,1), 0 < dt < 1 and the sawtooth branch of next_sample
-    bool lane_fast = !active || sub_lane_fast(s);
-    bool fast_ok = __all_sync(0xFFFFFFFFu, lane_fast);
+    // the straight-line group needs t in [0,1), 2^-20 <= dt < 1/4 and the sawtooth branch of next_sample
+    bool lane_fast = sub_lane_fast(s);
+    bool all_lp = __all_sync(0xFFFFFFFFu, sub_lane_lp(s));
     float omd = 1.0f - s.dt, rc = div_prep(s.dt);
+    EnvDerived d;
+    d.derive(s.est, s.ar, s.rr);
     for (uint32_t f0 = 0; f0 < a.n_frames; f0 += SUB_TILE) {
         const uint32_t nf = min((uint32_t)SUB_TILE, a.n_frames - f0);
 #pragma unroll 1
         for (uint32_t g0 = 0; g0 < SUB_TILE; g0 += SUB_SUB) {
             const uint32_t gf = f0 + g0;
-            const bool ev_group = __any_sync(0xFFFFFFFFu, next_frame < gf + SUB_SUB);
-            if (fast_ok && !ev_group && g0 + SUB_SUB <= nf) {
+            // a lane needs the per-frame path if an event is due inside the group, its envelope may
+            // change state inside the group, or its parameters are outside the fast domain
+            const float reach = __fmaf_rn(9.0f, d.delta, s.et);
+            const bool slow = next_frame < gf + SUB_SUB || reach >= d.hi || reach <= d.lo || !lane_fast;
+            if (!__any_sync(0xFFFFFFFFu, slow) && g0 + SUB_SUB <= nf) {
                 float o[SUB_SUB];
-                sub_group_fast(s, omd, rc, o);
+                if (all_lp) sub_group_fast<true>(s, d, omd, rc, o);
+                else sub_group_fast<false>(s, d, omd, rc, o);
 #pragma unroll
                 for (int k = 0; k < SUB_SUB; k++) {
-                    st[(g0 + k) * SUB_PAD + lane] = active ? o[k] : 0.f;
+                    st[(g0 + k) * SUB_PAD + lane] = o[k];
                     if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o[k];
                 }
             } else {
+                bool touched = false;
 #pragma unroll 1
                 for (uint32_t k = 0; k < SUB_SUB; k++) {
                     float o = 0.f;
                     if (g0 + k < nf) {
                         if (next_frame <= gf + k) {
                             do { // events are sorted by (frame, node, arrival)
-                                const DevEvent e = a.events[cur];
-                                if (e.op == OP_SET) s.set(e.reg, e.value);
-                                else if (e.op == OP_ASR_RELEASE) envasr_release(s.est, s.et, s.sc);
+                                if (ev.op == OP_SET) s.set(ev.reg, ev.value);
+                                else if (ev.op == OP_ASR_RELEASE) envasr_release(s.est, s.et, s.sc);
                                 cur++;
-                                next_frame = cur < end ? a.events[cur].frame : 0xFFFFFFFFu;
+                                if (cur < end) {
+                                    ev = ldg_event(a.events + cur);
+                                    next_frame = ev.frame;
+                                } else {
+                                    next_frame = 0xFFFFFFFFu;
+                                }
                             } while (next_frame <= gf + k);
                             omd = 1.0f - s.dt;
                             rc = div_prep(s.dt);
                             lane_fast = sub_lane_fast(s);
+                            touched = true;
                         }
                         if (lane_fast) {
                             const float ph = s.t;
@@ -219,9 +294,10 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
                         }
                         if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o;
                     }
-                    st[(g0 + k) * SUB_PAD + lane] = active ? o : 0.f;
+                    st[(g0 + k) * SUB_PAD + lane] = o;
                 }
-                fast_ok = __all_sync(0xFFFFFFFFu, lane_fast);
+                d.derive(s.est, s.ar, s.rr);
+                if (__any_sync(0xFFFFFFFFu, touched)) all_lp = __all_sync(0xFFFFFFFFu, sub_lane_lp(s));
             }
         }
         __syncwarp();
