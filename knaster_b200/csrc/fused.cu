@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "dev.h"
 #include "kernels.h"
 #include "nodes.cuh"
@@ -23,6 +25,7 @@ namespace {
 
 constexpr int SUB_TILE = 32;          // frames between mix-bus reductions
 constexpr int SUB_PAD = 33;           // smem row stride (bank-conflict-free transpose)
+constexpr int SUBW_PAD = 36;          // render_sub_asr: row stride that also keeps 16-byte row reads conflict-free
 
 // register file of the subtractive voice (absolute register indices inside the voice, fixed by
 // compile_template's allocation order: node 0 PolyBlep, node 1 Svf, node 2 EnvAsr + WrMul)
@@ -122,39 +125,50 @@ KN_DEV float saw_eval(float t, float dt, float omd, float rc) {
 }
 
 #ifndef SUB_SUB
-#define SUB_SUB 8 // frames per straight-line group
+#define SUB_SUB 16 // frames per straight-line group
 #endif
 
 // envelope registers derived from the state machine, constant while no transition happens
 struct EnvDerived {
     float delta;   // per-frame increment of t: +attack_rate, -release_rate or 0
     float cval;    // output of the constant states: Sustaining 1, Stopped 0
-    float hi, lo;  // group pre-check thresholds (t + 9*delta beyond them => a transition may be near)
     bool att, rel;
     KN_DEV void derive(uint32_t est, float ar, float rr) {
         att = est == ASR_ATTACKING;
         rel = est == ASR_RELEASING;
         delta = att ? ar : (rel ? -rr : 0.0f);
         cval = est == ASR_SUSTAINING ? 1.0f : 0.0f;
-        hi = att ? 0.9999f : __int_as_float(0x7f800000);
-        lo = rel ? 0.0001f : __int_as_float(0xff800000);
     }
 };
 
-// SUB_SUB frames, no events, no envelope transition, fast conditions hold for every lane: the
-// three recurrences (phase, envelope, filter) are independent dependency chains that ptxas
-// interleaves in one basic block.  LP: m0 == 0, m1 == 0, m2 == 1 (lowpass) for every lane, where
-// m0*v0 + m1*v1 + m2*v2 == v2 for finite signals.
-template <bool LP>
-KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc, float *out8) {
-    float ph[SUB_SUB], env[SUB_SUB];
+// Number of coming frames in which the envelope state machine provably cannot change state.
+// Attacking: t_n = t + n*ar + err with |err| <= n*2^-25 (one rounding of a value below 2 per add),
+// so the first tick whose sum can reach 1 is no earlier than (1-t)/(ar + 2^-25); the same bound
+// holds for the release ramp reaching 0.  The margin used here is twice that, minus two frames.
+KN_DEV uint32_t envasr_safe_frames(uint32_t est, float t, float ar, float rr) {
+    const bool att = est == ASR_ATTACKING, rel = est == ASR_RELEASING;
+    if (!att && !rel) return 0x40000000u;
+    const float dist = att ? 1.0f - t : t;
+    const float rate = (att ? ar : rr) + 5.9604644775390625e-8f;
+    const float n = __fdividef(dist, rate) - 2.0f;
+    return n >= 1.0f ? (uint32_t)fminf(n, 1073741824.0f) : 0u; // NaN -> 0: always the exact path
+}
+
+// N frames, no events, no envelope transition, fast conditions hold for every lane: the three
+// recurrences (phase, envelope, filter) are independent dependency chains that ptxas interleaves
+// in one basic block.  LP: m0 == 0, m1 == 0, m2 == 1 (lowpass) for every lane, where
+// m0*v0 + m1*v1 + m2*v2 == v2 for finite signals.  Frame k goes to strow[k * SUBW_PAD] (the
+// lane's column of the staging tile) and, when the voice is tapped, to tap[k].
+template <bool LP, int N, bool TAPS>
+KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc, float *strow, float *tap) {
+    float ph[N], env[N];
 #pragma unroll
-    for (int k = 0; k < SUB_SUB; k++) {
+    for (int k = 0; k < N; k++) {
         ph[k] = s.t;
         s.t = wrap01(s.t + s.dt); // inc(), polyblep.rs:232-235
     }
 #pragma unroll
-    for (int k = 0; k < SUB_SUB; k++) {
+    for (int k = 0; k < N; k++) {
         // EnvAsr::next_sample (envelopes.rs:52-81) with the state fixed over the group
         const float cube = ((s.et * s.et) * s.et) * s.sc;
         const float o = d.att ? s.et : (d.rel ? cube : d.cval);
@@ -162,7 +176,7 @@ KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc
         env[k] = o * s.gain;      // WrMul, wrappers_core/math.rs:63-67
     }
 #pragma unroll
-    for (int k = 0; k < SUB_SUB; k++) {
+    for (int k = 0; k < N; k++) {
         const float v0 = saw_eval(ph[k], s.dt, omd, rc);
         float y;
         if (LP) {                 // svf.rs:272-278; 2*v is exact, so fma(2,v,-ic) == 2*v - ic
@@ -175,7 +189,9 @@ KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc
         } else {
             y = svf_tick(v0, s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2);
         }
-        out8[k] = y * env[k];     // MathUGen<Mul>, math.rs:45-47
+        const float o = y * env[k]; // MathUGen<Mul>, math.rs:45-47
+        strow[k * SUBW_PAD] = o;
+        if (TAPS && tap) tap[k] = o;
     }
 }
 
@@ -197,9 +213,48 @@ KN_DEV DevEvent ldg_event(const DevEvent *p) {
     return e;
 }
 
+// Per-lane event cursor with the next FOUR events in registers.  e[0] is complete by construction;
+// the slot freed by a pop is refilled at once, so a load has four pops (or thousands of frames) to
+// land -- a scheduler that holds a single warp has nothing else to hide a load behind.  Events
+// arrive by H2D copy, i.e. from DRAM: the 32-byte sectors 16 events ahead are pulled into L2 early.
+struct EvCursor {
+    const DevEvent *events;
+    uint32_t cur, end, next_frame;
+    DevEvent e0, e1, e2, e3;
+    static constexpr uint32_t AHEAD = 16;
+    KN_DEV void prefetch(uint32_t i) const {
+        if (i < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(events + i));
+    }
+    KN_DEV void init(const DevEvent *ev, const uint32_t *off, uint32_t v, bool on) {
+        events = ev;
+        cur = end = 0;
+        next_frame = 0xFFFFFFFFu;
+        e0 = e1 = e2 = e3 = DevEvent{};
+        if (ev && on) {
+            cur = off[v];
+            end = off[v + 1];
+            if (cur < end) e0 = ldg_event(events + cur);
+            if (cur + 1 < end) e1 = ldg_event(events + cur + 1);
+            if (cur + 2 < end) e2 = ldg_event(events + cur + 2);
+            if (cur + 3 < end) e3 = ldg_event(events + cur + 3);
+            for (uint32_t i = 4; i < AHEAD; i += 2) prefetch(cur + i);
+            if (cur < end) next_frame = e0.frame;
+        }
+    }
+    KN_DEV void pop() {
+        cur++;
+        e0 = e1;
+        e1 = e2;
+        e2 = e3;
+        next_frame = cur < end ? e0.frame : 0xFFFFFFFFu;
+        if (cur + 3 < end) e3 = ldg_event(events + cur + 3);
+        prefetch(cur + AHEAD);
+    }
+};
+
 template <bool TAPS>
 __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
-    __shared__ float st[SUB_TILE * SUB_PAD];
+    __shared__ __align__(16) float st[SUB_TILE * SUBW_PAD];
     const uint32_t lane = threadIdx.x;
     const uint32_t gwarp = blockIdx.x;
     const uint32_t v = gwarp * 32 + lane;
@@ -218,22 +273,13 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
         s.ic1 = s.ic2 = s.a1 = s.a2 = s.a3 = s.m0 = s.m1 = 0.f; s.m2 = 1.f;
         s.est = ASR_STOPPED; s.et = 0.f; s.ar = s.rr = 1.f; s.sc = 0.f; s.gain = 0.f;
     }
-    // event cursor: `ev` is the next event of this lane, already in registers (loaded one event
-    // ahead so that its latency is never on the critical path of a single-warp scheduler)
-    uint32_t cur = 0, end = 0, next_frame = 0xFFFFFFFFu;
-    DevEvent ev = {};
-    if (a.events && active) {
-        cur = a.ev_off[v];
-        end = a.ev_off[v + 1];
-        if (cur < end) {
-            ev = ldg_event(a.events + cur);
-            next_frame = ev.frame;
-        }
-    }
+    EvCursor ec;
+    ec.init(a.events, a.ev_off, v, active);
     int tap_row = -1;
     if (TAPS)
         for (uint32_t i = 0; i < a.n_taps; i++)
             if (a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
+    float *tap = TAPS && tap_row >= 0 ? a.tap_out + (size_t)tap_row * a.tap_stride + a.tap_frame0 : nullptr;
 
     float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
     // the straight-line group needs t in [0,1), 2^-20 <= dt < 1/4 and the sawtooth branch of next_sample
@@ -242,77 +288,105 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
     float omd = 1.0f - s.dt, rc = div_prep(s.dt);
     EnvDerived d;
     d.derive(s.est, s.ar, s.rr);
-    for (uint32_t f0 = 0; f0 < a.n_frames; f0 += SUB_TILE) {
-        const uint32_t nf = min((uint32_t)SUB_TILE, a.n_frames - f0);
-#pragma unroll 1
-        for (uint32_t g0 = 0; g0 < SUB_TILE; g0 += SUB_SUB) {
-            const uint32_t gf = f0 + g0;
-            // a lane needs the per-frame path if an event is due inside the group, its envelope may
-            // change state inside the group, or its parameters are outside the fast domain
-            const float reach = __fmaf_rn(9.0f, d.delta, s.et);
-            const bool slow = next_frame < gf + SUB_SUB || reach >= d.hi || reach <= d.lo || !lane_fast;
-            if (!__any_sync(0xFFFFFFFFu, slow) && g0 + SUB_SUB <= nf) {
-                float o[SUB_SUB];
-                if (all_lp) sub_group_fast<true>(s, d, omd, rc, o);
-                else sub_group_fast<false>(s, d, omd, rc, o);
-#pragma unroll
-                for (int k = 0; k < SUB_SUB; k++) {
-                    st[(g0 + k) * SUB_PAD + lane] = o[k];
-                    if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o[k];
-                }
-            } else {
-                bool touched = false;
-#pragma unroll 1
-                for (uint32_t k = 0; k < SUB_SUB; k++) {
-                    float o = 0.f;
-                    if (g0 + k < nf) {
-                        if (next_frame <= gf + k) {
-                            do { // events are sorted by (frame, node, arrival)
-                                if (ev.op == OP_SET) s.set(ev.reg, ev.value);
-                                else if (ev.op == OP_ASR_RELEASE) envasr_release(s.est, s.et, s.sc);
-                                cur++;
-                                if (cur < end) {
-                                    ev = ldg_event(a.events + cur);
-                                    next_frame = ev.frame;
-                                } else {
-                                    next_frame = 0xFFFFFFFFu;
-                                }
-                            } while (next_frame <= gf + k);
-                            omd = 1.0f - s.dt;
-                            rc = div_prep(s.dt);
-                            lane_fast = sub_lane_fast(s);
-                            touched = true;
-                        }
-                        if (lane_fast) {
-                            const float ph = s.t;
-                            s.t = wrap01(s.t + s.dt);
-                            const float e = envasr_tick_sel(s.est, s.et, s.ar, s.rr, s.sc) * s.gain;
-                            o = svf_tick(saw_eval(ph, s.dt, omd, rc), s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * e;
-                        } else {
-                            o = s.tick();
-                            lane_fast = sub_lane_fast(s); // t is back in [0,1) after one generic tick
-                        }
-                        if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o;
-                    }
-                    st[(g0 + k) * SUB_PAD + lane] = o;
-                }
-                d.derive(s.est, s.ar, s.rr);
-                if (__any_sync(0xFFFFFFFFu, touched)) all_lp = __all_sync(0xFFFFFFFFu, sub_lane_lp(s));
-            }
-        }
+    // `limit`: first frame at which SOME lane needs the exact per-frame path (an event is due, its
+    // envelope may change state, or its parameters are outside the fast domain).  Warp-uniform.
+    auto lane_limit = [&](uint32_t f) -> uint32_t {
+        if (!lane_fast) return 0u;
+        const uint32_t safe = f + envasr_safe_frames(s.est, s.et, s.ar, s.rr);
+        return min(ec.next_frame, safe);
+    };
+    uint32_t limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(0));
+    bool all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
+
+    uint32_t NF = a.n_frames;
+    asm volatile("" : "+r"(NF)); // keep it in a register (ptxas would re-read the constant bank in every loop test)
+    uint32_t f = 0;      // next frame to render
+    uint32_t rows = 0;   // frames staged in st[] since the last flush (frame f - rows is row 0)
+    // lane l sums staged frame l over the warp's 32 voices (fixed order => deterministic)
+    auto flush = [&]() {
         __syncwarp();
-        // lane l sums frame l over the warp's 32 voices (fixed order => deterministic)
+        const float4 *row = reinterpret_cast<const float4 *>(st + lane * SUBW_PAD);
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            acc0 = acc0 + st[lane * SUB_PAD + j];
-            acc1 = acc1 + st[lane * SUB_PAD + j + 1];
-            acc2 = acc2 + st[lane * SUB_PAD + j + 2];
-            acc3 = acc3 + st[lane * SUB_PAD + j + 3];
+        for (int j = 0; j < 8; j++) {
+            const float4 q = row[j];
+            acc0 = acc0 + q.x;
+            acc1 = acc1 + q.y;
+            acc2 = acc2 + q.z;
+            acc3 = acc3 + q.w;
         }
-        if (lane < nf) prow[f0 + lane] = (acc0 + acc1) + (acc2 + acc3);
+        if (lane < rows) prow[f - rows + lane] = (acc0 + acc1) + (acc2 + acc3);
+        rows = 0;
         __syncwarp();
+    };
+    // straight-line groups of N frames while N frames are safe and fit the tile
+    auto run_groups = [&](auto lp_tag, auto n_tag, uint32_t lim) {
+        constexpr bool LP = decltype(lp_tag)::value;
+        constexpr int N = decltype(n_tag)::value;
+#pragma unroll 1
+        while (f + N <= lim) {
+            if (rows + N > SUB_TILE) flush();
+            sub_group_fast<LP, N, TAPS>(s, d, omd, rc, st + rows * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr);
+            rows += N;
+            f += N;
+        }
+    };
+    auto run_fast = [&](auto lp_tag, uint32_t lim) {
+        run_groups(lp_tag, std::integral_constant<int, SUB_SUB>{}, lim);
+        run_groups(lp_tag, std::integral_constant<int, 4>{}, lim);
+        run_groups(lp_tag, std::integral_constant<int, 1>{}, lim);
+    };
+    for (;;) {
+        const uint32_t lim = min(limit, NF);
+        if (all_lp) run_fast(std::true_type{}, lim);
+        else run_fast(std::false_type{}, lim);
+        if (f >= NF) break;
+        // frame `limit`: the exact path (events, envelope state machine, generic lanes)
+        {
+            bool touched = false;
+            while (ec.next_frame <= f) { // events are sorted by (frame, node, arrival)
+                if (ec.e0.op == OP_SET) s.set(ec.e0.reg, ec.e0.value);
+                else if (ec.e0.op == OP_ASR_RELEASE) envasr_release(s.est, s.et, s.sc);
+                ec.pop();
+                touched = true;
+            }
+            if (touched) {
+                omd = 1.0f - s.dt;
+                rc = div_prep(s.dt);
+                lane_fast = sub_lane_fast(s);
+            }
+            if (__any_sync(0xFFFFFFFFu, touched)) {
+                all_lp = __all_sync(0xFFFFFFFFu, sub_lane_lp(s));
+                all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
+            }
+            float o;
+            if (all_fast) {
+                const float ph = s.t;
+                s.t = wrap01(s.t + s.dt);
+                const float e = envasr_tick_sel(s.est, s.et, s.ar, s.rr, s.sc) * s.gain;
+                o = svf_tick(saw_eval(ph, s.dt, omd, rc), s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * e;
+            } else {
+                if (lane_fast) {
+                    const float ph = s.t;
+                    s.t = wrap01(s.t + s.dt);
+                    const float e = envasr_tick_sel(s.est, s.et, s.ar, s.rr, s.sc) * s.gain;
+                    o = svf_tick(saw_eval(ph, s.dt, omd, rc), s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * e;
+                } else {
+                    o = s.tick();
+                    lane_fast = sub_lane_fast(s); // t is back in [0,1) after one generic tick
+                }
+                all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
+            }
+            if (rows + 1 > SUB_TILE) flush();
+            st[rows * SUBW_PAD + lane] = o;
+            if (TAPS && tap) tap[f] = o;
+            rows += 1;
+            f += 1;
+            d.derive(s.est, s.ar, s.rr);
+            limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(f));
+        }
     }
+    if (rows) flush();
     if (active) {
         a.regs[(size_t)R_T * V + v] = __float_as_uint(s.t);
         a.regs[(size_t)R_IC1 * V + v] = __float_as_uint(s.ic1);
