@@ -57,6 +57,38 @@ template <class T> struct DevBuf {
     }
 };
 
+// page-locked host memory (async copies that really are asynchronous to the host)
+template <class T> struct PinBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        size_t want = std::max(n, cap + cap / 2);
+        cudaError_t e = cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            cap = 0;
+            KGPU_THROW(KGPU_ERR_CUDA, "cudaHostAlloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+        }
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// one in-flight upload of a launch's device events (host side of the render pipeline)
+struct Staging {
+    PinBuf<DevEvent> ev;
+    PinBuf<uint32_t> off;
+    cudaEvent_t copied = nullptr; // recorded after the H2D copies that read this buffer
+    bool in_flight = false;
+};
+
 struct GroupDev {
     DevBuf<DevProgram> prog;
     DevBuf<uint32_t> regs;
@@ -101,6 +133,11 @@ struct kgpu_plan {
     uint64_t prepared_blocks = 0;
 
     uint64_t last_h2d_bytes = 0;
+    // pipelined render (kgpu_render without a prior kgpu_plan_prepare): launch L's events are
+    // compiled and staged while the device renders launch L-1
+    Staging staging[3];
+    uint32_t staging_next = 0;
+    PinBuf<float> out_pinned;
 };
 
 namespace {
@@ -186,7 +223,39 @@ uint64_t blocks_per_launch(kgpu_plan *p) {
     return std::min<uint64_t>(bpl, p->max_blocks_per_launch);
 }
 
-void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream_t stream) {
+// upload the events of ONE launch (the only launch in p->ce) through a pinned staging buffer
+void upload_launch_events(kgpu_plan *p, cudaStream_t stream) {
+    if (p->ce.events.empty()) return;
+    Staging &sg = p->staging[p->staging_next];
+    p->staging_next = (p->staging_next + 1) % 3;
+    if (!sg.copied) CUDA_TRY(cudaEventCreateWithFlags(&sg.copied, cudaEventDisableTiming));
+    if (sg.in_flight) CUDA_TRY(cudaEventSynchronize(sg.copied));
+    if (p->ce.events.size() > sg.ev.cap || p->ce.offsets.size() > sg.off.cap) {
+        // grow all three staging buffers together (with headroom): page-locked allocation is slow
+        // and synchronises, so it should happen in the first render call only
+        for (Staging &o : p->staging) {
+            if (o.in_flight && o.copied) CUDA_TRY(cudaEventSynchronize(o.copied));
+            o.ev.ensure(p->ce.events.size() + p->ce.events.size() / 2);
+            o.off.ensure(p->ce.offsets.size() + p->ce.offsets.size() / 2);
+        }
+    }
+    std::memcpy(sg.ev.p, p->ce.events.data(), p->ce.events.size() * sizeof(DevEvent));
+    std::memcpy(sg.off.p, p->ce.offsets.data(), p->ce.offsets.size() * 4);
+    if (p->ce.events.size() > p->d_events_all.cap) p->d_events_all.ensure(p->ce.events.size() + p->ce.events.size() / 2);
+    if (p->ce.offsets.size() > p->d_off_all.cap) p->d_off_all.ensure(p->ce.offsets.size() + p->ce.offsets.size() / 2);
+    CUDA_TRY(cudaMemcpyAsync(p->d_events_all.p, sg.ev.p, p->ce.events.size() * sizeof(DevEvent), cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_off_all.p, sg.off.p, p->ce.offsets.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaEventRecord(sg.copied, stream));
+    sg.in_flight = true;
+    p->last_h2d_bytes += p->ce.events.size() * sizeof(DevEvent) + p->ce.offsets.size() * 4;
+}
+
+// Renders n_blocks blocks into device_out.  If the range was prepared (kgpu_plan_prepare) the
+// device events are already resident and the launches go back to back; otherwise the host half
+// runs launch by launch, one launch ahead of the device: while launch L renders, the control
+// simulation of launch L+1 runs on the host threads and its events are staged in pinned memory.
+// pinned_out: optional page-locked mirror of device_out, filled launch by launch.
+void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream_t stream, float *pinned_out = nullptr) {
     const uint32_t bs = p->host.block_size, n_out = p->host.n_outputs;
     p->rendered = true;
     const uint64_t total_frames = n_blocks * bs;
@@ -195,12 +264,14 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
         p->tap_frames = total_frames;
     }
     const uint64_t bpl = blocks_per_launch(p);
-    if (!(p->prepared && p->prepared_blocks == n_blocks)) prepare_range(p, n_blocks, bpl, stream);
+    const bool was_prepared = p->prepared && p->prepared_blocks == n_blocks;
     p->prepared = false;
+    if (!was_prepared) p->last_h2d_bytes = 0;
     p->partials.ensure((size_t)std::max(1u, p->n_rows) * std::min<uint64_t>(bpl, n_blocks) * bs);
-    const uint64_t t_end = p->frame_clock + total_frames;
+    const uint64_t t_begin = p->frame_clock, t_end = t_begin + total_frames;
+    std::vector<uint32_t> chunks;
+    for (GroupDev &d : p->gd) chunks.push_back(d.chunk);
 
-    // ---- phase 2 (device): back-to-back kernel launches, timed with CUDA events ----
     if (p->timed) CUDA_TRY(cudaEventRecord(p->ev0, stream));
     size_t piece = 0;
     p->kev_used = 0;
@@ -214,14 +285,53 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
         CUDA_TRY(cudaEventRecord(p->kev[p->kev_used++], stream));
         if (begin) p->kev_class.push_back((uint8_t)cls);
     };
-    for (uint64_t done = 0; done < n_blocks; done += bpl) {
-        const uint64_t nb = std::min(bpl, n_blocks - done);
+    struct StreamGuard { // stream_begin is always paired with stream_end, also when a launch throws
+        HostPlan *h = nullptr;
+        ~StreamGuard() {
+            if (h) try { h->stream_end(); } catch (...) {}
+        }
+    } guard;
+    // launch sizes in blocks.  Prepared: bpl each.  Streaming: a short geometric ramp first, so the
+    // device starts as soon as the host has simulated 1/16 of a full launch and is never starved
+    // afterwards (the workers simulate a launch faster than the device renders it).
+    std::vector<uint64_t> sizes;
+    {
+        uint64_t left = n_blocks, next = was_prepared || bpl < 32 || n_blocks < 2 * bpl ? bpl : bpl / 16;
+        while (left) {
+            const uint64_t nb = std::min(next, left);
+            sizes.push_back(nb);
+            left -= nb;
+            next = std::min(bpl, next * 2);
+        }
+    }
+    if (!was_prepared) {
+        std::vector<uint64_t> bounds{t_begin};
+        for (uint64_t nb : sizes) bounds.push_back(bounds.back() + nb * bs);
+        p->host.stream_begin(bounds, chunks);
+        guard.h = &p->host;
+    }
+    uint64_t done = 0;
+    for (size_t launch = 0; launch < sizes.size(); done += sizes[launch], launch++) {
+        const uint64_t nb = sizes[launch];
         const uint32_t nf = (uint32_t)(nb * bs);
+        if (!was_prepared) {
+            static const bool timing = getenv("KGPU_TIMING") != nullptr;
+            const auto ta = std::chrono::steady_clock::now();
+            p->host.stream_launch(launch, p->ce);
+            const auto tb = std::chrono::steady_clock::now();
+            upload_launch_events(p, stream);
+            if (timing && n_blocks > 100)
+                fprintf(stderr, "[kgpu timing]   launch %zu: wait+merge %.2f ms, stage+enqueue %.2f ms\n", launch,
+                        std::chrono::duration<double, std::milli>(tb - ta).count(),
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb).count());
+            piece = 0;
+        }
         for (uint32_t gi = 0; gi < p->gd.size(); gi++, piece++) {
             Group &g = p->host.groups[gi];
             GroupDev &d = p->gd[gi];
-            const DevEvent *d_ev = p->ce.piece_any[piece] ? p->d_events_all.p + p->ce.piece_ev[piece] : nullptr;
-            const uint32_t *d_off = p->ce.piece_any[piece] ? p->d_off_all.p + p->ce.piece_off[piece] : nullptr;
+            const bool any = !p->ce.piece_any.empty() && p->ce.piece_any[piece];
+            const DevEvent *d_ev = any ? p->d_events_all.p + p->ce.piece_ev[piece] : nullptr;
+            const uint32_t *d_off = any ? p->d_off_all.p + p->ce.piece_off[piece] : nullptr;
             mark(0, true);
             if (d.recipe >= 0) {
                 FusedArgs a{};
@@ -242,9 +352,16 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             p->kernel_launches++;
         }
         mark(1, true);
-        CUDA_TRY(launch_reduce_bus(p->partials.p, p->row_mask.p, p->n_rows, nf, device_out + (size_t)done * n_out * bs, n_out, bs, stream));
+        float *dst = device_out + (size_t)done * n_out * bs;
+        CUDA_TRY(launch_reduce_bus(p->partials.p, p->row_mask.p, p->n_rows, nf, dst, n_out, bs, stream));
         mark(1, false);
         p->kernel_launches++;
+        if (pinned_out)
+            CUDA_TRY(cudaMemcpyAsync(pinned_out + (size_t)done * n_out * bs, dst, (size_t)nf * n_out * 4, cudaMemcpyDeviceToHost, stream));
+    }
+    if (guard.h) {
+        guard.h = nullptr;
+        p->host.stream_end();
     }
     p->frame_clock = t_end;
     if (p->timed) CUDA_TRY(cudaEventRecord(p->ev1, stream));
@@ -323,6 +440,11 @@ void kgpu_plan_destroy(kgpu_plan *p) {
         d.prog.release(); d.regs.release(); d.events.release(); d.ev_off.release(); d.taps.release();
     }
     p->d_events_all.release(); p->d_off_all.release();
+    for (Staging &sg : p->staging) {
+        sg.ev.release(); sg.off.release();
+        if (sg.copied) cudaEventDestroy(sg.copied);
+    }
+    p->out_pinned.release();
     p->partials.release(); p->row_mask.release(); p->out.release(); p->sine.release(); p->tap_out.release();
     for (cudaEvent_t e : p->kev) cudaEventDestroy(e);
     if (p->ev0) cudaEventDestroy(p->ev0);
@@ -361,12 +483,32 @@ int kgpu_render(kgpu_plan *p, uint64_t n_blocks, float *host_out) {
         const size_t per_block = (size_t)p->host.block_size * p->host.n_outputs;
         p->out.ensure(per_block * n_blocks);
         p->timed = true;
-        render_range(p, n_blocks, p->out.p, p->stream);
         if (host_out) {
-            CUDA_TRY(cudaMemcpyAsync(host_out, p->out.p, per_block * n_blocks * 4, cudaMemcpyDeviceToHost, p->stream));
+            static const bool timing = getenv("KGPU_TIMING") != nullptr;
+            auto now = [] { return std::chrono::steady_clock::now(); };
+            auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            const auto t0 = now();
+            p->out_pinned.ensure(per_block * n_blocks);
+            render_range(p, n_blocks, p->out.p, p->stream, p->out_pinned.p);
+            const auto t1 = now();
             CUDA_TRY(cudaStreamSynchronize(p->stream));
+            const auto t2 = now();
+            std::memcpy(host_out, p->out_pinned.p, per_block * n_blocks * 4);
             std::memcpy(p->last_block.data(), host_out + per_block * (n_blocks - 1), per_block * 4);
+            if (timing && n_blocks > 100) {
+                float span = 0.f, kern = 0.f, red = 0.f;
+                cudaEventElapsedTime(&span, p->ev0, p->ev1);
+                for (size_t i = 0; i < p->kev_class.size(); i++) {
+                    float m = 0.f;
+                    cudaEventElapsedTime(&m, p->kev[2 * i], p->kev[2 * i + 1]);
+                    (p->kev_class[i] == 0 ? kern : red) += m;
+                }
+                fprintf(stderr, "[kgpu timing] kgpu_render: device span %.2f ms (render kernels %.2f, reduce_bus %.2f, rest = copies + gaps)\n", span, kern, red);
+            }
+            if (timing && n_blocks > 100)
+                fprintf(stderr, "[kgpu timing] kgpu_render: host loop %.1f ms, device tail %.1f ms, copy out %.1f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, now()));
         } else {
+            render_range(p, n_blocks, p->out.p, p->stream);
             CUDA_TRY(cudaMemcpyAsync(p->last_block.data(), p->out.p + per_block * (n_blocks - 1), per_block * 4, cudaMemcpyDeviceToHost, p->stream));
             CUDA_TRY(cudaStreamSynchronize(p->stream));
         }

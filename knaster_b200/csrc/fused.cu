@@ -144,14 +144,26 @@ struct EnvDerived {
 // Number of coming frames in which the envelope state machine provably cannot change state.
 // Attacking: t_n = t + n*ar + err with |err| <= n*2^-25 (one rounding of a value below 2 per add),
 // so the first tick whose sum can reach 1 is no earlier than (1-t)/(ar + 2^-25); the same bound
-// holds for the release ramp reaching 0.  The margin used here is twice that, minus two frames.
+// holds for the release ramp reaching 0.  The margin used here is twice that, minus one frame
+// (ticks 0 .. m-2 are safe when tick m-1 is the first that can cross).
 KN_DEV uint32_t envasr_safe_frames(uint32_t est, float t, float ar, float rr) {
     const bool att = est == ASR_ATTACKING, rel = est == ASR_RELEASING;
     if (!att && !rel) return 0x40000000u;
     const float dist = att ? 1.0f - t : t;
     const float rate = (att ? ar : rr) + 5.9604644775390625e-8f;
-    const float n = __fdividef(dist, rate) - 2.0f;
+    const float n = __fdividef(dist, rate) - 1.0f;
     return n >= 1.0f ? (uint32_t)fminf(n, 1073741824.0f) : 0u; // NaN -> 0: always the exact path
+}
+
+// Canonical mix-bus order for one frame: T(voices 0..15) + T(voices 16..31), T a fixed tree over
+// four float4 reads.  Every path that sums a staged frame uses it, so a render is bit-identical
+// however it is split into launches.
+KN_DEV float sum16(const float *p) {
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    const float4 a = q[0], b = q[1], c = q[2], e = q[3];
+    const float s0 = (a.x + a.y) + (a.z + a.w), s1 = (b.x + b.y) + (b.z + b.w);
+    const float s2 = (c.x + c.y) + (c.z + c.w), s3 = (e.x + e.y) + (e.z + e.w);
+    return (s0 + s1) + (s2 + s3);
 }
 
 // N frames, no events, no envelope transition, fast conditions hold for every lane: the three
@@ -159,9 +171,17 @@ KN_DEV uint32_t envasr_safe_frames(uint32_t est, float t, float ar, float rr) {
 // in one basic block.  LP: m0 == 0, m1 == 0, m2 == 1 (lowpass) for every lane, where
 // m0*v0 + m1*v1 + m2*v2 == v2 for finite signals.  Frame k goes to strow[k * SUBW_PAD] (the
 // lane's column of the staging tile) and, when the voice is tapped, to tap[k].
-template <bool LP, int N, bool TAPS>
-KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc, float *strow, float *tap) {
+// SUM: the same basic block also reduces the 16 frames staged by the PREVIOUS group (lane = (frame
+// r = lane & 15, voice half c = lane >> 4)), so the mix-bus reduction costs issue slots only.
+template <bool LP, int N, bool TAPS, bool SUM>
+KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc, float *strow, float *tap,
+                           const float *sum_src = nullptr, float *sum_dst = nullptr, bool sum_store = false) {
     float ph[N], env[N];
+    if (SUM) {
+        const float h = sum16(sum_src);
+        const float tot = h + __shfl_xor_sync(0xFFFFFFFFu, h, 16);
+        if (sum_store) *sum_dst = tot;
+    }
 #pragma unroll
     for (int k = 0; k < N; k++) {
         ph[k] = s.t;
@@ -300,39 +320,57 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
 
     uint32_t NF = a.n_frames;
     asm volatile("" : "+r"(NF)); // keep it in a register (ptxas would re-read the constant bank in every loop test)
+    uint32_t next_ev = __reduce_min_sync(0xFFFFFFFFu, ec.next_frame);
     uint32_t f = 0;      // next frame to render
-    uint32_t rows = 0;   // frames staged in st[] since the last flush (frame f - rows is row 0)
-    // lane l sums staged frame l over the warp's 32 voices (fixed order => deterministic)
+    // frames staged in st[] since the last flush: rows [rbase, rbase + rows), frame f - rows first
+    uint32_t rows = 0, rbase = 0;
+    // lane l sums staged frame l over the warp's 32 voices
     auto flush = [&]() {
         __syncwarp();
-        const float4 *row = reinterpret_cast<const float4 *>(st + lane * SUBW_PAD);
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float4 q = row[j];
-            acc0 = acc0 + q.x;
-            acc1 = acc1 + q.y;
-            acc2 = acc2 + q.z;
-            acc3 = acc3 + q.w;
-        }
-        if (lane < rows) prow[f - rows + lane] = (acc0 + acc1) + (acc2 + acc3);
+        const float *row = st + (rbase + (lane < rows ? lane : 0u)) * SUBW_PAD;
+        const float tot = sum16(row) + sum16(row + 16);
+        if (lane < rows) prow[f - rows + lane] = tot;
         rows = 0;
+        rbase = 0;
         __syncwarp();
     };
-    // straight-line groups of N frames while N frames are safe and fit the tile
+    auto stage_room = [&](uint32_t n) {
+        if (rbase + rows + n > SUB_TILE) flush();
+    };
+    // straight-line groups of N frames while N frames are safe
     auto run_groups = [&](auto lp_tag, auto n_tag, uint32_t lim) {
         constexpr bool LP = decltype(lp_tag)::value;
         constexpr int N = decltype(n_tag)::value;
 #pragma unroll 1
         while (f + N <= lim) {
-            if (rows + N > SUB_TILE) flush();
-            sub_group_fast<LP, N, TAPS>(s, d, omd, rc, st + rows * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr);
+            stage_room(N);
+            sub_group_fast<LP, N, TAPS, false>(s, d, omd, rc, st + (rbase + rows) * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr);
             rows += N;
             f += N;
         }
     };
     auto run_fast = [&](auto lp_tag, uint32_t lim) {
-        run_groups(lp_tag, std::integral_constant<int, SUB_SUB>{}, lim);
+        constexpr bool LP = decltype(lp_tag)::value;
+        if (f + SUB_SUB <= lim) {
+            // 16-frame groups ping-pong between the two halves of the tile; each group also sums the
+            // half the previous one staged (the first finds nothing pending and stores nothing)
+            if (rows) flush();
+            uint32_t half = 0;
+            bool pending = false;
+            const uint32_t r = lane & 15u, c = lane >> 4;
+#pragma unroll 1
+            do {
+                __syncwarp();
+                sub_group_fast<LP, SUB_SUB, TAPS, true>(s, d, omd, rc, st + (half * SUB_SUB) * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr,
+                                                        st + ((half ^ 1u) * SUB_SUB + r) * SUBW_PAD + c * 16, prow + (f - SUB_SUB + r),
+                                                        pending && c == 0);
+                pending = true;
+                half ^= 1u;
+                f += SUB_SUB;
+            } while (f + SUB_SUB <= lim);
+            rbase = (half ^ 1u) * SUB_SUB;
+            rows = SUB_SUB;
+        }
         run_groups(lp_tag, std::integral_constant<int, 4>{}, lim);
         run_groups(lp_tag, std::integral_constant<int, 1>{}, lim);
     };
@@ -341,8 +379,8 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
         if (all_lp) run_fast(std::true_type{}, lim);
         else run_fast(std::false_type{}, lim);
         if (f >= NF) break;
-        // frame `limit`: the exact path (events, envelope state machine, generic lanes)
-        {
+        // frame `limit`: events are applied, then the frame runs with the envelope state machine checked
+        if (f >= next_ev) {
             bool touched = false;
             while (ec.next_frame <= f) { // events are sorted by (frame, node, arrival)
                 if (ec.e0.op == OP_SET) s.set(ec.e0.reg, ec.e0.value);
@@ -354,37 +392,43 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
                 omd = 1.0f - s.dt;
                 rc = div_prep(s.dt);
                 lane_fast = sub_lane_fast(s);
+                d.derive(s.est, s.ar, s.rr);
             }
-            if (__any_sync(0xFFFFFFFFu, touched)) {
-                all_lp = __all_sync(0xFFFFFFFFu, sub_lane_lp(s));
-                all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
+            all_lp = __all_sync(0xFFFFFFFFu, sub_lane_lp(s));
+            all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
+            next_ev = __reduce_min_sync(0xFFFFFFFFu, ec.next_frame);
+        }
+        stage_room(1);
+        float *strow = st + (rbase + rows) * SUBW_PAD + lane;
+        if (all_fast) {
+            // the straight-line frame, then EnvAsr's transitions (envelopes.rs:60-77): they only
+            // change what FOLLOWING frames do
+            if (all_lp) sub_group_fast<true, 1, TAPS, false>(s, d, omd, rc, strow, TAPS && tap ? tap + f : nullptr);
+            else sub_group_fast<false, 1, TAPS, false>(s, d, omd, rc, strow, TAPS && tap ? tap + f : nullptr);
+            if (d.att && s.et >= 1.0f) s.est = ASR_SUSTAINING;
+            if (d.rel && s.et <= 0.0f) {
+                s.est = ASR_STOPPED;
+                s.et = 0.0f;
             }
+        } else {
             float o;
-            if (all_fast) {
+            if (lane_fast) {
                 const float ph = s.t;
                 s.t = wrap01(s.t + s.dt);
                 const float e = envasr_tick_sel(s.est, s.et, s.ar, s.rr, s.sc) * s.gain;
                 o = svf_tick(saw_eval(ph, s.dt, omd, rc), s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * e;
             } else {
-                if (lane_fast) {
-                    const float ph = s.t;
-                    s.t = wrap01(s.t + s.dt);
-                    const float e = envasr_tick_sel(s.est, s.et, s.ar, s.rr, s.sc) * s.gain;
-                    o = svf_tick(saw_eval(ph, s.dt, omd, rc), s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * e;
-                } else {
-                    o = s.tick();
-                    lane_fast = sub_lane_fast(s); // t is back in [0,1) after one generic tick
-                }
-                all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
+                o = s.tick();
+                lane_fast = sub_lane_fast(s); // t is back in [0,1) after one generic tick
             }
-            if (rows + 1 > SUB_TILE) flush();
-            st[rows * SUBW_PAD + lane] = o;
+            all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
+            *strow = o;
             if (TAPS && tap) tap[f] = o;
-            rows += 1;
-            f += 1;
-            d.derive(s.est, s.ar, s.rr);
-            limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(f));
         }
+        rows += 1;
+        f += 1;
+        d.derive(s.est, s.ar, s.rr);
+        limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(f));
     }
     if (rows) flush();
     if (active) {

@@ -19,9 +19,13 @@
 #include "plan.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <memory>
 #include <cmath>
 #include <cstdarg>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1019,7 +1023,92 @@ static ParamRule param_rule(const HostNode &h, uint32_t p) {
     return r;
 }
 
+// ---- WorkPool -----------------------------------------------------------------------------------
+struct WorkPool::Impl {
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::thread> threads;
+    std::function<void(unsigned)> fn;
+    unsigned n_tasks = 0, next = 0, running = 0;
+    uint64_t generation = 0;
+    bool stop = false;
+    // claims and runs tasks of the current generation; called with the lock held
+    void drain(std::unique_lock<std::mutex> &lk) {
+        while (next < n_tasks) {
+            const unsigned i = next++;
+            running++;
+            lk.unlock();
+            fn(i);
+            lk.lock();
+            running--;
+        }
+        if (running == 0) cv_done.notify_all();
+    }
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        uint64_t seen = 0;
+        for (;;) {
+            cv_work.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            drain(lk);
+        }
+    }
+};
+WorkPool::WorkPool(unsigned n) : impl_(new Impl()), n_threads_(std::max(1u, n)) {
+    for (unsigned i = 0; i < n_threads_; i++) impl_->threads.emplace_back([this] { impl_->loop(); });
+}
+WorkPool::~WorkPool() {
+    {
+        std::lock_guard<std::mutex> lk(impl_->m);
+        impl_->stop = true;
+    }
+    impl_->cv_work.notify_all();
+    for (auto &t : impl_->threads) t.join();
+    delete impl_;
+}
+void WorkPool::start(unsigned n_tasks, std::function<void(unsigned)> fn) {
+    std::unique_lock<std::mutex> lk(impl_->m);
+    impl_->cv_done.wait(lk, [&] { return impl_->next >= impl_->n_tasks && impl_->running == 0; });
+    impl_->fn = std::move(fn);
+    impl_->n_tasks = n_tasks;
+    impl_->next = 0;
+    impl_->generation++;
+    lk.unlock();
+    impl_->cv_work.notify_all();
+}
+void WorkPool::wait() {
+    std::unique_lock<std::mutex> lk(impl_->m);
+    impl_->cv_done.wait(lk, [&] { return impl_->next >= impl_->n_tasks && impl_->running == 0; });
+}
+void WorkPool::run(unsigned n_tasks, std::function<void(unsigned)> fn) {
+    start(n_tasks, std::move(fn));
+    std::unique_lock<std::mutex> lk(impl_->m);
+    impl_->drain(lk); // the caller helps
+    impl_->cv_done.wait(lk, [&] { return impl_->next >= impl_->n_tasks && impl_->running == 0; });
+}
+WorkPool &HostPlan::workers() {
+    if (!pool) {
+        // one core is left to the thread that drives the device: it must not be starved while the
+        // workers are busy, or the first launch waits for ALL of the simulation
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        unsigned n = std::min<unsigned>(hw > 2 ? hw - 1 : hw, 16u);
+        if (const char *e = getenv("KGPU_THREADS")) n = (unsigned)std::max(1, atoi(e));
+        pool = new WorkPool(n);
+    }
+    return *pool;
+}
+
 void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
+    struct PushTimer {
+        std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+        size_t n;
+        ~PushTimer() {
+            static const bool on = getenv("KGPU_TIMING") != nullptr;
+            if (on && n > 1000) fprintf(stderr, "[kgpu timing]   push %zu events %.1f ms\n", n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count());
+        }
+    } push_timer;
+    push_timer.n = n;
     if (rules.empty()) { // [group][local][param], built from voice 0 of each group
         rules.resize(groups.size());
         for (size_t gi = 0; gi < groups.size(); gi++) {
@@ -1038,8 +1127,9 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
             }
         }
     }
-    // validate everything first so that a failing call queues nothing
-    for (size_t i = 0; i < n; i++) {
+    // validate everything first so that a failing call queues nothing; large batches are split
+    // over the pool (the first failing event, in event order, is the one reported)
+    auto validate = [&](size_t i) -> bool { // returns whether the event is queued
         const kgpu_event &e = evs[i];
         if (e.node >= node_ref.size()) KGPU_THROW(KGPU_ERR_INVALID, "event %zu: NodeNotFound (%u)", i, e.node);
         const NodeRef &nr = node_ref[e.node];
@@ -1048,7 +1138,7 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
         if (e.smoothing_kind != 0 && e.smooth_rate != 0)
             KGPU_THROW(KGPU_ERR_UNSUPPORTED, "event %zu: Rate::AudioRate smoothing is not supported (its branch is unreachable in knaster, "
                        "smooth_params.rs:140-146)", i);
-        if (nr.group < 0) continue; // unreachable node: knaster would run it, but nothing can hear it
+        if (nr.group < 0) return false; // unreachable node: knaster would run it, but nothing can hear it
         const Rule &r = rules[nr.group][nr.local][e.param];
         if (e.smoothing_kind != 0 && !r.smooth_ok)
             KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: smoothing sent to node %u param %u which has no WrSmoothParams around it "
@@ -1062,11 +1152,10 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
             if (r.svf_type && ((int64_t)e.value < 0 || (int64_t)e.value > 8))
                 KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: bad SvfFilterType", i);
         }
-    }
-    pending.reserve(pending.size() + n);
-    for (size_t i = 0; i < n; i++) {
+        return true;
+    };
+    auto convert = [&](size_t i) {
         const kgpu_event &e = evs[i];
-        if (node_ref[e.node].group < 0) continue;
         RawEvent r;
         r.node = e.node;
         r.param = (uint16_t)e.param;
@@ -1080,10 +1169,40 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
         else if (e.time_kind == 2) r.due_frame = frame_clock + samples; // scheduling.rs:110-119
         else r.due_frame = frame_clock;
         if (r.due_frame < frame_clock) r.due_frame = frame_clock;       // late: saturating_sub -> delay 0
-        if (!pending.empty() && r.due_frame < pending.back().due_frame) pending_sorted = false;
-        pending_max_due = std::max(pending_max_due, r.due_frame);
-        pending.push_back(r);
+        return r;
+    };
+    const unsigned T = n >= 65536 ? workers().size() : 1u;
+    if (T == 1) {
+        size_t kept = 0;
+        for (size_t i = 0; i < n; i++) kept += validate(i);
+        pending.reserve(pending.size() + kept);
+        for (size_t i = 0; i < n; i++)
+            if (node_ref[evs[i].node].group >= 0) pending.push_back(convert(i));
+        return;
     }
+    std::vector<size_t> kept(T + 1, 0);
+    std::vector<Error> errs(T, Error{0, ""});
+    workers().run(T, [&](unsigned c) {
+        const size_t i0 = n * c / T, i1 = n * (c + 1) / T;
+        size_t k = 0;
+        try {
+            for (size_t i = i0; i < i1; i++) k += validate(i);
+        } catch (const Error &e) {
+            errs[c] = e;
+        }
+        kept[c + 1] = k;
+    });
+    for (unsigned c = 0; c < T; c++)
+        if (errs[c].code) throw errs[c]; // chunks are in event order: this is the first failing event
+    for (unsigned c = 0; c < T; c++) kept[c + 1] += kept[c];
+    const size_t base = pending.size();
+    pending.resize(base + kept[T]);
+    workers().run(T, [&](unsigned c) {
+        const size_t i0 = n * c / T, i1 = n * (c + 1) / T;
+        size_t w = base + kept[c];
+        for (size_t i = i0; i < i1; i++)
+            if (node_ref[evs[i].node].group >= 0) pending[w++] = convert(i);
+    });
 }
 
 namespace {
@@ -1140,227 +1259,408 @@ bool process_node(HostPlan &P, Sink &out, uint32_t gi, uint32_t voice, uint32_t 
 }
 } // namespace
 
+// ------------------------------------------------------------------------------------------------
 // The host half of a render call for frames [bounds.front(), bounds.back()), launch L covering
-// [bounds[L], bounds[L+1]): run the control simulation for every voice (voices are independent:
-// the work is spread over host threads), and emit the device events per (launch, group), each
-// voice's events ordered the way its kernel consumes them: (frame / chunk, node, frame, arrival).
-void HostPlan::compile_events(const std::vector<uint64_t> &bounds, const std::vector<uint32_t> &chunk_of_group, CompiledEvents &out) {
-    PhaseTimer pt("compile_events");
+// [bounds[L], bounds[L+1]).  The control simulation runs per voice (voices are independent) on
+// worker threads that each own a slice of every group's voices and walk the launches IN ORDER,
+// publishing how many launches they have finished: the caller can upload launch L and start its
+// kernels while the workers are already simulating launch L+1 (stream_begin / stream_launch /
+// stream_end).  Each voice's events are ordered the way its kernel consumes them:
+// (frame / chunk, node, frame, arrival).
+struct StreamState {
+    struct PerGroup {
+        uint32_t v_begin = 0, v_end = 0;
+        std::vector<std::vector<DevEvent>> ev;   // per launch
+        std::vector<std::vector<uint32_t>> cnt;  // per launch, per voice of the slice
+        std::vector<uint32_t> cursor;            // per voice of the slice: next unconsumed entry of vorder
+        std::vector<VoiceEvent> carry, carry_next, later; // events beyond the window / beyond the call
+    };
+    struct alignas(128) ThreadCtx {
+        std::vector<PerGroup> g;
+        Sink sink;
+        int64_t ramp_delta = 0;
+        std::atomic<uint32_t> done{0};           // launches finished
+        std::string error;
+        int error_code = 0;
+    };
+    std::vector<uint64_t> bounds;
+    std::vector<uint32_t> chunks;
+    size_t n_launch = 0, n_ready = 0;
+    uint64_t b0 = 0;
+    bool any_work = false;
+    std::vector<std::vector<uint32_t>> lat_start; // per group: CSR of HostPlan::later by voice
+    std::vector<std::unique_ptr<ThreadCtx>> th;
+    bool pooled = false; // workers run on HostPlan::pool
+    std::chrono::steady_clock::time_point t_begin = std::chrono::steady_clock::now();
+};
+
+namespace {
+// one voice, one launch window: what a separate render call over that window would do
+void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &tc, uint32_t gi, uint32_t v, size_t L,
+                           std::vector<const RawEvent *> &evp, std::vector<const RawEvent *> &node_ev, size_t &carry_pos) {
+    Group &g = P.groups[gi];
+    StreamState::PerGroup &pg = tc.g[gi];
+    const uint64_t bs = P.block_size;
+    const uint32_t nn = (uint32_t)g.tpl.nodes.size();
+    const uint32_t chunk = S.chunks[gi];
+    const uint64_t t0 = S.bounds[L], t1 = S.bounds[L + 1];
+    const uint64_t wb0 = t0 / bs, wb1 = t1 / bs;
+    const size_t gv = P.voice_base[gi] + v;
+    // ready events of this voice inside the window (vorder is sorted by ready block inside a voice)
+    uint32_t &cur = pg.cursor[v - pg.v_begin];
+    const uint32_t e0 = cur, vend = P.vcount[gv + 1];
+    if (L == 0 && vend - e0 > 1) { // first visit: (ready block, arrival) order
+        auto rb = [&](uint32_t idx) { return std::max(P.pending[idx].due_frame / bs, S.b0); };
+        bool sorted = true;
+        for (uint32_t k = e0 + 1; k < vend && sorted; k++) sorted = rb(P.vorder[k - 1]) <= rb(P.vorder[k]);
+        if (!sorted) std::stable_sort(P.vorder.begin() + e0, P.vorder.begin() + vend, [&](uint32_t x, uint32_t y) { return rb(x) < rb(y); });
+    }
+    uint32_t e1 = e0;
+    while (e1 < vend && std::max(P.pending[P.vorder[e1]].due_frame / bs, S.b0) < wb1) e1++;
+    cur = e1;
+    const std::vector<uint32_t> &ls = S.lat_start[gi];
+    const bool has_later = L == 0 && !ls.empty() && ls[v + 1] > ls[v];
+    while (carry_pos < pg.carry.size() && pg.carry[carry_pos].voice < v) carry_pos++;
+    const bool has_carry = carry_pos < pg.carry.size() && pg.carry[carry_pos].voice == v;
+    if (e0 == e1 && !P.voice_ramps[gv] && !has_later && !has_carry) return;
+
+    auto key_less = [&](const VoiceEvent &a, const VoiceEvent &b) {
+        const uint64_t fa = a.frame < t0 ? t0 : a.frame, fb = b.frame < t0 ? t0 : b.frame;
+        const uint64_t ca = fa / chunk, cb = fb / chunk;
+        if (ca != cb) return ca < cb;
+        if (a.ev.node != b.ev.node) return a.ev.node < b.ev.node;
+        if (fa != fb) return fa < fb;
+        return a.seq < b.seq;
+    };
+    Sink &sk = tc.sink;
+    sk.buf.clear();
+    sk.run_start.clear();
+    sk.seq = 0;
+    sk.run_start.push_back(0);
+    if (has_later)
+        for (uint32_t k = ls[v]; k < ls[v + 1]; k++) {
+            VoiceEvent ve = P.later[gi][k];
+            ve.seq = sk.seq++;
+            sk.buf.push_back(ve);
+        }
+    while (carry_pos < pg.carry.size() && pg.carry[carry_pos].voice == v) {
+        VoiceEvent ve = pg.carry[carry_pos++];
+        ve.seq = sk.seq++;
+        sk.buf.push_back(ve);
+    }
+    evp.clear();
+    for (uint32_t k = e0; k < e1; k++) evp.push_back(&P.pending[P.vorder[k]]);
+    for (uint32_t li = 0; li < nn; li++) {
+        HostNode &hn = g.host[(size_t)v * nn + li];
+        node_ev.clear();
+        for (const RawEvent *r : evp)
+            if (P.node_ref[r->node].local == li) node_ev.push_back(r);
+        if (node_ev.empty() && !hn.ramp_active) continue;
+        const bool was = hn.ramp_active;
+        if (sk.run_start.back() != sk.buf.size()) sk.run_start.push_back((uint32_t)sk.buf.size());
+        hn.ramp_active = process_node(P, sk, gi, v, li, node_ev.data(), node_ev.size(), wb0, wb1);
+        if (hn.ramp_active != was) {
+            tc.ramp_delta += hn.ramp_active ? 1 : -1;
+            P.voice_ramps[gv] += hn.ramp_active ? 1 : -1;
+        }
+    }
+    // order for the device: k-way merge of the per-node runs (each already in time order)
+    sk.run_start.push_back((uint32_t)sk.buf.size());
+    std::vector<VoiceEvent> *bufp = &sk.buf;
+    const size_t n_runs = sk.run_start.size() - 1;
+    if (n_runs > 1 && !std::is_sorted(sk.buf.begin(), sk.buf.end(), key_less)) {
+        sk.merged.clear();
+        uint32_t head[MAX_NODES + 2];
+        if (n_runs > (size_t)MAX_NODES + 1) {
+            std::sort(sk.buf.begin(), sk.buf.end(), key_less);
+        } else {
+            for (size_t r = 0; r < n_runs; r++) head[r] = sk.run_start[r];
+            for (size_t done_n = 0; done_n < sk.buf.size(); done_n++) {
+                int best = -1;
+                for (size_t r = 0; r < n_runs; r++) {
+                    if (head[r] == sk.run_start[r + 1]) continue;
+                    if (best < 0 || key_less(sk.buf[head[r]], sk.buf[head[best]])) best = (int)r;
+                }
+                sk.merged.push_back(sk.buf[head[best]++]);
+            }
+            bufp = &sk.merged;
+        }
+    }
+    const bool last = L + 1 == S.n_launch;
+    for (const VoiceEvent &ve : *bufp) {
+        if (ve.frame >= t1) {
+            (last ? pg.later : pg.carry_next).push_back(ve);
+            continue;
+        }
+        DevEvent d = ve.ev;
+        d.frame = (uint32_t)(ve.frame < t0 ? 0 : ve.frame - t0); // late events: relative frame 0
+        pg.ev[L].push_back(d);
+        pg.cnt[L][v - pg.v_begin]++;
+    }
+}
+
+void stream_worker(HostPlan &P, StreamState &S, unsigned ti) {
+    StreamState::ThreadCtx &tc = *S.th[ti];
+    try {
+        std::vector<const RawEvent *> evp, node_ev;
+        for (size_t L = 0; L < S.n_launch; L++) {
+            for (uint32_t gi = 0; gi < P.groups.size(); gi++) {
+                StreamState::PerGroup &pg = tc.g[gi];
+                size_t carry_pos = 0;
+                for (uint32_t v = pg.v_begin; v < pg.v_end; v++) simulate_voice_window(P, S, tc, gi, v, L, evp, node_ev, carry_pos);
+                pg.carry.swap(pg.carry_next);
+                pg.carry_next.clear();
+            }
+            tc.done.store((uint32_t)L + 1, std::memory_order_release);
+            if (L < 2 && ti < 3 && getenv("KGPU_TIMING"))
+                fprintf(stderr, "[kgpu timing]     worker %u finished launch %zu at +%.2f ms\n", ti, L,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S.t_begin).count());
+        }
+    } catch (const Error &e) {
+        tc.error = e.msg;
+        tc.error_code = e.code;
+        tc.done.store((uint32_t)S.n_launch, std::memory_order_release);
+    }
+}
+} // namespace
+
+HostPlan::~HostPlan() {
+    if (stream) {
+        if (stream->pooled && pool) pool->wait();
+        delete stream;
+    }
+    delete pool;
+}
+
+void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vector<uint32_t> &chunk_of_group) {
+    PhaseTimer pt("stream_begin");
+    if (stream) KGPU_THROW(KGPU_ERR_STATE, "stream_begin: a render call is already in progress");
     const uint64_t bs = block_size;
     const uint64_t t0 = bounds.front(), t1 = bounds.back();
     const uint64_t b0 = t0 / bs, b1 = t1 / bs;
     const size_t n_launch = bounds.size() - 1, n_groups = groups.size();
-    out.events.clear();
-    out.offsets.clear();
-    out.piece_ev.assign(n_launch * n_groups, 0);
-    out.piece_off.assign(n_launch * n_groups, 0);
-    out.piece_any.assign(n_launch * n_groups, 0);
-    if (n_launch > 255) KGPU_THROW(KGPU_ERR_INVALID, "too many launches in one render call (%zu)", n_launch);
+    if (n_launch > 4096) KGPU_THROW(KGPU_ERR_INVALID, "too many launches in one render call (%zu)", n_launch);
     if (voice_base.size() != n_groups + 1) {
         voice_base.assign(n_groups + 1, 0);
         for (size_t gi = 0; gi < n_groups; gi++) voice_base[gi + 1] = voice_base[gi] + groups[gi].n_voices;
         voice_ramps.assign(voice_base.back(), 0);
         later.assign(n_groups, {});
     }
-    // ---- ready events: due block < b1 (graph_gen.rs:283: ready iff delay < block_size)
-    size_t n_ready = pending.size();
-    if (pending_max_due / bs >= b1) {
-        if (!pending_sorted) {
-            std::stable_sort(pending.begin(), pending.end(), [](const RawEvent &a, const RawEvent &b) { return a.due_frame < b.due_frame; });
-            pending_sorted = true;
-        }
-        RawEvent probe{};
-        probe.due_frame = b1 * bs;
-        n_ready = std::lower_bound(pending.begin(), pending.end(), probe, [](const RawEvent &a, const RawEvent &b) { return a.due_frame < b.due_frame; }) - pending.begin();
-    }
-    bool any_work = n_ready > 0 || n_active_ramps > 0;
-    for (auto &l : later) any_work |= !l.empty();
-    if (!any_work) return;
-    // bucket by global voice (stable counting sort keeps arrival order inside a voice)
+    // ---- ready events: due block < b1 (graph_gen.rs:283: ready iff delay < block_size).
+    // `pending` stays in arrival order.  Inside a voice the workers need (block in which the event
+    // becomes ready, arrival) order -- late events become ready in block b0 whatever their due time
+    // (saturating_sub, graph_gen.rs:276) and keep their arrival order among the events of that
+    // block, which is the order knaster's waiting queue applies them in.  Bucketing by voice keeps
+    // arrival order; each worker then stable-sorts the (rare) voices whose events did not arrive
+    // in time order.
+    size_t n_ready = 0;
     const size_t NV = voice_base.back();
+    const size_t NP = pending.size();
+    // per-chunk histograms over the voices (chunks in arrival order => a stable bucket sort)
+    const unsigned TB = NP >= 65536 ? workers().size() : 1u;
+    std::vector<std::vector<uint32_t>> hist(TB);
+    auto count_chunk = [&](unsigned c) {
+        std::vector<uint32_t> &hc = hist[c];
+        hc.assign(NV, 0);
+        const size_t i0 = NP * c / TB, i1 = NP * (c + 1) / TB;
+        for (size_t i = i0; i < i1; i++) {
+            const RawEvent &r = pending[i];
+            if (r.due_frame / bs >= b1) continue;
+            const NodeRef &nr = node_ref[r.node];
+            hc[voice_base[nr.group] + nr.voice]++;
+        }
+    };
+    if (TB == 1) count_chunk(0);
+    else workers().run(TB, count_chunk);
     vcount.assign(NV + 1, 0);
-    for (size_t i = 0; i < n_ready; i++) {
-        const NodeRef &nr = node_ref[pending[i].node];
-        vcount[voice_base[nr.group] + nr.voice + 1]++;
+    for (size_t v = 0; v < NV; v++) { // hist[c][v] becomes chunk c's first slot for voice v
+        uint32_t run = vcount[v];
+        for (unsigned c = 0; c < TB; c++) {
+            const uint32_t k = hist[c][v];
+            hist[c][v] = run;
+            run += k;
+        }
+        vcount[v + 1] = run;
     }
-    for (size_t v = 0; v < NV; v++) vcount[v + 1] += vcount[v];
+    n_ready = vcount[NV];
+    bool any_work = n_ready > 0 || n_active_ramps > 0;
+    size_t n_later = 0;
+    for (auto &l : later) n_later += l.size();
+    any_work |= n_later > 0;
+
+    StreamState *S = new StreamState();
+    stream = S;
+    S->bounds = bounds;
+    S->chunks = chunk_of_group;
+    S->n_launch = n_launch;
+    S->n_ready = n_ready;
+    S->b0 = b0;
+    S->any_work = any_work;
+    if (!any_work) return;
+    // bucket by global voice (arrival order inside a voice)
     vorder.resize(n_ready);
     {
-        vfill.assign(vcount.begin(), vcount.end() - 1);
-        for (size_t i = 0; i < n_ready; i++) {
-            const NodeRef &nr = node_ref[pending[i].node];
-            vorder[vfill[voice_base[nr.group] + nr.voice]++] = (uint32_t)i;
-        }
+        auto scatter_chunk = [&](unsigned c) {
+            std::vector<uint32_t> &hc = hist[c];
+            const size_t i0 = NP * c / TB, i1 = NP * (c + 1) / TB;
+            for (size_t i = i0; i < i1; i++) {
+                const RawEvent &r = pending[i];
+                if (r.due_frame / bs >= b1) continue;
+                const NodeRef &nr = node_ref[r.node];
+                vorder[hc[voice_base[nr.group] + nr.voice]++] = (uint32_t)i;
+            }
+        };
+        if (TB == 1) scatter_chunk(0);
+        else workers().run(TB, scatter_chunk);
+    }
+    // leftovers of the previous call (events at/after its end), bucketed by voice
+    S->lat_start.assign(n_groups, {});
+    for (size_t gi = 0; gi < n_groups; gi++) {
+        std::vector<VoiceEvent> &lat = later[gi];
+        if (lat.empty()) continue;
+        const uint32_t V = groups[gi].n_voices;
+        std::stable_sort(lat.begin(), lat.end(), [](const VoiceEvent &a, const VoiceEvent &b) { return a.voice < b.voice; });
+        S->lat_start[gi].assign(V + 1, 0);
+        for (auto &ve : lat) S->lat_start[gi][ve.voice + 1]++;
+        for (uint32_t v = 0; v < V; v++) S->lat_start[gi][v + 1] += S->lat_start[gi][v];
     }
     pt.lap("bucket");
+    const size_t work = n_ready + n_later + n_active_ramps;
+    unsigned T = work > 20000 ? workers().size() : 1u;
+    T = std::min<unsigned>(T, std::max<unsigned>(1u, (unsigned)(NV / 64)));
+    for (unsigned ti = 0; ti < T; ti++) {
+        S->th.emplace_back(new StreamState::ThreadCtx());
+        StreamState::ThreadCtx &tc = *S->th.back();
+        tc.g.resize(n_groups);
+        for (size_t gi = 0; gi < n_groups; gi++) {
+            StreamState::PerGroup &pg = tc.g[gi];
+            const uint32_t V = groups[gi].n_voices;
+            pg.v_begin = (uint32_t)((uint64_t)V * ti / T);
+            pg.v_end = (uint32_t)((uint64_t)V * (ti + 1) / T);
+            pg.ev.assign(n_launch, {});
+            pg.cnt.assign(n_launch, std::vector<uint32_t>(pg.v_end - pg.v_begin, 0));
+            pg.cursor.resize(pg.v_end - pg.v_begin);
+            for (uint32_t v = pg.v_begin; v < pg.v_end; v++) pg.cursor[v - pg.v_begin] = vcount[voice_base[gi] + v];
+        }
+    }
+    pt.lap("contexts");
+    if (T == 1) stream_worker(*this, *S, 0); // small jobs (block-by-block rendering): inline
+    else {
+        S->pooled = true;
+        workers().start(T, [this, S](unsigned ti) { stream_worker(*this, *S, ti); });
+    }
+}
+
+// Waits until every worker has finished launch L, then lays its events out per group: events in
+// voice order + CSR offsets (n_voices + 1), pieces indexed by group.
+void HostPlan::stream_launch(size_t L, CompiledEvents &out) {
+    StreamState *S = stream;
+    if (!S) KGPU_THROW(KGPU_ERR_STATE, "stream_launch without stream_begin");
+    const size_t n_groups = groups.size();
+    out.events.clear();
+    out.offsets.clear();
+    out.piece_ev.assign(n_groups, 0);
+    out.piece_off.assign(n_groups, 0);
+    out.piece_any.assign(n_groups, 0);
+    if (!S->any_work) return;
+    PhaseTimer pt("stream_launch");
+    for (auto &tc : S->th) {
+        unsigned spins = 0;
+        while (tc->done.load(std::memory_order_acquire) <= L) {
+            if (++spins < 64) std::this_thread::yield();
+            else std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+        if (tc->error_code) throw Error{tc->error_code, tc->error};
+    }
+    pt.lap("wait");
     for (size_t gi = 0; gi < n_groups; gi++) {
-        Group &g = groups[gi];
-        const uint32_t V = g.n_voices, nn = (uint32_t)g.tpl.nodes.size();
-        const uint32_t chunk = chunk_of_group[gi];
-        // leftovers of the previous call (events at/after its end), bucketed by voice
-        std::vector<VoiceEvent> &lat = later[gi];
-        std::vector<uint32_t> lat_start;
-        if (!lat.empty()) {
-            std::stable_sort(lat.begin(), lat.end(), [](const VoiceEvent &a, const VoiceEvent &b) { return a.voice < b.voice; });
-            lat_start.assign(V + 1, 0);
-            for (auto &ve : lat) lat_start[ve.voice + 1]++;
-            for (uint32_t v = 0; v < V; v++) lat_start[v + 1] += lat_start[v];
-        }
-        struct alignas(256) ThreadOut {
-            std::vector<std::vector<DevEvent>> ev;   // per launch
-            std::vector<std::vector<uint32_t>> cnt;  // per launch, per voice of the range
-            std::vector<VoiceEvent> later;
-            Sink sink;
-            int64_t ramp_delta = 0;
-        };
-        const size_t work = n_ready + lat.size() + n_active_ramps;
-        unsigned T = work > 20000 ? std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u) : 1u;
-        T = std::min<unsigned>(T, std::max(1u, V / 64));
-        if (const char *e = getenv("KGPU_THREADS")) T = std::max(1, atoi(e));
-        std::vector<ThreadOut> touts(T);
-        auto run = [&](unsigned ti) {
-            auto t_start = std::chrono::steady_clock::now();
-            double t_proc = 0, t_sort = 0;
-            ThreadOut &to = touts[ti];
-            const uint32_t v_begin = (uint32_t)((uint64_t)V * ti / T), v_end = (uint32_t)((uint64_t)V * (ti + 1) / T);
-            to.ev.assign(n_launch, {});
-            to.cnt.assign(n_launch, std::vector<uint32_t>(v_end - v_begin, 0));
-            std::vector<const RawEvent *> evp, node_ev;
-            auto key_less = [&](const VoiceEvent &a, const VoiceEvent &b) {
-                const uint64_t fa = a.frame < t0 ? t0 : a.frame, fb = b.frame < t0 ? t0 : b.frame;
-                const uint64_t ca = fa / chunk, cb = fb / chunk;
-                if (ca != cb) return ca < cb;
-                if (a.ev.node != b.ev.node) return a.ev.node < b.ev.node;
-                if (fa != fb) return fa < fb;
-                return a.seq < b.seq;
-            };
-            for (uint32_t v = v_begin; v < v_end; v++) {
-                const size_t gv = voice_base[gi] + v;
-                const uint32_t e0 = vcount[gv], e1 = vcount[gv + 1];
-                const bool has_later = !lat_start.empty() && lat_start[v + 1] > lat_start[v];
-                if (e0 == e1 && !voice_ramps[gv] && !has_later) continue;
-                Sink &sk = to.sink;
-                sk.buf.clear();
-                sk.run_start.clear();
-                sk.seq = 0;
-                sk.run_start.push_back(0);
-                if (has_later)
-                    for (uint32_t k = lat_start[v]; k < lat_start[v + 1]; k++) {
-                        VoiceEvent ve = lat[k];
-                        ve.seq = sk.seq++;
-                        sk.buf.push_back(ve);
-                    }
-                evp.clear();
-                for (uint32_t k = e0; k < e1; k++) evp.push_back(&pending[vorder[k]]);
-                for (uint32_t li = 0; li < nn; li++) {
-                    HostNode &hn = g.host[(size_t)v * nn + li];
-                    node_ev.clear();
-                    for (const RawEvent *r : evp)
-                        if (node_ref[r->node].local == li) node_ev.push_back(r);
-                    if (node_ev.empty() && !hn.ramp_active) continue;
-                    // (due block, arrival) order; arrival order is usually time order already
-                    bool sorted = true;
-                    for (size_t i = 1; i < node_ev.size() && sorted; i++)
-                        sorted = std::max(node_ev[i - 1]->due_frame / bs, b0) <= std::max(node_ev[i]->due_frame / bs, b0);
-                    if (!sorted)
-                        std::stable_sort(node_ev.begin(), node_ev.end(), [&](const RawEvent *x, const RawEvent *y) {
-                            return std::max(x->due_frame / bs, b0) < std::max(y->due_frame / bs, b0);
-                        });
-                    const bool was = hn.ramp_active;
-                    if (sk.run_start.back() != sk.buf.size()) sk.run_start.push_back((uint32_t)sk.buf.size());
-                    
-                    hn.ramp_active = process_node(*this, sk, (uint32_t)gi, v, li, node_ev.data(), node_ev.size(), b0, b1);
-                    
-                    if (hn.ramp_active != was) {
-                        to.ramp_delta += hn.ramp_active ? 1 : -1;
-                        voice_ramps[gv] += hn.ramp_active ? 1 : -1;
-                    }
-                }
-                // order for the device: k-way merge of the per-node runs (each already in time order)
-                
-                sk.run_start.push_back((uint32_t)sk.buf.size());
-                std::vector<VoiceEvent> *bufp = &sk.buf;
-                const size_t n_runs = sk.run_start.size() - 1;
-                if (n_runs > 1 && !std::is_sorted(sk.buf.begin(), sk.buf.end(), key_less)) {
-                    sk.merged.clear();
-                    uint32_t head[MAX_NODES + 2];
-                    if (n_runs > (size_t)MAX_NODES + 1) {
-                        std::sort(sk.buf.begin(), sk.buf.end(), key_less);
-                    } else {
-                        for (size_t r = 0; r < n_runs; r++) head[r] = sk.run_start[r];
-                        for (size_t done_n = 0; done_n < sk.buf.size(); done_n++) {
-                            int best = -1;
-                            for (size_t r = 0; r < n_runs; r++) {
-                                if (head[r] == sk.run_start[r + 1]) continue;
-                                if (best < 0 || key_less(sk.buf[head[r]], sk.buf[head[best]])) best = (int)r;
-                            }
-                            sk.merged.push_back(sk.buf[head[best]++]);
-                        }
-                        bufp = &sk.merged;
-                    }
-                }
-                std::vector<VoiceEvent> &buf = *bufp;
-                for (const VoiceEvent &ve : buf) {
-                    if (ve.frame >= t1) {
-                        to.later.push_back(ve);
-                        continue;
-                    }
-                    size_t L = std::upper_bound(bounds.begin(), bounds.end(), ve.frame) - bounds.begin();
-                    L = L == 0 ? 0 : L - 1; // late events (frame < bounds[0]): first launch, relative frame 0
-                    DevEvent d = ve.ev;
-                    d.frame = (uint32_t)(ve.frame < bounds[L] ? 0 : ve.frame - bounds[L]);
-                    to.ev[L].push_back(d);
-                    to.cnt[L][v - v_begin]++;
-                }
-                
+        size_t total = 0;
+        for (auto &tc : S->th) total += tc->g[gi].ev[L].size();
+        out.piece_ev[gi] = out.events.size();
+        if (!total) continue;
+        out.piece_any[gi] = 1;
+        out.piece_off[gi] = out.offsets.size();
+        uint32_t run_off = 0;
+        for (auto &tc : S->th) {
+            StreamState::PerGroup &pg = tc->g[gi];
+            out.events.insert(out.events.end(), pg.ev[L].begin(), pg.ev[L].end());
+            for (uint32_t c : pg.cnt[L]) {
+                out.offsets.push_back(run_off);
+                run_off += c;
             }
-            if (getenv("KGPU_TIMING"))
-                fprintf(stderr, "[kgpu timing]     thread %u: %.1f ms (process_node %.1f, sort+split %.1f)\n", ti,
-                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(), t_proc, t_sort);
-            (void)t_sort;
-        };
-        if (T == 1) run(0);
-        else {
-            std::vector<std::thread> th;
-            for (unsigned ti = 0; ti < T; ti++) th.emplace_back(run, ti);
-            for (auto &t : th) t.join();
+            std::vector<DevEvent>().swap(pg.ev[L]);
         }
-        pt.lap("simulate");
-        // merge thread outputs: per launch, events in voice order + CSR offsets
-        lat.clear();
-        for (ThreadOut &to : touts) {
-            lat.insert(lat.end(), to.later.begin(), to.later.end());
-            dropped_changes += to.sink.dropped;
-            ignored_delays += to.sink.ignored;
-            device_events += to.sink.devev;
-            n_active_ramps = (uint64_t)((int64_t)n_active_ramps + to.ramp_delta);
+        out.offsets.push_back(run_off);
+    }
+}
+
+// drops the events the finished call consumed (due block < b1), keeping arrival order
+void HostPlan::consume_ready(uint64_t b1) {
+    const uint64_t bs = block_size;
+    size_t w = 0;
+    for (size_t i = 0; i < pending.size(); i++)
+        if (pending[i].due_frame / bs >= b1) {
+            if (w != i) pending[w] = pending[i];
+            w++;
         }
+    pending.resize(w);
+}
+
+void HostPlan::stream_end() {
+    StreamState *S = stream;
+    if (!S) return;
+    if (S->pooled) workers().wait();
+    stream = nullptr;
+    std::unique_ptr<StreamState> guard(S);
+    if (!S->any_work) return;
+    for (size_t gi = 0; gi < groups.size(); gi++) later[gi].clear();
+    Error err{0, ""};
+    for (auto &tc : S->th) {
+        for (size_t gi = 0; gi < groups.size(); gi++) {
+            StreamState::PerGroup &pg = tc->g[gi];
+            later[gi].insert(later[gi].end(), pg.later.begin(), pg.later.end());
+        }
+        dropped_changes += tc->sink.dropped;
+        ignored_delays += tc->sink.ignored;
+        device_events += tc->sink.devev;
+        n_active_ramps = (uint64_t)((int64_t)n_active_ramps + tc->ramp_delta);
+        if (tc->error_code && !err.code) err = Error{tc->error_code, tc->error};
+    }
+    consume_ready(S->bounds.back() / block_size);
+    if (err.code) throw err;
+}
+
+// whole range at once (kgpu_plan_prepare, debug entry points): pieces indexed [launch * n_groups + group]
+void HostPlan::compile_events(const std::vector<uint64_t> &bounds, const std::vector<uint32_t> &chunk_of_group, CompiledEvents &out) {
+    PhaseTimer pt("compile_events");
+    const size_t n_launch = bounds.size() - 1, n_groups = groups.size();
+    out.events.clear();
+    out.offsets.clear();
+    out.piece_ev.assign(n_launch * n_groups, 0);
+    out.piece_off.assign(n_launch * n_groups, 0);
+    out.piece_any.assign(n_launch * n_groups, 0);
+    stream_begin(bounds, chunk_of_group);
+    try {
+        CompiledEvents one;
         for (size_t L = 0; L < n_launch; L++) {
-            size_t total = 0;
-            for (ThreadOut &to : touts) total += to.ev[L].size();
-            const size_t pi = L * n_groups + gi;
-            out.piece_ev[pi] = out.events.size();
-            if (!total) continue;
-            out.piece_any[pi] = 1;
-            out.piece_off[pi] = out.offsets.size();
-            out.offsets.reserve(out.offsets.size() + V + 1);
-            uint32_t run_off = 0;
-            for (ThreadOut &to : touts) {
-                out.events.insert(out.events.end(), to.ev[L].begin(), to.ev[L].end());
-                for (uint32_t c : to.cnt[L]) {
-                    out.offsets.push_back(run_off);
-                    run_off += c;
-                }
+            stream_launch(L, one);
+            for (size_t gi = 0; gi < n_groups; gi++) {
+                const size_t pi = L * n_groups + gi;
+                out.piece_ev[pi] = out.events.size();
+                if (!one.piece_any[gi]) continue;
+                out.piece_any[pi] = 1;
+                out.piece_off[pi] = out.offsets.size();
+                const size_t ev_end = gi + 1 < n_groups ? one.piece_ev[gi + 1] : one.events.size();
+                out.events.insert(out.events.end(), one.events.begin() + one.piece_ev[gi], one.events.begin() + ev_end);
+                const size_t V1 = groups[gi].n_voices + 1;
+                out.offsets.insert(out.offsets.end(), one.offsets.begin() + one.piece_off[gi], one.offsets.begin() + one.piece_off[gi] + V1);
             }
-            out.offsets.push_back(run_off);
         }
-        pt.lap("merge");
+    } catch (...) {
+        stream_end();
+        throw;
     }
-    pending.erase(pending.begin(), pending.begin() + n_ready);
-    if (pending.empty()) {
-        pending_sorted = true;
-        pending_max_due = 0;
-    }
+    stream_end();
 }
 
 } // namespace kgpu

@@ -2,6 +2,7 @@
 // control-rate simulation that turns knaster's parameter-change queue into device events.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <string>
 #include <vector>
@@ -123,6 +124,25 @@ struct VoiceEvent { // a device event tagged with its destination
     DevEvent ev;
 };
 
+struct StreamState;
+
+// A small persistent pool for the host half of a render call (thread creation per call costs more
+// than the work of a short call).  start() hands out task indices to the pool threads and returns
+// at once; wait() blocks until they are done; run() = start + help + wait.
+class WorkPool {
+  public:
+    explicit WorkPool(unsigned n_threads);
+    ~WorkPool();
+    unsigned size() const { return n_threads_; }
+    void start(unsigned n_tasks, std::function<void(unsigned)> fn);
+    void wait();
+    void run(unsigned n_tasks, std::function<void(unsigned)> fn);
+  private:
+    struct Impl;
+    Impl *impl_;
+    unsigned n_threads_;
+};
+
 struct HostPlan {
     uint32_t sample_rate = 48000, block_size = 64, n_outputs = 2;
     std::vector<Group> groups;
@@ -134,8 +154,6 @@ struct HostPlan {
     // caches / scratch of the hot host path (push / compile_events)
     struct Rule { char want; uint8_t smooth_ok, polyblep_wave, svf_type; };
     std::vector<std::vector<std::vector<Rule>>> rules;   // [group][local][param]
-    bool pending_sorted = true;
-    uint64_t pending_max_due = 0;
     uint64_t n_active_ramps = 0;
     std::vector<uint64_t> voice_base;                    // prefix sum of voices per group
     std::vector<int32_t> voice_ramps;                    // per global voice: nodes with active ramps / queues
@@ -154,6 +172,20 @@ struct HostPlan {
     void push(const kgpu_event *ev, size_t n, uint64_t frame_clock);
     // host half of a render call, see plan.cpp
     void compile_events(const std::vector<uint64_t> &bounds, const std::vector<uint32_t> &chunk_of_group, CompiledEvents &out);
+    // the same work as a stream: launch L can be fetched (and rendered) while later launches are
+    // still being simulated on the worker threads.  stream_launch fills `out` with ONE launch
+    // (pieces indexed by group).  Always pair stream_begin with stream_end.
+    void stream_begin(const std::vector<uint64_t> &bounds, const std::vector<uint32_t> &chunk_of_group);
+    void stream_launch(size_t launch, CompiledEvents &out);
+    void stream_end();
+    void consume_ready(uint64_t b1);
+    StreamState *stream = nullptr;
+    WorkPool *pool = nullptr;            // created on first use
+    WorkPool &workers();
+    HostPlan() = default;
+    HostPlan(const HostPlan &) = delete;
+    HostPlan &operator=(const HostPlan &) = delete;
+    ~HostPlan();
 };
 
 // fused-kernel recipes (kernels.cu): returns recipe index or -1
