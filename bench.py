@@ -358,9 +358,9 @@ def main():
         hbm_gbs = alg_bytes / (avg_launch_ms / 1e3) / 1e9
         traffic = None
         try:  # DRAM bytes of the dominant kernel from the committed ncu capture, scaled to this run's launch size
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                tj = json.load(f)
-            if tj["kernel"] == info["kernels"][0] and tj["voices"] == args.voices:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)[info["kernels"][0]]
+            if tj["voices"] == args.voices:
                 traffic = tj["traffic_bytes_per_launch"] * frames_per_launch / tj["frames_per_launch"]
         except (OSError, KeyError, ValueError):
             pass

@@ -138,6 +138,13 @@ struct kgpu_plan {
     Staging staging[3];
     uint32_t staging_next = 0;
     PinBuf<float> out_pinned;
+    // copies of the streaming path run beside the kernels: events of launch L+1 go up (h2d_stream,
+    // device buffers ping-pong) and the bus of launch L-1 comes down (d2h_stream) while launch L renders
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    DevBuf<DevEvent> d_events_pp[2];
+    DevBuf<uint32_t> d_off_pp[2];
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, kern_done[2] = {nullptr, nullptr}, red_done[2] = {nullptr, nullptr};
+    bool kern_recorded[2] = {false, false};
 };
 
 namespace {
@@ -223,9 +230,23 @@ uint64_t blocks_per_launch(kgpu_plan *p) {
     return std::min<uint64_t>(bpl, p->max_blocks_per_launch);
 }
 
-// upload the events of ONE launch (the only launch in p->ce) through a pinned staging buffer
-void upload_launch_events(kgpu_plan *p, cudaStream_t stream) {
+void ensure_stream_objects(kgpu_plan *p) {
+    if (p->h2d_stream) return;
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaEventCreateWithFlags(&p->h2d_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&p->kern_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&p->red_done[i], cudaEventDisableTiming));
+    }
+}
+
+// Uploads the events of ONE launch (the only launch in p->ce): pinned staging buffer -> device
+// buffer (launch & 1) on h2d_stream, which first waits until the kernels of launch - 2 (the last
+// readers of that buffer) are done.  `stream` then waits for the copy.
+void upload_launch_events(kgpu_plan *p, size_t launch, cudaStream_t stream) {
     if (p->ce.events.empty()) return;
+    const int pp = (int)(launch & 1);
     Staging &sg = p->staging[p->staging_next];
     p->staging_next = (p->staging_next + 1) % 3;
     if (!sg.copied) CUDA_TRY(cudaEventCreateWithFlags(&sg.copied, cudaEventDisableTiming));
@@ -241,11 +262,19 @@ void upload_launch_events(kgpu_plan *p, cudaStream_t stream) {
     }
     std::memcpy(sg.ev.p, p->ce.events.data(), p->ce.events.size() * sizeof(DevEvent));
     std::memcpy(sg.off.p, p->ce.offsets.data(), p->ce.offsets.size() * 4);
-    if (p->ce.events.size() > p->d_events_all.cap) p->d_events_all.ensure(p->ce.events.size() + p->ce.events.size() / 2);
-    if (p->ce.offsets.size() > p->d_off_all.cap) p->d_off_all.ensure(p->ce.offsets.size() + p->ce.offsets.size() / 2);
-    CUDA_TRY(cudaMemcpyAsync(p->d_events_all.p, sg.ev.p, p->ce.events.size() * sizeof(DevEvent), cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaMemcpyAsync(p->d_off_all.p, sg.off.p, p->ce.offsets.size() * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaEventRecord(sg.copied, stream));
+    if (p->ce.events.size() > p->d_events_pp[pp].cap || p->ce.offsets.size() > p->d_off_pp[pp].cap) {
+        CUDA_TRY(cudaStreamSynchronize(stream)); // cudaFree of a buffer a queued kernel still reads: first render call only
+        for (int i = 0; i < 2; i++) {
+            p->d_events_pp[i].ensure(p->ce.events.size() + p->ce.events.size() / 2);
+            p->d_off_pp[i].ensure(p->ce.offsets.size() + p->ce.offsets.size() / 2);
+        }
+    }
+    if (p->kern_recorded[pp]) CUDA_TRY(cudaStreamWaitEvent(p->h2d_stream, p->kern_done[pp], 0));
+    CUDA_TRY(cudaMemcpyAsync(p->d_events_pp[pp].p, sg.ev.p, p->ce.events.size() * sizeof(DevEvent), cudaMemcpyHostToDevice, p->h2d_stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_off_pp[pp].p, sg.off.p, p->ce.offsets.size() * 4, cudaMemcpyHostToDevice, p->h2d_stream));
+    CUDA_TRY(cudaEventRecord(sg.copied, p->h2d_stream));
+    CUDA_TRY(cudaEventRecord(p->h2d_done[pp], p->h2d_stream));
+    CUDA_TRY(cudaStreamWaitEvent(stream, p->h2d_done[pp], 0));
     sg.in_flight = true;
     p->last_h2d_bytes += p->ce.events.size() * sizeof(DevEvent) + p->ce.offsets.size() * 4;
 }
@@ -305,6 +334,7 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
         }
     }
     if (!was_prepared) {
+        ensure_stream_objects(p);
         std::vector<uint64_t> bounds{t_begin};
         for (uint64_t nb : sizes) bounds.push_back(bounds.back() + nb * bs);
         p->host.stream_begin(bounds, chunks);
@@ -319,7 +349,7 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             const auto ta = std::chrono::steady_clock::now();
             p->host.stream_launch(launch, p->ce);
             const auto tb = std::chrono::steady_clock::now();
-            upload_launch_events(p, stream);
+            upload_launch_events(p, launch, stream);
             if (timing && n_blocks > 100)
                 fprintf(stderr, "[kgpu timing]   launch %zu: wait+merge %.2f ms, stage+enqueue %.2f ms\n", launch,
                         std::chrono::duration<double, std::milli>(tb - ta).count(),
@@ -330,8 +360,10 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             Group &g = p->host.groups[gi];
             GroupDev &d = p->gd[gi];
             const bool any = !p->ce.piece_any.empty() && p->ce.piece_any[piece];
-            const DevEvent *d_ev = any ? p->d_events_all.p + p->ce.piece_ev[piece] : nullptr;
-            const uint32_t *d_off = any ? p->d_off_all.p + p->ce.piece_off[piece] : nullptr;
+            const DevEvent *ev_base = was_prepared ? p->d_events_all.p : p->d_events_pp[launch & 1].p;
+            const uint32_t *off_base = was_prepared ? p->d_off_all.p : p->d_off_pp[launch & 1].p;
+            const DevEvent *d_ev = any ? ev_base + p->ce.piece_ev[piece] : nullptr;
+            const uint32_t *d_off = any ? off_base + p->ce.piece_off[piece] : nullptr;
             mark(0, true);
             if (d.recipe >= 0) {
                 FusedArgs a{};
@@ -351,13 +383,27 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             mark(0, false);
             p->kernel_launches++;
         }
+        if (!was_prepared) {
+            CUDA_TRY(cudaEventRecord(p->kern_done[launch & 1], stream));
+            p->kern_recorded[launch & 1] = true;
+        }
         mark(1, true);
         float *dst = device_out + (size_t)done * n_out * bs;
         CUDA_TRY(launch_reduce_bus(p->partials.p, p->row_mask.p, p->n_rows, nf, dst, n_out, bs, stream));
         mark(1, false);
         p->kernel_launches++;
-        if (pinned_out)
-            CUDA_TRY(cudaMemcpyAsync(pinned_out + (size_t)done * n_out * bs, dst, (size_t)nf * n_out * 4, cudaMemcpyDeviceToHost, stream));
+        if (pinned_out) {
+            cudaStream_t cs = was_prepared ? stream : p->d2h_stream;
+            if (!was_prepared) {
+                CUDA_TRY(cudaEventRecord(p->red_done[launch & 1], stream));
+                CUDA_TRY(cudaStreamWaitEvent(cs, p->red_done[launch & 1], 0));
+            }
+            CUDA_TRY(cudaMemcpyAsync(pinned_out + (size_t)done * n_out * bs, dst, (size_t)nf * n_out * 4, cudaMemcpyDeviceToHost, cs));
+        }
+    }
+    if (pinned_out && !was_prepared) { // `stream` ends after the last download
+        CUDA_TRY(cudaEventRecord(p->red_done[0], p->d2h_stream));
+        CUDA_TRY(cudaStreamWaitEvent(stream, p->red_done[0], 0));
     }
     if (guard.h) {
         guard.h = nullptr;
@@ -445,6 +491,14 @@ void kgpu_plan_destroy(kgpu_plan *p) {
         if (sg.copied) cudaEventDestroy(sg.copied);
     }
     p->out_pinned.release();
+    for (int i = 0; i < 2; i++) {
+        p->d_events_pp[i].release(); p->d_off_pp[i].release();
+        if (p->h2d_done[i]) cudaEventDestroy(p->h2d_done[i]);
+        if (p->kern_done[i]) cudaEventDestroy(p->kern_done[i]);
+        if (p->red_done[i]) cudaEventDestroy(p->red_done[i]);
+    }
+    if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
+    if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
     p->partials.release(); p->row_mask.release(); p->out.release(); p->sine.release(); p->tap_out.release();
     for (cudaEvent_t e : p->kev) cudaEventDestroy(e);
     if (p->ev0) cudaEventDestroy(p->ev0);

@@ -23,7 +23,7 @@ namespace kgpu {
 
 namespace {
 
-constexpr int SUB_TILE = 32;          // frames between mix-bus reductions
+constexpr int SUB_TILE = 32;          // frames between mix-bus reductions (render_fm2)
 constexpr int SUB_PAD = 33;           // smem row stride (bank-conflict-free transpose)
 constexpr int SUBW_PAD = 36;          // render_sub_asr: row stride that also keeps 16-byte row reads conflict-free
 
@@ -125,8 +125,9 @@ KN_DEV float saw_eval(float t, float dt, float omd, float rc) {
 }
 
 #ifndef SUB_SUB
-#define SUB_SUB 16 // frames per straight-line group
+#define SUB_SUB 16 // frames per straight-line group (16 or 32; 32 measured 1 % faster for twice the code)
 #endif
+constexpr int SUBW_TILE = 2 * SUB_SUB; // render_sub_asr staging tile: two halves of SUB_SUB frames
 
 // envelope registers derived from the state machine, constant while no transition happens
 struct EnvDerived {
@@ -178,8 +179,13 @@ KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc
                            const float *sum_src = nullptr, float *sum_dst = nullptr, bool sum_store = false) {
     float ph[N], env[N];
     if (SUM) {
-        const float h = sum16(sum_src);
-        const float tot = h + __shfl_xor_sync(0xFFFFFFFFu, h, 16);
+        float tot;
+        if (N == 32) { // lane = frame: all 32 voices
+            tot = sum16(sum_src) + sum16(sum_src + 16);
+        } else {       // N == 16: lane = (frame, voice half)
+            const float h = sum16(sum_src);
+            tot = h + __shfl_xor_sync(0xFFFFFFFFu, h, 16);
+        }
         if (sum_store) *sum_dst = tot;
     }
 #pragma unroll
@@ -274,7 +280,7 @@ struct EvCursor {
 
 template <bool TAPS>
 __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
-    __shared__ __align__(16) float st[SUB_TILE * SUBW_PAD];
+    __shared__ __align__(16) float st[SUBW_TILE * SUBW_PAD];
     const uint32_t lane = threadIdx.x;
     const uint32_t gwarp = blockIdx.x;
     const uint32_t v = gwarp * 32 + lane;
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
         __syncwarp();
     };
     auto stage_room = [&](uint32_t n) {
-        if (rbase + rows + n > SUB_TILE) flush();
+        if (rows + n > 32 || rbase + rows + n > SUBW_TILE) flush(); // flush() sums one staged frame per lane
     };
     // straight-line groups of N frames while N frames are safe
     auto run_groups = [&](auto lp_tag, auto n_tag, uint32_t lim) {
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
             if (rows) flush();
             uint32_t half = 0;
             bool pending = false;
-            const uint32_t r = lane & 15u, c = lane >> 4;
+            const uint32_t r = SUB_SUB == 32 ? lane : (lane & 15u), c = SUB_SUB == 32 ? 0u : (lane >> 4);
 #pragma unroll 1
             do {
                 __syncwarp();
