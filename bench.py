@@ -261,6 +261,10 @@ def main():
     info = proc.info()
     if args.blocks_per_launch:
         proc.set_blocks_per_launch(args.blocks_per_launch)
+    # one process per GPU shares the box's host cores: each plan's event-pipeline workers get their share
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, local_world) - 1))
+    proc.set_host_threads(host_threads)
     step_no = [0]
 
     def push_step_events():
@@ -387,6 +391,7 @@ def main():
             "clocks": clocks,
             "plan": {k: info[k] for k in ("n_groups", "n_voices", "n_mix_nodes", "n_fused_groups", "state_bytes")},
             "build_graph_s": build_s,
+            "host": {"cores": os.cpu_count(), "event_pipeline_threads_per_gpu": host_threads},
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args)

@@ -221,6 +221,11 @@ uint64_t kgpu_plan_last_upload_bytes(kgpu_plan *plan);
 /* K = blocks rendered per kernel launch (default: as many as fit a 256 MiB partial-sum buffer,
  * at most 1024).  K = 1 reproduces "one launch per 64-frame block". */
 int kgpu_plan_set_blocks_per_launch(kgpu_plan *plan, uint64_t blocks);
+/* Host worker threads a plan uses for the control-rate simulation (validation, bucketing and the
+ * per-voice event replay that runs one launch ahead of the device).  0 = default: hardware threads
+ * - 1, at most 16.  Call before the first render; with several plans/processes per box (one per
+ * GPU) give each its share of the cores.  No counterpart in knaster, which renders on one thread. */
+int kgpu_plan_set_host_threads(kgpu_plan *plan, uint32_t n_threads);
 
 const char *kgpu_last_error(void); /* thread-local */
 uint32_t kgpu_abi_version(void);

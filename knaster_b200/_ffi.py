@@ -127,6 +127,7 @@ def lib() -> C.CDLL:
     L.kgpu_plan_last_upload_bytes.argtypes = [vp]
     L.kgpu_plan_last_upload_bytes.restype = u64
     L.kgpu_plan_set_blocks_per_launch.argtypes = [vp, u64]
+    L.kgpu_plan_set_host_threads.argtypes = [vp, u32]
     L.kgpu_debug_simulate.argtypes = [C.POINTER(GraphDesc), vp, C.c_size_t, u64, u64, vp, C.c_size_t,
                                       C.POINTER(C.c_size_t), vp, C.POINTER(PlanInfo)]
     L.kgpu_debug_init_reg.argtypes = [C.POINTER(GraphDesc), u32, u32, C.POINTER(u32)]

@@ -677,6 +677,13 @@ float kgpu_plan_last_kernel_ms(kgpu_plan *p, uint32_t kernel_class, uint32_t *n_
 
 uint64_t kgpu_plan_last_upload_bytes(kgpu_plan *p) { return p ? p->last_h2d_bytes : 0; }
 
+int kgpu_plan_set_host_threads(kgpu_plan *p, uint32_t n_threads) {
+    if (!p) return fail(KGPU_ERR_INVALID, "kgpu_plan_set_host_threads: NULL plan");
+    if (p->host.pool) return fail(KGPU_ERR_STATE, "kgpu_plan_set_host_threads must be called before the first render / large push");
+    p->host.pool_threads = n_threads;
+    return KGPU_OK;
+}
+
 int kgpu_plan_set_blocks_per_launch(kgpu_plan *p, uint64_t blocks) {
     if (!p || blocks == 0) return fail(KGPU_ERR_INVALID, "kgpu_plan_set_blocks_per_launch: bad argument");
     p->max_blocks_per_launch = blocks;

@@ -1093,6 +1093,7 @@ WorkPool &HostPlan::workers() {
         // workers are busy, or the first launch waits for ALL of the simulation
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         unsigned n = std::min<unsigned>(hw > 2 ? hw - 1 : hw, 16u);
+        if (pool_threads) n = pool_threads;
         if (const char *e = getenv("KGPU_THREADS")) n = (unsigned)std::max(1, atoi(e));
         pool = new WorkPool(n);
     }

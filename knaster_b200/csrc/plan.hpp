@@ -181,6 +181,7 @@ struct HostPlan {
     void consume_ready(uint64_t b1);
     StreamState *stream = nullptr;
     WorkPool *pool = nullptr;            // created on first use
+    uint32_t pool_threads = 0;           // 0: hardware threads - 1, at most 16
     WorkPool &workers();
     HostPlan() = default;
     HostPlan(const HostPlan &) = delete;

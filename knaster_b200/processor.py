@@ -197,5 +197,10 @@ class AudioProcessor:
         self._ensure_plan()
         _ffi.check(self._lib.kgpu_plan_set_blocks_per_launch(self._plan, blocks))
 
+    def set_host_threads(self, n_threads: int) -> None:
+        """Worker threads of the host event pipeline (0 = hardware threads - 1, at most 16)."""
+        self._ensure_plan()
+        _ffi.check(self._lib.kgpu_plan_set_host_threads(self._plan, n_threads))
+
     def last_render_ms(self) -> float:
         return float(self._lib.kgpu_plan_last_render_ms(self._plan))
