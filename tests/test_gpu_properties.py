@@ -1,0 +1,286 @@
+"""GPU property and edge-case tests for the fused voice-bank path (through the C ABI).
+
+The parity tests in test_gpu_parity.py compare against the CPU oracle at sizes the oracle renders
+in seconds.  At BASELINE.json's full size (16 384 voices) the oracle is too slow, so the full-size
+cases here use properties that do not depend on it: invariance under the way a render is split
+into launches, exact scaling by a power of two, silence without notes, determinism, and
+bus == sum of the voices.  The edge cases (ragged voice counts, odd block sizes and frame counts,
+event collisions, dense event streams, events on the first and last frame, parameters outside the
+straight-line domain) are small and are checked against the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import knaster_b200 as kn
+from knaster_b200 import banks
+from knaster_b200.graph import Graph
+from knaster_b200.processor import AudioProcessor, AudioProcessorOptions
+from oracle.oracle import OracleProcessor
+
+pytestmark = pytest.mark.gpu
+SR = 48000
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def render_bank(n_voices, seconds, n_blocks, blocks_per_launch=0, gain_scale=1.0, n_notes=8, seed=2002):
+    graph, proc = AudioProcessor.new(0, 2, AudioProcessorOptions())
+    banks.subtractive_bank(graph, n_voices, seconds, seed=seed, n_notes=n_notes)
+    if gain_scale != 1.0:  # WrMul's parameter ("wr_mul", index 4 of EnvAsr.wr_mul) on every envelope node
+        from knaster_b200 import ugens as U
+
+        with graph.edit() as g:
+            for node, n in enumerate(graph.nodes):
+                if n.ugen.kind == U.KIND_ENV_ASR:
+                    g.set(node, "wr_mul", gain_scale / n_voices, kn.Time.asap())
+    if blocks_per_launch:
+        proc.set_blocks_per_launch(blocks_per_launch)
+    out = proc.render(n_blocks)
+    return out, proc
+
+
+def oracle_render(build, n_blocks, outputs=1, block_size=64, taps=()):
+    g = Graph(0, outputs, block_size, SR)
+    ids = build(g)
+    orc = OracleProcessor(g, ring_buffer_size=1 << 22)
+    for i in taps or ids:
+        orc.add_tap(i, 0)
+    return orc.render(n_blocks)
+
+
+def gpu_render(build, n_blocks, outputs=1, block_size=64, blocks_per_launch=0, taps=True):
+    graph, proc = AudioProcessor.new(0, outputs, AudioProcessorOptions(block_size=block_size, sample_rate=SR))
+    ids = build(graph)
+    if taps:
+        for i in ids:
+            proc.add_tap(i, 0)
+    if blocks_per_launch:
+        proc.set_blocks_per_launch(blocks_per_launch)
+    out = proc.render(n_blocks)
+    return out, (proc.read_taps() if taps and ids else None), proc
+
+
+# ---- full size: BASELINE.json configs[2], 16 384 voices ----------------------------------------
+FULL_V, FULL_SECONDS, FULL_BLOCKS = 16384, 2.0, 1500
+
+
+@pytest.fixture(scope="module")
+def full_render():
+    out, proc = render_bank(FULL_V, FULL_SECONDS, FULL_BLOCKS)
+    assert proc.info()["kernels"] == ["render_sub_asr"]
+    return out
+
+
+def test_full_size_launch_split_invariance(full_render):
+    # 1024-block launches vs 96-block launches vs 7-block launches (frame counts that are not
+    # multiples of the 16-frame group either way): bit-identical audio
+    for bpl in (96, 7):
+        out, _ = render_bank(FULL_V, FULL_SECONDS, FULL_BLOCKS, blocks_per_launch=bpl)
+        assert np.array_equal(out, full_render), f"render differs with {bpl} blocks per launch"
+
+
+def test_full_size_determinism_and_stereo(full_render):
+    out, _ = render_bank(FULL_V, FULL_SECONDS, FULL_BLOCKS)
+    assert np.array_equal(out, full_render)
+    assert np.array_equal(full_render[:, 0, :], full_render[:, 1, :])  # .out([0, 0]): both channels carry the same bus
+    assert np.isfinite(full_render).all()
+    assert 1e-4 < np.abs(full_render).max() < 1.0
+
+
+def test_full_size_gain_scaling_is_exact(full_render):
+    # every voice's WrMul gain doubled: each voice sample, each partial sum and the bus double exactly
+    out, _ = render_bank(FULL_V, FULL_SECONDS, FULL_BLOCKS, gain_scale=2.0)
+    assert np.array_equal(out, 2.0 * full_render)
+
+
+def test_full_size_silence_without_notes():
+    out, _ = render_bank(FULL_V, 1.0, 750, n_notes=0)
+    assert not out.any()
+
+
+def test_bus_is_the_sum_of_the_voices():
+    # 200 voices (6 full warps + a ragged one): the bus against the f64 sum of every tapped voice
+    def build(graph):
+        return banks.subtractive_bank(graph, 200, 1.0, n_notes=4, stereo=False)
+
+    out, taps, proc = gpu_render(build, 750)
+    assert proc.info()["kernels"] == ["render_sub_asr"]
+    ref = taps.astype(np.float64).sum(axis=0).reshape(750, 64)
+    assert np.abs(out[:, 0, :] - ref).max() <= 2e-7
+    assert np.abs(ref).max() > 1e-3
+
+
+# ---- edge cases against the oracle ---------------------------------------------------------------
+@pytest.mark.parametrize("n_voices", [1, 31, 33, 65])
+def test_ragged_voice_counts(n_voices):
+    def build(graph):
+        return banks.subtractive_bank(graph, n_voices, 0.5, n_notes=3, stereo=False)
+
+    out, taps, proc = gpu_render(build, 375)
+    ref, ref_taps = oracle_render(build, 375)
+    assert proc.info()["kernels"] == ["render_sub_asr"]
+    assert np.abs(taps - ref_taps).max() <= 1e-6
+    assert np.abs(out - ref).max() <= 1e-6
+
+
+@pytest.mark.parametrize("block_size,n_blocks", [(16, 333), (8, 1001), (1, 700), (256, 41)])
+def test_block_sizes_and_frame_counts(block_size, n_blocks):
+    # frame counts that are not multiples of the 16-frame group, one-frame blocks, long blocks
+    def build(graph):
+        return banks.subtractive_bank(graph, 40, n_blocks * block_size / SR, n_notes=3, stereo=False)
+
+    out, taps, _ = gpu_render(build, n_blocks, block_size=block_size)
+    ref, ref_taps = oracle_render(build, n_blocks, block_size=block_size)
+    assert np.abs(taps - ref_taps).max() <= 1e-6
+    assert np.abs(out - ref).max() <= 1e-6
+    assert np.abs(ref).max() > 1e-4
+
+
+def _voice(g, f=220.0, fc=1200.0, q=2.0, att=0.003, rel=0.05, gain=0.25):
+    saw = g.push(kn.PolyBlep(kn.Waveform.Sawtooth, f).precise_timing(8))
+    svf = g.push(kn.SvfFilter(kn.SvfFilterType.Low, fc, q, 0.0).precise_timing(8))
+    env = g.push(kn.EnvAsr(att, rel).wr_mul(gain).precise_timing(8))
+    sig = (saw >> svf) * env
+    sig.to_graph_out()
+    return saw, svf, env, sig
+
+
+def at(frame):
+    return kn.Seconds.from_samples(frame, SR)
+
+
+def test_event_collisions_and_boundaries():
+    # every voice gets its note-on at the SAME frame; events on frame 0, on a launch boundary
+    # (64 blocks per launch = frame 4096) and on the very last frame; a release during the attack
+    n_blocks = 200
+    last = n_blocks * 64 - 1
+
+    def build(graph):
+        ids = []
+        with graph.edit() as g:
+            for i in range(40):
+                saw, svf, env, sig = _voice(g, f=110.0 + 7.0 * i, fc=500.0 + 100.0 * i, att=0.002 + 0.001 * (i % 5))
+                env.param("t_restart").trig_at(at(0))
+                saw.param("freq").set_at(150.0 + i, at(0))
+                env.param("t_release").trig_at(at(50 + i))            # still attacking: release_scale = t
+                env.param("t_restart").trig_at(at(4096))              # all voices, launch boundary
+                svf.param("cutoff_freq").set_at(2000.0 + 10.0 * i, at(4096))
+                svf.param("q").set_at(0.7 + 0.1 * (i % 7), at(4097))
+                env.param("t_release").trig_at(at(9000))
+                env.param("t_restart").trig_at(at(last))
+                saw.param("freq").set_at(300.0 + i, at(last))
+                ids.append(sig._outputs[0][0])
+        return ids
+
+    out, taps, proc = gpu_render(build, n_blocks, blocks_per_launch=64)
+    ref, ref_taps = oracle_render(build, n_blocks)
+    assert proc.info()["kernels"] == ["render_sub_asr"]
+    assert np.abs(taps - ref_taps).max() <= 1e-6
+    assert np.abs(out - ref).max() <= 1e-6
+    assert np.abs(ref_taps[:, 4200:5000]).max() > 1e-3
+
+
+def test_dense_event_stream():
+    # one voice receives a cutoff change on every frame of a block and 8 frequency changes inside
+    # one block (the precise_timing::<8> queue is full), its neighbours none
+    def build(graph):
+        ids = []
+        with graph.edit() as g:
+            voices = [_voice(g, f=200.0 + 50 * i) for i in range(5)]
+            for saw, svf, env, sig in voices:
+                env.param("t_restart").trig_at(at(10))
+                ids.append(sig._outputs[0][0])
+            saw, svf, env, _ = voices[2]
+            for k in range(8):
+                saw.param("freq").set_at(300.0 + 40.0 * k, at(640 + 3 + 7 * k))
+            for k in range(64):
+                svf.param("cutoff_freq").set_at(600.0 + 25.0 * k, at(1280 + k))
+        return ids
+
+    out, taps, proc = gpu_render(build, 60)
+    ref, ref_taps = oracle_render(build, 60)
+    assert np.abs(taps - ref_taps).max() <= 1e-6
+    assert np.abs(out - ref).max() <= 1e-6
+    assert proc.info()["dropped_changes"] > 0  # queue overflow is counted, like knaster's rt_log warning
+
+
+def test_parameters_outside_the_straight_line_domain():
+    # freq >= sr/4 (PolyBlep's sine guard), freq 0 (dt = 0), negative freq (t leaves [0,1)), a
+    # non-lowpass filter in the same warp, very slow envelopes: lanes fall back to the generic tick
+    def build(graph):
+        ids = []
+        with graph.edit() as g:
+            specs = [(13000.0, 900.0), (0.0, 900.0), (-220.0, 900.0), (220.0, 900.0), (30.0, 50.0)]
+            for i, (f, fc) in enumerate(specs):
+                saw, svf, env, sig = _voice(g, f=f, fc=fc, att=0.2 if i == 4 else 0.003, rel=2.0 if i == 4 else 0.05)
+                env.param("t_restart").trig_at(at(5 + i))
+                env.param("t_release").trig_at(at(6000 + i))
+                ids.append(sig._outputs[0][0])
+            saw, svf, env, sig = _voice(g, f=330.0)
+            svf.param("filter").set_at(int(kn.SvfFilterType.Band), at(2000))   # warp leaves the lowpass specialisation
+            saw.param("freq").set_at(14000.0, at(3000))
+            saw.param("freq").set_at(-5.0, at(4000))
+            saw.param("freq").set_at(440.0, at(5000))
+            env.param("t_restart").trig_at(at(1))
+            ids.append(sig._outputs[0][0])
+        return ids
+
+    out, taps, proc = gpu_render(build, 150)
+    ref, ref_taps = oracle_render(build, 150)
+    assert proc.info()["kernels"] == ["render_sub_asr"]
+    assert np.isfinite(ref_taps).all()
+    # the negative-frequency voice runs the blep far outside its window (|t/dt| is large): per-voice
+    # errors are compared relative to that voice's peak, the bus relative to the largest voice
+    # (the mix bus is a tree sum here and a left fold in knaster)
+    peak = np.maximum(1.0, np.abs(ref_taps).max(axis=1, keepdims=True))
+    assert (np.abs(taps - ref_taps) / peak).max() <= 1e-5
+    assert np.abs(out - ref).max() <= 1e-6 * peak.max()
+    assert np.abs(ref_taps).max() > 1e-2
+
+
+def test_late_events_keep_arrival_order():
+    # events pushed after their due time become ready in the next block, in ARRIVAL order
+    # (graph_gen.rs:276 saturating_sub): the last one pushed wins
+    def run(proc, graph, handles):
+        saw, svf, env, sig = handles
+        proc.render(10)
+        with graph.edit():
+            saw.param("freq").set_at(500.0, at(300))   # due in the past (frame clock is 640)
+            saw.param("freq").set_at(250.0, at(100))   # due even earlier, pushed later: applied last
+            env.param("t_restart").trig_at(at(0))
+        return proc.render(20)
+
+    graph, proc = AudioProcessor.new(0, 1, AudioProcessorOptions())
+    with graph.edit() as g:
+        handles = _voice(g)
+    gpu = run(proc, graph, handles)
+    g2 = Graph(0, 1, 64, SR)
+    with g2.edit() as g:
+        handles2 = _voice(g)
+    orc = OracleProcessor(g2, ring_buffer_size=1 << 16)
+    ref = run(orc, g2, handles2)[0]
+    assert np.abs(gpu - ref).max() <= 1e-6
+    assert np.abs(ref).max() > 1e-3
+
+
+def test_two_warp_kernel_variant_matches():
+    # the warp-specialised experiment (KGPU_SUB_TWO_WARPS=1) must stay bit-identical to the default
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from knaster_b200 import banks\n"
+        "from knaster_b200.processor import AudioProcessor, AudioProcessorOptions\n"
+        "g, p = AudioProcessor.new(0, 2, AudioProcessorOptions())\n"
+        "banks.subtractive_bank(g, 100, 1.0, n_notes=4)\n"
+        "np.save(sys.argv[1], p.render(750))\n" % ROOT
+    )
+    outs = []
+    for flag in ("0", "1"):
+        path = os.path.join(ROOT, "gpurun_out", f"_two_warp_{flag}.npy") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else f"/tmp/_two_warp_{flag}.npy"
+        env = dict(os.environ, KGPU_SUB_TWO_WARPS=flag)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        outs.append(np.load(path))
+        os.remove(path)
+    assert np.array_equal(outs[0], outs[1])
+    assert np.abs(outs[0]).max() > 1e-3
