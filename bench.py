@@ -185,7 +185,7 @@ def workload_config(args, world):
             "seconds_per_step": args.seconds, "blocks_per_step": int(round(args.seconds * SR)) // BLOCK, "block_size": BLOCK,
             "sample_rate": SR, "notes_per_voice_per_step": 8 if args.workload == "subtractive" else 0,
             "l2": "per-voice state + events stream once per launch; working set changes every launch (no L2 reuse to flush)",
-            "reduce": f"NCCL reduce(sum) of the stereo bus to rank 0, {args.chunks} chunks per step" if world > 1 else "none (1 GPU)"}
+            "reduce": "none (1 GPU)" if world == 1 else "see config.bus"}
 
 
 def cpu_baseline(args):
@@ -222,7 +222,10 @@ def main():
     ap.add_argument("--workload", default="subtractive", choices=["subtractive", "additive", "fm"])
     ap.add_argument("--voices", type=int, default=16384, help="voices per GPU")
     ap.add_argument("--seconds", type=float, default=10.0, help="audio seconds per step")
-    ap.add_argument("--chunks", type=int, default=10, help="NCCL reduce chunks per step (N>1)")
+    ap.add_argument("--chunks", type=int, default=10, help="NCCL reduce chunks per step (N>1, --bus nccl)")
+    ap.add_argument("--bus", default="peer", choices=["peer", "nccl"],
+                    help="N>1: sum the mix bus over peer memory inside the engine's own kernels (falls back to nccl if torch "
+                         "symmetric memory is unavailable) or with an NCCL reduce of the rank-local buses")
     ap.add_argument("--blocks-per-launch", type=int, default=0)
     ap.add_argument("--force-interpreter", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -278,11 +281,31 @@ def main():
     chunks = max(1, min(args.chunks, n_blocks)) if world > 1 else 1
     bounds = [round(i * n_blocks / chunks) for i in range(chunks + 1)]
 
+    bus_mode, peer_bus = ("none (1 GPU)" if world == 1 else "nccl"), None
+    if world > 1 and args.bus == "peer":
+        try:
+            from knaster_b200.multi_gpu import PeerBus
+
+            peer_bus = PeerBus(proc, n_blocks)
+            ok = torch.ones(1, device="cuda")
+        except Exception as e:  # no symmetric memory / no peer access on this box
+            sys.stderr.write(f"[bench] peer bus unavailable ({type(e).__name__}: {e}); using the NCCL reduce\n")
+            ok = torch.zeros(1, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # all ranks or none
+        if ok.item() < 1:
+            if peer_bus is not None:
+                peer_bus.close()
+            peer_bus = None
+        else:
+            bus_mode = "peer"
+
     def device_step():
-        """kernels (+ NCCL reduce of the rank-local bus to rank 0) with inputs already in HBM"""
+        """kernels + mix-bus sum onto rank 0 (peer-memory stores inside the engine, or an NCCL reduce of
+        the rank-local buses) with inputs already in HBM"""
         cur = torch.cuda.current_stream()
         proc.render_device(n_blocks, bus.data_ptr(), cur.cuda_stream)
-        reduce_bus(bus, dst=0, chunks=chunks)
+        if peer_bus is None:
+            reduce_bus(bus, dst=0, chunks=chunks)
 
     def barrier():
         torch.cuda.synchronize()
@@ -372,7 +395,10 @@ def main():
             "metric": "voice-samples/sec (f32, 48 kHz)", "value": value, "unit": "voice-samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": dict(workload_config(args, world), bus=(
+                "peer memory: every rank's reduce_bus kernel stores its bus into rank 0 over NVLink, rank 0 folds the slots per launch"
+                if bus_mode == "peer" else f"NCCL reduce(sum) of the rank-local stereo bus to rank 0, {chunks} chunks per step"
+                if bus_mode == "nccl" else bus_mode)),
             "kernels": info["kernels"],
             "roofline": {
                 "bound": "fp32", "achieved": achieved, "peak": peak_fp32, "unit": "GFLOP/s (un-fused FP32 instr)",
@@ -396,6 +422,8 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line))
+    if peer_bus is not None and peer_bus.timed_out():
+        sys.stderr.write("[bench] WARNING: a rank timed out waiting for peer-bus data\n")
     if world > 1:
         dist.destroy_process_group()
 

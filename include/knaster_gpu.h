@@ -221,6 +221,28 @@ uint64_t kgpu_plan_last_upload_bytes(kgpu_plan *plan);
 /* K = blocks rendered per kernel launch (default: as many as fit a 256 MiB partial-sum buffer,
  * at most 1024).  K = 1 reproduces "one launch per 64-frame block". */
 int kgpu_plan_set_blocks_per_launch(kgpu_plan *plan, uint64_t blocks);
+/* ---- multi-GPU mix bus over peer memory -------------------------------------------------------
+ * One process per GPU, voices sharded across ranks.  Instead of reducing the rank-local
+ * buses with a collective afterwards, every rank's bus-reduction kernel stores straight into its slot
+ * of ONE buffer that lives in rank 0's memory (peer stores over NVLink) and publishes each launch
+ * with a system-scope flag; rank 0 folds the slots in rank order as the launches arrive, beside the
+ * rendering of the next launch.  knaster has no counterpart (one process, one audio thread): this is
+ * the distributed form of the graph-out Add chain (graph.rs:850-864).
+ *
+ * root_buffer: device pointer, valid ON THIS RANK, to the same allocation in rank 0's memory (rank 0:
+ * its own allocation; other ranks: a peer mapping of it, e.g. from CUDA IPC or torch symmetric
+ * memory), kgpu_peer_bus_bytes(world, floats_per_rank) bytes, zero-filled before the first render,
+ * 16-byte aligned.  floats_per_rank >= n_blocks * block_size * outputs of the largest render call.
+ * Every rank must make the same sequence of kgpu_render* calls.  Only rank 0's output buffer
+ * receives audio (the sum over all ranks); the other ranks' output buffers are left untouched.
+ * world <= 1 or root_buffer == NULL detaches. */
+#define KGPU_PEER_MAX_LAUNCHES 4096
+uint64_t kgpu_peer_bus_header_bytes(uint32_t world);
+uint64_t kgpu_peer_bus_bytes(uint32_t world, uint64_t floats_per_rank);
+int kgpu_plan_set_peer_bus(kgpu_plan *plan, uint32_t rank, uint32_t world, void *root_buffer, uint64_t buffer_bytes);
+/* 1 if a rank gave up waiting (~2 s) for another rank's data since the buffer was zero-filled. */
+int kgpu_plan_peer_bus_timed_out(kgpu_plan *plan);
+
 /* Host worker threads a plan uses for the control-rate simulation (validation, bucketing and the
  * per-voice event replay that runs one launch ahead of the device).  0 = default: hardware threads
  * - 1, at most 16.  Call before the first render; with several plans/processes per box (one per

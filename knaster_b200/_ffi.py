@@ -128,6 +128,12 @@ def lib() -> C.CDLL:
     L.kgpu_plan_last_upload_bytes.restype = u64
     L.kgpu_plan_set_blocks_per_launch.argtypes = [vp, u64]
     L.kgpu_plan_set_host_threads.argtypes = [vp, u32]
+    L.kgpu_plan_set_peer_bus.argtypes = [vp, u32, u32, vp, u64]
+    L.kgpu_plan_peer_bus_timed_out.argtypes = [vp]
+    L.kgpu_peer_bus_header_bytes.argtypes = [u32]
+    L.kgpu_peer_bus_header_bytes.restype = u64
+    L.kgpu_peer_bus_bytes.argtypes = [u32, u64]
+    L.kgpu_peer_bus_bytes.restype = u64
     L.kgpu_debug_simulate.argtypes = [C.POINTER(GraphDesc), vp, C.c_size_t, u64, u64, vp, C.c_size_t,
                                       C.POINTER(C.c_size_t), vp, C.POINTER(PlanInfo)]
     L.kgpu_debug_init_reg.argtypes = [C.POINTER(GraphDesc), u32, u32, C.POINTER(u32)]

@@ -145,6 +145,14 @@ struct kgpu_plan {
     DevBuf<uint32_t> d_off_pp[2];
     cudaEvent_t h2d_done[2] = {nullptr, nullptr}, kern_done[2] = {nullptr, nullptr}, red_done[2] = {nullptr, nullptr};
     bool kern_recorded[2] = {false, false};
+    // multi-GPU mix bus over peer memory (kgpu_plan_set_peer_bus): every rank's reduce_bus writes into
+    // its slot of a buffer that lives in rank 0's memory, rank 0 folds the slots
+    uint32_t peer_rank = 0, peer_world = 0, peer_epoch = 0;
+    uint32_t *peer_flags = nullptr, *peer_consumed = nullptr, *peer_timeout = nullptr;
+    float *peer_slots = nullptr;
+    uint64_t peer_slot_floats = 0;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t peer_ev[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -301,6 +309,19 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
     std::vector<uint32_t> chunks;
     for (GroupDev &d : p->gd) chunks.push_back(d.chunk);
 
+    const bool peer = p->peer_world > 1;
+    if (peer) {
+        if ((uint64_t)total_frames * n_out > p->peer_slot_floats)
+            KGPU_THROW(KGPU_ERR_INVALID, "peer bus holds %llu floats per rank, this render needs %llu", (unsigned long long)p->peer_slot_floats,
+                       (unsigned long long)(total_frames * n_out));
+        if (!p->aux_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
+            for (auto &e : p->peer_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        p->peer_epoch++;
+        // a slot may be overwritten only after rank 0 has folded the previous call's data
+        if (p->peer_epoch > 1) CUDA_TRY(launch_wait_flag(p->peer_consumed, p->peer_epoch - 1, p->peer_timeout, stream));
+    }
     if (p->timed) CUDA_TRY(cudaEventRecord(p->ev0, stream));
     size_t piece = 0;
     p->kev_used = 0;
@@ -333,6 +354,8 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             next = std::min(bpl, next * 2);
         }
     }
+    if (peer && sizes.size() > KGPU_PEER_MAX_LAUNCHES)
+        KGPU_THROW(KGPU_ERR_INVALID, "a render call with a peer bus is limited to %d launches", KGPU_PEER_MAX_LAUNCHES);
     if (!was_prepared) {
         ensure_stream_objects(p);
         std::vector<uint64_t> bounds{t_begin};
@@ -389,10 +412,27 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
         }
         mark(1, true);
         float *dst = device_out + (size_t)done * n_out * bs;
-        CUDA_TRY(launch_reduce_bus(p->partials.p, p->row_mask.p, p->n_rows, nf, dst, n_out, bs, stream));
+        if (peer) { // reduce straight into this rank's slot in rank 0's memory (NVLink stores), then publish the launch
+            float *slot = p->peer_slots + (size_t)p->peer_rank * p->peer_slot_floats + (size_t)done * n_out * bs;
+            CUDA_TRY(launch_reduce_bus(p->partials.p, p->row_mask.p, p->n_rows, nf, slot, n_out, bs, stream));
+            CUDA_TRY(launch_signal_flag(p->peer_flags + (size_t)p->peer_rank * KGPU_PEER_MAX_LAUNCHES + launch, p->peer_epoch, stream));
+            p->kernel_launches++;
+        } else {
+            CUDA_TRY(launch_reduce_bus(p->partials.p, p->row_mask.p, p->n_rows, nf, dst, n_out, bs, stream));
+        }
         mark(1, false);
         p->kernel_launches++;
-        if (pinned_out) {
+        if (peer) {
+            if (p->peer_rank == 0) { // fold the slots beside the next launch's rendering
+                CUDA_TRY(cudaEventRecord(p->peer_ev[launch & 1], stream));
+                CUDA_TRY(cudaStreamWaitEvent(p->aux_stream, p->peer_ev[launch & 1], 0));
+                CUDA_TRY(launch_sum_slots(p->peer_slots + (size_t)done * n_out * bs, p->peer_slot_floats, p->peer_world, p->peer_flags + launch,
+                                          KGPU_PEER_MAX_LAUNCHES, p->peer_epoch, dst, (size_t)nf * n_out, p->peer_timeout, p->aux_stream));
+                p->kernel_launches++;
+                if (pinned_out)
+                    CUDA_TRY(cudaMemcpyAsync(pinned_out + (size_t)done * n_out * bs, dst, (size_t)nf * n_out * 4, cudaMemcpyDeviceToHost, p->aux_stream));
+            }
+        } else if (pinned_out) {
             cudaStream_t cs = was_prepared ? stream : p->d2h_stream;
             if (!was_prepared) {
                 CUDA_TRY(cudaEventRecord(p->red_done[launch & 1], stream));
@@ -401,7 +441,13 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             CUDA_TRY(cudaMemcpyAsync(pinned_out + (size_t)done * n_out * bs, dst, (size_t)nf * n_out * 4, cudaMemcpyDeviceToHost, cs));
         }
     }
-    if (pinned_out && !was_prepared) { // `stream` ends after the last download
+    if (peer) {
+        if (p->peer_rank == 0) { // tell the ranks their slots are free again; `stream` ends after the last fold
+            CUDA_TRY(launch_signal_flag(p->peer_consumed, p->peer_epoch, p->aux_stream));
+            CUDA_TRY(cudaEventRecord(p->peer_ev[0], p->aux_stream));
+            CUDA_TRY(cudaStreamWaitEvent(stream, p->peer_ev[0], 0));
+        }
+    } else if (pinned_out && !was_prepared) { // `stream` ends after the last download
         CUDA_TRY(cudaEventRecord(p->red_done[0], p->d2h_stream));
         CUDA_TRY(cudaStreamWaitEvent(stream, p->red_done[0], 0));
     }
@@ -497,6 +543,9 @@ void kgpu_plan_destroy(kgpu_plan *p) {
         if (p->kern_done[i]) cudaEventDestroy(p->kern_done[i]);
         if (p->red_done[i]) cudaEventDestroy(p->red_done[i]);
     }
+    if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
+    for (cudaEvent_t e : p->peer_ev)
+        if (e) cudaEventDestroy(e);
     if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
     if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
     p->partials.release(); p->row_mask.release(); p->out.release(); p->sine.release(); p->tap_out.release();
@@ -676,6 +725,39 @@ float kgpu_plan_last_kernel_ms(kgpu_plan *p, uint32_t kernel_class, uint32_t *n_
 }
 
 uint64_t kgpu_plan_last_upload_bytes(kgpu_plan *p) { return p ? p->last_h2d_bytes : 0; }
+
+int kgpu_plan_set_peer_bus(kgpu_plan *p, uint32_t rank, uint32_t world, void *root_buffer, uint64_t buffer_bytes) {
+    if (!p) return fail(KGPU_ERR_INVALID, "kgpu_plan_set_peer_bus: NULL plan");
+    if (world <= 1 || !root_buffer) { // detach
+        p->peer_world = 0;
+        return KGPU_OK;
+    }
+    const uint64_t header = kgpu_peer_bus_header_bytes(world);
+    if (rank >= world || buffer_bytes <= header || ((uintptr_t)root_buffer & 15u))
+        return fail(KGPU_ERR_INVALID, "kgpu_plan_set_peer_bus: bad rank / buffer");
+    uint8_t *base = (uint8_t *)root_buffer;
+    p->peer_rank = rank;
+    p->peer_world = world;
+    p->peer_flags = (uint32_t *)base;
+    p->peer_consumed = p->peer_flags + (size_t)world * KGPU_PEER_MAX_LAUNCHES;
+    p->peer_timeout = p->peer_consumed + 1;
+    p->peer_slots = (float *)(base + header);
+    p->peer_slot_floats = ((buffer_bytes - header) / 4 / world) & ~(uint64_t)63;
+    p->peer_epoch = 0;
+    return KGPU_OK;
+}
+
+uint64_t kgpu_peer_bus_header_bytes(uint32_t world) { return (((uint64_t)world * KGPU_PEER_MAX_LAUNCHES + 2) * 4 + 255) & ~(uint64_t)255; }
+uint64_t kgpu_peer_bus_bytes(uint32_t world, uint64_t floats_per_rank) {
+    return kgpu_peer_bus_header_bytes(world) + (uint64_t)world * ((floats_per_rank + 63) & ~(uint64_t)63) * 4;
+}
+
+int kgpu_plan_peer_bus_timed_out(kgpu_plan *p) {
+    if (!p || !p->peer_world) return 0;
+    uint32_t v = 0;
+    if (cudaMemcpy(&v, p->peer_timeout, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int)v;
+}
 
 int kgpu_plan_set_host_threads(kgpu_plan *p, uint32_t n_threads) {
     if (!p) return fail(KGPU_ERR_INVALID, "kgpu_plan_set_host_threads: NULL plan");

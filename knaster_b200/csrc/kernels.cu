@@ -10,6 +10,8 @@
 //                   [block][channel][frame] output layout (graph.rs:850-864 + graph_gen.rs:205-224).
 //   fused kernels   see fused.cuh (register-resident specialisations for known voice shapes).
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <stdint.h>
 
 #include "dev.h"
@@ -347,25 +349,102 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
         for (uint32_t r = 0; r < n_regs; r++) a.regs[(size_t)r * a.n_voices + v] = sreg[r * 32];
 }
 
-// out[block][ch][i] = sum over partial rows feeding ch, rows in index order (deterministic)
-__global__ void reduce_bus(const float *__restrict__ partials, const uint32_t *__restrict__ row_mask, uint32_t n_rows,
-                           uint32_t n_frames, float *__restrict__ out, uint32_t n_out, uint32_t block_size) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_frames) return;
+// out[block][ch][i] = sum over the partial rows feeding ch (graph.rs:850-864 as a fixed tree):
+// the rows are cut into RB_GROUPS contiguous groups, each summed in row order by one thread per
+// frame (a warp reads 32 consecutive frames of a row: one 128-byte line), and the group sums are
+// folded left to right.  The order depends on n_rows only, so a render is bit-identical however it
+// is split into launches.  `out` may be peer memory (the multi-GPU bus slot on rank 0).
+constexpr int RB_GROUPS = 8, RB_FRAMES = 32;
+__global__ void __launch_bounds__(RB_GROUPS *RB_FRAMES) reduce_bus(const float *__restrict__ partials, const uint32_t *__restrict__ row_mask,
+                                                                    uint32_t n_rows, uint32_t n_frames, float *__restrict__ out,
+                                                                    uint32_t n_out, uint32_t block_size) {
+    __shared__ float part[RB_GROUPS][MAX_BUS][RB_FRAMES];
+    const uint32_t fi = threadIdx.x & (RB_FRAMES - 1), g = threadIdx.x / RB_FRAMES;
+    const uint32_t t = blockIdx.x * RB_FRAMES + fi;
+    const uint32_t per = (n_rows + RB_GROUPS - 1) / RB_GROUPS;
+    const uint32_t r0 = min(n_rows, g * per), r1 = min(n_rows, r0 + per);
     float acc[MAX_BUS];
 #pragma unroll
     for (int c = 0; c < MAX_BUS; c++) acc[c] = 0.f;
-    for (uint32_t r = 0; r < n_rows; r++) {
-        const float x = partials[(size_t)r * n_frames + t];
-        const uint32_t m = row_mask[r];
+    if (t < n_frames) {
+        const float *src = partials + t;
+        uint32_t r = r0;
+        for (; r + 4 <= r1; r += 4) { // four loads in flight per thread
+            const float x0 = src[(size_t)r * n_frames], x1 = src[(size_t)(r + 1) * n_frames];
+            const float x2 = src[(size_t)(r + 2) * n_frames], x3 = src[(size_t)(r + 3) * n_frames];
+            const uint32_t m0 = row_mask[r], m1 = row_mask[r + 1], m2 = row_mask[r + 2], m3 = row_mask[r + 3];
 #pragma unroll
-        for (int c = 0; c < MAX_BUS; c++)
-            if ((m >> c) & 1u) acc[c] = acc[c] + x;
+            for (int c = 0; c < MAX_BUS; c++) {
+                if ((m0 >> c) & 1u) acc[c] = acc[c] + x0;
+                if ((m1 >> c) & 1u) acc[c] = acc[c] + x1;
+                if ((m2 >> c) & 1u) acc[c] = acc[c] + x2;
+                if ((m3 >> c) & 1u) acc[c] = acc[c] + x3;
+            }
+        }
+        for (; r < r1; r++) {
+            const float x = src[(size_t)r * n_frames];
+            const uint32_t m = row_mask[r];
+#pragma unroll
+            for (int c = 0; c < MAX_BUS; c++)
+                if ((m >> c) & 1u) acc[c] = acc[c] + x;
+        }
     }
-    const uint32_t blk = t / block_size, i = t % block_size;
 #pragma unroll
     for (int c = 0; c < MAX_BUS; c++)
-        if (c < (int)n_out) out[((size_t)blk * n_out + c) * block_size + i] = acc[c];
+        if (c < (int)n_out) part[g][c][fi] = acc[c];
+    __syncthreads();
+    // thread (g = channel slot, fi): folds the groups of one channel of one frame
+    for (uint32_t c = g; c < n_out; c += RB_GROUPS) {
+        float sum = part[0][c][fi];
+#pragma unroll
+        for (int k = 1; k < RB_GROUPS; k++) sum = sum + part[k][c][fi];
+        if (t < n_frames) {
+            const uint32_t blk = t / block_size, i = t % block_size;
+            out[((size_t)blk * n_out + c) * block_size + i] = sum;
+        }
+    }
+}
+
+// ---- multi-GPU mix bus over peer memory (NVLink) ------------------------------------------------
+// Every rank's reduce_bus writes its bus straight into its slot of a buffer in rank 0's memory;
+// signal_flag then publishes "launch L of epoch E is there" with a system-scope release store, and
+// rank 0's sum_slots waits for all ranks' flags before it folds the slots (rank order: fixed).
+// Spins give up after ~2 s and raise *timeout_flag instead of hanging the device.
+KN_DEV uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+KN_DEV void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// epochs are compared as signed distances so that the counter may wrap
+KN_DEV bool spin_until_at_least(const uint32_t *flag, uint32_t epoch, uint32_t *timeout_flag) {
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
+        if (clock64() - t0 > 4000000000ll) {
+            if (timeout_flag) *timeout_flag = 1u;
+            return false;
+        }
+        __nanosleep(200);
+    }
+    return true;
+}
+
+__global__ void signal_flag(uint32_t *flag, uint32_t value) {
+    __threadfence_system();
+    st_release_sys(flag, value);
+}
+__global__ void wait_flag(const uint32_t *flag, uint32_t value, uint32_t *timeout_flag) { spin_until_at_least(flag, value, timeout_flag); }
+
+__global__ void sum_slots(const float *__restrict__ slots, size_t slot_stride, uint32_t world, const uint32_t *flags, uint32_t flag_stride,
+                          uint32_t epoch, float *__restrict__ out, size_t n, uint32_t *timeout_flag) {
+    if (threadIdx.x == 0)
+        for (uint32_t r = 0; r < world; r++) spin_until_at_least(flags + (size_t)r * flag_stride, epoch, timeout_flag);
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float acc = slots[i];
+        for (uint32_t r = 1; r < world; r++) acc = acc + slots[(size_t)r * slot_stride + i];
+        out[i] = acc;
+    }
 }
 
 // host-callable launchers ---------------------------------------------------------------------
@@ -382,8 +461,22 @@ cudaError_t launch_interp(const InterpArgs &a, uint32_t n_regs, uint32_t n_slots
 
 cudaError_t launch_reduce_bus(const float *partials, const uint32_t *row_mask, uint32_t n_rows, uint32_t n_frames, float *out,
                               uint32_t n_out, uint32_t block_size, cudaStream_t stream) {
-    const uint32_t threads = 128;
-    reduce_bus<<<(n_frames + threads - 1) / threads, threads, 0, stream>>>(partials, row_mask, n_rows, n_frames, out, n_out, block_size);
+    reduce_bus<<<(n_frames + RB_FRAMES - 1) / RB_FRAMES, RB_GROUPS * RB_FRAMES, 0, stream>>>(partials, row_mask, n_rows, n_frames, out, n_out, block_size);
+    return cudaGetLastError();
+}
+cudaError_t launch_signal_flag(uint32_t *flag, uint32_t value, cudaStream_t stream) {
+    signal_flag<<<1, 1, 0, stream>>>(flag, value);
+    return cudaGetLastError();
+}
+cudaError_t launch_wait_flag(const uint32_t *flag, uint32_t value, uint32_t *timeout_flag, cudaStream_t stream) {
+    wait_flag<<<1, 1, 0, stream>>>(flag, value, timeout_flag);
+    return cudaGetLastError();
+}
+cudaError_t launch_sum_slots(const float *slots, size_t slot_stride, uint32_t world, const uint32_t *flags, uint32_t flag_stride, uint32_t epoch,
+                             float *out, size_t n, uint32_t *timeout_flag, cudaStream_t stream) {
+    const uint32_t threads = 256;
+    const uint32_t blocks = (uint32_t)std::min<size_t>((n + threads - 1) / threads, 148 * 4);
+    sum_slots<<<std::max(1u, blocks), threads, 0, stream>>>(slots, slot_stride, world, flags, flag_stride, epoch, out, n, timeout_flag);
     return cudaGetLastError();
 }
 

@@ -29,6 +29,12 @@ cudaError_t launch_interp(const InterpArgs &a, uint32_t n_regs, uint32_t n_slots
 cudaError_t launch_reduce_bus(const float *partials, const uint32_t *row_mask, uint32_t n_rows, uint32_t n_frames, float *out,
                               uint32_t n_out, uint32_t block_size, cudaStream_t stream);
 
+// multi-GPU mix bus over peer memory (kernels.cu)
+cudaError_t launch_signal_flag(uint32_t *flag, uint32_t value, cudaStream_t stream);
+cudaError_t launch_wait_flag(const uint32_t *flag, uint32_t value, uint32_t *timeout_flag, cudaStream_t stream);
+cudaError_t launch_sum_slots(const float *slots, size_t slot_stride, uint32_t world, const uint32_t *flags, uint32_t flag_stride, uint32_t epoch,
+                             float *out, size_t n, uint32_t *timeout_flag, cudaStream_t stream);
+
 // fused bank kernels (fused.cu)
 struct FusedArgs {
     const DevProgram *prog;

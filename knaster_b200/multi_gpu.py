@@ -5,6 +5,15 @@ slice with its own plan, and the rank-local stereo mix bus is summed onto rank 0
 knaster has no counterpart (single process, single audio thread: README.md:25); the reduce is
 the distributed form of the graph-out Add chain (graph.rs:850-864).  There is no other data-path
 collective: voices are independent.
+
+Two ways to sum the bus:
+
+* ``PeerBus`` (GPUs of one NVLink/NVSwitch box): the engine's own bus-reduction kernel stores each
+  rank's bus straight into rank 0's memory and rank 0 folds the slots as the launches arrive
+  (include/knaster_gpu.h, kgpu_plan_set_peer_bus).  torch only provides the peer mapping
+  (``torch.distributed._symmetric_memory``); no collective runs in the data path.
+* ``reduce_bus``: a ``torch.distributed`` reduce of the rank-local bus (NCCL; gloo on CPU) -- the
+  fallback when peer memory is unavailable, and what the CPU tests exercise.
 """
 from __future__ import annotations
 
@@ -31,3 +40,37 @@ def reduce_bus(bus, dst: int = 0, chunks: int = 1):
         if b1 > b0:
             dist.reduce(bus[b0:b1], dst=dst)
     return bus
+
+
+class PeerBus:
+    """The multi-GPU mix bus over peer memory.  Allocate once per processor (every rank, same
+    arguments), then ``proc.render*`` sums all ranks' buses into RANK 0's output buffer.
+
+    torch symmetric memory gives every rank a device pointer to rank 0's allocation; the buffer
+    layout and the kernels that use it belong to the engine (kgpu_plan_set_peer_bus)."""
+
+    def __init__(self, proc, n_blocks: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _ffi
+
+        group = group or dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        lib = _ffi.lib()
+        floats = n_blocks * proc.block_size() * proc.outputs()
+        nbytes = int(lib.kgpu_peer_bus_bytes(self.world, floats))
+        self.buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group.group_name)
+        torch.cuda.synchronize()
+        dist.barrier(group)  # every rank's zero-fill is done before anyone's first store
+        self.proc = proc
+        proc.set_peer_bus(self.rank, self.world, int(self.hdl.buffer_ptrs[0]), nbytes)
+
+    def timed_out(self) -> bool:
+        return self.proc.peer_bus_timed_out()
+
+    def close(self) -> None:
+        self.proc.set_peer_bus(0, 0, 0, 0)

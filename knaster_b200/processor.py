@@ -197,6 +197,14 @@ class AudioProcessor:
         self._ensure_plan()
         _ffi.check(self._lib.kgpu_plan_set_blocks_per_launch(self._plan, blocks))
 
+    def set_peer_bus(self, rank: int, world: int, root_buffer_ptr: int, nbytes: int) -> None:
+        """Attach (or, with world <= 1, detach) the multi-GPU mix bus over peer memory."""
+        self._ensure_plan()
+        _ffi.check(self._lib.kgpu_plan_set_peer_bus(self._plan, rank, world, C.c_void_p(root_buffer_ptr or None), nbytes))
+
+    def peer_bus_timed_out(self) -> bool:
+        return bool(self._plan) and int(self._lib.kgpu_plan_peer_bus_timed_out(self._plan)) != 0
+
     def set_host_threads(self, n_threads: int) -> None:
         """Worker threads of the host event pipeline (0 = hardware threads - 1, at most 16)."""
         self._ensure_plan()
