@@ -1295,6 +1295,16 @@ struct StreamState {
     std::chrono::steady_clock::time_point t_begin = std::chrono::steady_clock::now();
 };
 
+#ifdef KGPU_PROFILE_HOST
+#include <x86intrin.h>
+namespace { thread_local uint64_t g_prof[8]; struct ProfDump { ~ProfDump() { fprintf(stderr, "[prof] select %.1f gather %.1f nodes %.1f (process_node %.1f) merge %.1f split %.1f Mcycles\n", g_prof[0]/1e6, g_prof[1]/1e6, g_prof[2]/1e6, g_prof[3]/1e6, g_prof[4]/1e6, g_prof[5]/1e6); } }; thread_local ProfDump g_prof_dump; }
+#define PROF_T(var) const uint64_t var = __rdtsc()
+#define PROF_ADD(i, a, b) g_prof[i] += (b) - (a)
+#else
+#define PROF_T(var)
+#define PROF_ADD(i, a, b)
+#endif
+
 namespace {
 // one voice, one launch window: what a separate render call over that window would do
 void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &tc, uint32_t gi, uint32_t v, size_t L,
@@ -1307,6 +1317,7 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     const uint64_t t0 = S.bounds[L], t1 = S.bounds[L + 1];
     const uint64_t wb0 = t0 / bs, wb1 = t1 / bs;
     const size_t gv = P.voice_base[gi] + v;
+    PROF_T(p0);
     // ready events of this voice inside the window (vorder is sorted by ready block inside a voice)
     uint32_t &cur = pg.cursor[v - pg.v_begin];
     const uint32_t e0 = cur, vend = P.vcount[gv + 1];
@@ -1323,6 +1334,8 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     const bool has_later = L == 0 && !ls.empty() && ls[v + 1] > ls[v];
     while (carry_pos < pg.carry.size() && pg.carry[carry_pos].voice < v) carry_pos++;
     const bool has_carry = carry_pos < pg.carry.size() && pg.carry[carry_pos].voice == v;
+    PROF_T(p1);
+    PROF_ADD(0, p0, p1);
     if (e0 == e1 && !P.voice_ramps[gv] && !has_later && !has_carry) return;
 
     auto key_less = [&](const VoiceEvent &a, const VoiceEvent &b) {
@@ -1351,6 +1364,8 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     }
     evp.clear();
     for (uint32_t k = e0; k < e1; k++) evp.push_back(&P.pending[P.vorder[k]]);
+    PROF_T(p2);
+    PROF_ADD(1, p1, p2);
     for (uint32_t li = 0; li < nn; li++) {
         HostNode &hn = g.host[(size_t)v * nn + li];
         node_ev.clear();
@@ -1359,12 +1374,17 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
         if (node_ev.empty() && !hn.ramp_active) continue;
         const bool was = hn.ramp_active;
         if (sk.run_start.back() != sk.buf.size()) sk.run_start.push_back((uint32_t)sk.buf.size());
+        PROF_T(q0);
         hn.ramp_active = process_node(P, sk, gi, v, li, node_ev.data(), node_ev.size(), wb0, wb1);
+        PROF_T(q1);
+        PROF_ADD(3, q0, q1);
         if (hn.ramp_active != was) {
             tc.ramp_delta += hn.ramp_active ? 1 : -1;
             P.voice_ramps[gv] += hn.ramp_active ? 1 : -1;
         }
     }
+    PROF_T(p3);
+    PROF_ADD(2, p2, p3);
     // order for the device: k-way merge of the per-node runs (each already in time order)
     sk.run_start.push_back((uint32_t)sk.buf.size());
     std::vector<VoiceEvent> *bufp = &sk.buf;
@@ -1387,6 +1407,8 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
             bufp = &sk.merged;
         }
     }
+    PROF_T(p4);
+    PROF_ADD(4, p3, p4);
     const bool last = L + 1 == S.n_launch;
     for (const VoiceEvent &ve : *bufp) {
         if (ve.frame >= t1) {
@@ -1398,6 +1420,8 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
         pg.ev[L].push_back(d);
         pg.cnt[L][v - pg.v_begin]++;
     }
+    PROF_T(p5);
+    PROF_ADD(5, p4, p5);
 }
 
 void stream_worker(HostPlan &P, StreamState &S, unsigned ti) {
@@ -1611,6 +1635,10 @@ void HostPlan::stream_end() {
     StreamState *S = stream;
     if (!S) return;
     if (S->pooled) workers().wait();
+#ifdef KGPU_PROFILE_HOST
+    fprintf(stderr, "[prof] select %.1f gather %.1f nodes %.1f (process_node %.1f) merge %.1f split %.1f Mcycles\n", g_prof[0]/1e6, g_prof[1]/1e6, g_prof[2]/1e6, g_prof[3]/1e6, g_prof[4]/1e6, g_prof[5]/1e6);
+    memset(g_prof, 0, sizeof g_prof);
+#endif
     stream = nullptr;
     std::unique_ptr<StreamState> guard(S);
     if (!S->any_work) return;
