@@ -113,6 +113,7 @@ struct kgpu_plan {
     DevBuf<float> out;
     DevBuf<float> sine;
     DevBuf<float> tap_out;
+    DevBuf<uint8_t> scratch;               // fused_scratch_bytes() of the largest group, reused launch after launch
     uint32_t n_rows = 0, n_taps = 0;
     uint64_t tap_frames = 0;
     uint64_t frame_clock = 0;
@@ -193,7 +194,11 @@ void choose_kernels(kgpu_plan *p) {
     for (uint32_t gi = 0; gi < p->gd.size(); gi++) {
         Group &g = p->host.groups[gi];
         GroupDev &d = p->gd[gi];
-        int recipe = p->force_interp ? -1 : match_fused_recipe(g.prog);
+        int recipe = p->force_interp ? -1 : match_fused_recipe(g.prog, p->host.block_size);
+        if (recipe == 2) // the block-table recipe needs every parameter change on a block boundary
+            for (const TemplateNode &tn : g.tpl.nodes)
+                for (const kgpu_wrapper_desc &w : tn.wrappers)
+                    if (w.kind == KGPU_WR_PRECISE_TIMING) recipe = -1;
         // a fused kernel can only tap signals that reach the bus (everything else lives in registers)
         if (recipe >= 0)
             for (auto &pin : d.pinned) {
@@ -394,6 +399,13 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
                 a.n_frames = nf; a.partials = p->partials.p; a.row0 = d.row0;
                 a.taps = d.taps.p; a.n_taps = (uint32_t)d.host_taps.size(); a.tap_out = p->tap_out.p;
                 a.tap_stride = total_frames; a.tap_frame0 = done * bs; a.sine_table = p->sine.p;
+                a.host_prog = &g.prog; a.block_size = bs;
+                const size_t sb = fused_scratch_bytes(d.recipe, g.n_voices, nf, bs);
+                if (sb > p->scratch.cap) {
+                    CUDA_TRY(cudaStreamSynchronize(stream)); // a queued launch may still use the old buffer
+                    p->scratch.ensure(sb);
+                }
+                a.scratch = p->scratch.p;
                 CUDA_TRY(launch_fused(d.recipe, a, stream));
             } else {
                 InterpArgs a{};
@@ -548,6 +560,7 @@ void kgpu_plan_destroy(kgpu_plan *p) {
         if (e) cudaEventDestroy(e);
     if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
     if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
+    p->scratch.release();
     p->partials.release(); p->row_mask.release(); p->out.release(); p->sine.release(); p->tap_out.release();
     for (cudaEvent_t e : p->kev) cudaEventDestroy(e);
     if (p->ev0) cudaEventDestroy(p->ev0);

@@ -950,21 +950,26 @@ bool match_fm2(const DevProgram &p) {
 
 } // namespace
 
-int match_fused_recipe(const DevProgram &p) {
+int match_fused_recipe(const DevProgram &p, uint32_t block_size) {
     if (match_sub_asr(p)) return 0;
     if (match_fm2(p)) return 1;
+    if (match_add_wt(p, block_size)) return 2;
     return -1;
 }
 const char *fused_recipe_name(int recipe) {
     switch (recipe) {
     case 0: return "render_sub_asr";
     case 1: return "render_fm2";
+    case 2: return "render_add_wt";
     default: return "render_interp";
     }
 }
 uint32_t fused_rows(int recipe, uint32_t n_voices, uint32_t n_ubus) {
-    (void)recipe;
-    return ((n_voices + 31) / 32) * n_ubus; // one partial row per warp
+    if (recipe == 2) return add_wt_slices(n_voices) * n_ubus; // one partial row per voice slice
+    return ((n_voices + 31) / 32) * n_ubus;                   // one partial row per warp
+}
+size_t fused_scratch_bytes(int recipe, uint32_t n_voices, uint32_t n_frames, uint32_t block_size) {
+    return recipe == 2 ? add_wt_scratch_bytes(n_voices, n_frames, block_size) : 0;
 }
 cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream) {
     if (recipe == 1) {
@@ -973,6 +978,7 @@ cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream) {
         else render_fm2<false><<<nw, 32, 0, stream>>>(a);
         return cudaGetLastError();
     }
+    if (recipe == 2) return launch_add_wt(a, stream);
     if (recipe != 0) return cudaErrorNotSupported;
     // one CTA per 32 voices: 512 CTAs spread over all 148 SMs (3-4 per SM)
     const uint32_t n_warps = (a.n_voices + 31) / 32;

@@ -481,7 +481,8 @@ cudaError_t launch_sum_slots(const float *slots, size_t slot_stride, uint32_t wo
 }
 
 #ifndef KGPU_HAVE_FUSED
-int match_fused_recipe(const DevProgram &) { return -1; }
+int match_fused_recipe(const DevProgram &, uint32_t) { return -1; }
+size_t fused_scratch_bytes(int, uint32_t, uint32_t, uint32_t) { return 0; }
 const char *fused_recipe_name(int) { return "render_interp"; }
 uint32_t fused_rows(int, uint32_t, uint32_t) { return 0; }
 cudaError_t launch_fused(int, const FusedArgs &, cudaStream_t) { return cudaErrorNotSupported; }

@@ -51,9 +51,21 @@ struct FusedArgs {
     uint64_t tap_stride;
     uint64_t tap_frame0;
     const float *sine_table;
+    const DevProgram *host_prog; // host copy of *prog (launch-time decisions)
+    uint32_t block_size;
+    void *scratch;               // fused_scratch_bytes() bytes of device memory, private to the launch
+    uint32_t *regs_out;          // recipe-internal: where a kernel leaves the launch-end registers (default: regs)
 };
 // number of partial rows a fused recipe produces for n_voices voices
 uint32_t fused_rows(int recipe, uint32_t n_voices, uint32_t n_ubus);
 cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream);
+// device scratch a recipe needs for one launch of n_frames frames (0 for most)
+size_t fused_scratch_bytes(int recipe, uint32_t n_voices, uint32_t n_frames, uint32_t block_size);
+
+// recipe 2 (fused_wt.cu)
+bool match_add_wt(const DevProgram &p, uint32_t block_size);
+uint32_t add_wt_slices(uint32_t n_voices);
+size_t add_wt_scratch_bytes(uint32_t n_voices, uint32_t n_frames, uint32_t block_size);
+cudaError_t launch_add_wt(const FusedArgs &a, cudaStream_t stream);
 
 } // namespace kgpu

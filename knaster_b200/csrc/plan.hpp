@@ -190,7 +190,7 @@ struct HostPlan {
 };
 
 // fused-kernel recipes (kernels.cu): returns recipe index or -1
-int match_fused_recipe(const DevProgram &p);
+int match_fused_recipe(const DevProgram &p, uint32_t block_size);
 const char *fused_recipe_name(int recipe);
 
 } // namespace kgpu

@@ -284,3 +284,56 @@ def test_two_warp_kernel_variant_matches():
         os.remove(path)
     assert np.array_equal(outs[0], outs[1])
     assert np.abs(outs[0]).max() > 1e-3
+
+
+# ---- additive wavetable bank (configs[1]): the time-parallel recipe -------------------------------
+def test_additive_bank_fused_kernel_without_taps():
+    # no taps: the unrolled accumulation path of render_add_wt; bus against the oracle's left fold
+    def build(graph):
+        banks.additive_bank(graph, 300, 1.0)
+        return []
+
+    out, _, proc = gpu_render(build, 750, outputs=2, taps=False)
+    ref, _ = oracle_render(build, 750, outputs=2)
+    assert proc.info()["kernels"] == ["render_add_wt"]
+    assert np.abs(out - ref).max() <= 1e-6
+    assert np.abs(ref).max() > 1e-3
+    # launch-split invariance and the interpreter agree bit for bit / within the summation order
+    out7, _, _ = gpu_render(build, 750, outputs=2, taps=False, blocks_per_launch=7)
+    assert np.array_equal(out7, out)
+    graph, p = AudioProcessor.new(0, 2, AudioProcessorOptions(force_interpreter=True))
+    build(graph)
+    assert np.abs(p.render(750) - out).max() <= 1e-6
+
+
+def test_additive_bank_full_size_properties():
+    # BASELINE.json configs[1]: 4096 partials, 10 s.  Launch-split invariance + determinism.
+    def render(bpl=0):
+        graph, proc = AudioProcessor.new(0, 2, AudioProcessorOptions())
+        banks.additive_bank(graph, 4096, 10.0)
+        if bpl:
+            proc.set_blocks_per_launch(bpl)
+        return proc.render(7500), proc
+
+    a, proc = render()
+    assert proc.info()["kernels"] == ["render_add_wt"]
+    b, _ = render(bpl=333)
+    assert np.array_equal(a, b)
+    assert np.isfinite(a).all() and 1e-3 < np.abs(a).max() < 1.0
+    assert np.array_equal(a[:, 0], a[:, 1])
+
+
+def test_sinwt_with_precise_timing_stays_on_the_interpreter():
+    # sample-accurate changes inside a block cannot be expressed per block: no fused recipe
+    def build(graph):
+        with graph.edit() as g:
+            v = g.push(kn.SinWt(330.0).wr_mul(0.5).precise_timing(4))
+            v.to_graph_out()
+            v.param("freq").set_at(500.0, at(1000))
+            v.param("wr_mul").set_at(0.25, at(1501))
+        return [v.id()]
+
+    out, taps, proc = gpu_render(build, 40)
+    ref, ref_taps = oracle_render(build, 40)
+    assert proc.info()["kernels"] == ["render_interp"]
+    assert np.array_equal(taps, ref_taps)
