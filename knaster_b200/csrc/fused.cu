@@ -819,7 +819,7 @@ bool match_sub_asr(const DevProgram &p) {
 // recipe 1 "render_fm2": (SinNumeric mod * idx + fc) -> SinNumeric.ar_params() "freq", * amp  (configs[3])
 // template order: 0 mod, 1 Constant idx, 2 Mul, 3 Constant fc, 4 Add, 5 car, 6 Constant amp, 7 Mul
 enum : uint32_t { F_MPH = 0, F_MOFF = 1, F_MINC = 2, F_IDX = 3, F_FC = 4, F_CPH = 5, F_COFF = 6, F_CINC = 7, F_AMP = 8, FM_NREGS = 9 };
-constexpr int FM_SUB = 4;
+constexpr int FM_SUB = 8; // frames per straight-line group: 16 independent f64 sine chains in flight
 
 struct FmVoice {
     float mph, moff, minc, idx, fc, cph, coff, cinc, amp;
@@ -839,18 +839,33 @@ struct FmVoice {
         }
     }
     // one frame in graph order: mod.process, Mul, Add, WrArParams(car): freq(v) then process, Mul
-    KN_DEV float tick(float sr, float rc_sr) {
-        const float m = kn_sinf((mph + moff) * KN_TAU);          // osc.rs:264
-        mph = mph + minc;
-        if (mph > 1.0f) mph = mph - 1.0f;                        // osc.rs:266-268
+    // INRANGE: |phase_offset| < 16 on both oscillators, so every sine argument is below 120 and the
+    // branch-free restatement applies: the frames of a group then form one basic block and their
+    // (long, f64) sine chains overlap
+    template <bool INRANGE> KN_DEV float tick(float sr, float rc_sr) {
+        const float am = (mph + moff) * KN_TAU;
+        const float m = INRANGE ? kn_sinf_glibc_inrange(am) : kn_sinf(am);  // osc.rs:264
+        const float mn = mph + minc;
+        mph = mn > 1.0f ? mn - 1.0f : mn;                        // osc.rs:266-268
         const float v = m * idx + fc;                            // MathUGen<Mul>, MathUGen<Add>
         // audio_rate.rs:42-57 + osc.rs:240-242: phase_increment = F::new(v as f64) / F::new(sr as f32)
-        cinc = fabsf(v) > 1e-20f ? div_rc(v, sr, rc_sr) : v / sr;
-        const float c = kn_sinf((cph + coff) * KN_TAU);
-        cph = cph + cinc;
-        if (cph > 1.0f) cph = cph - 1.0f;
+        if (INRANGE) {
+            // div_rc needs a quotient well inside the normal range: tiny numerators are scaled by 2^64
+            // (exact) and the quotient scaled back (exact unless it is subnormal, |v| < 6e-34, where
+            // the last bit of a 1e-45 increment cannot move a phase)
+            const bool tiny = fabsf(v) <= 1e-20f;
+            const float q = div_rc(tiny ? v * 0x1p64f : v, sr, rc_sr);
+            cinc = tiny ? q * 0x1p-64f : q;
+        } else {
+            cinc = fabsf(v) > 1e-20f ? div_rc(v, sr, rc_sr) : v / sr;
+        }
+        const float ac = (cph + coff) * KN_TAU;
+        const float c = INRANGE ? kn_sinf_glibc_inrange(ac) : kn_sinf(ac);
+        const float cn = cph + cinc;
+        cph = cn > 1.0f ? cn - 1.0f : cn;
         return c * amp;
     }
+    KN_DEV bool inrange() const { return fabsf(moff) < 16.0f && fabsf(coff) < 16.0f && fabsf(mph) <= 2.0f && fabsf(cph) <= 2.0f; }
 };
 
 template <bool TAPS>
@@ -879,16 +894,17 @@ __global__ void __launch_bounds__(32, 8) render_fm2(FusedArgs a) {
             if (a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
 
     float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
+    bool all_inrange = __all_sync(0xFFFFFFFFu, !active || s.inrange());
     for (uint32_t f0 = 0; f0 < a.n_frames; f0 += SUB_TILE) {
         const uint32_t nf = min((uint32_t)SUB_TILE, a.n_frames - f0);
 #pragma unroll 1
         for (uint32_t g0 = 0; g0 < SUB_TILE; g0 += FM_SUB) {
             const uint32_t gf = f0 + g0;
             const bool ev_group = __any_sync(0xFFFFFFFFu, next_frame < gf + FM_SUB);
-            if (!ev_group && g0 + FM_SUB <= nf) {
+            if (!ev_group && all_inrange && g0 + FM_SUB <= nf) {
 #pragma unroll
                 for (int k = 0; k < FM_SUB; k++) {
-                    const float o = s.tick(sr, rc_sr);
+                    const float o = s.tick<true>(sr, rc_sr);
                     st[(g0 + k) * SUB_PAD + lane] = active ? o : 0.f;
                     if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o;
                 }
@@ -897,13 +913,16 @@ __global__ void __launch_bounds__(32, 8) render_fm2(FusedArgs a) {
                 for (uint32_t k = 0; k < FM_SUB; k++) {
                     float o = 0.f;
                     if (g0 + k < nf) {
+                        bool touched = false;
                         while (next_frame <= gf + k) {
                             const DevEvent e = a.events[cur];
                             if (e.op == OP_SET) s.set(e.reg, e.value);
                             cur++;
                             next_frame = cur < end ? a.events[cur].frame : 0xFFFFFFFFu;
+                            touched = true;
                         }
-                        o = s.tick(sr, rc_sr);
+                        if (__any_sync(0xFFFFFFFFu, touched)) all_inrange = __all_sync(0xFFFFFFFFu, !active || s.inrange());
+                        o = s.tick<false>(sr, rc_sr);
                         if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o;
                     }
                     st[(g0 + k) * SUB_PAD + lane] = active ? o : 0.f;

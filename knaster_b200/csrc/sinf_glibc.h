@@ -32,8 +32,18 @@ KN_SINF_HD double kn_fma(double a, double b, double c) {
 #endif
 }
 
-// Returns true and the sine in *out for |y| < 120 (glibc's reduce_fast domain); false otherwise.
-KN_SINF_HD bool kn_sinf_glibc(float y, float *out) {
+// glibc's sinf for |y| < 120 (its reduce_fast domain).
+//
+// glibc branches three ways (|y| < 2^-12: y itself; |y| < pi/4: sine polynomial without reduction;
+// else reduce and pick the sine or cosine polynomial by the quadrant's parity).  On a GPU those
+// branches diverge in every warp, so the same arithmetic is laid out straight-line here:
+//   * for |y| < pi/4 the reduction yields n = 0 and leaves x untouched, so the general path IS the
+//     small-argument path;
+//   * both polynomials are evaluated (they share x2) and one is selected -- a diverged warp would
+//     execute both anyway;
+//   * |y| < 2^-12 still returns y (select), which also keeps the sign of -0.
+// Every f64 operation is the one glibc performs for the selected path, in the same order.
+KN_SINF_HD float kn_sinf_glibc_inrange(float y) { // requires |y| < 120
     const double HPI_INV = 0x1.45F306DC9C883p+23; // 2^24 / (pi/2)
     const double HPI = 0x1.921FB54442D18p0;       // pi/2
     const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
@@ -47,16 +57,8 @@ KN_SINF_HD bool kn_sinf_glibc(float y, float *out) {
 #endif
     const uint32_t top = (iy >> 20) & 0x7ff;          // abstop12
     double x = (double)y;
-    if (top < 0x3f4) {                                // |y| < pi/4  (abstop12(0x1.921FB6p-1f) = 0x3f4)
-        if (top < 0x398) {                            // |y| < 2^-12: sin(y) = y to f32 precision
-            *out = y;
-            return true;
-        }
-        const double x2 = x * x, x3 = x * x2, s1 = kn_fma(x2, S3, S2), x7 = x3 * x2, s = kn_fma(x3, S1, x);
-        *out = (float)kn_fma(x7, s1, s);
-        return true;
-    }
-    if (top >= 0x42f) return false;                   // |y| >= 120: large-argument reduction not restated
+    // reduce_fast.  glibc skips it for |y| < pi/4 (abstop12 < 0x3f4); there |r| < 2^23, so n = 0 and
+    // fma(-0, HPI, x) == x: running it unconditionally changes nothing
     const double r = x * HPI_INV;
 #if defined(__CUDA_ARCH__)
     const int n = (__double2int_rz(r) + 0x800000) >> 24;
@@ -65,17 +67,37 @@ KN_SINF_HD bool kn_sinf_glibc(float y, float *out) {
 #endif
     x = kn_fma(-(double)n, HPI, x);
     const double x2 = x * x;
-    double res;
-    if ((n & 1) == 0) {                               // sine polynomial (odd in x)
-        const double x3 = x * x2, s1 = kn_fma(x2, S3, S2), x7 = x3 * x2, s = kn_fma(x3, S1, x);
-        res = kn_fma(x7, s1, s);
-        if (((n + 1) & 2) != 0) res = -res;           // sign table {1,-1,-1,1}[n & 3]
-    } else {                                          // cosine polynomial (even in x)
-        const double x4 = x2 * x2, c2 = kn_fma(x2, C4, C3), c1 = kn_fma(x2, C1, C0), x6 = x4 * x2, c = kn_fma(x4, C2, c1);
-        res = kn_fma(x6, c2, c);
-        if ((n & 2) != 0) res = -res;                 // __sincosf_table[1]: negated cosine coefficients
-    }
-    *out = (float)res;
+    // sine polynomial (odd in x); sign table {1,-1,-1,1}[n & 3]
+    const double x3 = x * x2, s1 = kn_fma(x2, S3, S2), x7 = x3 * x2, sp = kn_fma(x3, S1, x);
+    const double rs = kn_fma(x7, s1, sp);
+    // cosine polynomial (even in x); __sincosf_table[1] (negated coefficients) when n & 2
+    const double x4 = x2 * x2, c2 = kn_fma(x2, C4, C3), c1 = kn_fma(x2, C1, C0), x6 = x4 * x2, cp = kn_fma(x4, C2, c1);
+    double rc = kn_fma(x6, c2, cp);
+    double rs_ = rs;
+#if defined(__CUDA_ARCH__)
+    // keep both polynomials unconditional: nvcc would otherwise sink each into a branch on the
+    // quadrant's parity, and a diverging branch per sine ends the basic block (no overlap of the
+    // frames' f64 chains)
+    asm volatile("" : "+d"(rs_), "+d"(rc));
+#endif
+    const bool odd = (n & 1) != 0;
+    const bool neg = odd ? (n & 2) != 0 : ((n + 1) & 2) != 0;
+    double res = odd ? rc : rs_;
+    res = neg ? -res : res;
+    return top < 0x398 ? y : (float)res;              // |y| < 2^-12: sin(y) = y to f32 precision
+}
+
+// Returns true and the sine in *out for |y| < 120 (glibc's reduce_fast domain); false otherwise
+// (the large-argument reduction is not restated).
+KN_SINF_HD bool kn_sinf_glibc(float y, float *out) {
+    uint32_t iy;
+#if defined(__CUDA_ARCH__)
+    iy = __float_as_uint(y);
+#else
+    memcpy(&iy, &y, 4);
+#endif
+    if (((iy >> 20) & 0x7ff) >= 0x42f) return false;  // abstop12(120.0f)
+    *out = kn_sinf_glibc_inrange(y);
     return true;
 }
 
