@@ -37,6 +37,7 @@ enum ArCode : uint8_t {
     AR_SINWT_OFFSET = 4,  // offset = ((f64)v * 65536) as u32  osc.rs:133-135
     AR_POLYBLEP_FREQ = 5, // dt = v / sr                       polyblep.rs:163-165,181-184
     AR_REG0 = 6,          // regs[0] = v (Constant.value, TestInPlusParam.number)
+    AR_POLYBLEP_PW = 7,   // pulse_width = v                   polyblep.rs:167-170
     AR_POST = 8,          // AR_POST + k: value of arithmetic wrapper k = v (wr_mul)   math.rs:92-98
 };
 

@@ -39,6 +39,8 @@ enum : uint32_t {
 struct SubVoice {
     float t, dt;
     uint32_t use_sin;
+    float pw;      // pulse_width and waveform: only the generic tick reads them (straight-line code = Sawtooth)
+    uint32_t wf;
     float ic1, ic2, a1, a2, a3, m0, m1, m2;
     uint32_t est;
     float et, ar, rr, sc, gain;
@@ -48,6 +50,8 @@ struct SubVoice {
         case R_T: t = f; break;
         case R_DT: dt = f; break;
         case R_USESIN: use_sin = bits; break;
+        case R_PW: pw = f; break;
+        case R_WF: wf = bits; break;
         case R_IC1: ic1 = f; break;
         case R_IC2: ic2 = f; break;
         case R_A1: a1 = f; break;
@@ -62,12 +66,12 @@ struct SubVoice {
         case R_RR: rr = f; break;
         case R_SC: sc = f; break;
         case R_GAIN: gain = f; break;
-        default: break; // pulse_width / waveform: not read by the sawtooth path
+        default: break;
         }
     }
     // reference-order evaluation, any parameter values (used on tiles with events / odd dt)
     KN_DEV float tick() {
-        const float saw = polyblep_saw_tick(t, dt, use_sin);
+        const float saw = polyblep_tick(t, dt, use_sin, pw, wf);
         const float y = svf_tick(saw, ic1, ic2, a1, a2, a3, m0, m1, m2);
         const float e = envasr_tick(est, et, ar, rr, sc) * gain; // WrMul, wrappers_core/math.rs:63-67
         return y * e;                                            // MathUGen<Mul>, math.rs:45-47
@@ -224,7 +228,7 @@ KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc
 
 // per-lane validity of the straight-line formulation
 KN_DEV bool sub_lane_fast(const SubVoice &s) {
-    return s.dt >= 9.5367431640625e-7f && s.dt < 0.25f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin;
+    return s.dt >= 9.5367431640625e-7f && s.dt < 0.25f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin && s.wf == 0u;
 }
 KN_DEV bool sub_lane_lp(const SubVoice &s) { return s.m0 == 0.0f && s.m1 == 0.0f && s.m2 == 1.0f; }
 
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
 #pragma unroll
         for (int i = 0; i < SUB_NREGS; i++) s.set(i, r[i]);
     } else { // idle lane: a silent voice whose arithmetic stays finite (its output is +-0)
-        s.t = 0.f; s.dt = 0.125f; s.use_sin = 0;
+        s.t = 0.f; s.dt = 0.125f; s.use_sin = 0; s.pw = 0.5f; s.wf = 0;
         s.ic1 = s.ic2 = s.a1 = s.a2 = s.a3 = s.m0 = s.m1 = 0.f; s.m2 = 1.f;
         s.est = ASR_STOPPED; s.et = 0.f; s.ar = s.rr = 1.f; s.sc = 0.f; s.gain = 0.f;
     }
@@ -448,6 +452,8 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
         // parameter registers change only through events: write them back as well
         a.regs[(size_t)R_DT * V + v] = __float_as_uint(s.dt);
         a.regs[(size_t)R_USESIN * V + v] = s.use_sin;
+        a.regs[(size_t)R_PW * V + v] = __float_as_uint(s.pw);
+        a.regs[(size_t)R_WF * V + v] = s.wf;
         a.regs[(size_t)R_A1 * V + v] = __float_as_uint(s.a1);
         a.regs[(size_t)R_A2 * V + v] = __float_as_uint(s.a2);
         a.regs[(size_t)R_A3 * V + v] = __float_as_uint(s.a3);
@@ -492,8 +498,8 @@ KN_DEV bool ev_is_osc(const DevEvent &e) { return e.op == OP_SET && e.reg <= R_W
 template <bool OSC> KN_DEV void cursor_skip(EvCursor &ec) {
     while (ec.next_frame != 0xFFFFFFFFu && ev_is_osc(ec.e0) != OSC) ec.pop();
 }
-KN_DEV bool osc_lane_fast(float t, float dt, uint32_t use_sin) {
-    return dt >= 9.5367431640625e-7f && dt < 0.25f && t >= 0.0f && t < 1.0f && !use_sin;
+KN_DEV bool osc_lane_fast(float t, float dt, uint32_t use_sin, uint32_t wf) {
+    return dt >= 9.5367431640625e-7f && dt < 0.25f && t >= 0.0f && t < 1.0f && !use_sin && wf == 0u;
 }
 
 template <int N> KN_DEV void osc_group(float &t, float dt, float omd, float rc, float *dst) {
@@ -509,17 +515,19 @@ template <int N> KN_DEV void osc_group(float &t, float dt, float omd, float rc, 
 
 KN_DEV void sub2_osc_role(const FusedArgs &a, float *ring, uint32_t lane, uint32_t v, bool active) {
     const uint32_t V = a.n_voices;
-    float t = 0.f, dt = 0.125f;
-    uint32_t use_sin = 0;
+    float t = 0.f, dt = 0.125f, pw = 0.5f;
+    uint32_t use_sin = 0, wf = 0;
     if (active) {
         t = __uint_as_float(a.regs[(size_t)R_T * V + v]);
         dt = __uint_as_float(a.regs[(size_t)R_DT * V + v]);
         use_sin = a.regs[(size_t)R_USESIN * V + v];
+        pw = __uint_as_float(a.regs[(size_t)R_PW * V + v]);
+        wf = a.regs[(size_t)R_WF * V + v];
     }
     EvCursor ec;
     ec.init(a.events, a.ev_off, v, active);
     cursor_skip<true>(ec);
-    bool lane_fast = osc_lane_fast(t, dt, use_sin);
+    bool lane_fast = osc_lane_fast(t, dt, use_sin, wf);
     bool all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
     float omd = 1.0f - dt, rc = div_prep(dt);
     uint32_t next_ev = __reduce_min_sync(0xFFFFFFFFu, ec.next_frame);
@@ -544,6 +552,8 @@ KN_DEV void sub2_osc_role(const FusedArgs &a, float *ring, uint32_t lane, uint32
                         if (ec.e0.reg == R_T) t = val;
                         else if (ec.e0.reg == R_DT) dt = val;
                         else if (ec.e0.reg == R_USESIN) use_sin = ec.e0.value;
+                        else if (ec.e0.reg == R_PW) pw = val;
+                        else if (ec.e0.reg == R_WF) wf = ec.e0.value;
                         ec.pop();
                         cursor_skip<true>(ec);
                         touched = true;
@@ -551,7 +561,7 @@ KN_DEV void sub2_osc_role(const FusedArgs &a, float *ring, uint32_t lane, uint32
                     if (touched) {
                         omd = 1.0f - dt;
                         rc = div_prep(dt);
-                        lane_fast = osc_lane_fast(t, dt, use_sin);
+                        lane_fast = osc_lane_fast(t, dt, use_sin, wf);
                     }
                     all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
                     next_ev = __reduce_min_sync(0xFFFFFFFFu, ec.next_frame);
@@ -566,8 +576,8 @@ KN_DEV void sub2_osc_role(const FusedArgs &a, float *ring, uint32_t lane, uint32
                         t = wrap01(t + dt);
                         y = saw_eval(ph, dt, omd, rc);
                     } else {
-                        y = polyblep_saw_tick(t, dt, use_sin);
-                        lane_fast = osc_lane_fast(t, dt, use_sin); // t is back in [0,1) after one generic tick
+                        y = polyblep_tick(t, dt, use_sin, pw, wf);
+                        lane_fast = osc_lane_fast(t, dt, use_sin, wf); // t is back in [0,1) after one generic tick
                     }
                     *dst = y;
                     all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
@@ -580,6 +590,8 @@ KN_DEV void sub2_osc_role(const FusedArgs &a, float *ring, uint32_t lane, uint32
         a.regs[(size_t)R_T * V + v] = __float_as_uint(t);
         a.regs[(size_t)R_DT * V + v] = __float_as_uint(dt);
         a.regs[(size_t)R_USESIN * V + v] = use_sin;
+        a.regs[(size_t)R_PW * V + v] = __float_as_uint(pw);
+        a.regs[(size_t)R_WF * V + v] = wf;
     }
 }
 

@@ -173,21 +173,30 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             case DK_POLYBLEP: {
                 float t = __uint_as_float(sreg[rb * 32]), dt = __uint_as_float(sreg[(rb + 1) * 32]);
                 uint32_t use_sin = sreg[(rb + 2) * 32];
+                float pw = __uint_as_float(sreg[(rb + 3) * 32]);
+                uint32_t wf = sreg[(rb + 4) * 32];
                 for (uint32_t f = 0; f < nf; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(t),
-                              (t = __uint_as_float(sreg[rb * 32]), dt = __uint_as_float(sreg[(rb + 1) * 32]), use_sin = sreg[(rb + 2) * 32]))
+                              (t = __uint_as_float(sreg[rb * 32]), dt = __uint_as_float(sreg[(rb + 1) * 32]), use_sin = sreg[(rb + 2) * 32],
+                               pw = __uint_as_float(sreg[(rb + 3) * 32]), wf = sreg[(rb + 4) * 32]))
                     for (int ai = 0; ai < dn.n_ar; ai++) {
                         float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
                         if (dn.ar_code[ai] == AR_POLYBLEP_FREQ) {
                             dt = x / sr;
                             use_sin = (dt * sr >= sr / 4.0f) ? 1u : 0u;
+                        } else if (dn.ar_code[ai] == AR_POLYBLEP_PW) {
+                            pw = x;
                         } else pv[dn.ar_code[ai] - AR_POST] = x;
                     }
-                    float y = polyblep_saw_tick(t, dt, use_sin);
+                    float y = polyblep_tick(t, dt, use_sin, pw, wf);
                     EMIT(f, 0, y)
                 }
                 sreg[rb * 32] = __float_as_uint(t);
-                if (dn.n_ar) { sreg[(rb + 1) * 32] = __float_as_uint(dt); sreg[(rb + 2) * 32] = use_sin; }
+                if (dn.n_ar) {
+                    sreg[(rb + 1) * 32] = __float_as_uint(dt);
+                    sreg[(rb + 2) * 32] = use_sin;
+                    sreg[(rb + 3) * 32] = __float_as_uint(pw);
+                }
                 break;
             }
             case DK_SVF: {

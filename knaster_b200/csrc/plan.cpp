@@ -115,8 +115,7 @@ void validate_node(const kgpu_node_desc &d, uint32_t idx) {
             KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: MathUGen with %u channels (1..%d supported)", idx, d.channels, MAX_OUT);
         if (d.mode > KGPU_OP_DIV) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: MathUGen Pow is not supported yet", idx);
     }
-    if (d.kind == KGPU_POLYBLEP && d.mode != 0)
-        KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: PolyBlep waveform %u not supported yet (Sawtooth only)", idx, d.mode);
+    if (d.kind == KGPU_POLYBLEP && d.mode > 13) KGPU_THROW(KGPU_ERR_INVALID, "node %u: bad PolyBlep Waveform %u", idx, d.mode);
     if (d.kind == KGPU_SVF && d.mode > 8) KGPU_THROW(KGPU_ERR_INVALID, "node %u: bad SvfFilterType %u", idx, d.mode);
     if (d.kind == KGPU_ENVELOPE) {
         if (d.n_segments < 1 || !d.segments) KGPU_THROW(KGPU_ERR_INVALID, "node %u: Envelope needs >= 1 segment", idx);
@@ -257,9 +256,7 @@ void ugen_param_apply(Sim &s, uint32_t param, const PV &v, uint64_t frame) {
             s.set_f(frame, r + 1, dt);
             s.set_u(frame, r + 2, (dt * sr >= sr / 4.0f) ? 1u : 0u); // guard of next_sample, polyblep.rs:210
         } else if (param == 1) s.set_f(frame, r + 3, (float)v.f);
-        else if (param == 2) {
-            if ((int64_t)v.f != 0) s.out.ignored++; // unsupported waveform change: kept as Sawtooth (rejected at push)
-        }
+        else if (param == 2) s.set_u(frame, r + 4, (uint32_t)(int64_t)v.f); // polyblep.rs:172-175
         break;
     case KGPU_SVF: { // svf.rs:81-133
         if (param == 0) h.f0 = (float)v.f;
@@ -562,7 +559,10 @@ uint8_t ar_code_for(const TemplateNode &tn, uint32_t param, int ar_level) {
     switch (tn.kind) {
     case KGPU_SIN_NUMERIC: if (param == 0) return AR_SINNUM_FREQ; if (param == 1) return AR_SINNUM_OFFSET; break;
     case KGPU_SIN_WT: if (param == 0) return AR_SINWT_FREQ; if (param == 1) return AR_SINWT_OFFSET; break;
-    case KGPU_POLYBLEP: if (param == 0) return AR_POLYBLEP_FREQ; break;
+    case KGPU_POLYBLEP:
+        if (param == 0) return AR_POLYBLEP_FREQ;
+        if (param == 1) return AR_POLYBLEP_PW;
+        break;
     case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: if (param == 0) return AR_REG0; break;
     default: break;
     }
@@ -1148,8 +1148,8 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
             const char want = r.want;
             bool ok = want == 't' || (want == 'f' && e.value_kind == 1) || (want == 'i' && e.value_kind == 3) || (want == 'b' && e.value_kind == 4);
             if (!ok) KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: wrong value type for node %u param %u", i, e.node, e.param);
-            if (r.polyblep_wave && (int64_t)e.value != 0)
-                KGPU_THROW(KGPU_ERR_UNSUPPORTED, "event %zu: PolyBlep waveform %lld not supported yet", i, (long long)e.value);
+            if (r.polyblep_wave && ((int64_t)e.value < 0 || (int64_t)e.value > 13))
+                KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: bad PolyBlep Waveform %lld", i, (long long)e.value);
             if (r.svf_type && ((int64_t)e.value < 0 || (int64_t)e.value > 8))
                 KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: bad SvfFilterType", i);
         }

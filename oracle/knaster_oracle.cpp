@@ -283,7 +283,8 @@ inline F boz(F t) { return truncf(t); } // polyblep.rs:70-72
 
 struct PolyBlep : UGenT<PolyBlep, 0, 1, 3> {
     // polyblep.rs:90-120 enum Waveform
-    enum { Sawtooth = 0, Sine, Cosine, Triangle, Square, Rectangle, Ramp };
+    enum { Sawtooth = 0, Sine, Cosine, Triangle, Square, Rectangle, Ramp, ModifiedTriangle, ModifiedSquare,
+           HalfWaveRectifiedSine, FullWaveRectifiedSine, TriangularPulse, TrapezoidFixed, TrapezoidVariable };
     int waveform;
     F sample_rate = 0.f, freq_in_hz, dt = 0.f, pulse_width = 0.5f, t = 0.f; // polyblep.rs:139-148
     PolyBlep(int wf, F f) : waveform(wf), freq_in_hz(f) {}
@@ -338,6 +339,107 @@ struct PolyBlep : UGenT<PolyBlep, 0, 1, 3> {
         y += 4.0f * dt * (blamp(t1, dt) - blamp(t2, dt));
         return y;
     }
+    inline F fold4() { // the 4t fold shared by tri / trap / trap2, polyblep.rs:286-292
+        F y = t * 4.0f;
+        if (y >= 3.0f) y -= 4.0f;
+        else if (y > 1.0f) y = 2.0f - y;
+        return y;
+    }
+    static inline F clamp1(F x) { return x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x); } // f32::clamp(-1, 1)
+    inline F w_half() { // polyblep.rs:251-266
+        F t2 = t + 0.5f;
+        t2 -= boz(t2);
+        F y = t < 0.5f ? 2.0f * sinf(t * F_TAU) - 2.0f / F_PI : -2.0f / F_PI;
+        y += F_TAU * dt * (blamp(t, dt) + blamp(t2, dt));
+        return y;
+    }
+    inline F w_full() { // polyblep.rs:268-276
+        F _t = t + 0.25f;
+        _t -= boz(_t);
+        F y = 2.0f * sinf(_t * F_PI) - 4.0f / F_PI;
+        y += F_TAU * dt * blamp(_t, dt);
+        return y;
+    }
+    inline F w_tri2() { // polyblep.rs:301-324
+        F pw = pulse_width;
+        if (pw > 0.9999f) pw = 0.9999f; // .min(0.9999).max(0.0001)
+        if (pw < 0.0001f) pw = 0.0001f;
+        F t1 = t + 0.5f * pw;
+        t1 -= boz(t1);
+        F t2 = t + 1.0f - 0.5f * pw;
+        t2 -= boz(t2);
+        F y = t * 2.0f;
+        if (y >= 2.0f - pw) y = (y - 2.0f) / pw;
+        else if (y >= pw) y = 1.0f - (y - pw) / (1.0f - pw);
+        else y /= pw;
+        y += dt / (pw - pw * pw) * (blamp(t1, dt) - blamp(t2, dt));
+        return y;
+    }
+    inline F w_trip() { // polyblep.rs:326-353
+        const F pw = pulse_width;
+        F t1 = t + 0.75f + 0.5f * pw;
+        t1 -= boz(t1);
+        F y;
+        if (t1 >= pw) {
+            y = -pw;
+        } else {
+            y = 4.0f * t1;
+            y = y >= 2.0f * pw ? 4.0f - y / pw - pw : y / pw - pw;
+        }
+        if (pw > 0.0f) {
+            F t2 = t1 + 1.0f - 0.5f * pw;
+            t2 -= boz(t2);
+            F t3 = t1 + 1.0f - pw;
+            t3 -= boz(t3);
+            y += 2.0f * dt / pw * (blamp(t1, dt) - 2.0f * blamp(t2, dt) + blamp(t3, dt));
+        }
+        return y;
+    }
+    inline F w_trap() { // polyblep.rs:355-388
+        F y = clamp1(2.0f * fold4());
+        F t1 = t + 0.125f;
+        t1 -= boz(t1);
+        F t2 = t1 + 0.5f;
+        t2 -= boz(t2);
+        y += 4.0f * dt * (blamp(t1, dt) - blamp(t2, dt)); // triangle #1
+        t1 = t + 0.375f;
+        t1 -= boz(t1);
+        t2 = t1 + 0.5f;
+        t2 -= boz(t2);
+        y += 4.0f * dt * (blamp(t1, dt) - blamp(t2, dt)); // triangle #2
+        return y;
+    }
+    inline F w_trap2() { // polyblep.rs:390-432
+        F pw = pulse_width < 0.9999f ? pulse_width : 0.9999f;
+        const F scale = 1.0f / (1.0f - pw);
+        F y = clamp1(scale * fold4());
+        F t1 = t + 0.25f - 0.25f * pw;
+        t1 -= boz(t1);
+        F t2 = t1 + 0.5f;
+        t2 -= boz(t2);
+        y += scale * 2.0f * dt * (blamp(t1, dt) - blamp(t2, dt));
+        t1 = t + 0.25f + 0.25f * pw;
+        t1 -= boz(t1);
+        t2 = t1 + 0.5f;
+        t2 -= boz(t2);
+        y += scale * 2.0f * dt * (blamp(t1, dt) - blamp(t2, dt));
+        return y;
+    }
+    inline F w_sqr2() { // polyblep.rs:449-473
+        F t1 = t + 0.875f + 0.25f * (pulse_width - 0.5f);
+        t1 -= boz(t1);
+        F t2 = t + 0.375f + 0.25f * (pulse_width - 0.5f);
+        t2 -= boz(t2);
+        F y = t1 < 0.5f ? 1.0f : -1.0f; // square #1
+        y += blep(t1, dt) - blep(t2, dt);
+        t1 += 0.5f * (1.0f - pulse_width);
+        t1 -= boz(t1);
+        t2 += 0.5f * (1.0f - pulse_width);
+        t2 -= boz(t2);
+        y += t1 < 0.5f ? 1.0f : -1.0f; // square #2
+        y += blep(t1, dt) - blep(t2, dt);
+        return 0.5f * y;
+    }
     inline F next_sample() { // polyblep.rs:209-230
         if (get_freq_in_hz() >= sample_rate / 4.0f) return w_sin();
         switch (waveform) {
@@ -347,6 +449,13 @@ struct PolyBlep : UGenT<PolyBlep, 0, 1, 3> {
         case Square: return w_sqr();
         case Rectangle: return w_rect();
         case Ramp: return w_ramp();
+        case ModifiedTriangle: return w_tri2();
+        case ModifiedSquare: return w_sqr2();
+        case HalfWaveRectifiedSine: return w_half();
+        case FullWaveRectifiedSine: return w_full();
+        case TriangularPulse: return w_trip();
+        case TrapezoidFixed: return w_trap();
+        case TrapezoidVariable: return w_trap2();
         default: return w_saw();
         }
     }
@@ -1039,7 +1148,7 @@ std::unique_ptr<UGen> make_ugen(const ko_node_desc &d) {
     case KO_SIN_WT: u.reset(new SinWt((F)d.args[0])); break;
     case KO_SIN_NUMERIC: u.reset(new SinNumeric((F)d.args[0])); break;
     case KO_POLYBLEP:
-        if (d.mode > PolyBlep::Ramp) { g_last_error = "oracle: PolyBlep waveform not restated"; return nullptr; }
+        if (d.mode > PolyBlep::TrapezoidVariable) { g_last_error = "oracle: bad PolyBlep waveform"; return nullptr; }
         u.reset(new PolyBlep((int)d.mode, (F)d.args[0]));
         break;
     case KO_SVF: u.reset(new SvfFilter((int)d.mode, (F)d.args[0], (F)d.args[1], (F)d.args[2])); break;

@@ -229,10 +229,45 @@ def test_all_svf_types_and_math_ops():
     assert proc.info()["n_groups"] == 10   # 9 filter types are 9 different voice shapes + the wrapper chain
 
 
+def test_all_polyblep_waveforms():
+    # polyblep.rs:90-120: all 14 waveforms, three pitches each (one above the sr/4 sine guard), with
+    # pulse-width changes, a waveform switch by event and an audio-rate pulse width
+    def build(graph):
+        ids = []
+        with graph.edit() as g:
+            for wf in kn.Waveform:
+                for k, f in enumerate((55.0, 1234.5, 12500.0)):
+                    osc = g.push(kn.PolyBlep(wf, f).precise_timing(4))
+                    osc.to_graph_out()
+                    osc.param("pulse_width").set_at(0.2 + 0.1 * k, kn.Seconds.from_samples(3000 + 7 * int(wf), SR))
+                    osc.param("pulse_width").set_at(0.93, kn.Seconds.from_samples(9000, SR))
+                    osc.param("freq").set_at(f * 1.5 if k < 2 else 300.0, kn.Seconds.from_samples(6000 + k, SR))
+                    ids.append(osc.id())
+            sw = g.push(kn.PolyBlep(kn.Waveform.Sawtooth, 220.0).precise_timing(4))
+            sw.to_graph_out()
+            for i, wf in enumerate(kn.Waveform):
+                sw.param("waveform").set_at(int(wf), kn.Seconds.from_samples(800 * (i + 1) + i, SR))
+            ids.append(sw.id())
+            lfo = g.push(kn.SinWt(3.0))
+            pwm = g.push(kn.PolyBlep(kn.Waveform.Rectangle, 110.0).ar_params())
+            pwm.link("pulse_width", lfo * 0.4 + 0.5)
+            pwm.to_graph_out()
+            ids.append(pwm.id())
+        return ids
+
+    gpu, ref, gt, rt, proc = both(build, 200, outputs=1)
+    assert np.isfinite(rt).all()
+    assert np.abs(gt - rt).max() <= 1e-5
+    assert np.abs(gpu - ref).max() <= 1e-4     # 44 voices summed in a different order
+    assert (np.abs(rt).max(axis=1) > 0.3).all()
+
+
 def test_unsupported_graph_fails_loudly_on_gpu_too():
     graph, p = AudioProcessor.new(0, 1, AudioProcessorOptions())
     with graph.edit() as g:
-        g.push(kn.PolyBlep(kn.Waveform.Triangle, 100.0)).to_graph_out()
+        a = g.push(kn.SinWt(100.0))
+        b = g.push(kn.SinWt(3.0))
+        a.pow(b).to_graph_out()          # MathUGen<Pow>: not built yet
     from knaster_b200._ffi import KgpuError
 
     with pytest.raises(KgpuError):

@@ -264,8 +264,17 @@ def test_unsupported_shapes_are_rejected_not_faked():
 
     g = Graph(0, 1, 64, SR)
     with g.edit() as e:
-        e.push(kn.PolyBlep(kn.Waveform.Square, 100.0)).to_graph_out()
-    expect_error(g, _ffi.KGPU_ERR_UNSUPPORTED)          # waveform not built yet
+        a = e.push(kn.SinWt(100.0))
+        b = e.push(kn.SinWt(3.0))
+        a.pow(b).to_graph_out()
+    expect_error(g, _ffi.KGPU_ERR_UNSUPPORTED)          # MathUGen<Pow> not built yet
+
+    g = Graph(0, 1, 64, SR)
+    with g.edit() as e:
+        n = e.push(kn.PolyBlep(kn.Waveform.Square, 100.0))
+        n.to_graph_out()
+        n.param("waveform").set(14)
+    expect_error(g, _ffi.KGPU_ERR_PARAMETER)            # no such Waveform
 
     g = Graph(0, 1, 64, SR)
     with g.edit() as e:
