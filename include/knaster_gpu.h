@@ -49,11 +49,15 @@ typedef enum {
     KGPU_MATH = 10,              /* math.rs:94-165       no params; inputs a0..aN-1,b0..bN-1                */
     KGPU_CONSTANT = 11,          /* util.rs:37-64        params: 0 value                                    */
     KGPU_TEST_NUM = 12,          /* knaster_graph/src/tests/utils.rs:4-17  (reference test fixture)          */
-    KGPU_TEST_IN_PLUS_PARAM = 13 /* knaster_graph/src/tests/utils.rs:20-67 (reference test fixture)          */
+    KGPU_TEST_IN_PLUS_PARAM = 13,/* knaster_graph/src/tests/utils.rs:20-67 (reference test fixture)          */
+    KGPU_MATH1 = 14,             /* math.rs:167-305      Math1UGen: 1 in, 1 out, no params; mode = kgpu_math1_op */
+    KGPU_PHASOR = 15             /* osc.rs:170-213       params: 0 freq (f64 phase, 0..1 ramp)               */
 } kgpu_ugen_kind;
 
 /* kgpu_node_desc.mode for KGPU_MATH (math.rs:22-85) */
 typedef enum { KGPU_OP_ADD = 0, KGPU_OP_SUB = 1, KGPU_OP_MUL = 2, KGPU_OP_DIV = 3, KGPU_OP_POW = 4 } kgpu_math_op;
+/* kgpu_node_desc.mode for KGPU_MATH1 (math.rs:172-243) */
+typedef enum { KGPU_OP1_CEIL = 0, KGPU_OP1_SQRT = 1, KGPU_OP1_FLOOR = 2, KGPU_OP1_TRUNC = 3, KGPU_OP1_FRACT = 4, KGPU_OP1_EXP = 5 } kgpu_math1_op;
 
 /* Wrappers (knaster_core_dsp/src/wrappers_core.rs:26-56), listed innermost first. */
 typedef enum {
@@ -63,8 +67,8 @@ typedef enum {
     KGPU_WR_VSUB = 4,            /* math.rs:272-349  value - x */
     KGPU_WR_DIV = 5,             /* math.rs:351-427 */
     KGPU_WR_VDIV = 6,            /* math.rs:429-505  value / x */
-    KGPU_WR_POWF = 7,            /* rejected: KGPU_ERR_UNSUPPORTED ("next" row) */
-    KGPU_WR_POWI = 8,            /* rejected: KGPU_ERR_UNSUPPORTED ("next" row) */
+    KGPU_WR_POWF = 7,            /* math.rs:507-583  x.powf(value) */
+    KGPU_WR_POWI = 8,            /* math.rs:586-661  x.powi(value), value = the i32 exponent */
     KGPU_WR_SMOOTH_PARAMS = 9,   /* smooth_params.rs */
     KGPU_WR_PRECISE_TIMING = 10, /* precise_timing.rs; capacity = DELAYED_CHANGES_PER_BLOCK */
     KGPU_WR_AR_PARAMS = 11       /* audio_rate.rs:11-85 */

@@ -14,9 +14,9 @@ CUDA library is missing.
 """
 from .graph import (Graph, GraphEdit, GraphError, Parameter, ParameterError, ParameterSmoothing, PTrigger,
                     SchedulingEvent, Seconds, SH, Time)
-from .ugens import (Constant, EnvAr, EnvAsr, Envelope, EnvelopeSegment, MathOp, MathUGen, OnePoleHpf,
-                    OnePoleLpf, PolyBlep, SinNumeric, SinWt, SvfFilter, SvfFilterType, TestInPlusParamUGen,
-                    TestNumUGen, UGen, Waveform)
+from .ugens import (Constant, EnvAr, EnvAsr, Envelope, EnvelopeSegment, Math1Op, Math1UGen, MathOp, MathUGen,
+                    OnePoleHpf, OnePoleLpf, Phasor, PolyBlep, SinNumeric, SinWt, SvfFilter, SvfFilterType,
+                    TestInPlusParamUGen, TestNumUGen, UGen, Waveform)
 
 __all__ = [n for n in dir() if not n.startswith("_")]
 

@@ -20,13 +20,15 @@ enum DevKind : uint8_t {
     DK_MATH = 10,    // no regs                                                            math.rs:94-100
     DK_CONST = 11,   // regs: 0 value   (Constant and the TestNumUGen fixture)             util.rs:37-40
     DK_INPLUS = 12,  // regs: 0 number  (TestInPlusParamUGen fixture)
+    DK_MATH1 = 13,   // no regs; mode = kgpu_math1_op                                      math.rs:167-305
+    DK_PHASOR = 14,  // regs: 0,1 phase(f64) 2,3 step(f64)                                 osc.rs:170-213
 };
 enum { REGS_SINWT = 3, REGS_SINNUM = 3, REGS_POLYBLEP = 5, REGS_SVF = 8, REGS_ONEPOLE = 3, REGS_ENV = 5,
-       REGS_ENVELOPE_BASE = 8, REGS_ENVELOPE_PER_SEG = 6, REGS_CONST = 1 };
+       REGS_ENVELOPE_BASE = 8, REGS_ENVELOPE_PER_SEG = 6, REGS_CONST = 1, REGS_PHASOR = 4 };
 enum { ASR_STOPPED = 0, ASR_ATTACKING = 1, ASR_SUSTAINING = 2, ASR_RELEASING = 3 };
 
 // arithmetic wrappers applied to a node's outputs, innermost first (wrappers_core/math.rs)
-enum PostOp : uint8_t { PO_MUL = 1, PO_ADD = 2, PO_SUB = 3, PO_VSUB = 4, PO_DIV = 5, PO_VDIV = 6 };
+enum PostOp : uint8_t { PO_MUL = 1, PO_ADD = 2, PO_SUB = 3, PO_VSUB = 4, PO_DIV = 5, PO_VDIV = 6, PO_POWF = 7, PO_POWI = 8 };
 
 // audio-rate parameter routes (WrArParams, audio_rate.rs:42-57): what to do with the sample
 enum ArCode : uint8_t {

@@ -307,6 +307,27 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 }
                 break;
             }
+            case DK_MATH1: {
+                const int is = dn.in_slot[0];
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, (void)0, (void)0)
+                    AR_POST_ROUTES(f)
+                    float y = math1_apply(dn.mode, is >= 0 ? sval[(is * CH + f) * 32] : 0.f);
+                    EMIT(f, 0, y)
+                }
+                break;
+            }
+            case DK_PHASOR: {
+                double phase = ld_d(sreg, rb), step = ld_d(sreg, rb + 2);
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, st_d(sreg, rb, phase), (phase = ld_d(sreg, rb), step = ld_d(sreg, rb + 2)))
+                    AR_POST_ROUTES(f)
+                    float y = phasor_tick(phase, step);
+                    EMIT(f, 0, y)
+                }
+                st_d(sreg, rb, phase);
+                break;
+            }
             case DK_CONST:
             case DK_INPLUS: {
                 float val = __uint_as_float(sreg[rb * 32]);

@@ -89,6 +89,8 @@ KindInfo kind_info(const kgpu_node_desc &d) {
     case KGPU_CONSTANT: return {0, 1, 1, DK_CONST, REGS_CONST};
     case KGPU_TEST_NUM: return {0, 1, 0, DK_CONST, REGS_CONST};
     case KGPU_TEST_IN_PLUS_PARAM: return {1, 1, 1, DK_INPLUS, REGS_CONST};
+    case KGPU_MATH1: return {1, 1, 0, DK_MATH1, 0};
+    case KGPU_PHASOR: return {0, 1, 1, DK_PHASOR, REGS_PHASOR};
     default: KGPU_THROW(KGPU_ERR_UNSUPPORTED, "unknown ugen kind %u", d.kind);
     }
 }
@@ -102,7 +104,7 @@ const char *param_types(uint32_t kind) {
     case KGPU_ENV_ASR: return "fftt";
     case KGPU_ENV_AR: return "fft";
     case KGPU_ENVELOPE: return "fitt";
-    case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: return "f";
+    case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: case KGPU_PHASOR: return "f";
     default: return "";
     }
 }
@@ -113,8 +115,9 @@ void validate_node(const kgpu_node_desc &d, uint32_t idx) {
     if (d.kind == KGPU_MATH) {
         if (d.channels < 1 || d.channels > (uint32_t)MAX_OUT)
             KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: MathUGen with %u channels (1..%d supported)", idx, d.channels, MAX_OUT);
-        if (d.mode > KGPU_OP_DIV) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: MathUGen Pow is not supported yet", idx);
+        if (d.mode > KGPU_OP_POW) KGPU_THROW(KGPU_ERR_INVALID, "node %u: bad MathUGen operation %u", idx, d.mode);
     }
+    if (d.kind == KGPU_MATH1 && d.mode > KGPU_OP1_EXP) KGPU_THROW(KGPU_ERR_INVALID, "node %u: bad Math1UGen operation %u", idx, d.mode);
     if (d.kind == KGPU_POLYBLEP && d.mode > 13) KGPU_THROW(KGPU_ERR_INVALID, "node %u: bad PolyBlep Waveform %u", idx, d.mode);
     if (d.kind == KGPU_SVF && d.mode > 8) KGPU_THROW(KGPU_ERR_INVALID, "node %u: bad SvfFilterType %u", idx, d.mode);
     if (d.kind == KGPU_ENVELOPE) {
@@ -125,7 +128,6 @@ void validate_node(const kgpu_node_desc &d, uint32_t idx) {
     int n_post = 0, n_ar = 0, n_smooth = 0, n_precise = 0;
     for (uint32_t i = 0; i < d.n_wrappers; i++) {
         uint32_t k = d.wrappers[i].kind;
-        if (k == KGPU_WR_POWF || k == KGPU_WR_POWI) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %u: WrPowf/WrPowi are not supported yet", idx);
         if (is_math_wrapper(k)) n_post++;
         else if (k == KGPU_WR_AR_PARAMS) {
             n_ar++;
@@ -249,6 +251,9 @@ void ugen_param_apply(Sim &s, uint32_t param, const PV &v, uint64_t frame) {
         else if (param == 1) s.set_f(frame, r + 1, (float)v.f);
         else if (param == 2) s.set_f(frame, r + 0, 0.0f);
         break;
+    case KGPU_PHASOR: // osc.rs:191-197
+        if (param == 0) s.set_d(frame, r + 2, v.f * h.d0);
+        break;
     case KGPU_POLYBLEP: // polyblep.rs:162-184
         if (param == 0) {
             h.f0 = (float)v.f;
@@ -351,6 +356,7 @@ void wr_param_apply(Sim &s, int level, uint32_t param, const PV &v, uint64_t fra
         wr_param_apply(s, level - 1, param, v, frame);
         return;
     case KGPU_WR_ADD: case KGPU_WR_SUB: case KGPU_WR_VSUB: case KGPU_WR_DIV: case KGPU_WR_VDIV:
+    case KGPU_WR_POWF: case KGPU_WR_POWI:
         wr_param_apply(s, level - 1, param, v, frame);
         return;
     case KGPU_WR_AR_PARAMS: // audio_rate.rs:70-74
@@ -602,7 +608,7 @@ void compile_template(Group &g, uint32_t sample_rate, const std::vector<std::pai
         for (size_t l = 0; l < tn.wrappers.size(); l++) {
             uint32_t k = tn.wrappers[l].kind;
             if (is_math_wrapper(k)) {
-                dn.post_op[dn.n_post] = (uint8_t)k; // PO_* == KGPU_WR_* for 1..6
+                dn.post_op[dn.n_post] = (uint8_t)k; // PO_* == KGPU_WR_* for 1..8
                 dn.post_reg[dn.n_post] = (uint16_t)reg;
                 post_regs[i].push_back((uint16_t)reg);
                 dn.n_post++;
@@ -916,6 +922,15 @@ void HostPlan::build(const kgpu_graph_desc &d) {
                 case KGPU_SIN_NUMERIC: { // osc.rs:231-237,253-261
                     float f = (float)nd.args[0];
                     R(r + 2, v) = fbits(f / sr);
+                    break;
+                }
+                case KGPU_PHASOR: { // osc.rs:179-202: phase 0; init(): step = freq * (1 / sr), all f64
+                    h.d0 = 1.0 / (double)sample_rate;
+                    uint32_t lo, hi;
+                    dbits(0.0, lo, hi);
+                    R(r + 0, v) = lo; R(r + 1, v) = hi;
+                    dbits(nd.args[0] * h.d0, lo, hi);
+                    R(r + 2, v) = lo; R(r + 3, v) = hi;
                     break;
                 }
                 case KGPU_POLYBLEP: { // polyblep.rs:139-155

@@ -855,6 +855,43 @@ struct MathUGen : UGen {
     void param_apply(Ctx &, size_t, const ParamValue &) override {}
 };
 // knaster_core_dsp/src/ugens/util.rs:37-64
+// Math1UGen: math.rs:167-305 (Operation1 = Ceil / Sqrt / Floor / Trunc / Fract / Exp)
+struct Math1UGen : UGenT<Math1UGen, 1, 1, 0> {
+    int op;
+    explicit Math1UGen(int op_) : op(op_) {}
+    inline void tick(Ctx &, const F *in, F *out) {
+        const F a = in[0];
+        switch (op) {
+        case 0: out[0] = ceilf(a); break;        // math.rs:172-183
+        case 1: out[0] = sqrtf(a); break;        // :184-195
+        case 2: out[0] = floorf(a); break;       // :196-207
+        case 3: out[0] = truncf(a); break;       // :208-219
+        case 4: out[0] = a - truncf(a); break;   // :220-231  f32::fract = self - self.trunc()
+        default: out[0] = expf(a); break;        // :232-243
+        }
+    }
+    void param_apply(Ctx &, size_t, const ParamValue &) override {}
+};
+
+// Phasor: osc.rs:170-213.  All f64; the output is F::new(phase).
+struct Phasor : UGenT<Phasor, 0, 1, 1> {
+    double phase = 0.0, step, mult = 0.0;
+    explicit Phasor(double freq) : step(freq) {}
+    void set_freq(double f) { step = mult == 0.0 ? f : f * mult; } // osc.rs:191-197
+    void init(uint32_t sr, size_t) override {                      // osc.rs:199-202
+        mult = 1.0 / (double)sr;
+        set_freq(step);
+    }
+    inline void tick(Ctx &, const F *, F *out) {                   // osc.rs:204-212
+        out[0] = (F)phase;
+        phase += step;
+        while (phase >= 1.0) phase -= 1.0;
+    }
+    void param_apply(Ctx &, size_t index, const ParamValue &v) override {
+        if (index == 0 && v.kind == PK::Float) set_freq(v.f);
+    }
+};
+
 struct Constant : UGenT<Constant, 0, 1, 1> {
     F value;
     explicit Constant(F v) : value(v) {}
@@ -1170,6 +1207,11 @@ std::unique_ptr<UGen> make_ugen(const ko_node_desc &d) {
     case KO_CONSTANT: u.reset(new Constant((F)d.args[0])); break;
     case KO_TEST_NUM: u.reset(new TestNumUGen((F)d.args[0])); break;
     case KO_TEST_IN_PLUS_PARAM: u.reset(new TestInPlusParam()); break;
+    case KO_MATH1:
+        if (d.mode > 5) { g_last_error = "oracle: bad Math1UGen operation"; return nullptr; }
+        u.reset(new Math1UGen((int)d.mode));
+        break;
+    case KO_PHASOR: u.reset(new Phasor(d.args[0])); break;
     default: g_last_error = "oracle: unknown ugen kind"; return nullptr;
     }
     for (uint32_t i = 0; i < d.n_wrappers; i++) {

@@ -46,6 +46,8 @@ enum {
     KO_CONSTANT = 11,
     KO_TEST_NUM = 12,           /* reference test fixture TestNumUGen */
     KO_TEST_IN_PLUS_PARAM = 13, /* reference test fixture TestInPlusParamUGen */
+    KO_MATH1 = 14,              /* Math1UGen, mode: 0 Ceil 1 Sqrt 2 Floor 3 Trunc 4 Fract 5 Exp */
+    KO_PHASOR = 15,
 };
 /* MathUGen ops */
 enum { KO_OP_ADD = 0, KO_OP_SUB = 1, KO_OP_MUL = 2, KO_OP_DIV = 3, KO_OP_POW = 4 };

@@ -262,12 +262,53 @@ def test_all_polyblep_waveforms():
     assert (np.abs(rt).max(axis=1) > 0.3).all()
 
 
+def test_math1_pow_phasor_and_pow_wrappers():
+    # math.rs:72-85,172-243 (Pow, Ceil/Sqrt/Floor/Trunc/Fract/Exp), osc.rs:170-213 (Phasor),
+    # wrappers_core/math.rs:507-661 (WrPowf, WrPowi).  powf / expf come from libm in knaster and from
+    # CUDA's math library here (<= 2 ulp): compared relative to the signal peak.
+    def build(graph):
+        ids = []
+        with graph.edit() as g:
+            ph = g.push(kn.Phasor(3.7).precise_timing(2))
+            ph.param("freq").set_at(911.3, kn.Seconds.from_samples(5000, SR))
+            ids.append(ph.id())
+            ph.to_graph_out()
+            for op in kn.Math1Op:
+                src = g.push(kn.SinWt(97.0 + 11 * int(op)).wr_mul(3.0).wr_add(3.5 if op == kn.Math1Op.Sqrt else 0.0))
+                m = g.push(kn.Math1UGen(op))
+                src.to(m).to_graph_out()
+                ids.append(m.id())
+            a = g.push(kn.SinWt(220.0).wr_mul(0.5).wr_add(1.0))      # base in [0.5, 1.5]
+            b = g.push(kn.Phasor(2.0).wr_mul(4.0).wr_sub(2.0))        # exponent in [-2, 2]
+            p = a.pow(b)
+            p.to_graph_out()
+            ids.append(p._outputs[0][0])
+            w1 = g.push(kn.SinWt(330.0).wr_mul(0.4).wr_add(0.6).wr_powf(2.5))
+            w2 = g.push(kn.SinWt(331.0).wr_powi(5))
+            w3 = g.push(kn.SinWt(332.0).wr_add(1.5).wr_powi(-3))
+            for w in (w1, w2, w3):
+                w.to_graph_out()
+                ids.append(w.id())
+        return ids
+
+    gpu, ref, gt, rt, _ = both(build, 300, outputs=1)
+    assert np.isfinite(rt).all() and np.isfinite(gt).all()
+    peak = np.maximum(1.0, np.abs(rt).max(axis=1, keepdims=True))
+    assert (np.abs(gt - rt) / peak).max() <= 1e-6
+    assert np.array_equal(gt[0], rt[0])            # Phasor: f64 phase, bit-identical
+    for i in (1, 2, 3, 4, 5):                      # Ceil, Sqrt, Floor, Trunc, Fract: IEEE-exact
+        assert np.array_equal(gt[i], rt[i])
+    assert np.array_equal(gt[-2], rt[-2]) and np.array_equal(gt[-1], rt[-1])   # powi: multiplications only
+    assert np.abs(gpu - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
 def test_unsupported_graph_fails_loudly_on_gpu_too():
     graph, p = AudioProcessor.new(0, 1, AudioProcessorOptions())
     with graph.edit() as g:
-        a = g.push(kn.SinWt(100.0))
-        b = g.push(kn.SinWt(3.0))
-        a.pow(b).to_graph_out()          # MathUGen<Pow>: not built yet
+        lfo = g.push(kn.SinWt(3.0))
+        f = g.push(kn.SvfFilter(kn.SvfFilterType.Low, 500.0, 1.0, 0.0).ar_params())
+        f.link("cutoff_freq", lfo * 100.0 + 500.0)   # audio-rate route into filter coefficients: not built yet
+        g.push(kn.SinWt(100.0)).to(f).to_graph_out()
     from knaster_b200._ffi import KgpuError
 
     with pytest.raises(KgpuError):

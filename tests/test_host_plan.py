@@ -264,10 +264,11 @@ def test_unsupported_shapes_are_rejected_not_faked():
 
     g = Graph(0, 1, 64, SR)
     with g.edit() as e:
-        a = e.push(kn.SinWt(100.0))
-        b = e.push(kn.SinWt(3.0))
-        a.pow(b).to_graph_out()
-    expect_error(g, _ffi.KGPU_ERR_UNSUPPORTED)          # MathUGen<Pow> not built yet
+        lfo = e.push(kn.SinWt(3.0))
+        f = e.push(kn.SvfFilter(kn.SvfFilterType.Low, 500.0, 1.0, 0.0).ar_params())
+        f.link("cutoff_freq", lfo * 100.0 + 500.0)
+        e.push(kn.SinWt(100.0)).to(f).to_graph_out()
+    expect_error(g, _ffi.KGPU_ERR_UNSUPPORTED)          # audio-rate route into filter coefficients: not built yet
 
     g = Graph(0, 1, 64, SR)
     with g.edit() as e:
@@ -276,10 +277,6 @@ def test_unsupported_shapes_are_rejected_not_faked():
         n.param("waveform").set(14)
     expect_error(g, _ffi.KGPU_ERR_PARAMETER)            # no such Waveform
 
-    g = Graph(0, 1, 64, SR)
-    with g.edit() as e:
-        e.push(kn.SinWt(100.0).wr_powf(2.0)).to_graph_out()
-    expect_error(g, _ffi.KGPU_ERR_UNSUPPORTED)
 
     g = Graph(0, 1, 64, SR)
     with g.edit() as e:
