@@ -1,0 +1,37 @@
+"""Output sinks for rendered audio: the step after the hot path.
+
+``save_to_disk`` mirrors ``Buffer::save_to_disk`` (knaster_core_dsp/src/dsp/buffer.rs:315-331): a
+16-bit PCM WAVE file, samples interleaved by frame, each ``(x * i16::MAX) as i16`` -- Rust's ``as``
+truncates toward zero and saturates (NaN -> 0)."""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+
+def to_pcm16(audio: np.ndarray) -> np.ndarray:
+    """[n_blocks, channels, block] f32 (the engine's RawContiguousBlock layout per block,
+    block.rs:449-456) -> interleaved int16 [frames * channels]."""
+    a = np.asarray(audio, dtype=np.float32)
+    if a.ndim != 3:
+        raise ValueError("expected [n_blocks, channels, block_size]")
+    inter = np.ascontiguousarray(a.transpose(0, 2, 1)).reshape(-1)          # frame-major, channel-minor
+    scaled = inter * np.float32(32767.0)                                    # F::from(i16::MAX)
+    scaled = np.where(np.isnan(scaled), np.float32(0.0), scaled)
+    return np.clip(np.trunc(scaled), -32768.0, 32767.0).astype(np.int16)    # `as i16`
+
+
+def save_to_disk(audio: np.ndarray, path: str, sample_rate: int) -> None:
+    """Write `audio` as a 16-bit PCM WAVE file (hound::WavSpec {bits_per_sample: 16, Int})."""
+    a = np.asarray(audio)
+    channels = a.shape[1]
+    pcm = to_pcm16(a)
+    data = pcm.astype("<i2").tobytes()
+    block_align = channels * 2
+    header = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE"
+    header += b"fmt " + struct.pack("<IHHIIHH", 16, 1, channels, sample_rate, sample_rate * block_align, block_align, 16)
+    header += b"data" + struct.pack("<I", len(data))
+    with open(path, "wb") as f:
+        f.write(header)
+        f.write(data)
