@@ -230,7 +230,7 @@ def main():
     ap.add_argument("--force-interpreter", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-voices", type=int, default=4096)
-    ap.add_argument("--cpu-seconds", type=float, default=2.0)
+    ap.add_argument("--cpu-seconds", type=float, default=4.0)
     ap.add_argument("--ref-seconds", type=float, default=1.0, help="--impl reference: audio seconds per step")
     args = ap.parse_args()
 

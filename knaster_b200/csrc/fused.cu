@@ -172,6 +172,13 @@ KN_DEV float sum16(const float *p) {
     return (s0 + s1) + (s2 + s3);
 }
 
+// the first level of sum16's tree over 8 voices: (s0 + s1) of the canonical order
+KN_DEV float sum8(const float *p) {
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+    const float4 a = q[0], b = q[1];
+    return ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+}
+
 // N frames, no events, no envelope transition, fast conditions hold for every lane: the three
 // recurrences (phase, envelope, filter) are independent dependency chains that ptxas interleaves
 // in one basic block.  LP: m0 == 0, m1 == 0, m2 == 1 (lowpass) for every lane, where
@@ -185,10 +192,14 @@ KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc
     float ph[N], env[N];
     if (SUM) {
         float tot;
-        if (N == 32) { // lane = frame: all 32 voices
+        if (N == 32) {        // lane = frame: all 32 voices
             tot = sum16(sum_src) + sum16(sum_src + 16);
-        } else {       // N == 16: lane = (frame, voice half)
+        } else if (N == 16) { // lane = (frame, voice half)
             const float h = sum16(sum_src);
+            tot = h + __shfl_xor_sync(0xFFFFFFFFu, h, 16);
+        } else {              // N == 8: lane = (frame, voice quarter); same tree: ((q0 + q1) + (q2 + q3))
+            const float q = sum8(sum_src);
+            const float h = q + __shfl_xor_sync(0xFFFFFFFFu, q, 8);
             tot = h + __shfl_xor_sync(0xFFFFFFFFu, h, 16);
         }
         if (sum_store) *sum_dst = tot;
@@ -368,12 +379,13 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
             if (rows) flush();
             uint32_t half = 0;
             bool pending = false;
-            const uint32_t r = SUB_SUB == 32 ? lane : (lane & 15u), c = SUB_SUB == 32 ? 0u : (lane >> 4);
+            // lane = (staged frame r, voice group c of 32 / (32 / SUB_SUB) voices)
+            const uint32_t r = lane & (SUB_SUB - 1u), c = lane / SUB_SUB, cw = SUB_SUB == 32 ? 32u : (SUB_SUB == 16 ? 16u : 8u);
 #pragma unroll 1
             do {
                 __syncwarp();
                 sub_group_fast<LP, SUB_SUB, TAPS, true>(s, d, omd, rc, st + (half * SUB_SUB) * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr,
-                                                        st + ((half ^ 1u) * SUB_SUB + r) * SUBW_PAD + c * 16, prow + (f - SUB_SUB + r),
+                                                        st + ((half ^ 1u) * SUB_SUB + r) * SUBW_PAD + c * cw, prow + (f - SUB_SUB + r),
                                                         pending && c == 0);
                 pending = true;
                 half ^= 1u;
