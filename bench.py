@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SR, BLOCK = 48000, 64
-W_FLOPS = {"subtractive": 40.0, "additive": 6.0, "fm": 15.0}  # algorithmic ops / voice-sample
+W_FLOPS = {"subtractive": 40.0, "subtractive_seg": 42.0, "additive": 6.0, "fm": 15.0}  # algorithmic ops / voice-sample (Envelope: 7 f64 + cvt in place of EnvAsr's 5 + scale)
 N_SM, FP32_LANES = 148, 128
 
 
@@ -92,9 +92,10 @@ def build_bank(graph, workload, voices, seconds, rank, world):
     from knaster_b200 import banks
 
     total = voices * world
-    if workload == "subtractive":
+    if workload in ("subtractive", "subtractive_seg"):
         seed = 2002 if world == 1 else 4004  # configs[2] / configs[4]
-        banks.subtractive_bank(graph, voices, seconds, seed=seed, voice_offset=rank * voices, total_voices=total)
+        banks.subtractive_bank(graph, voices, seconds, seed=seed, voice_offset=rank * voices, total_voices=total,
+                               envelope="asr" if workload == "subtractive" else "segments")
     elif workload == "additive":
         banks.additive_bank(graph, voices, seconds, voice_offset=rank * voices, total_voices=total)
     elif workload == "fm":
@@ -127,8 +128,9 @@ def run_reference(args, rank, world):
         from knaster_b200 import banks
 
         seed = 2002
-        if args.workload == "subtractive":
-            banks.subtractive_bank(g, nv, args.seconds, seed=seed, voice_offset=c * per, total_voices=voices)
+        if args.workload in ("subtractive", "subtractive_seg"):
+            banks.subtractive_bank(g, nv, args.seconds, seed=seed, voice_offset=c * per, total_voices=voices,
+                                   envelope="asr" if args.workload == "subtractive" else "segments")
         elif args.workload == "additive":
             banks.additive_bank(g, nv, args.seconds, voice_offset=c * per, total_voices=voices)
         else:
@@ -179,11 +181,12 @@ def run_reference(args, rank, world):
 
 def workload_config(args, world):
     names = {"subtractive": "subtractive polysynth: saw -> SvfFilter lowpass -> EnvAsr -> VCA, sample-accurate note events",
+             "subtractive_seg": "subtractive polysynth, Envelope variant: saw -> SvfFilter lowpass -> Envelope (A/D/R segments) -> VCA, sample-accurate note events",
              "additive": "additive bank: SinWt partials with per-partial amp smoothing",
              "fm": "FM bank: SinNumeric -> SinNumeric audio-rate freq"}
     return {"workload": names[args.workload], "voices_per_gpu": args.voices, "total_voices": args.voices * world,
             "seconds_per_step": args.seconds, "blocks_per_step": int(round(args.seconds * SR)) // BLOCK, "block_size": BLOCK,
-            "sample_rate": SR, "notes_per_voice_per_step": 8 if args.workload == "subtractive" else 0,
+            "sample_rate": SR, "notes_per_voice_per_step": 8 if args.workload.startswith("subtractive") else 0,
             "l2": "per-voice state + events stream once per launch; working set changes every launch (no L2 reuse to flush)",
             "reduce": "none (1 GPU)" if world == 1 else "see config.bus"}
 
@@ -197,8 +200,8 @@ def cpu_baseline(args):
     voices = min(args.voices, args.cpu_voices)
     secs = min(args.seconds, args.cpu_seconds)
     g = Graph(0, 2, BLOCK, SR)
-    if args.workload == "subtractive":
-        banks.subtractive_bank(g, voices, secs, total_voices=args.voices)
+    if args.workload.startswith("subtractive"):
+        banks.subtractive_bank(g, voices, secs, total_voices=args.voices, envelope="asr" if args.workload == "subtractive" else "segments")
     elif args.workload == "additive":
         banks.additive_bank(g, voices, secs, total_voices=args.voices)
     else:
@@ -219,7 +222,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="subtractive", choices=["subtractive", "additive", "fm"])
+    ap.add_argument("--workload", default="subtractive", choices=["subtractive", "subtractive_seg", "additive", "fm"])
     ap.add_argument("--voices", type=int, default=16384, help="voices per GPU")
     ap.add_argument("--seconds", type=float, default=10.0, help="audio seconds per step")
     ap.add_argument("--chunks", type=int, default=10, help="NCCL reduce chunks per step (N>1, --bus nccl)")

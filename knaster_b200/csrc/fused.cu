@@ -9,6 +9,8 @@
 //
 //   recipe 0  "render_sub_asr"   PolyBlep(saw) -> SvfFilter -> (* EnvAsr.wr_mul) [MathUGen<Mul>]   (configs[2], [4])
 //   recipe 1  "render_fm2"       (SinNumeric * idx + fc) -> SinNumeric.ar_params() freq, * amp       (configs[3])
+//   recipe 2  "render_add_wt"    SinWt[.wr_mul][.smooth_params] -> bus (fused_wt.cu)                     (configs[1])
+//   recipe 3  "render_sub_seg"   recipe 0 with Envelope (f64 segments) in place of EnvAsr                (configs[2] variant B)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -36,15 +38,16 @@ enum : uint32_t {
     R_EST = 13, R_ET = 14, R_AR = 15, R_RR = 16, R_SC = 17, R_GAIN = 18, SUB_NREGS = 19,
 };
 
-struct SubVoice {
+// The voice minus its envelope: PolyBlep + SvfFilter registers; the envelope (and the WrMul gain that
+// wraps it) is a policy, AsrEnv or SegEnv below.
+template <class ENV> struct SubVoice {
     float t, dt;
     uint32_t use_sin;
     float pw;      // pulse_width and waveform: only the generic tick reads them (straight-line code = Sawtooth)
     uint32_t wf;
     float ic1, ic2, a1, a2, a3, m0, m1, m2;
-    uint32_t est;
-    float et, ar, rr, sc, gain;
-    KN_DEV void set(uint32_t reg, uint32_t bits) {
+    ENV e;
+    KN_DEV void set_core(uint32_t reg, uint32_t bits) { // registers below R_EST
         const float f = __uint_as_float(bits);
         switch (reg) {
         case R_T: t = f; break;
@@ -60,39 +63,29 @@ struct SubVoice {
         case R_M0: m0 = f; break;
         case R_M1: m1 = f; break;
         case R_M2: m2 = f; break;
-        case R_EST: est = bits; break;
-        case R_ET: et = f; break;
-        case R_AR: ar = f; break;
-        case R_RR: rr = f; break;
-        case R_SC: sc = f; break;
-        case R_GAIN: gain = f; break;
         default: break;
         }
+    }
+    KN_DEV void set(uint32_t reg, uint32_t bits) {
+        set_core(reg, bits);
+        e.set(reg, bits); // two flat switches of plain assignments: ptxas turns both into selects
     }
     // reference-order evaluation, any parameter values (used on tiles with events / odd dt)
     KN_DEV float tick() {
         const float saw = polyblep_tick(t, dt, use_sin, pw, wf);
         const float y = svf_tick(saw, ic1, ic2, a1, a2, a3, m0, m1, m2);
-        const float e = envasr_tick(est, et, ar, rr, sc) * gain; // WrMul, wrappers_core/math.rs:63-67
-        return y * e;                                            // MathUGen<Mul>, math.rs:45-47
+        const float env = e.tick_ref(); // envelope * WrMul gain, wrappers_core/math.rs:63-67
+        return y * env;                 // MathUGen<Mul>, math.rs:45-47
+    }
+    KN_DEV void idle() { // idle lane: a silent voice whose arithmetic stays finite (its output is +-0)
+        t = 0.f; dt = 0.125f; use_sin = 0; pw = 0.5f; wf = 0;
+        ic1 = ic2 = a1 = a2 = a3 = m0 = m1 = 0.f; m2 = 1.f;
+        e.idle();
     }
 };
 
 // x - trunc(x) for x in [0, 2): trunc(x) is 0 or 1, and x - 1 is exact for x in [1, 2)
 KN_DEV float wrap01(float x) { return x >= 1.0f ? x - 1.0f : x; }
-
-// EnvAsr::next_sample (envelopes.rs:52-81) as straight-line selects: same values, no divergence
-KN_DEV float envasr_tick_sel(uint32_t &st, float &t, float ar, float rr, float sc) {
-    const bool att = st == ASR_ATTACKING, rel = st == ASR_RELEASING;
-    const float cube = ((t * t) * t) * sc;
-    const float out = att ? t : (st == ASR_SUSTAINING ? 1.0f : (rel ? cube : 0.0f));
-    float tn = att ? t + ar : (rel ? t - rr : t);
-    const bool to_sus = att && tn >= 1.0f;
-    const bool to_stop = rel && tn <= 0.0f;
-    st = to_sus ? (uint32_t)ASR_SUSTAINING : (to_stop ? (uint32_t)ASR_STOPPED : st);
-    t = to_stop ? 0.0f : tn;
-    return out;
-}
 
 // The refined reciprocal nvcc's IEEE division computes per call (MUFU.RCP + one Newton step).
 // It only depends on the divisor, so it is hoisted: recomputed when dt changes.
@@ -134,32 +127,252 @@ KN_DEV float saw_eval(float t, float dt, float omd, float rc) {
 #endif
 constexpr int SUBW_TILE = 2 * SUB_SUB; // render_sub_asr staging tile: two halves of SUB_SUB frames
 
-// envelope registers derived from the state machine, constant while no transition happens
-struct EnvDerived {
-    float delta;   // per-frame increment of t: +attack_rate, -release_rate or 0
-    float cval;    // output of the constant states: Sustaining 1, Stopped 0
-    bool att, rel;
-    KN_DEV void derive(uint32_t est, float ar, float rr) {
-        att = est == ASR_ATTACKING;
-        rel = est == ASR_RELEASING;
-        delta = att ? ar : (rel ? -rr : 0.0f);
-        cval = est == ASR_SUSTAINING ? 1.0f : 0.0f;
+// ---- envelope policies of the subtractive recipe ------------------------------------------------
+// What a policy provides: the envelope's registers (loaded from / stored to the voice's register
+// columns from R_EST on), `D` = what a straight-line group needs and is constant while the state
+// machine does not move, group<N>() = N frames of `envelope * gain` with the state fixed,
+// safe_frames() = how many coming frames provably stay in that state, exact1() = one frame with
+// the whole state machine, and the event operations.
+
+// EnvAsr.wr_mul: regs R_EST state, R_ET t, R_AR attack_rate, R_RR release_rate, R_SC release_scale, R_GAIN
+struct AsrEnv {
+    uint32_t est;
+    float et, ar, rr, sc, gain;
+    struct D {
+        float delta;   // per-frame increment of t: +attack_rate, -release_rate or 0
+        float cval;    // output of the constant states: Sustaining 1, Stopped 0
+        bool att, rel;
+    };
+    KN_DEV void load(const FusedArgs &a, uint32_t v) {
+        const uint32_t V = a.n_voices;
+        uint32_t r[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) r[i] = a.regs[(size_t)(R_EST + i) * V + v];
+#pragma unroll
+        for (int i = 0; i < 6; i++) set(R_EST + i, r[i]);
+    }
+    KN_DEV void idle() { est = ASR_STOPPED; et = 0.f; ar = rr = 1.f; sc = 0.f; gain = 0.f; }
+    KN_DEV void set(uint32_t reg, uint32_t bits) {
+        const float f = __uint_as_float(bits);
+        switch (reg) {
+        case R_EST: est = bits; break;
+        case R_ET: et = f; break;
+        case R_AR: ar = f; break;
+        case R_RR: rr = f; break;
+        case R_SC: sc = f; break;
+        case R_GAIN: gain = f; break;
+        default: break;
+        }
+    }
+    KN_DEV void op(uint32_t o) {
+        if (o == OP_ASR_RELEASE) envasr_release(est, et, sc);
+    }
+    KN_DEV void derive(D &d) const {
+        d.att = est == ASR_ATTACKING;
+        d.rel = est == ASR_RELEASING;
+        d.delta = d.att ? ar : (d.rel ? -rr : 0.0f);
+        d.cval = est == ASR_SUSTAINING ? 1.0f : 0.0f;
+    }
+    // Number of coming frames in which the envelope state machine provably cannot change state.
+    // Attacking: t_n = t + n*ar + err with |err| <= n*2^-25 (one rounding of a value below 2 per add),
+    // so the first tick whose sum can reach 1 is no earlier than (1-t)/(ar + 2^-25); the same bound
+    // holds for the release ramp reaching 0.  The margin used here is twice that, minus one frame
+    // (ticks 0 .. m-2 are safe when tick m-1 is the first that can cross).
+    KN_DEV uint32_t safe_frames() const {
+        const bool att = est == ASR_ATTACKING, rel = est == ASR_RELEASING;
+        if (!att && !rel) return 0x40000000u;
+        const float dist = att ? 1.0f - et : et;
+        const float rate = (att ? ar : rr) + 5.9604644775390625e-8f;
+        const float n = __fdividef(dist, rate) - 1.0f;
+        return n >= 1.0f ? (uint32_t)fminf(n, 1073741824.0f) : 0u; // NaN -> 0: always the exact path
+    }
+    // EnvAsr::next_sample (envelopes.rs:52-81) with the state fixed over the group
+    template <int N> KN_DEV void group(const D &d, float (&env)[N]) {
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            const float cube = ((et * et) * et) * sc;
+            const float o = d.att ? et : (d.rel ? cube : d.cval);
+            et = et + d.delta;
+            env[k] = o * gain;      // WrMul, wrappers_core/math.rs:63-67
+        }
+    }
+    // one frame, then EnvAsr's transitions (envelopes.rs:60-77): they only change what FOLLOWING frames do
+    KN_DEV float exact1(const D &d) {
+        float env[1];
+        group<1>(d, env);
+        if (d.att && et >= 1.0f) est = ASR_SUSTAINING;
+        if (d.rel && et <= 0.0f) {
+            est = ASR_STOPPED;
+            et = 0.0f;
+        }
+        return env[0];
+    }
+    // EnvAsr::next_sample as straight-line selects: same values, no divergence
+    KN_DEV float tick_sel() {
+        const bool att = est == ASR_ATTACKING, rel = est == ASR_RELEASING;
+        const float cube = ((et * et) * et) * sc;
+        const float out = att ? et : (est == ASR_SUSTAINING ? 1.0f : (rel ? cube : 0.0f));
+        float tn = att ? et + ar : (rel ? et - rr : et);
+        const bool to_sus = att && tn >= 1.0f;
+        const bool to_stop = rel && tn <= 0.0f;
+        est = to_sus ? (uint32_t)ASR_SUSTAINING : (to_stop ? (uint32_t)ASR_STOPPED : est);
+        et = to_stop ? 0.0f : tn;
+        return out * gain;
+    }
+    KN_DEV float tick_ref() { return envasr_tick(est, et, ar, rr, sc) * gain; }
+    KN_DEV void store(const FusedArgs &a, uint32_t v) const {
+        const uint32_t V = a.n_voices;
+        a.regs[(size_t)R_EST * V + v] = est;
+        a.regs[(size_t)R_ET * V + v] = __float_as_uint(et);
+        a.regs[(size_t)R_SC * V + v] = __float_as_uint(sc);
+        a.regs[(size_t)R_AR * V + v] = __float_as_uint(ar);
+        a.regs[(size_t)R_RR * V + v] = __float_as_uint(rr);
+        a.regs[(size_t)R_GAIN * V + v] = __float_as_uint(gain);
     }
 };
 
-// Number of coming frames in which the envelope state machine provably cannot change state.
-// Attacking: t_n = t + n*ar + err with |err| <= n*2^-25 (one rounding of a value below 2 per add),
-// so the first tick whose sum can reach 1 is no earlier than (1-t)/(ar + 2^-25); the same bound
-// holds for the release ramp reaching 0.  The margin used here is twice that, minus one frame
-// (ticks 0 .. m-2 are safe when tick m-1 is the first that can cross).
-KN_DEV uint32_t envasr_safe_frames(uint32_t est, float t, float ar, float rr) {
-    const bool att = est == ASR_ATTACKING, rel = est == ASR_RELEASING;
-    if (!att && !rel) return 0x40000000u;
-    const float dist = att ? 1.0f - t : t;
-    const float rate = (att ? ar : rr) + 5.9604644775390625e-8f;
-    const float n = __fdividef(dist, rate) - 1.0f;
-    return n >= 1.0f ? (uint32_t)fminf(n, 1073741824.0f) : 0u; // NaN -> 0: always the exact path
-}
+// Envelope.wr_mul (envelopes.rs:359-527): f64 segment envelope.  Registers from R_EST: +0 running,
+// +1 segment, +2,3 time, +4,5 from_value, +6,7 step = time_scale * (1/sr), then per segment
+// {reciprocal_duration, duration, value} (f64 each, never written by events), then the WrMul gain.
+// The current segment's three numbers are cached in registers and re-read from the voice's register
+// columns whenever the segment index changes (a few times per note).
+struct SegEnv {
+    uint32_t running, seg;
+    double time, from, step;
+    double recip, dur, val;       // segments[seg]
+    float gain;
+    uint32_t n_seg, looping, gain_reg;
+    const uint32_t *segs;         // &regs[(R_EST + 8) * V + v]
+    uint32_t V;
+    struct D {
+        double recip, diff, step; // 0, -0, 0 while stopped: from + (0*0)*(-0) == from, for every from
+        bool run;
+    };
+    KN_DEV static double mk(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
+    KN_DEV void reload() {
+        uint32_t r[6];
+        const uint32_t sg = seg < n_seg ? seg : 0u;
+#pragma unroll
+        for (int i = 0; i < 6; i++) r[i] = __ldg(segs + (size_t)(REGS_ENVELOPE_PER_SEG * sg + i) * V);
+        recip = mk(r[0], r[1]);
+        dur = mk(r[2], r[3]);
+        val = mk(r[4], r[5]);
+    }
+    KN_DEV void load(const FusedArgs &a, uint32_t v) {
+        V = a.n_voices;
+        n_seg = a.prog->nodes[2].n_seg;
+        looping = a.prog->nodes[2].looping;
+        gain_reg = R_EST + REGS_ENVELOPE_BASE + REGS_ENVELOPE_PER_SEG * n_seg;
+        segs = a.regs + (size_t)(R_EST + REGS_ENVELOPE_BASE) * V + v;
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = a.regs[(size_t)(R_EST + i) * V + v];
+        running = r[0];
+        seg = r[1];
+        time = mk(r[2], r[3]);
+        from = mk(r[4], r[5]);
+        step = mk(r[6], r[7]);
+        gain = __uint_as_float(a.regs[(size_t)gain_reg * V + v]);
+        reload();
+    }
+    KN_DEV void idle() {
+        running = seg = 0;
+        time = from = step = recip = dur = val = 0.0;
+        gain = 0.f;
+        n_seg = 1; looping = 0; gain_reg = 0xFFFFFFFFu; segs = nullptr; V = 0;
+    }
+    KN_DEV void set(uint32_t reg, uint32_t bits) {
+        if (reg == gain_reg) {
+            gain = __uint_as_float(bits);
+            return;
+        }
+        switch (reg - R_EST) {
+        case 0: running = bits; break;
+        case 1: seg = bits; reload(); break; // a t_stop later in the same frame reads the new segment
+        case 2: time = mk(bits, (uint32_t)__double2hiint(time)); break;
+        case 3: time = mk((uint32_t)__double2loint(time), bits); break;
+        case 4: from = mk(bits, (uint32_t)__double2hiint(from)); break;
+        case 5: from = mk((uint32_t)__double2loint(from), bits); break;
+        case 6: step = mk(bits, (uint32_t)__double2hiint(step)); break;
+        case 7: step = mk((uint32_t)__double2loint(step), bits); break;
+        default: break;
+        }
+    }
+    KN_DEV double level() const { // from_value + (t * reciprocal_duration) * (value - from_value), envelopes.rs:425-429
+        return __dadd_rn(from, __dmul_rn(__dmul_rn(time, recip), __dsub_rn(val, from)));
+    }
+    KN_DEV void op(uint32_t o) {
+        if (o == OP_ENV_STOP) { // t_stop, envelopes.rs:511-523
+            if (running) from = level();
+            running = 0;
+        }
+    }
+    KN_DEV void derive(D &d) const {
+        d.run = running != 0;
+        d.recip = d.run ? recip : 0.0;
+        d.diff = d.run ? __dsub_rn(val, from) : -0.0;
+        d.step = d.run ? step : 0.0;
+    }
+    // Leading frames that take the `t < duration` branch (envelopes.rs:423-433) for certain: the k-th
+    // coming frame sees t_k = time + k*step up to k roundings of 2^-53 relative each, so the first
+    // frame with t_k >= duration is no earlier than (duration - time)/step * (1 - 1e-6) - 1 for any
+    // frame count below 2^30 (the f32 quotient itself is within 3e-7 of the exact one).
+    KN_DEV uint32_t safe_frames() const {
+        if (!running) return 0x40000000u;
+        if (!(time < dur)) return 0u;
+        if (!(step > 0.0)) return step <= 0.0 ? 0x40000000u : 0u; // time only falls / NaN: exact path
+        const float n = __fdividef((float)__dsub_rn(dur, time), (float)step) * 0.999999f - 1.0f;
+        return n >= 1.0f ? (uint32_t)fminf(n, 1073741824.0f) : 0u;
+    }
+    template <int N> KN_DEV void group(const D &d, float (&env)[N]) {
+        double tl = d.run ? time : 0.0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            const double y = __dadd_rn(from, __dmul_rn(__dmul_rn(tl, d.recip), d.diff));
+            tl = __dadd_rn(tl, d.step);
+            env[k] = (float)y * gain; // F::new(f64) rounds to nearest; WrMul, wrappers_core/math.rs:63-67
+        }
+        time = d.run ? tl : time;
+    }
+    // Envelope::process (envelopes.rs:407-463), the whole state machine
+    KN_DEV float tick_ref() {
+        float y;
+        if (!running) {
+            y = (float)from;
+        } else if (time < dur) {
+            y = (float)level();
+            time = __dadd_rn(time, step);
+        } else if (seg + 1 < n_seg) {
+            from = val;
+            y = (float)level();
+            time = __dadd_rn(__dsub_rn(time, dur), step);
+            seg = seg + 1;
+            reload();
+        } else {
+            from = val;
+            y = (float)from;
+            if (looping) {
+                seg = 0;
+                time = 0.0;
+                reload();
+            } else {
+                running = 0;
+            }
+        }
+        return y * gain;
+    }
+    KN_DEV float tick_sel() { return tick_ref(); }
+    KN_DEV float exact1(const D &) { return tick_ref(); }
+    KN_DEV void store(const FusedArgs &a, uint32_t v) const {
+        const uint32_t Vn = a.n_voices;
+        const uint32_t r[8] = {running, seg, (uint32_t)__double2loint(time), (uint32_t)__double2hiint(time),
+                               (uint32_t)__double2loint(from), (uint32_t)__double2hiint(from),
+                               (uint32_t)__double2loint(step), (uint32_t)__double2hiint(step)};
+#pragma unroll
+        for (int i = 0; i < 8; i++) a.regs[(size_t)(R_EST + i) * Vn + v] = r[i];
+        a.regs[(size_t)gain_reg * Vn + v] = __float_as_uint(gain);
+    }
+};
 
 // Canonical mix-bus order for one frame: T(voices 0..15) + T(voices 16..31), T a fixed tree over
 // four float4 reads.  Every path that sums a staged frame uses it, so a render is bit-identical
@@ -186,8 +399,8 @@ KN_DEV float sum8(const float *p) {
 // lane's column of the staging tile) and, when the voice is tapped, to tap[k].
 // SUM: the same basic block also reduces the 16 frames staged by the PREVIOUS group (lane = (frame
 // r = lane & 15, voice half c = lane >> 4)), so the mix-bus reduction costs issue slots only.
-template <bool LP, int N, bool TAPS, bool SUM>
-KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc, float *strow, float *tap,
+template <class ENV, bool LP, int N, bool TAPS, bool SUM, bool EXACT = false>
+KN_DEV void sub_group_fast(SubVoice<ENV> &s, const typename ENV::D &d, float omd, float rc, float *strow, float *tap,
                            const float *sum_src = nullptr, float *sum_dst = nullptr, bool sum_store = false) {
     float ph[N], env[N];
     if (SUM) {
@@ -209,14 +422,8 @@ KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc
         ph[k] = s.t;
         s.t = wrap01(s.t + s.dt); // inc(), polyblep.rs:232-235
     }
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-        // EnvAsr::next_sample (envelopes.rs:52-81) with the state fixed over the group
-        const float cube = ((s.et * s.et) * s.et) * s.sc;
-        const float o = d.att ? s.et : (d.rel ? cube : d.cval);
-        s.et = s.et + d.delta;
-        env[k] = o * s.gain;      // WrMul, wrappers_core/math.rs:63-67
-    }
+    if constexpr (EXACT) env[0] = s.e.exact1(d); // N == 1: the envelope's whole state machine
+    else s.e.template group<N>(d, env);           // envelope * WrMul gain with the state fixed over the group
 #pragma unroll
     for (int k = 0; k < N; k++) {
         const float v0 = saw_eval(ph[k], s.dt, omd, rc);
@@ -238,10 +445,10 @@ KN_DEV void sub_group_fast(SubVoice &s, const EnvDerived &d, float omd, float rc
 }
 
 // per-lane validity of the straight-line formulation
-KN_DEV bool sub_lane_fast(const SubVoice &s) {
+template <class ENV> KN_DEV bool sub_lane_fast(const SubVoice<ENV> &s) {
     return s.dt >= 9.5367431640625e-7f && s.dt < 0.25f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin && s.wf == 0u;
 }
-KN_DEV bool sub_lane_lp(const SubVoice &s) { return s.m0 == 0.0f && s.m1 == 0.0f && s.m2 == 1.0f; }
+template <class ENV> KN_DEV bool sub_lane_lp(const SubVoice<ENV> &s) { return s.m0 == 0.0f && s.m1 == 0.0f && s.m2 == 1.0f; }
 
 // one parameter event (16 B) through the read-only path
 KN_DEV DevEvent ldg_event(const DevEvent *p) {
@@ -294,33 +501,32 @@ struct EvCursor {
     }
 };
 
-template <bool TAPS>
-__global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
-    __shared__ __align__(16) float st[SUBW_TILE * SUBW_PAD];
+// The body of render_sub_asr / render_sub_seg: ENV = AsrEnv or SegEnv.
+template <class ENV, bool TAPS>
+KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
     const uint32_t lane = threadIdx.x;
     const uint32_t gwarp = blockIdx.x;
     const uint32_t v = gwarp * 32 + lane;
     const uint32_t V = a.n_voices;
     const bool active = v < V;
 
-    SubVoice s;
+    SubVoice<ENV> s;
     if (active) {
-        uint32_t r[SUB_NREGS];
+        uint32_t r[R_EST];
 #pragma unroll
-        for (int i = 0; i < SUB_NREGS; i++) r[i] = a.regs[(size_t)i * V + v];
+        for (int i = 0; i < R_EST; i++) r[i] = a.regs[(size_t)i * V + v];
 #pragma unroll
-        for (int i = 0; i < SUB_NREGS; i++) s.set(i, r[i]);
-    } else { // idle lane: a silent voice whose arithmetic stays finite (its output is +-0)
-        s.t = 0.f; s.dt = 0.125f; s.use_sin = 0; s.pw = 0.5f; s.wf = 0;
-        s.ic1 = s.ic2 = s.a1 = s.a2 = s.a3 = s.m0 = s.m1 = 0.f; s.m2 = 1.f;
-        s.est = ASR_STOPPED; s.et = 0.f; s.ar = s.rr = 1.f; s.sc = 0.f; s.gain = 0.f;
+        for (int i = 0; i < R_EST; i++) s.set_core(i, r[i]); // not set(): the envelope is not loaded yet (SegEnv::set reads gain_reg)
+        s.e.load(a, v);
+    } else {
+        s.idle();
     }
     EvCursor ec;
     ec.init(a.events, a.ev_off, v, active);
     int tap_row = -1;
     if (TAPS)
         for (uint32_t i = 0; i < a.n_taps; i++)
-            if (a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
+            if (active && a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
     float *tap = TAPS && tap_row >= 0 ? a.tap_out + (size_t)tap_row * a.tap_stride + a.tap_frame0 : nullptr;
 
     float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
@@ -328,13 +534,13 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
     bool lane_fast = sub_lane_fast(s);
     bool all_lp = __all_sync(0xFFFFFFFFu, sub_lane_lp(s));
     float omd = 1.0f - s.dt, rc = div_prep(s.dt);
-    EnvDerived d;
-    d.derive(s.est, s.ar, s.rr);
+    typename ENV::D d;
+    s.e.derive(d);
     // `limit`: first frame at which SOME lane needs the exact per-frame path (an event is due, its
     // envelope may change state, or its parameters are outside the fast domain).  Warp-uniform.
     auto lane_limit = [&](uint32_t f) -> uint32_t {
         if (!lane_fast) return 0u;
-        const uint32_t safe = f + envasr_safe_frames(s.est, s.et, s.ar, s.rr);
+        const uint32_t safe = f + s.e.safe_frames();
         return min(ec.next_frame, safe);
     };
     uint32_t limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(0));
@@ -366,7 +572,7 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
 #pragma unroll 1
         while (f + N <= lim) {
             stage_room(N);
-            sub_group_fast<LP, N, TAPS, false>(s, d, omd, rc, st + (rbase + rows) * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr);
+            sub_group_fast<ENV, LP, N, TAPS, false>(s, d, omd, rc, st + (rbase + rows) * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr);
             rows += N;
             f += N;
         }
@@ -384,9 +590,9 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
 #pragma unroll 1
             do {
                 __syncwarp();
-                sub_group_fast<LP, SUB_SUB, TAPS, true>(s, d, omd, rc, st + (half * SUB_SUB) * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr,
-                                                        st + ((half ^ 1u) * SUB_SUB + r) * SUBW_PAD + c * cw, prow + (f - SUB_SUB + r),
-                                                        pending && c == 0);
+                sub_group_fast<ENV, LP, SUB_SUB, TAPS, true>(s, d, omd, rc, st + (half * SUB_SUB) * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr,
+                                                             st + ((half ^ 1u) * SUB_SUB + r) * SUBW_PAD + c * cw, prow + (f - SUB_SUB + r),
+                                                             pending && c == 0);
                 pending = true;
                 half ^= 1u;
                 f += SUB_SUB;
@@ -407,7 +613,7 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
             bool touched = false;
             while (ec.next_frame <= f) { // events are sorted by (frame, node, arrival)
                 if (ec.e0.op == OP_SET) s.set(ec.e0.reg, ec.e0.value);
-                else if (ec.e0.op == OP_ASR_RELEASE) envasr_release(s.est, s.et, s.sc);
+                else s.e.op(ec.e0.op);
                 ec.pop();
                 touched = true;
             }
@@ -415,7 +621,7 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
                 omd = 1.0f - s.dt;
                 rc = div_prep(s.dt);
                 lane_fast = sub_lane_fast(s);
-                d.derive(s.est, s.ar, s.rr);
+                s.e.derive(d);
             }
             all_lp = __all_sync(0xFFFFFFFFu, sub_lane_lp(s));
             all_fast = __all_sync(0xFFFFFFFFu, lane_fast);
@@ -424,21 +630,15 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
         stage_room(1);
         float *strow = st + (rbase + rows) * SUBW_PAD + lane;
         if (all_fast) {
-            // the straight-line frame, then EnvAsr's transitions (envelopes.rs:60-77): they only
-            // change what FOLLOWING frames do
-            if (all_lp) sub_group_fast<true, 1, TAPS, false>(s, d, omd, rc, strow, TAPS && tap ? tap + f : nullptr);
-            else sub_group_fast<false, 1, TAPS, false>(s, d, omd, rc, strow, TAPS && tap ? tap + f : nullptr);
-            if (d.att && s.et >= 1.0f) s.est = ASR_SUSTAINING;
-            if (d.rel && s.et <= 0.0f) {
-                s.est = ASR_STOPPED;
-                s.et = 0.0f;
-            }
+            // the straight-line frame with the envelope's state machine checked (ENV::exact1)
+            if (all_lp) sub_group_fast<ENV, true, 1, TAPS, false, true>(s, d, omd, rc, strow, TAPS && tap ? tap + f : nullptr);
+            else sub_group_fast<ENV, false, 1, TAPS, false, true>(s, d, omd, rc, strow, TAPS && tap ? tap + f : nullptr);
         } else {
             float o;
             if (lane_fast) {
                 const float ph = s.t;
                 s.t = wrap01(s.t + s.dt);
-                const float e = envasr_tick_sel(s.est, s.et, s.ar, s.rr, s.sc) * s.gain;
+                const float e = s.e.tick_sel();
                 o = svf_tick(saw_eval(ph, s.dt, omd, rc), s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2) * e;
             } else {
                 o = s.tick();
@@ -450,7 +650,7 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
         }
         rows += 1;
         f += 1;
-        d.derive(s.est, s.ar, s.rr);
+        s.e.derive(d);
         limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(f));
     }
     if (rows) flush();
@@ -458,9 +658,6 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
         a.regs[(size_t)R_T * V + v] = __float_as_uint(s.t);
         a.regs[(size_t)R_IC1 * V + v] = __float_as_uint(s.ic1);
         a.regs[(size_t)R_IC2 * V + v] = __float_as_uint(s.ic2);
-        a.regs[(size_t)R_EST * V + v] = s.est;
-        a.regs[(size_t)R_ET * V + v] = __float_as_uint(s.et);
-        a.regs[(size_t)R_SC * V + v] = __float_as_uint(s.sc);
         // parameter registers change only through events: write them back as well
         a.regs[(size_t)R_DT * V + v] = __float_as_uint(s.dt);
         a.regs[(size_t)R_USESIN * V + v] = s.use_sin;
@@ -472,10 +669,23 @@ __global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
         a.regs[(size_t)R_M0 * V + v] = __float_as_uint(s.m0);
         a.regs[(size_t)R_M1 * V + v] = __float_as_uint(s.m1);
         a.regs[(size_t)R_M2 * V + v] = __float_as_uint(s.m2);
-        a.regs[(size_t)R_AR * V + v] = __float_as_uint(s.ar);
-        a.regs[(size_t)R_RR * V + v] = __float_as_uint(s.rr);
-        a.regs[(size_t)R_GAIN * V + v] = __float_as_uint(s.gain);
+        s.e.store(a, v);
     }
+}
+
+template <bool TAPS>
+__global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
+    __shared__ __align__(16) float st[SUBW_TILE * SUBW_PAD];
+    render_sub_body<AsrEnv, TAPS>(a, st);
+}
+
+// recipe 3: the same voice with Envelope (f64 linear segments) in place of EnvAsr -- configs[2]
+// variant B.  The envelope's 4 f64 operations per frame run on the FP64 pipe
+// beside the FP32 work; its state machine only moves at segment boundaries (SegEnv::safe_frames).
+template <bool TAPS>
+__global__ void __launch_bounds__(32, 8) render_sub_seg(FusedArgs a) {
+    __shared__ __align__(16) float st[SUBW_TILE * SUBW_PAD];
+    render_sub_body<SegEnv, TAPS>(a, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -609,7 +819,7 @@ KN_DEV void sub2_osc_role(const FusedArgs &a, float *ring, uint32_t lane, uint32
 
 // the filter warp's straight-line group: envelope + filter + VCA on saw frames read from the ring
 template <bool LP, int N, bool TAPS, bool SUM>
-KN_DEV void filt_group_fast(SubVoice &s, const EnvDerived &d, const float *v0src, float *strow, float *tap,
+KN_DEV void filt_group_fast(SubVoice<AsrEnv> &s, const AsrEnv::D &d, const float *v0src, float *strow, float *tap,
                             const float *sum_src = nullptr, float *sum_dst = nullptr, bool sum_store = false) {
     float env[N], saw[N];
     // all shared-memory reads first: the compiler cannot move a ring load above a staging store
@@ -628,10 +838,10 @@ KN_DEV void filt_group_fast(SubVoice &s, const EnvDerived &d, const float *v0src
 #pragma unroll
     for (int k = 0; k < N; k++) {
         // EnvAsr::next_sample (envelopes.rs:52-81) with the state fixed over the group
-        const float cube = ((s.et * s.et) * s.et) * s.sc;
-        const float o = d.att ? s.et : (d.rel ? cube : d.cval);
-        s.et = s.et + d.delta;
-        env[k] = o * s.gain;      // WrMul, wrappers_core/math.rs:63-67
+        const float cube = ((s.e.et * s.e.et) * s.e.et) * s.e.sc;
+        const float o = d.att ? s.e.et : (d.rel ? cube : d.cval);
+        s.e.et = s.e.et + d.delta;
+        env[k] = o * s.e.gain;      // WrMul, wrappers_core/math.rs:63-67
     }
 #pragma unroll
     for (int k = 0; k < N; k++) {
@@ -657,14 +867,14 @@ template <bool TAPS>
 KN_DEV void sub2_filter_role(const FusedArgs &a, const float *ring, float *st, uint32_t lane, uint32_t v, bool active) {
     const uint32_t V = a.n_voices;
     const uint32_t gwarp = blockIdx.x;
-    SubVoice s;
+    SubVoice<AsrEnv> s;
     s.t = 0.f; s.dt = 0.125f; s.use_sin = 0; // the osc warp's registers: unused here
     if (active) {
 #pragma unroll
         for (int i = R_IC1; i < SUB_NREGS; i++) s.set(i, a.regs[(size_t)i * V + v]);
     } else { // idle lane: a silent voice whose arithmetic stays finite (its output is +-0)
         s.ic1 = s.ic2 = s.a1 = s.a2 = s.a3 = s.m0 = s.m1 = 0.f; s.m2 = 1.f;
-        s.est = ASR_STOPPED; s.et = 0.f; s.ar = s.rr = 1.f; s.sc = 0.f; s.gain = 0.f;
+        s.e.est = ASR_STOPPED; s.e.et = 0.f; s.e.ar = s.e.rr = 1.f; s.e.sc = 0.f; s.e.gain = 0.f;
     }
     EvCursor ec;
     ec.init(a.events, a.ev_off, v, active);
@@ -672,16 +882,16 @@ KN_DEV void sub2_filter_role(const FusedArgs &a, const float *ring, float *st, u
     int tap_row = -1;
     if (TAPS)
         for (uint32_t i = 0; i < a.n_taps; i++)
-            if (a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
+            if (active && a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
     float *tap = TAPS && tap_row >= 0 ? a.tap_out + (size_t)tap_row * a.tap_stride + a.tap_frame0 : nullptr;
     float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
 
     bool all_lp = __all_sync(0xFFFFFFFFu, sub_lane_lp(s));
-    EnvDerived d;
-    d.derive(s.est, s.ar, s.rr);
+    AsrEnv::D d;
+    s.e.derive(d);
     // `limit`: first frame at which SOME lane has an event due or may change envelope state
     auto lane_limit = [&](uint32_t f) -> uint32_t {
-        const uint32_t safe = f + envasr_safe_frames(s.est, s.et, s.ar, s.rr);
+        const uint32_t safe = f + s.e.safe_frames();
         return min(ec.next_frame, safe);
     };
     uint32_t limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(0));
@@ -772,12 +982,12 @@ KN_DEV void sub2_filter_role(const FusedArgs &a, const float *ring, float *st, u
             bool touched = false;
             while (ec.next_frame <= f) { // this role's events only, sorted by (frame, node, arrival)
                 if (ec.e0.op == OP_SET) s.set(ec.e0.reg, ec.e0.value);
-                else if (ec.e0.op == OP_ASR_RELEASE) envasr_release(s.est, s.et, s.sc);
+                else if (ec.e0.op == OP_ASR_RELEASE) envasr_release(s.e.est, s.e.et, s.e.sc);
                 ec.pop();
                 cursor_skip<false>(ec);
                 touched = true;
             }
-            if (touched) d.derive(s.est, s.ar, s.rr);
+            if (touched) s.e.derive(d);
             all_lp = __all_sync(0xFFFFFFFFu, sub_lane_lp(s));
             next_ev = __reduce_min_sync(0xFFFFFFFFu, ec.next_frame);
         }
@@ -788,24 +998,24 @@ KN_DEV void sub2_filter_role(const FusedArgs &a, const float *ring, float *st, u
         // what FOLLOWING frames do
         if (all_lp) filt_group_fast<true, 1, TAPS, false>(s, d, ring_at(f), strow, TAPS && tap ? tap + f : nullptr);
         else filt_group_fast<false, 1, TAPS, false>(s, d, ring_at(f), strow, TAPS && tap ? tap + f : nullptr);
-        if (d.att && s.et >= 1.0f) s.est = ASR_SUSTAINING;
-        if (d.rel && s.et <= 0.0f) {
-            s.est = ASR_STOPPED;
-            s.et = 0.0f;
+        if (d.att && s.e.et >= 1.0f) s.e.est = ASR_SUSTAINING;
+        if (d.rel && s.e.et <= 0.0f) {
+            s.e.est = ASR_STOPPED;
+            s.e.et = 0.0f;
         }
         rows += 1;
         f += 1;
         release();
-        d.derive(s.est, s.ar, s.rr);
+        s.e.derive(d);
         limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(f));
     }
     if (rows) flush();
     if (active) {
         const uint32_t out_regs[] = {R_IC1, R_IC2, R_A1, R_A2, R_A3, R_M0, R_M1, R_M2, R_ET, R_AR, R_RR, R_SC, R_GAIN};
-        const float out_vals[] = {s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2, s.et, s.ar, s.rr, s.sc, s.gain};
+        const float out_vals[] = {s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2, s.e.et, s.e.ar, s.e.rr, s.e.sc, s.e.gain};
 #pragma unroll
         for (int i = 0; i < 13; i++) a.regs[(size_t)out_regs[i] * V + v] = __float_as_uint(out_vals[i]);
-        a.regs[(size_t)R_EST * V + v] = s.est;
+        a.regs[(size_t)R_EST * V + v] = s.e.est;
     }
 }
 
@@ -838,6 +1048,21 @@ bool match_sub_asr(const DevProgram &p) {
     return p.ubus_slot[0] == mul.out_slot[0];
 }
 
+
+// recipe 3: node 2 is Envelope.wr_mul instead of EnvAsr.wr_mul
+bool match_sub_seg(const DevProgram &p) {
+    if (p.n_nodes != 4 || p.n_ubus != 1) return false;
+    const DevNode &saw = p.nodes[0], &svf = p.nodes[1], &env = p.nodes[2], &mul = p.nodes[3];
+    if (env.kind != DK_ENVELOPE || env.n_seg < 1) return false;
+    const uint32_t gain_reg = R_EST + REGS_ENVELOPE_BASE + REGS_ENVELOPE_PER_SEG * env.n_seg;
+    if (p.n_regs != gain_reg + 1) return false;
+    if (saw.kind != DK_POLYBLEP || saw.mode != 0 || saw.n_post || saw.n_ar || saw.reg != R_T) return false;
+    if (svf.kind != DK_SVF || svf.n_post || svf.n_ar || svf.reg != R_IC1 || svf.in_slot[0] != (int)saw.out_slot[0]) return false;
+    if (env.n_post != 1 || env.post_op[0] != PO_MUL || env.post_reg[0] != gain_reg || env.n_ar || env.reg != R_EST) return false;
+    if (mul.kind != DK_MATH || mul.mode != 2 || mul.n_out != 1 || mul.n_post || mul.n_ar) return false;
+    if (mul.in_slot[0] != (int)svf.out_slot[0] || mul.in_slot[1] != (int)env.out_slot[0]) return false;
+    return p.ubus_slot[0] == mul.out_slot[0];
+}
 
 // ------------------------------------------------------------------------------------------------
 // recipe 1 "render_fm2": (SinNumeric mod * idx + fc) -> SinNumeric.ar_params() "freq", * amp  (configs[3])
@@ -915,7 +1140,7 @@ __global__ void __launch_bounds__(32, 8) render_fm2(FusedArgs a) {
     int tap_row = -1;
     if (TAPS)
         for (uint32_t i = 0; i < a.n_taps; i++)
-            if (a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
+            if (active && a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
 
     float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
     bool all_inrange = __all_sync(0xFFFFFFFFu, !active || s.inrange());
@@ -997,6 +1222,7 @@ int match_fused_recipe(const DevProgram &p, uint32_t block_size) {
     if (match_sub_asr(p)) return 0;
     if (match_fm2(p)) return 1;
     if (match_add_wt(p, block_size)) return 2;
+    if (match_sub_seg(p)) return 3;
     return -1;
 }
 const char *fused_recipe_name(int recipe) {
@@ -1004,6 +1230,7 @@ const char *fused_recipe_name(int recipe) {
     case 0: return "render_sub_asr";
     case 1: return "render_fm2";
     case 2: return "render_add_wt";
+    case 3: return "render_sub_seg";
     default: return "render_interp";
     }
 }
@@ -1022,8 +1249,14 @@ cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream) {
         return cudaGetLastError();
     }
     if (recipe == 2) return launch_add_wt(a, stream);
+    if (recipe == 3) {
+        const uint32_t nw = (a.n_voices + 31) / 32;
+        if (a.n_taps) render_sub_seg<true><<<nw, 32, 0, stream>>>(a);
+        else render_sub_seg<false><<<nw, 32, 0, stream>>>(a);
+        return cudaGetLastError();
+    }
     if (recipe != 0) return cudaErrorNotSupported;
-    // one CTA per 32 voices: 512 CTAs spread over all 148 SMs (3-4 per SM)
+    // one CTA = one warp per 32 voices: 16384 voices = 512 CTAs spread over all 148 SMs (3-4 per SM)
     const uint32_t n_warps = (a.n_voices + 31) / 32;
     // Default: one warp per 32 voices (render_sub_asr).  KGPU_SUB_TWO_WARPS=1 selects the
     // warp-specialised pair (render_sub_asr2), kept as a measured negative result: 18.1 ms per 10 s

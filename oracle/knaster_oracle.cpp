@@ -752,8 +752,9 @@ struct Envelope : UGenT<Envelope, 0, 1, 4> {
     std::vector<EnvelopeSegment> segments;
     double start_value, from_value, time_scale = 1.0, base_scale = 0.0;
     bool looping = false;
-    Envelope(double start, std::vector<EnvelopeSegment> segs, bool loop)
-        : segments(std::move(segs)), start_value(start), from_value(start), looping(loop) {}
+    // new() :372-384, then the builders time_scale() :386-389 and looping() :392-395
+    Envelope(double start, std::vector<EnvelopeSegment> segs, bool loop, double ts)
+        : segments(std::move(segs)), start_value(start), from_value(start), time_scale(ts), looping(loop) {}
     void init(uint32_t sr, size_t) override { base_scale = 1.0 / (double)sr; } // :403-405
     inline void tick(Ctx &, const F *, F *out) {                               // :407-463
         F o;
@@ -1197,7 +1198,7 @@ std::unique_ptr<UGen> make_ugen(const ko_node_desc &d) {
         std::vector<EnvelopeSegment> segs;
         for (uint32_t i = 0; i < d.n_segments; i++) segs.emplace_back(d.segments[2 * i], d.segments[2 * i + 1]);
         if (segs.empty()) { g_last_error = "oracle: Envelope needs >=1 segment"; return nullptr; }
-        u.reset(new Envelope(d.args[0], std::move(segs), (d.flags & 1) != 0));
+        u.reset(new Envelope(d.args[0], std::move(segs), (d.flags & 1) != 0, d.args[1]));
         break;
     }
     case KO_MATH:

@@ -150,6 +150,75 @@ def test_subtractive_bank_with_note_events(envelope, force_interp):
     assert proc.info()["dropped_changes"] == 0
 
 
+def test_subtractive_segments_variant_runs_the_fused_kernel_bit_identical_to_the_interpreter():
+    # configs[2] variant B: Envelope (f64 segments) in place of EnvAsr => recipe "render_sub_seg"
+    def run(force_interp):
+        opts = AudioProcessorOptions(sample_rate=SR, force_interpreter=force_interp)
+        graph, proc = AudioProcessor.new(0, 2, opts)
+        ids = banks.subtractive_bank(graph, 70, 1.0, envelope="segments")
+        for i in ids:
+            proc.add_tap(i, 0)
+        out = proc.render(750)
+        return out, proc.read_taps(), proc.info()["kernels"]
+
+    fo, ft, fk = run(False)
+    io, it, ik = run(True)
+    assert fk == ["render_sub_seg"] and ik == ["render_interp"]
+    assert np.array_equal(ft, it)              # per-voice: same arithmetic in the same order
+    assert np.abs(fo - io).max() <= 1e-6       # bus: the summation trees differ
+    opts = AudioProcessorOptions(sample_rate=SR)
+    graph, proc = AudioProcessor.new(0, 2, opts)   # and without taps (the TAPS=false instantiation)
+    banks.subtractive_bank(graph, 70, 1.0, envelope="segments")
+    assert np.array_equal(proc.render(750), fo)
+
+
+def test_envelope_choreography_in_the_fused_voice_shape():
+    # Envelope state machine edge cases inside the render_sub_seg voice shape: looping, a shorter-than-a-sample
+    # segment, five segments, time_scale changes (incl. 0 and negative), jump_to_segment while stopped
+    # and while running, t_stop in the middle of a segment, two events on one frame, restart while running
+    def build(graph):
+        ids = []
+        with graph.edit() as g:
+            for i in range(40):
+                segs = [kn.EnvelopeSegment(0.004 + 0.001 * (i % 7), 1.0), kn.EnvelopeSegment(1e-5 if i % 5 == 0 else 0.01, 0.7),
+                        kn.EnvelopeSegment(0.02, 0.3 + 0.01 * i), kn.EnvelopeSegment(0.003, 0.9), kn.EnvelopeSegment(0.05, 0.0)]
+                envu = kn.Envelope(0.1 if i % 3 == 0 else 0.0, segs[: 2 + i % 4])
+                if i % 4 == 1:
+                    envu = envu.looping(True)
+                if i % 6 == 2:
+                    envu = envu.time_scale(1.7)
+                saw = g.push(kn.PolyBlep(kn.Waveform.Sawtooth, 110.0 * (1 + i % 9)).precise_timing(8))
+                svf = g.push(kn.SvfFilter(kn.SvfFilterType.Low, 700.0 + 90.0 * i, 2.0, 0.0).precise_timing(8))
+                env = g.push(envu.wr_mul(0.05).precise_timing(8))
+                sig = (saw >> svf) * env
+                sig.out([0, 0]).to_graph_out()
+                at = lambda n: kn.Seconds.from_samples(n, SR)
+                env.param("t_restart").trig_at(at(100 + 13 * i))
+                if i % 2 == 0:
+                    env.param("time_scale").set_at([0.5, 0.0, -0.05, 3.0][(i // 2) % 4], at(600 + i))
+                    env.param("time_scale").set_at(1.0, at(2500 + i))
+                if i % 3 == 1:
+                    env.param("t_stop").trig_at(at(900 + 7 * i))
+                    env.param("jump_to_segment").set_at(i % 4, at(1500 + i))      # while stopped
+                if i % 3 == 2:
+                    env.param("jump_to_segment").set_at(7, at(1000 + i))          # clamps to the last segment
+                    env.param("jump_to_segment").set_at(0, at(4000))
+                    env.param("t_stop").trig_at(at(4000))                         # same frame, after the jump
+                env.param("t_restart").trig_at(at(6000 + 11 * i))                # restart while running / stopped
+                env.param("wr_mul").set_at(0.02, at(7000 + i))
+                ids.append(sig._outputs[0][0])
+        return ids
+
+    gpu, ref, gt, rt, proc = both(build, 200)
+    kernels = proc.info()["kernels"]           # one group per (segment count, looping) template
+    assert len(kernels) > 1 and set(kernels) == {"render_sub_seg"}
+    assert np.abs(rt).max() > 1e-3
+    assert np.abs(gt - rt).max() <= 1e-4
+    assert np.abs(gpu - ref).max() <= 1e-5
+    _, _, gi, _, _ = both(build, 200, force_interpreter=True)
+    assert np.array_equal(gt, gi)
+
+
 def test_subtractive_intermediate_nodes_match():
     # tap every node of a voice (forces the interpreter): oscillators <= 1e-5, filter <= 1e-4
     ids = {}

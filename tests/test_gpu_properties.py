@@ -337,3 +337,4 @@ def test_sinwt_with_precise_timing_stays_on_the_interpreter():
     ref, ref_taps = oracle_render(build, 40)
     assert proc.info()["kernels"] == ["render_interp"]
     assert np.array_equal(taps, ref_taps)
+

@@ -285,3 +285,22 @@ def test_event_without_precise_timing_applies_at_block_start():
     flat = out[:, 0, :].reshape(-1)
     assert flat.tolist() == [0.0] * 16 + [1.0] * 32
     assert p.log_count() == 1
+
+
+def test_envelope_builder_time_scale_and_looping():
+    # envelopes.rs:386-395: the builders set time_scale / looping before init(); :423-433 the ramp
+    # advances by time_scale * (1 / sr) per frame.  A 0.01 s segment at time_scale 2 ends after 240 frames.
+    seg = [kn.EnvelopeSegment(0.01, 1.0)]
+    outs = {}
+    for ts in (1.0, 2.0):
+        u = OracleUGen(kn.Envelope(0.0, seg).time_scale(ts), 48000, 64)
+        u.param(2, kn.PTrigger)  # t_restart
+        outs[ts] = np.concatenate([u.process_block(np.zeros((1, 64), np.float32), 64)[0] for _ in range(10)])
+    assert outs[1.0][240] == pytest.approx(0.5, abs=1e-6) and outs[1.0][481] == 1.0
+    assert outs[2.0][120] == pytest.approx(0.5, abs=1e-6) and outs[2.0][241] == 1.0
+    assert np.array_equal(outs[2.0][:240], outs[1.0][:480:2])
+    lo = OracleUGen(kn.Envelope(0.0, seg).looping(True), 48000, 64)
+    lo.param(2, kn.PTrigger)
+    y = np.concatenate([lo.process_block(np.zeros((1, 64), np.float32), 64)[0] for _ in range(20)])
+    # :446-452 looping restarts segment and time but keeps from_value = the last target: 1 -> 1 from then on
+    assert y[481] == 1.0 and np.all(y[481:] == 1.0)
