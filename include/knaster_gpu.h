@@ -51,7 +51,14 @@ typedef enum {
     KGPU_TEST_NUM = 12,          /* knaster_graph/src/tests/utils.rs:4-17  (reference test fixture)          */
     KGPU_TEST_IN_PLUS_PARAM = 13,/* knaster_graph/src/tests/utils.rs:20-67 (reference test fixture)          */
     KGPU_MATH1 = 14,             /* math.rs:167-305      Math1UGen: 1 in, 1 out, no params; mode = kgpu_math1_op */
-    KGPU_PHASOR = 15             /* osc.rs:170-213       params: 0 freq (f64 phase, 0..1 ramp)               */
+    KGPU_PHASOR = 15,            /* osc.rs:170-213       params: 0 freq (f64 phase, 0..1 ramp)               */
+    /* noise.rs: the RNG is the fastrand 2.3.0 crate (wyrand), which is NOT under the reference tree;
+       its published algorithm is restated (csrc/nodes.cuh wy_next).  args[last] = the seed the
+       reference would have drawn from its global construction-order counter (noise.rs:11-22).     */
+    KGPU_WHITE_NOISE = 16,       /* noise.rs:26-46       no params; args[0] = seed                          */
+    KGPU_PINK_NOISE = 17,        /* noise.rs:53-115      no params; args[0] = seed                          */
+    KGPU_BROWN_NOISE = 18,       /* noise.rs:122-153     no params; args[0] = seed                          */
+    KGPU_RANDOM_LIN = 19         /* noise.rs:156-217     params: 0 freq; args[0] = freq, args[1] = seed (already *94+53) */
 } kgpu_ugen_kind;
 
 /* kgpu_node_desc.mode for KGPU_MATH (math.rs:22-85) */

@@ -328,6 +328,64 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 st_d(sreg, rb, phase);
                 break;
             }
+            case DK_WHITE:
+            case DK_BROWN: { // noise.rs:26-46,122-153 (no parameters: only wrapper events can be due)
+                uint64_t rng = ((uint64_t)sreg[(rb + 1) * 32] << 32) | sreg[rb * 32];
+                float last = dn.kind == DK_BROWN ? __uint_as_float(sreg[(rb + 2) * 32]) : 0.f;
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, (void)0, (void)0)
+                    AR_POST_ROUTES(f)
+                    float y = dn.kind == DK_BROWN ? brown_tick(rng, last) : white_sample(rng);
+                    EMIT(f, 0, y)
+                }
+                sreg[rb * 32] = (uint32_t)rng;
+                sreg[(rb + 1) * 32] = (uint32_t)(rng >> 32);
+                if (dn.kind == DK_BROWN) sreg[(rb + 2) * 32] = __float_as_uint(last);
+                break;
+            }
+            case DK_PINK: { // noise.rs:94-114; white_noises[] stays in the lane's shared-memory registers
+                uint64_t rng = ((uint64_t)sreg[(rb + 1) * 32] << 32) | sreg[rb * 32];
+                uint32_t counter = sreg[(rb + 12) * 32];
+                float pink = __uint_as_float(sreg[(rb + 13) * 32]), always = __uint_as_float(sreg[(rb + 11) * 32]);
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, (void)0, (void)0)
+                    AR_POST_ROUTES(f)
+                    const uint32_t idx = (uint32_t)(__ffs((int)counter) - 1); // counter.trailing_zeros(), 0..8
+                    pink = pink - __uint_as_float(sreg[(rb + 2 + idx) * 32]);
+                    const float w = white_sample(rng);
+                    sreg[(rb + 2 + idx) * 32] = __float_as_uint(w);
+                    pink = pink + w;
+                    pink = pink - always;
+                    always = white_sample(rng);
+                    pink = pink + always;
+                    counter = (counter & 255u) + 1u;                           // mask = 2^(9-1) = 256
+                    float y = pink / 10.0f;                                    // PINK_NOISE_OCTAVES + 1
+                    EMIT(f, 0, y)
+                }
+                sreg[rb * 32] = (uint32_t)rng;
+                sreg[(rb + 1) * 32] = (uint32_t)(rng >> 32);
+                sreg[(rb + 11) * 32] = __float_as_uint(always);
+                sreg[(rb + 12) * 32] = counter;
+                sreg[(rb + 13) * 32] = __float_as_uint(pink);
+                break;
+            }
+            case DK_RANDLIN: { // noise.rs:186-203
+                uint64_t rng = ((uint64_t)sreg[(rb + 1) * 32] << 32) | sreg[rb * 32];
+                float cur = __uint_as_float(sreg[(rb + 2) * 32]), width = __uint_as_float(sreg[(rb + 3) * 32]),
+                      phase = __uint_as_float(sreg[(rb + 4) * 32]), step = __uint_as_float(sreg[(rb + 5) * 32]);
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, (void)0, step = __uint_as_float(sreg[(rb + 5) * 32]))
+                    AR_POST_ROUTES(f)
+                    float y = randlin_tick(rng, cur, width, phase, step);
+                    EMIT(f, 0, y)
+                }
+                sreg[rb * 32] = (uint32_t)rng;
+                sreg[(rb + 1) * 32] = (uint32_t)(rng >> 32);
+                sreg[(rb + 2) * 32] = __float_as_uint(cur);
+                sreg[(rb + 3) * 32] = __float_as_uint(width);
+                sreg[(rb + 4) * 32] = __float_as_uint(phase);
+                break;
+            }
             case DK_CONST:
             case DK_INPLUS: {
                 float val = __uint_as_float(sreg[rb * 32]);

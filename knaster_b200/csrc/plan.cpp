@@ -70,6 +70,17 @@ inline void dbits(double d, uint32_t &lo, uint32_t &hi) {
     hi = (uint32_t)(u >> 32);
 }
 
+// fastrand 2.3.0 (wyrand), restated for RandomLin's constructor draws (noise.rs:173-185): see csrc/nodes.cuh wy_next
+inline float wy_f32(uint64_t &state) {
+    state += 0x2d358dccaa6c78a5ull;
+    const unsigned __int128 t = (unsigned __int128)state * (unsigned __int128)(state ^ 0x8bb84b93962eacc9ull);
+    const uint32_t u = (uint32_t)((uint64_t)t ^ (uint64_t)(t >> 64));
+    uint32_t bits = 0x3F800000u + (u >> 9);
+    float f;
+    std::memcpy(&f, &bits, 4);
+    return f - 1.0f;
+}
+
 // ---- static facts about node kinds ------------------------------------------------------
 struct KindInfo {
     int n_in, n_out, n_params, dev_kind, n_regs;
@@ -91,6 +102,10 @@ KindInfo kind_info(const kgpu_node_desc &d) {
     case KGPU_TEST_IN_PLUS_PARAM: return {1, 1, 1, DK_INPLUS, REGS_CONST};
     case KGPU_MATH1: return {1, 1, 0, DK_MATH1, 0};
     case KGPU_PHASOR: return {0, 1, 1, DK_PHASOR, REGS_PHASOR};
+    case KGPU_WHITE_NOISE: return {0, 1, 0, DK_WHITE, REGS_WHITE};
+    case KGPU_PINK_NOISE: return {0, 1, 0, DK_PINK, REGS_PINK};
+    case KGPU_BROWN_NOISE: return {0, 1, 0, DK_BROWN, REGS_BROWN};
+    case KGPU_RANDOM_LIN: return {0, 1, 1, DK_RANDLIN, REGS_RANDLIN};
     default: KGPU_THROW(KGPU_ERR_UNSUPPORTED, "unknown ugen kind %u", d.kind);
     }
 }
@@ -104,7 +119,7 @@ const char *param_types(uint32_t kind) {
     case KGPU_ENV_ASR: return "fftt";
     case KGPU_ENV_AR: return "fft";
     case KGPU_ENVELOPE: return "fitt";
-    case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: case KGPU_PHASOR: return "f";
+    case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: case KGPU_PHASOR: case KGPU_RANDOM_LIN: return "f";
     default: return "";
     }
 }
@@ -253,6 +268,9 @@ void ugen_param_apply(Sim &s, uint32_t param, const PV &v, uint64_t frame) {
         break;
     case KGPU_PHASOR: // osc.rs:191-197
         if (param == 0) s.set_d(frame, r + 2, v.f * h.d0);
+        break;
+    case KGPU_RANDOM_LIN: // noise.rs:206-213 (after init(): phase_step = F::new(value) * freq_to_phase_inc)
+        if (param == 0) s.set_f(frame, r + 5, (float)v.f * h.f0);
         break;
     case KGPU_POLYBLEP: // polyblep.rs:162-184
         if (param == 0) {
@@ -931,6 +949,25 @@ void HostPlan::build(const kgpu_graph_desc &d) {
                     R(r + 0, v) = lo; R(r + 1, v) = hi;
                     dbits(nd.args[0] * h.d0, lo, hi);
                     R(r + 2, v) = lo; R(r + 3, v) = hi;
+                    break;
+                }
+                case KGPU_WHITE_NOISE: case KGPU_PINK_NOISE: case KGPU_BROWN_NOISE: { // noise.rs:33-38,69-78,134-139
+                    const uint64_t seed = (uint64_t)nd.args[0];    // fastrand::Rng::with_seed(seed): the state IS the seed
+                    R(r + 0, v) = (uint32_t)seed; R(r + 1, v) = (uint32_t)(seed >> 32);
+                    if (nd.kind == KGPU_PINK_NOISE) R(r + 12, v) = 1u; // counter: 1 (noise.rs:74)
+                    break;
+                }
+                case KGPU_RANDOM_LIN: { // noise.rs:170-185: new() draws current_value, init() scales the step and calls new_value()
+                    uint64_t st = (uint64_t)nd.args[1];
+                    const float current = wy_f32(st);
+                    h.f0 = 1.0f / (float)sample_rate;                  // freq_to_phase_inc = F::ONE / F::from(sample_rate)
+                    const float step = (float)nd.args[0] * h.f0;       // phase_step *= freq_to_phase_inc
+                    const float old_target = current + 0.0f, nv = wy_f32(st);
+                    R(r + 0, v) = (uint32_t)st; R(r + 1, v) = (uint32_t)(st >> 32);
+                    R(r + 2, v) = fbits(old_target);
+                    R(r + 3, v) = fbits(nv - old_target);
+                    R(r + 4, v) = fbits(0.0f);
+                    R(r + 5, v) = fbits(step);
                     break;
                 }
                 case KGPU_POLYBLEP: { // polyblep.rs:139-155

@@ -893,6 +893,103 @@ struct Phasor : UGenT<Phasor, 0, 1, 1> {
     }
 };
 
+// ---------------------------------------------------------------- noise
+// knaster_core_dsp/src/ugens/noise.rs.  The generator is the `fastrand` crate, pinned at 2.3.0
+// (Cargo.lock:937-938; knaster_core_dsp/Cargo.toml:34), which is NOT vendored under the reference:
+// PARITY UNPINNED for the random stream -- wyrand restated from fastrand's published source:
+//   Rng::with_seed(seed) = Rng(seed);
+//   gen_u64: s = state + 0x2d358dccaa6c78a5 (wrapping), state = s,
+//            t = u128(s) * u128(s ^ 0x8bb84b93962eacc9), return lo(t) ^ hi(t);
+//   u32(..) = gen_u64() as u32;  f32() = from_bits(0x3F800000 + (u32(..) >> 9)) - 1.0.
+// Everything downstream of rng.f32() follows noise.rs line by line and is pinned like the other UGens.
+struct FastRand {
+    uint64_t state;
+    explicit FastRand(uint64_t seed) : state(seed) {}
+    uint64_t gen_u64() {
+        state += 0x2d358dccaa6c78a5ull;
+        const unsigned __int128 t = (unsigned __int128)state * (unsigned __int128)(state ^ 0x8bb84b93962eacc9ull);
+        return (uint64_t)t ^ (uint64_t)(t >> 64);
+    }
+    float f32() {
+        uint32_t bits = 0x3F800000u + ((uint32_t)gen_u64() >> 9);
+        float f;
+        std::memcpy(&f, &bits, 4);
+        return f - 1.0f;
+    }
+};
+// noise.rs:26-46.  The seed is the value next_randomness_seed() returned at construction (:11-22).
+struct WhiteNoise : UGenT<WhiteNoise, 0, 1, 0> {
+    FastRand rng;
+    explicit WhiteNoise(uint64_t seed) : rng(seed) {}
+    inline void tick(Ctx &, const F *, F *out) { out[0] = (F)(rng.f32() * 2.0f - 1.0f); } // :40-42
+    void param_apply(Ctx &, size_t, const ParamValue &) override {}
+};
+// noise.rs:53-115 (Voss-McCartney)
+struct PinkNoise : UGenT<PinkNoise, 0, 1, 0> {
+    static constexpr uint32_t OCTAVES = 9;
+    F white_noises[OCTAVES] = {0};
+    F always_on_white_noise = 0;
+    uint32_t counter = 1, mask = 256; // 2^(OCTAVES - 1)
+    F pink = 0;
+    FastRand rng;
+    explicit PinkNoise(uint64_t seed) : rng(seed) {}
+    inline void tick(Ctx &, const F *, F *out) {                  // :94-114
+        const size_t index = (size_t)__builtin_ctz(counter);      // counter.trailing_zeros()
+        pink -= white_noises[index];
+        white_noises[index] = (F)(rng.f32() * 2.0f - 1.0f);
+        pink += white_noises[index];
+        pink -= always_on_white_noise;
+        always_on_white_noise = (F)(rng.f32() * 2.0f - 1.0f);
+        pink += always_on_white_noise;
+        counter &= mask - 1;                                      // increment_counter :85-91
+        counter += 1;
+        out[0] = pink / ((F)OCTAVES + (F)1);
+    }
+    void param_apply(Ctx &, size_t, const ParamValue &) override {}
+};
+// noise.rs:122-153
+struct BrownNoise : UGenT<BrownNoise, 0, 1, 0> {
+    FastRand rng;
+    F last_output = 0;
+    explicit BrownNoise(uint64_t seed) : rng(seed) {}
+    inline void tick(Ctx &, const F *, F *out) {                  // :141-149
+        const F white = (F)(rng.f32() * 2.0f - 1.0f);
+        last_output += white * (F)0.1;
+        last_output = std::fmin(std::fmax(last_output, (F)-1), (F)1); // f32::clamp
+        out[0] = last_output;
+    }
+    void param_apply(Ctx &, size_t, const ParamValue &) override {}
+};
+// noise.rs:156-217
+struct RandomLin : UGenT<RandomLin, 0, 1, 1> {
+    FastRand rng;
+    F current_value, current_change_width = 0, phase = 0, phase_step, freq_to_phase_inc = 0;
+    RandomLin(F freq, uint64_t seed) : rng(seed), phase_step(freq) { current_value = (F)rng.f32(); } // :172-182
+    void new_value() {                                             // :185-191
+        const F old_target = current_value + current_change_width;
+        const F nv = (F)rng.f32();
+        current_value = old_target;
+        current_change_width = nv - old_target;
+        phase = (F)0.0;
+    }
+    void init(uint32_t sr, size_t) override {                      // :192-197
+        freq_to_phase_inc = (F)1 / (F)sr;
+        phase_step *= freq_to_phase_inc;
+        new_value();
+    }
+    inline void tick(Ctx &, const F *, F *out) {                   // :198-206
+        out[0] = current_value + phase * current_change_width;
+        phase += phase_step;
+        if (phase >= (F)1) new_value();
+    }
+    void param_apply(Ctx &, size_t index, const ParamValue &v) override { // :208-216
+        if (index == 0 && v.kind == PK::Float) {
+            if (freq_to_phase_inc == (F)0) phase_step = (F)v.f;
+            else phase_step = (F)v.f * freq_to_phase_inc;
+        }
+    }
+};
+
 struct Constant : UGenT<Constant, 0, 1, 1> {
     F value;
     explicit Constant(F v) : value(v) {}
@@ -1213,6 +1310,10 @@ std::unique_ptr<UGen> make_ugen(const ko_node_desc &d) {
         u.reset(new Math1UGen((int)d.mode));
         break;
     case KO_PHASOR: u.reset(new Phasor(d.args[0])); break;
+    case KO_WHITE_NOISE: u.reset(new WhiteNoise((uint64_t)d.args[0])); break;
+    case KO_PINK_NOISE: u.reset(new PinkNoise((uint64_t)d.args[0])); break;
+    case KO_BROWN_NOISE: u.reset(new BrownNoise((uint64_t)d.args[0])); break;
+    case KO_RANDOM_LIN: u.reset(new RandomLin((F)d.args[0], (uint64_t)d.args[1])); break;
     default: g_last_error = "oracle: unknown ugen kind"; return nullptr;
     }
     for (uint32_t i = 0; i < d.n_wrappers; i++) {

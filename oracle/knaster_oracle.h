@@ -48,6 +48,10 @@ enum {
     KO_TEST_IN_PLUS_PARAM = 13, /* reference test fixture TestInPlusParamUGen */
     KO_MATH1 = 14,              /* Math1UGen, mode: 0 Ceil 1 Sqrt 2 Floor 3 Trunc 4 Fract 5 Exp */
     KO_PHASOR = 15,
+    KO_WHITE_NOISE = 16, /* noise.rs; args[0] = seed */
+    KO_PINK_NOISE = 17,
+    KO_BROWN_NOISE = 18,
+    KO_RANDOM_LIN = 19,  /* args[0] = freq, args[1] = seed */
 };
 /* MathUGen ops */
 enum { KO_OP_ADD = 0, KO_OP_SUB = 1, KO_OP_MUL = 2, KO_OP_DIV = 3, KO_OP_POW = 4 };
