@@ -1068,8 +1068,16 @@ bool match_sub_seg(const DevProgram &p) {
 // recipe 1 "render_fm2": (SinNumeric mod * idx + fc) -> SinNumeric.ar_params() "freq", * amp  (configs[3])
 // template order: 0 mod, 1 Constant idx, 2 Mul, 3 Constant fc, 4 Add, 5 car, 6 Constant amp, 7 Mul
 enum : uint32_t { F_MPH = 0, F_MOFF = 1, F_MINC = 2, F_IDX = 3, F_FC = 4, F_CPH = 5, F_COFF = 6, F_CINC = 7, F_AMP = 8, FM_NREGS = 9 };
-constexpr int FM_SUB = 8; // frames per straight-line group: 16 independent f64 sine chains in flight
+#ifndef FM_SUB_N
+#define FM_SUB_N 16 // frames per straight-line group of render_fm2 (8 or 16: measured)
+#endif
+constexpr int FM_SUB = FM_SUB_N; // independent f64 sine chains in flight per lane
 
+// ---- one lane per voice ("render_fm2_wide"): the form for banks with more warps than SM sub-partitions.
+// Both oscillators of a voice run in sequence on one lane: 94 instructions per 32 voice-frames against
+// 2 x 62 for the two-lane form below, which in exchange halves the time of ONE warp -- so the two-lane
+// form wins while its warps (n_voices / 16) still find a sub-partition each (fm_two_lanes()).
+constexpr int FM1_SUB = 8; // frames per straight-line group: 16 independent f64 sine chains in flight
 struct FmVoice {
     float mph, moff, minc, idx, fc, cph, coff, cinc, amp;
     KN_DEV void set(uint32_t reg, uint32_t bits) {
@@ -1118,7 +1126,7 @@ struct FmVoice {
 };
 
 template <bool TAPS>
-__global__ void __launch_bounds__(32, 8) render_fm2(FusedArgs a) {
+__global__ void __launch_bounds__(32, 8) render_fm2_wide(FusedArgs a) {
     __shared__ float st[SUB_TILE * SUB_PAD];
     const uint32_t lane = threadIdx.x;
     const uint32_t gwarp = blockIdx.x;
@@ -1147,19 +1155,19 @@ __global__ void __launch_bounds__(32, 8) render_fm2(FusedArgs a) {
     for (uint32_t f0 = 0; f0 < a.n_frames; f0 += SUB_TILE) {
         const uint32_t nf = min((uint32_t)SUB_TILE, a.n_frames - f0);
 #pragma unroll 1
-        for (uint32_t g0 = 0; g0 < SUB_TILE; g0 += FM_SUB) {
+        for (uint32_t g0 = 0; g0 < SUB_TILE; g0 += FM1_SUB) {
             const uint32_t gf = f0 + g0;
-            const bool ev_group = __any_sync(0xFFFFFFFFu, next_frame < gf + FM_SUB);
-            if (!ev_group && all_inrange && g0 + FM_SUB <= nf) {
+            const bool ev_group = __any_sync(0xFFFFFFFFu, next_frame < gf + FM1_SUB);
+            if (!ev_group && all_inrange && g0 + FM1_SUB <= nf) {
 #pragma unroll
-                for (int k = 0; k < FM_SUB; k++) {
+                for (int k = 0; k < FM1_SUB; k++) {
                     const float o = s.tick<true>(sr, rc_sr);
                     st[(g0 + k) * SUB_PAD + lane] = active ? o : 0.f;
                     if (TAPS && tap_row >= 0) a.tap_out[(size_t)tap_row * a.tap_stride + a.tap_frame0 + gf + k] = o;
                 }
             } else {
 #pragma unroll 1
-                for (uint32_t k = 0; k < FM_SUB; k++) {
+                for (uint32_t k = 0; k < FM1_SUB; k++) {
                     float o = 0.f;
                     if (g0 + k < nf) {
                         bool touched = false;
@@ -1194,6 +1202,201 @@ __global__ void __launch_bounds__(32, 8) render_fm2(FusedArgs a) {
         const float regs_out[FM_NREGS] = {s.mph, s.moff, s.minc, s.idx, s.fc, s.cph, s.coff, s.cinc, s.amp};
 #pragma unroll
         for (int i = 0; i < FM_NREGS; i++) a.regs[(size_t)i * V + v] = __float_as_uint(regs_out[i]);
+    }
+}
+
+// ---- two lanes per voice ("render_fm2") ---------------------------------------------------------------
+// A voice is two SinNumeric oscillators, so it occupies TWO lanes that run one instruction stream
+// (arg = (phase + offset) * TAU, sinf(arg), phase update): lane j is the modulator, lane j + 16 the
+// carrier of voice (warp * 16 + j).  The carrier's phase increment at frame k is made from the
+// modulator's sample of frame k (osc.rs:240-242 through WrArParams), which in one SIMT stream would
+// chain every sine behind the previous one.  So the carrier lanes run TWO GROUPS BEHIND the modulator
+// lanes: a group's sines are independent on every lane (the carriers read modulator samples that
+// were exchanged an iteration earlier), their f64 chains overlap, and a warp executes one sine per
+// frame instead of two.  Twice the warps for the same bank (8192 voices = 512 warps, one per SM
+// sub-partition), half the instructions per warp.  A launch runs three extra iterations: the
+// carriers sit out the first two, the modulators the last ones, so the state saved at the end of a
+// launch has both oscillators at the same frame.
+constexpr int FM_VPW = 16; // voices per warp
+
+struct FmLane {
+    float ph, off, inc;   // this lane's oscillator: modulator (F_MPH..) or carrier (F_CPH..)
+    float idx, fc, amp;   // carrier lanes: the Mul / Add constants of the route and the output gain
+    uint32_t base;        // F_MPH or F_CPH
+    bool car;
+    KN_DEV void set(uint32_t reg, uint32_t bits) {
+        const float f = __uint_as_float(bits);
+        if (reg == base) ph = f;
+        else if (reg == base + 1) off = f;
+        else if (reg == base + 2) inc = f;
+        else if (reg == F_IDX) idx = f;
+        else if (reg == F_FC) fc = f;
+        else if (reg == F_AMP) amp = f;
+    }
+    // The phase half of one frame, in graph order: mod.process / Mul, Add, WrArParams(car): freq(v),
+    // then process: returns the sine argument of this frame and advances the phase.  m = the
+    // modulator's sample of this frame (carrier lanes).  commit = false leaves the state untouched.
+    template <bool INRANGE> KN_DEV float advance(float m, float sr, float rc_sr, bool commit) {
+        const float arg = (ph + off) * KN_TAU;                                // osc.rs:264
+        // carrier lanes only, but evaluated branch-free on every lane (modulator lanes discard it): a
+        // branch here would cut the group into basic blocks and keep its sine chains from overlapping
+        const float v = m * idx + fc;                                         // MathUGen<Mul>, MathUGen<Add>
+        // audio_rate.rs:42-57 + osc.rs:240-242: phase_increment = F::new(v as f64) / F::new(sr as f32)
+        float q;
+        if (INRANGE) {
+            // div_rc needs a quotient well inside the normal range: tiny numerators are scaled by 2^64
+            // (exact) and the quotient scaled back (exact unless it is subnormal, |v| < 6e-34, where
+            // the last bit of a 1e-45 increment cannot move a phase)
+            const bool tiny = fabsf(v) <= 1e-20f;
+            const float q0 = div_rc(tiny ? v * 0x1p64f : v, sr, rc_sr);
+            q = tiny ? q0 * 0x1p-64f : q0;
+        } else {
+            q = fabsf(v) > 1e-20f ? div_rc(v, sr, rc_sr) : v / sr;
+        }
+        const float ninc = car ? q : inc;
+        const float pn = ph + ninc;
+        const float nph = pn > 1.0f ? pn - 1.0f : pn;                         // osc.rs:266-268
+        if (commit) {
+            inc = ninc;
+            ph = nph;
+        }
+        return arg;
+    }
+    // |phase_offset| < 16 and |phase| <= 2: every sine argument is below 120 and the branch-free
+    // restatement of sinf applies
+    KN_DEV bool inrange() const { return fabsf(off) < 16.0f && fabsf(ph) <= 2.0f; }
+};
+
+template <bool TAPS>
+__global__ void __launch_bounds__(32, 8) render_fm2(FusedArgs a) {
+    __shared__ float st[SUB_TILE * SUB_PAD];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t gwarp = blockIdx.x;
+    const uint32_t mod_lane = lane & (FM_VPW - 1);
+    const uint32_t v = gwarp * FM_VPW + mod_lane;
+    const uint32_t V = a.n_voices;
+    const bool active = v < V;
+    const float sr = a.prog->sample_rate;
+    const float rc_sr = div_prep(sr);
+
+    FmLane s;
+    s.car = lane >= FM_VPW;
+    s.base = s.car ? (uint32_t)F_CPH : (uint32_t)F_MPH;
+    s.ph = s.off = s.inc = s.idx = s.fc = s.amp = 0.f;
+    if (active) {
+        s.ph = __uint_as_float(a.regs[(size_t)s.base * V + v]);
+        s.off = __uint_as_float(a.regs[(size_t)(s.base + 1) * V + v]);
+        s.inc = __uint_as_float(a.regs[(size_t)(s.base + 2) * V + v]);
+        s.idx = __uint_as_float(a.regs[(size_t)F_IDX * V + v]);
+        s.fc = __uint_as_float(a.regs[(size_t)F_FC * V + v]);
+        s.amp = __uint_as_float(a.regs[(size_t)F_AMP * V + v]);
+    }
+    const bool emit = active && s.car;
+    uint32_t cur = 0, end = 0, next_frame = 0xFFFFFFFFu; // both lanes of a voice walk its event list, each at its own frame
+    if (a.events && active) {
+        cur = a.ev_off[v];
+        end = a.ev_off[v + 1];
+        if (cur < end) next_frame = a.events[cur].frame;
+    }
+    int tap_row = -1;
+    if (TAPS)
+        for (uint32_t i = 0; i < a.n_taps; i++)
+            if (emit && a.taps[i].voice == v) tap_row = (int)a.taps[i].tap;
+    float *tap = TAPS && tap_row >= 0 ? a.tap_out + (size_t)tap_row * a.tap_stride + a.tap_frame0 : nullptr;
+
+    float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
+    const uint32_t NF = a.n_frames, NG = (NF + FM_SUB - 1) / FM_SUB;
+    const uint32_t lag = s.car ? 2u * FM_SUB : 0u;       // the carriers run two groups behind the modulators
+    // Software pipeline, per iteration G:  (1) phases of this lane's group, using the modulator samples
+    // the previous iteration exchanged (mcur);  (2) this group's sines are ISSUED (sn_new);  (3) the
+    // previous iteration's sines (sn_old, complete by now) are shuffled to the carrier lanes (-> mcur of
+    // the next iteration) and, on carrier lanes, staged as output.  Nothing in an iteration waits for a
+    // sine issued in the same iteration.
+    float mcur[FM_SUB], sn_old[FM_SUB], amp_old[FM_SUB];
+#pragma unroll
+    for (int k = 0; k < FM_SUB; k++) mcur[k] = sn_old[k] = amp_old[k] = 0.f;
+    bool all_inrange = __all_sync(0xFFFFFFFFu, !active || s.inrange());
+    uint32_t tile0 = 0;                                  // first frame of the staging tile the carriers are filling
+#pragma unroll 1
+    for (uint32_t G = 0; G <= NG + 2; G++) {
+        const uint32_t gf = G * FM_SUB;                  // the modulators' first frame in this iteration
+        const uint32_t lf = gf - lag;                    // this lane's first frame (meaningful while role_on)
+        const bool role_on = s.car ? (G >= 2 && G < NG + 2) : G < NG;
+        const bool ev_group = __any_sync(0xFFFFFFFFu, role_on && next_frame < lf + FM_SUB);
+        float sn_new[FM_SUB], amp_new[FM_SUB];
+        if (!ev_group && all_inrange && G >= 2 && gf + FM_SUB <= NF) { // both roles have a whole group
+            float arg[FM_SUB];
+#pragma unroll
+            for (int k = 0; k < FM_SUB; k++) {
+                arg[k] = s.advance<true>(mcur[k], sr, rc_sr, true);
+                amp_new[k] = s.amp;
+            }
+#pragma unroll
+            for (int k = 0; k < FM_SUB; k++) sn_new[k] = kn_sinf_glibc_inrange(arg[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < FM_SUB; k++) {
+                const uint32_t fr = lf + k;
+                const bool valid = role_on && fr < NF;
+                bool touched = false;
+                while (valid && next_frame <= fr) {
+                    const DevEvent e = a.events[cur];
+                    if (e.op == OP_SET) s.set(e.reg, e.value);
+                    cur++;
+                    next_frame = cur < end ? a.events[cur].frame : 0xFFFFFFFFu;
+                    touched = true;
+                }
+                if (__any_sync(0xFFFFFFFFu, touched)) all_inrange = __all_sync(0xFFFFFFFFu, !active || s.inrange());
+                amp_new[k] = s.amp;
+                sn_new[k] = kn_sinf(s.advance<false>(mcur[k], sr, rc_sr, valid));
+            }
+        }
+        if (G >= 3) { // the carriers' sines of the previous iteration: frames (G - 3) * FM_SUB + k
+#pragma unroll
+            for (int k = 0; k < FM_SUB; k++) {
+                const uint32_t fr = gf - 3u * FM_SUB + k;
+                const float o = sn_old[k] * amp_old[k];  // MathUGen<Mul> with the gain as it was at that frame
+                const bool ok = emit && fr < NF;
+                st[(fr - tile0) * SUB_PAD + lane] = ok ? o : 0.f;
+                if (TAPS && tap && ok) tap[fr] = o;
+            }
+        }
+        // the modulators' sines of the previous iteration (frames (G - 1) * FM_SUB + k) reach the
+        // carrier lanes, which get to those frames in the next iteration
+#pragma unroll
+        for (int k = 0; k < FM_SUB; k++) {
+            mcur[k] = __shfl_sync(0xFFFFFFFFu, sn_old[k], mod_lane);
+            sn_old[k] = sn_new[k];
+            amp_old[k] = amp_new[k];
+        }
+        if (G >= 3) {
+            const uint32_t cend = min(gf - 2u * FM_SUB, NF); // every frame below cend is staged
+            if (cend - tile0 == SUB_TILE || G == NG + 2) {
+                __syncwarp();
+                // lane = frame: sum the 16 carrier columns (the modulator columns hold zeros)
+                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+                for (int j = FM_VPW; j < 32; j += 4) {
+                    acc0 = acc0 + st[lane * SUB_PAD + j];
+                    acc1 = acc1 + st[lane * SUB_PAD + j + 1];
+                    acc2 = acc2 + st[lane * SUB_PAD + j + 2];
+                    acc3 = acc3 + st[lane * SUB_PAD + j + 3];
+                }
+                if (lane < cend - tile0) prow[tile0 + lane] = (acc0 + acc1) + (acc2 + acc3);
+                tile0 = cend;
+                __syncwarp();
+            }
+        }
+    }
+    if (active) {
+        a.regs[(size_t)s.base * V + v] = __float_as_uint(s.ph);
+        a.regs[(size_t)(s.base + 1) * V + v] = __float_as_uint(s.off);
+        a.regs[(size_t)(s.base + 2) * V + v] = __float_as_uint(s.inc);
+        if (s.car) {
+            a.regs[(size_t)F_IDX * V + v] = __float_as_uint(s.idx);
+            a.regs[(size_t)F_FC * V + v] = __float_as_uint(s.fc);
+            a.regs[(size_t)F_AMP * V + v] = __float_as_uint(s.amp);
+        }
     }
 }
 
@@ -1234,8 +1437,11 @@ const char *fused_recipe_name(int recipe) {
     default: return "render_interp";
     }
 }
+// recipe 1: two lanes per voice while that still leaves at most one warp per SM sub-partition (148 x 4)
+bool fm_two_lanes(uint32_t n_voices) { return (n_voices + FM_VPW - 1) / FM_VPW <= 148u * 4u; }
 uint32_t fused_rows(int recipe, uint32_t n_voices, uint32_t n_ubus) {
     if (recipe == 2) return add_wt_slices(n_voices) * n_ubus; // one partial row per voice slice
+    if (recipe == 1 && fm_two_lanes(n_voices)) return ((n_voices + FM_VPW - 1) / FM_VPW) * n_ubus;
     return ((n_voices + 31) / 32) * n_ubus;                   // one partial row per warp
 }
 size_t fused_scratch_bytes(int recipe, uint32_t n_voices, uint32_t n_frames, uint32_t block_size) {
@@ -1243,9 +1449,15 @@ size_t fused_scratch_bytes(int recipe, uint32_t n_voices, uint32_t n_frames, uin
 }
 cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream) {
     if (recipe == 1) {
-        const uint32_t nw = (a.n_voices + 31) / 32;
-        if (a.n_taps) render_fm2<true><<<nw, 32, 0, stream>>>(a);
-        else render_fm2<false><<<nw, 32, 0, stream>>>(a);
+        if (fm_two_lanes(a.n_voices)) {
+            const uint32_t nw = (a.n_voices + FM_VPW - 1) / FM_VPW;
+            if (a.n_taps) render_fm2<true><<<nw, 32, 0, stream>>>(a);
+            else render_fm2<false><<<nw, 32, 0, stream>>>(a);
+        } else {
+            const uint32_t nw = (a.n_voices + 31) / 32;
+            if (a.n_taps) render_fm2_wide<true><<<nw, 32, 0, stream>>>(a);
+            else render_fm2_wide<false><<<nw, 32, 0, stream>>>(a);
+        }
         return cudaGetLastError();
     }
     if (recipe == 2) return launch_add_wt(a, stream);

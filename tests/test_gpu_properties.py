@@ -338,3 +338,25 @@ def test_sinwt_with_precise_timing_stays_on_the_interpreter():
     assert proc.info()["kernels"] == ["render_interp"]
     assert np.array_equal(taps, ref_taps)
 
+
+
+def test_fm_bank_one_lane_form_above_the_two_lane_threshold():
+    # recipe "render_fm2" has two forms (fused.cu fm_two_lanes): two lanes per voice up to 9472 voices,
+    # one lane per voice above.  The parity tests run the first; this one runs the second against the
+    # interpreter (same arithmetic, same order => per-voice bit-identical).
+    n_voices, n_blocks = 9600, 24
+
+    def run(force_interp):
+        graph, proc = AudioProcessor.new(0, 2, AudioProcessorOptions(sample_rate=SR, force_interpreter=force_interp))
+        ids = banks.fm_bank(graph, n_voices)
+        for i in (ids[0], ids[1], ids[4735], ids[-2], ids[-1]):
+            proc.add_tap(i, 0)
+        out = proc.render(n_blocks)
+        return out, proc.read_taps(), proc.info()["kernels"]
+
+    fo, ft, fk = run(False)
+    io, it, ik = run(True)
+    assert fk == ["render_fm2"] and ik == ["render_interp"]
+    assert np.abs(ft).max() > 1e-5
+    assert np.array_equal(ft, it)
+    assert np.abs(fo - io).max() <= 1e-6
