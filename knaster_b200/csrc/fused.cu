@@ -85,7 +85,9 @@ template <class ENV> struct SubVoice {
 };
 
 // x - trunc(x) for x in [0, 2): trunc(x) is 0 or 1, and x - 1 is exact for x in [1, 2)
-KN_DEV float wrap01(float x) { return x >= 1.0f ? x - 1.0f : x; }
+// As "x minus a 0/1 flag": one FSET + one FADD where the select form costs FADD + FSETP + FSEL, and
+// one instruction instead of two on the half-rate ALU pipe; x - 0 is x.
+KN_DEV float wrap01(float x) { return x - (x >= 1.0f ? 1.0f : 0.0f); }
 
 // The refined reciprocal nvcc's IEEE division computes per call (MUFU.RCP + one Newton step).
 // It only depends on the divisor, so it is hoisted: recomputed when dt changes.
@@ -113,10 +115,9 @@ KN_DEV float div_rc(float n, float d, float rc) {
 KN_DEV float saw_eval(float t, float dt, float omd, float rc) {
     const float _t = wrap01(t + 0.5f);
     const float y = __fmaf_rn(2.0f, _t, -1.0f);
-    const bool lo = _t < dt;
-    const bool hi = _t > omd;                    // else-if: lo and hi exclude each other for dt < 1/2
-    const float hf = hi ? 1.0f : 0.0f;
-    const float c = lo ? 1.0f : -hf;
+    const float lf = _t < dt ? 1.0f : 0.0f;
+    const float hf = _t > omd ? 1.0f : 0.0f;     // else-if: the two windows exclude each other for dt < 1/2
+    const float c = lf - hf;                     // exact; a subtraction instead of a select (FMA pipe, not ALU)
     const float q = div_rc(_t - hf, dt, rc);     // _t - 1 is exact for _t in (1/2, 1)
     const float x = q - c;
     return __fmaf_rn(c, x * x, y);
@@ -138,8 +139,16 @@ constexpr int SUBW_TILE = 2 * SUB_SUB; // render_sub_asr staging tile: two halve
 struct AsrEnv {
     uint32_t est;
     float et, ar, rr, sc, gain;
+    // What a straight-line group needs, fixed while the state machine does not move.  The group is
+    // select-free: every lane evaluates ((tl * u) * u) * sc2 with
+    //   Releasing  tl = u = t (both step by -release_rate, so they stay equal), sc2 = release_scale:
+    //              ((t * t) * t) * release_scale, the reference's t.powi(3) * release_scale;
+    //   Attacking  u = 1 (step 0), sc2 = 1: ((t * 1) * 1) * 1 == t;
+    //   Sustaining / Stopped  tl = 1 / 0 (step 0), u = 1, sc2 = 1: the constant itself.
     struct D {
         float delta;   // per-frame increment of t: +attack_rate, -release_rate or 0
+        float du;      // per-frame increment of u: -release_rate or 0
+        float sc2;     // release_scale while Releasing, else 1
         float cval;    // output of the constant states: Sustaining 1, Stopped 0
         bool att, rel;
     };
@@ -171,6 +180,8 @@ struct AsrEnv {
         d.att = est == ASR_ATTACKING;
         d.rel = est == ASR_RELEASING;
         d.delta = d.att ? ar : (d.rel ? -rr : 0.0f);
+        d.du = d.rel ? -rr : 0.0f;
+        d.sc2 = d.rel ? sc : 1.0f;
         d.cval = est == ASR_SUSTAINING ? 1.0f : 0.0f;
     }
     // Number of coming frames in which the envelope state machine provably cannot change state.
@@ -188,13 +199,17 @@ struct AsrEnv {
     }
     // EnvAsr::next_sample (envelopes.rs:52-81) with the state fixed over the group
     template <int N> KN_DEV void group(const D &d, float (&env)[N]) {
+        const bool ramp = d.att || d.rel;
+        float tl = ramp ? et : d.cval;
+        float u = d.rel ? et : 1.0f;
 #pragma unroll
         for (int k = 0; k < N; k++) {
-            const float cube = ((et * et) * et) * sc;
-            const float o = d.att ? et : (d.rel ? cube : d.cval);
-            et = et + d.delta;
+            const float o = ((tl * u) * u) * d.sc2;
+            tl = tl + d.delta;
+            u = u + d.du;
             env[k] = o * gain;      // WrMul, wrappers_core/math.rs:63-67
         }
+        et = ramp ? tl : et;
     }
     // one frame, then EnvAsr's transitions (envelopes.rs:60-77): they only change what FOLLOWING frames do
     KN_DEV float exact1(const D &d) {
