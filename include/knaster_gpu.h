@@ -230,7 +230,7 @@ float kgpu_plan_last_kernel_ms(kgpu_plan *plan, uint32_t kernel_class, uint32_t 
 /* Host-to-device bytes (compiled parameter events) uploaded by the last kgpu_render* call. */
 uint64_t kgpu_plan_last_upload_bytes(kgpu_plan *plan);
 /* K = blocks rendered per kernel launch (default: as many as fit a 256 MiB partial-sum buffer,
- * at most 1024).  K = 1 reproduces "one launch per 64-frame block". */
+ * at most 2048).  K = 1 reproduces "one launch per 64-frame block". */
 int kgpu_plan_set_blocks_per_launch(kgpu_plan *plan, uint64_t blocks);
 /* ---- multi-GPU mix bus over peer memory -------------------------------------------------------
  * One process per GPU, voices sharded across ranks.  Instead of reducing the rank-local
