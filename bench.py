@@ -176,7 +176,7 @@ def run_reference(args, rank, world):
         "note": "C++ restatement of knaster's CPU render path (oracle/); knaster itself is Rust and cannot be built here. "
                 "knaster renders on ONE audio thread; the all-core figure is an upper bound it does not offer.",
     }
-    print(json.dumps(line))
+    emit_json(line)
 
 
 def workload_config(args, world):
@@ -216,7 +216,23 @@ def cpu_baseline(args):
                       f"one-audio-thread render path (oracle/), host has {os.cpu_count()} cores"}
 
 
+_JSON_FD = None
+
+
+def emit_json(line) -> None:
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line
+    to stdout when NCCL_DEBUG asks for it), so main() points fd 1 at stderr for the duration of the run
+    and the result goes to the saved original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -236,6 +252,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=4.0)
     ap.add_argument("--ref-seconds", type=float, default=1.0, help="--impl reference: audio seconds per step")
     args = ap.parse_args()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)   # see emit_json
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -424,7 +443,7 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line))
+        emit_json(line)
     if peer_bus is not None and peer_bus.timed_out():
         sys.stderr.write("[bench] WARNING: a rank timed out waiting for peer-bus data\n")
     if world > 1:
