@@ -33,6 +33,17 @@ def test_library_exports_every_declared_symbol():
     assert lib.kgpu_device_count() >= 0
 
 
+def test_rust_binding_declares_every_entry_point():
+    # rust/knaster_gpu/src/ffi.rs (the text of INTEGRATION.md as a crate; not compiled here: no cargo/rustc in
+    # this image) must at least name every function the header exports, and nothing else
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = re.sub(r"/\*.*?\*/", "", open(_ffi.HEADER).read(), flags=re.S)
+    names = set(re.findall(r"\b(kgpu_[a-z_0-9]+)\s*\(", src))
+    for path in ("rust/knaster_gpu/src/ffi.rs", "INTEGRATION.md"):
+        decl = set(re.findall(r"pub fn (kgpu_[a-z_0-9]+)\(", open(os.path.join(root, path)).read()))
+        assert decl == names, (path, sorted(names ^ decl))
+
+
 def test_event_struct_layout_matches_header():
     from knaster_b200.graph import EVENT_DTYPE
 
