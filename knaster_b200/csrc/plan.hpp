@@ -106,6 +106,14 @@ struct NodeRef {
     uint32_t n_params = 0;
 };
 
+// std::allocator whose value-less construct() default-initialises: vector::resize() of a POD then leaves
+// the new elements uninitialised instead of zero-filling them (HostPlan::push fills them in parallel)
+template <class T> struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+    template <class U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+
 struct RawEvent { // 32 bytes
     uint32_t node;
     uint16_t param;
@@ -149,7 +157,7 @@ struct HostPlan {
     std::vector<NodeRef> node_ref; // per graph node
     uint32_t n_mix_nodes = 0;
     uint64_t dropped_changes = 0, ignored_delays = 0, device_events = 0;
-    std::vector<RawEvent> pending;                  // not yet simulated
+    std::vector<RawEvent, DefaultInitAllocator<RawEvent>> pending; // not yet simulated
 
     // caches / scratch of the hot host path (push / compile_events)
     struct Rule { char want; uint8_t smooth_ok, polyblep_wave, svf_type; };
