@@ -360,3 +360,36 @@ def test_fm_bank_one_lane_form_above_the_two_lane_threshold():
     assert np.abs(ft).max() > 1e-5
     assert np.array_equal(ft, it)
     assert np.abs(fo - io).max() <= 1e-6
+
+
+@pytest.mark.parametrize("block_size,n_blocks,per_block", [(24, 60, True), (1, 90, True), (100, 13, False), (7, 301, False), (64, 5, True)])
+@pytest.mark.parametrize("bank", ["fm", "segments"])
+def test_fused_fm_and_segment_kernels_with_odd_launch_lengths(bank, block_size, n_blocks, per_block):
+    # render_fm2 pipelines its carriers two 16-frame groups behind its modulators and drains that
+    # pipeline at every launch end; render_sub_seg carries f64 envelope state across launches.  Launch
+    # lengths that are not multiples of 16 (or shorter than one group), and one launch per block
+    # (run_without_inputs), must give what one long render gives and what the oracle gives.
+    def build(graph):
+        if bank == "fm":
+            ids = banks.fm_bank(graph, 37)
+            with graph.edit() as g:      # parameter events through the slow path of the two-lane kernel
+                for k, frame in enumerate((3, block_size * n_blocks // 3, block_size * n_blocks // 2 + 5)):
+                    # node 0 / 1: modulator / carrier of voice 0 (fm_bank pushes them first)
+                    g.set(k % 2, "phase_offset", 0.1 * (k + 1), kn.Time.at(kn.Seconds.from_samples(frame, SR)))
+            return ids
+        return banks.subtractive_bank(graph, 37, n_blocks * block_size / SR, n_notes=3, envelope="segments")
+
+    out, taps, proc = gpu_render(build, n_blocks, block_size=block_size, outputs=2)
+    assert proc.info()["kernels"] == ["render_fm2" if bank == "fm" else "render_sub_seg"]
+    ref, ref_taps = oracle_render(build, n_blocks, block_size=block_size, outputs=2)
+    assert np.abs(taps - ref_taps).max() <= 1e-5
+    assert np.abs(out - ref).max() <= 1e-5
+    assert np.abs(ref).max() > 1e-4
+    if per_block:
+        graph, p1 = AudioProcessor.new(0, 2, AudioProcessorOptions(block_size=block_size, sample_rate=SR))
+        build(graph)
+        blocks = []
+        for _ in range(n_blocks):
+            p1.run_without_inputs()
+            blocks.append(p1.output_block())
+        assert np.array_equal(np.stack(blocks), out)
