@@ -168,12 +168,31 @@ __global__ void __launch_bounds__(WT_THREADS) add_wt_render(FusedArgs a, const W
 
 } // namespace
 
-bool match_add_wt(const DevProgram &p, uint32_t block_size) {
-    if (p.n_nodes != 1 || p.n_ubus != 1 || block_size % 32 != 0) return false;
+// Two voice shapes: SinWt[.wr_mul][.smooth_params] alone, and SinWt -> MathUGen<Mul> with a Constant (the
+// README example `sine * 0.2`, README.md:35-47: table[..] * 0.2 is the same single f32 product as
+// wr_mul(0.2), and a `value` event on the Constant is a write to the gain register like a `wr_mul` event).
+static bool add_wt_shape(const DevProgram &p, uint32_t &gain_reg) {
+    if (p.n_ubus != 1) return false;
     const DevNode &n = p.nodes[0];
-    if (n.kind != DK_SINWT || n.reg != 0 || n.n_ar || n.n_post > 1) return false;
-    if (n.n_post == 1 && n.post_op[0] != PO_MUL) return false;
-    return p.ubus_slot[0] == n.out_slot[0];
+    if (n.kind != DK_SINWT || n.reg != 0 || n.n_ar) return false;
+    if (p.n_nodes == 1) {
+        if (n.n_post > 1 || (n.n_post == 1 && n.post_op[0] != PO_MUL)) return false;
+        gain_reg = n.n_post == 1 ? n.post_reg[0] : 0xFFFFFFFFu;
+        return p.ubus_slot[0] == n.out_slot[0];
+    }
+    if (p.n_nodes != 3 || n.n_post) return false;
+    const DevNode &c = p.nodes[1], &m = p.nodes[2];
+    if (c.kind != DK_CONST || c.n_post || c.n_ar) return false;
+    if (m.kind != DK_MATH || m.mode != 2 || m.n_out != 1 || m.n_post || m.n_ar) return false;
+    const bool ab = m.in_slot[0] == (int)n.out_slot[0] && m.in_slot[1] == (int)c.out_slot[0];
+    const bool ba = m.in_slot[1] == (int)n.out_slot[0] && m.in_slot[0] == (int)c.out_slot[0];
+    if (!ab && !ba) return false;
+    gain_reg = c.reg;
+    return p.ubus_slot[0] == m.out_slot[0];
+}
+bool match_add_wt(const DevProgram &p, uint32_t block_size) {
+    uint32_t gain_reg;
+    return block_size % 32 == 0 && add_wt_shape(p, gain_reg);
 }
 uint32_t add_wt_slices(uint32_t n_voices) { return std::max(1u, std::min(32u, (n_voices + 127) / 128)); }
 size_t add_wt_scratch_bytes(uint32_t n_voices, uint32_t n_frames, uint32_t block_size) {
@@ -181,8 +200,8 @@ size_t add_wt_scratch_bytes(uint32_t n_voices, uint32_t n_frames, uint32_t block
     return (size_t)n_voices * (n_frames / block_size) * sizeof(WtParam) + (size_t)n_voices * MAX_REGS * 4;
 }
 cudaError_t launch_add_wt(const FusedArgs &a, cudaStream_t stream) {
-    const DevNode n = a.host_prog->nodes[0];
-    const uint32_t gain_reg = n.n_post == 1 ? n.post_reg[0] : 0xFFFFFFFFu;
+    uint32_t gain_reg = 0xFFFFFFFFu;
+    if (!add_wt_shape(*a.host_prog, gain_reg)) return cudaErrorNotSupported;
     WtParam *table = reinterpret_cast<WtParam *>(a.scratch);
     FusedArgs ap = a;
     ap.regs_out = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(a.scratch) + (size_t)a.n_voices * (a.n_frames / a.block_size) * sizeof(WtParam));

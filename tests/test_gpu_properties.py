@@ -393,3 +393,31 @@ def test_fused_fm_and_segment_kernels_with_odd_launch_lengths(bank, block_size, 
             p1.run_without_inputs()
             blocks.append(p1.output_block())
         assert np.array_equal(np.stack(blocks), out)
+
+
+def test_readme_shape_bank_runs_the_time_parallel_wavetable_kernel():
+    # `sine * 0.2` (README.md:35-47) = SinWt -> MathUGen<Mul> with a Constant: rendered by render_add_wt
+    # (time is the parallel axis), with `value` events on the Constant acting as gain changes and
+    # `freq` / `phase_offset` / `reset_phase` events on the oscillator; both operand orders of the Mul
+    def build(graph):
+        ids = []
+        with graph.edit() as g:
+            for i in range(9):
+                sine = g.push(kn.SinWt(110.0 * (i + 1)))
+                c = g.push(kn.Constant(0.05 + 0.01 * i))
+                sig = sine * c
+                sig.out([0, 0]).to_graph_out()
+                c.param("value").set_at(0.02 * (i + 1), at(64 * (3 + i)))
+                c.param("value").set_at(0.01, at(64 * 40 + 17))           # inside a block: applies at its start
+                sine.param("freq").set_at(333.0 + i, at(64 * 20))
+                sine.param("phase_offset").set_at(0.25, at(64 * 30))
+                sine.param("reset_phase").trig_at(at(64 * 50))
+                ids.append(sig._outputs[0][0])
+        return ids
+
+    out, taps, proc = gpu_render(build, 120, outputs=2)
+    assert proc.info()["kernels"] == ["render_add_wt"]
+    ref, ref_taps = oracle_render(build, 120, outputs=2)
+    assert np.array_equal(taps, ref_taps)          # integer phase, one f32 product
+    assert np.abs(out - ref).max() <= 1e-6
+    assert np.abs(ref).max() > 0.05
