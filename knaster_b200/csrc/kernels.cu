@@ -113,6 +113,23 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             float pv[MAX_POST];
 #pragma unroll
             for (int k = 0; k < MAX_POST; k++) pv[k] = k < dn.n_post ? __uint_as_float(sreg[dn.post_reg[k] * 32]) : 0.f;
+            // Fast path of a node over a whole 16-frame chunk: no event of this node falls into the chunk, no
+            // audio-rate route, at most one arithmetic wrapper and that one a WrMul.  The 16 frames are then
+            // unrolled into one basic block (the per-frame event / route / wrapper checks of the generic loops
+            // below cost more than the arithmetic and serialise it), and the wrapper is "times g_" with
+            // g_ = 1 when there is none (x * 1 == x exactly).
+            const uint32_t n_post_ = dn.n_post, o0_ = dn.out_slot[0];
+            const bool plain = !evc && dn.n_ar == 0 && nf == 16 && CH == 16 && (n_post_ == 0 || (n_post_ == 1 && dn.post_op[0] == PO_MUL));
+            const float g_ = n_post_ ? pv[0] : 1.0f;
+#define PLAIN16(EXPR_)                                                                 \
+    {                                                                                  \
+        float y_[16];                                                                  \
+        _Pragma("unroll") for (int k = 0; k < 16; k++) y_[k] = (EXPR_);                \
+        _Pragma("unroll") for (int k = 0; k < 16; k++) sval[(o0_ * 16 + k) * 32] = y_[k] * g_; \
+    }
+#define LOAD16(x_, slot_)                                                              \
+    float x_[16];                                                                      \
+    _Pragma("unroll") for (int k = 0; k < 16; k++) x_[k] = (slot_) >= 0 ? sval[((slot_) * 16 + k) * 32] : 0.f;
 #define EVENTS_AT(f_, STORE_, LOAD_)                                                   \
     if (evc && L.next_node == n && L.next_frame <= c0 + (f_)) {                        \
         STORE_;                                                                        \
@@ -134,6 +151,11 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             switch (dn.kind) {
             case DK_SINWT: {
                 uint32_t phase = sreg[rb * 32], off = sreg[(rb + 1) * 32], inc = sreg[(rb + 2) * 32];
+                if (plain) {
+                    PLAIN16(sinwt_tick(phase, off, inc, a.sine_table))
+                    sreg[rb * 32] = phase;
+                    break;
+                }
                 for (uint32_t f = 0; f < nf; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = phase, (phase = sreg[rb * 32], off = sreg[(rb + 1) * 32], inc = sreg[(rb + 2) * 32]))
                     for (int ai = 0; ai < dn.n_ar; ai++) {
@@ -153,6 +175,11 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             case DK_SINNUM: {
                 float phase = __uint_as_float(sreg[rb * 32]), off = __uint_as_float(sreg[(rb + 1) * 32]),
                       inc = __uint_as_float(sreg[(rb + 2) * 32]);
+                if (plain) {
+                    PLAIN16(sinnum_tick(phase, off, inc))
+                    sreg[rb * 32] = __float_as_uint(phase);
+                    break;
+                }
                 for (uint32_t f = 0; f < nf; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(phase),
                               (phase = __uint_as_float(sreg[rb * 32]), off = __uint_as_float(sreg[(rb + 1) * 32]),
@@ -175,6 +202,15 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 uint32_t use_sin = sreg[(rb + 2) * 32];
                 float pw = __uint_as_float(sreg[(rb + 3) * 32]);
                 uint32_t wf = sreg[(rb + 4) * 32];
+                if (plain) {
+                    if (__all_sync(0xFFFFFFFFu, wf == 0u && !use_sin)) { // every lane a sawtooth below sr/4: no waveform switch per frame
+                        PLAIN16(polyblep_saw_tick(t, dt, 0u))
+                    } else {
+                        PLAIN16(polyblep_tick(t, dt, use_sin, pw, wf))
+                    }
+                    sreg[rb * 32] = __float_as_uint(t);
+                    break;
+                }
                 for (uint32_t f = 0; f < nf; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(t),
                               (t = __uint_as_float(sreg[rb * 32]), dt = __uint_as_float(sreg[(rb + 1) * 32]), use_sin = sreg[(rb + 2) * 32],
@@ -208,6 +244,12 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
 #define SVF_STORE (sreg[rb * 32] = __float_as_uint(ic1), sreg[(rb + 1) * 32] = __float_as_uint(ic2))
                 SVF_LOAD;
                 const int is = dn.in_slot[0];
+                if (plain) {
+                    LOAD16(x_, is)
+                    PLAIN16(svf_tick(x_[k], ic1, ic2, a1, a2, a3, m0, m1, m2))
+                    SVF_STORE;
+                    break;
+                }
                 for (uint32_t f = 0; f < nf; f++) {
                     EVENTS_AT(f, SVF_STORE, SVF_LOAD)
                     AR_POST_ROUTES(f)
@@ -223,6 +265,13 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 float y1 = __uint_as_float(sreg[rb * 32]), a0 = __uint_as_float(sreg[(rb + 1) * 32]), b1 = __uint_as_float(sreg[(rb + 2) * 32]);
                 const int is = dn.in_slot[0];
                 const bool hp = dn.kind == DK_ONEPOLE_HP;
+                if (plain) {
+                    LOAD16(x_, is)
+                    if (hp) PLAIN16(onepole_hp_tick(x_[k], y1, a0, b1))
+                    else PLAIN16(onepole_lp_tick(x_[k], y1, a0, b1))
+                    sreg[rb * 32] = __float_as_uint(y1);
+                    break;
+                }
                 for (uint32_t f = 0; f < nf; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(y1),
                               (y1 = __uint_as_float(sreg[rb * 32]), a0 = __uint_as_float(sreg[(rb + 1) * 32]), b1 = __uint_as_float(sreg[(rb + 2) * 32])))
@@ -243,6 +292,12 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
 #define ENV_STORE (sreg[rb * 32] = st, sreg[(rb + 1) * 32] = __float_as_uint(t), sreg[(rb + 4) * 32] = __float_as_uint(sc))
                 ENV_LOAD;
                 const bool asr = dn.kind == DK_ENVASR;
+                if (plain) {
+                    if (asr) PLAIN16(envasr_tick(st, t, ar, rr, sc))
+                    else PLAIN16(envar_tick(st, t, ar, rr, sc))
+                    ENV_STORE;
+                    break;
+                }
                 for (uint32_t f = 0; f < nf; f++) {
                     EVENTS_AT(f, ENV_STORE, ENV_LOAD)
                     AR_POST_ROUTES(f)
@@ -292,6 +347,19 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             }
             case DK_MATH: {
                 const uint32_t nch = dn.n_out;
+                if (plain && nch == 1) {
+                    const int sa = dn.in_slot[0], sb = dn.in_slot[1];
+                    LOAD16(a_, sa)
+                    LOAD16(b_, sb)
+                    switch (dn.mode) { // the operation is chosen once per chunk, not once per frame
+                    case 0: PLAIN16(a_[k] + b_[k]) break;
+                    case 1: PLAIN16(a_[k] - b_[k]) break;
+                    case 2: PLAIN16(a_[k] * b_[k]) break;
+                    case 3: PLAIN16(a_[k] / b_[k]) break;
+                    default: PLAIN16(math_apply(4, a_[k], b_[k])) break;
+                    }
+                    break;
+                }
                 for (uint32_t f = 0; f < nf; f++) {
                     EVENTS_AT(f, (void)0, (void)0)
                     AR_POST_ROUTES(f)
@@ -390,6 +458,15 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             case DK_INPLUS: {
                 float val = __uint_as_float(sreg[rb * 32]);
                 const int is = dn.kind == DK_INPLUS ? dn.in_slot[0] : -1;
+                if (plain) {
+                    if (dn.kind == DK_INPLUS) {
+                        LOAD16(x_, is)
+                        PLAIN16(val + x_[k])
+                    } else {
+                        PLAIN16(val)
+                    }
+                    break;
+                }
                 for (uint32_t f = 0; f < nf; f++) {
                     EVENTS_AT(f, (void)0, val = __uint_as_float(sreg[rb * 32]))
                     for (int ai = 0; ai < dn.n_ar; ai++) {
