@@ -488,7 +488,27 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 if (dn.ar_code[ai] >= AR_POST) sreg[dn.post_reg[dn.ar_code[ai] - AR_POST] * 32] = __float_as_uint(pv[dn.ar_code[ai] - AR_POST]);
             // events due in this chunk but after its last processed frame cannot exist (sorted by chunk)
         }
-        // mix bus: per-warp partial sums, fixed butterfly order => deterministic
+        // mix bus: per-warp partial sums in a fixed order => deterministic
+        if (CH == 16 && nf == 16) {
+            // lane f < 16 sums frame f of the chunk over the warp's active voices straight from the value slots
+            // ([slot][frame][lane] in shared memory), four accumulators, columns visited from lane f onwards so
+            // that the 16 readers hit 16 different banks.  The order is a function of the frame's position in
+            // its chunk only, and chunks start on block boundaries: independent of how a render is split.
+            __syncwarp();
+            const float *vbase = reinterpret_cast<const float *>(smem + n_regs * 32);
+            const uint32_t na = min(32u, a.n_voices - warp * 32);
+            for (uint32_t u = 0; u < prog->n_ubus; u++) {
+                const float *row = vbase + ((size_t)prog->ubus_slot[u] * 16 + (lane & 15u)) * 32;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const uint32_t col = (j + lane) & 31u;
+                    const float x = row[col];
+                    acc[j & 3] = acc[j & 3] + (col < na ? x : 0.f);
+                }
+                if (lane < 16) a.partials[(size_t)(a.row0 + warp * prog->n_ubus + u) * a.n_frames + c0 + lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            }
+        } else
         for (uint32_t u = 0; u < prog->n_ubus; u++) {
             const uint32_t slot = prog->ubus_slot[u];
             float mine = 0.f;
