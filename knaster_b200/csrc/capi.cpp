@@ -158,9 +158,13 @@ struct kgpu_plan {
 
 namespace {
 
-uint32_t pick_chunk(uint32_t block_size) {
-    uint32_t c = 16;
-    while (c > 1 && block_size % c) c >>= 1;
+// Frames a node of the interpreter processes per visit: the largest power of two <= 64 that divides the
+// block size and whose value slots ([slot][chunk][32 lanes] f32) + registers fit 48 KB of shared memory.
+// A long chunk amortises what a node visit costs beside its arithmetic (dispatch, register load / store,
+// and above all instruction fetch: every node kind is its own block of code and a scheduler holds ONE warp).
+uint32_t pick_chunk(uint32_t block_size, uint32_t n_regs, uint32_t n_slots) {
+    uint32_t c = 64;
+    while (c > 1 && (block_size % c || ((size_t)n_regs + (size_t)n_slots * c) * 128 > 48 * 1024)) c >>= 1;
     return c;
 }
 
@@ -208,7 +212,7 @@ void choose_kernels(kgpu_plan *p) {
                 if (!on_bus) recipe = -1;
             }
         d.recipe = recipe;
-        d.chunk = recipe >= 0 ? 1 : pick_chunk(p->host.block_size);
+        d.chunk = recipe >= 0 ? 1 : pick_chunk(p->host.block_size, g.prog.n_regs, g.prog.n_slots);
         g.fused_recipe = recipe;
         g.kernel_name = recipe >= 0 ? fused_recipe_name(recipe) : "render_interp";
     }

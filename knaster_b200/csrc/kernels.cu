@@ -113,23 +113,23 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             float pv[MAX_POST];
 #pragma unroll
             for (int k = 0; k < MAX_POST; k++) pv[k] = k < dn.n_post ? __uint_as_float(sreg[dn.post_reg[k] * 32]) : 0.f;
-            // Fast path of a node over a whole 16-frame chunk: no event of this node falls into the chunk, no
-            // audio-rate route, at most one arithmetic wrapper and that one a WrMul.  The 16 frames are then
-            // unrolled into one basic block (the per-frame event / route / wrapper checks of the generic loops
+            // Fast path of a node over a whole chunk (16, 32 or 64 frames, in groups of 16 at offset g0_): no event
+            // of this node falls into the chunk, no audio-rate route, at most one arithmetic wrapper and that one
+            // a WrMul.  The 16 frames of a group are unrolled into one basic block (the per-frame event / route / wrapper checks of the generic loops
             // below cost more than the arithmetic and serialise it), and the wrapper is "times g_" with
             // g_ = 1 when there is none (x * 1 == x exactly).
             const uint32_t n_post_ = dn.n_post, o0_ = dn.out_slot[0];
-            const bool plain = !evc && dn.n_ar == 0 && nf == 16 && CH == 16 && (n_post_ == 0 || (n_post_ == 1 && dn.post_op[0] == PO_MUL));
+            const bool plain = !evc && dn.n_ar == 0 && nf == CH && (CH & 15u) == 0 && (n_post_ == 0 || (n_post_ == 1 && dn.post_op[0] == PO_MUL));
             const float g_ = n_post_ ? pv[0] : 1.0f;
 #define PLAIN16(EXPR_)                                                                 \
     {                                                                                  \
         float y_[16];                                                                  \
         _Pragma("unroll") for (int k = 0; k < 16; k++) y_[k] = (EXPR_);                \
-        _Pragma("unroll") for (int k = 0; k < 16; k++) sval[(o0_ * 16 + k) * 32] = y_[k] * g_; \
+        _Pragma("unroll") for (int k = 0; k < 16; k++) sval[(o0_ * CH + g0_ + k) * 32] = y_[k] * g_; \
     }
 #define LOAD16(x_, slot_)                                                              \
     float x_[16];                                                                      \
-    _Pragma("unroll") for (int k = 0; k < 16; k++) x_[k] = (slot_) >= 0 ? sval[((slot_) * 16 + k) * 32] : 0.f;
+    _Pragma("unroll") for (int k = 0; k < 16; k++) x_[k] = (slot_) >= 0 ? sval[((slot_) * CH + g0_ + k) * 32] : 0.f;
 #define EVENTS_AT(f_, STORE_, LOAD_)                                                   \
     if (evc && L.next_node == n && L.next_frame <= c0 + (f_)) {                        \
         STORE_;                                                                        \
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             case DK_SINWT: {
                 uint32_t phase = sreg[rb * 32], off = sreg[(rb + 1) * 32], inc = sreg[(rb + 2) * 32];
                 if (plain) {
-                    PLAIN16(sinwt_tick(phase, off, inc, a.sine_table))
+                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) PLAIN16(sinwt_tick(phase, off, inc, a.sine_table))
                     sreg[rb * 32] = phase;
                     break;
                 }
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 float phase = __uint_as_float(sreg[rb * 32]), off = __uint_as_float(sreg[(rb + 1) * 32]),
                       inc = __uint_as_float(sreg[(rb + 2) * 32]);
                 if (plain) {
-                    PLAIN16(sinnum_tick(phase, off, inc))
+                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) PLAIN16(sinnum_tick(phase, off, inc))
                     sreg[rb * 32] = __float_as_uint(phase);
                     break;
                 }
@@ -204,9 +204,9 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 uint32_t wf = sreg[(rb + 4) * 32];
                 if (plain) {
                     if (__all_sync(0xFFFFFFFFu, wf == 0u && !use_sin)) { // every lane a sawtooth below sr/4: no waveform switch per frame
-                        PLAIN16(polyblep_saw_tick(t, dt, 0u))
+                        for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) PLAIN16(polyblep_saw_tick_sel(t, dt))
                     } else {
-                        PLAIN16(polyblep_tick(t, dt, use_sin, pw, wf))
+                        for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) PLAIN16(polyblep_tick(t, dt, use_sin, pw, wf))
                     }
                     sreg[rb * 32] = __float_as_uint(t);
                     break;
@@ -245,8 +245,10 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 SVF_LOAD;
                 const int is = dn.in_slot[0];
                 if (plain) {
-                    LOAD16(x_, is)
-                    PLAIN16(svf_tick(x_[k], ic1, ic2, a1, a2, a3, m0, m1, m2))
+                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) {
+                        LOAD16(x_, is)
+                        PLAIN16(svf_tick(x_[k], ic1, ic2, a1, a2, a3, m0, m1, m2))
+                    }
                     SVF_STORE;
                     break;
                 }
@@ -266,9 +268,11 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 const int is = dn.in_slot[0];
                 const bool hp = dn.kind == DK_ONEPOLE_HP;
                 if (plain) {
-                    LOAD16(x_, is)
-                    if (hp) PLAIN16(onepole_hp_tick(x_[k], y1, a0, b1))
-                    else PLAIN16(onepole_lp_tick(x_[k], y1, a0, b1))
+                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) {
+                        LOAD16(x_, is)
+                        if (hp) PLAIN16(onepole_hp_tick(x_[k], y1, a0, b1))
+                        else PLAIN16(onepole_lp_tick(x_[k], y1, a0, b1))
+                    }
                     sreg[rb * 32] = __float_as_uint(y1);
                     break;
                 }
@@ -293,8 +297,10 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 ENV_LOAD;
                 const bool asr = dn.kind == DK_ENVASR;
                 if (plain) {
-                    if (asr) PLAIN16(envasr_tick(st, t, ar, rr, sc))
-                    else PLAIN16(envar_tick(st, t, ar, rr, sc))
+                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) {
+                        if (asr) PLAIN16(envasr_tick_sel(st, t, ar, rr, sc))
+                        else PLAIN16(envar_tick(st, t, ar, rr, sc))
+                    }
                     ENV_STORE;
                     break;
                 }
@@ -349,14 +355,16 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 const uint32_t nch = dn.n_out;
                 if (plain && nch == 1) {
                     const int sa = dn.in_slot[0], sb = dn.in_slot[1];
-                    LOAD16(a_, sa)
-                    LOAD16(b_, sb)
-                    switch (dn.mode) { // the operation is chosen once per chunk, not once per frame
-                    case 0: PLAIN16(a_[k] + b_[k]) break;
-                    case 1: PLAIN16(a_[k] - b_[k]) break;
-                    case 2: PLAIN16(a_[k] * b_[k]) break;
-                    case 3: PLAIN16(a_[k] / b_[k]) break;
-                    default: PLAIN16(math_apply(4, a_[k], b_[k])) break;
+                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) {
+                        LOAD16(a_, sa)
+                        LOAD16(b_, sb)
+                        switch (dn.mode) { // the operation is chosen once per group, not once per frame
+                        case 0: PLAIN16(a_[k] + b_[k]) break;
+                        case 1: PLAIN16(a_[k] - b_[k]) break;
+                        case 2: PLAIN16(a_[k] * b_[k]) break;
+                        case 3: PLAIN16(a_[k] / b_[k]) break;
+                        default: PLAIN16(math_apply(4, a_[k], b_[k])) break;
+                        }
                     }
                     break;
                 }
@@ -459,11 +467,13 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 float val = __uint_as_float(sreg[rb * 32]);
                 const int is = dn.kind == DK_INPLUS ? dn.in_slot[0] : -1;
                 if (plain) {
-                    if (dn.kind == DK_INPLUS) {
-                        LOAD16(x_, is)
-                        PLAIN16(val + x_[k])
-                    } else {
-                        PLAIN16(val)
+                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) {
+                        if (dn.kind == DK_INPLUS) {
+                            LOAD16(x_, is)
+                            PLAIN16(val + x_[k])
+                        } else {
+                            PLAIN16(val)
+                        }
                     }
                     break;
                 }
@@ -489,25 +499,26 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             // events due in this chunk but after its last processed frame cannot exist (sorted by chunk)
         }
         // mix bus: per-warp partial sums in a fixed order => deterministic
-        if (CH == 16 && nf == 16) {
-            // lane f < 16 sums frame f of the chunk over the warp's active voices straight from the value slots
-            // ([slot][frame][lane] in shared memory), four accumulators, columns visited from lane f onwards so
-            // that the 16 readers hit 16 different banks.  The order is a function of the frame's position in
-            // its chunk only, and chunks start on block boundaries: independent of how a render is split.
+        if ((CH & 15u) == 0 && nf == CH) {
+            // lane f < 16 sums frame g0 + f of the chunk over the warp's active voices straight from the value
+            // slots ([slot][frame][lane] in shared memory), four accumulators, columns visited from lane f
+            // onwards so that the readers hit different banks.  The order is a function of the frame's position
+            // in its chunk only, and chunks start on block boundaries: independent of how a render is split.
             __syncwarp();
             const float *vbase = reinterpret_cast<const float *>(smem + n_regs * 32);
             const uint32_t na = min(32u, a.n_voices - warp * 32);
-            for (uint32_t u = 0; u < prog->n_ubus; u++) {
-                const float *row = vbase + ((size_t)prog->ubus_slot[u] * 16 + (lane & 15u)) * 32;
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (uint32_t u = 0; u < prog->n_ubus; u++)
+                for (uint32_t g0 = 0; g0 < CH; g0 += 16) {
+                    const float *row = vbase + ((size_t)prog->ubus_slot[u] * CH + g0 + (lane & 15u)) * 32;
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const uint32_t col = (j + lane) & 31u;
-                    const float x = row[col];
-                    acc[j & 3] = acc[j & 3] + (col < na ? x : 0.f);
+                    for (int j = 0; j < 32; j++) {
+                        const uint32_t col = (j + lane) & 31u;
+                        const float x = row[col];
+                        acc[j & 3] = acc[j & 3] + (col < na ? x : 0.f);
+                    }
+                    if (lane < 16) a.partials[(size_t)(a.row0 + warp * prog->n_ubus + u) * a.n_frames + c0 + g0 + lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
                 }
-                if (lane < 16) a.partials[(size_t)(a.row0 + warp * prog->n_ubus + u) * a.n_frames + c0 + lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-            }
         } else
         for (uint32_t u = 0; u < prog->n_ubus; u++) {
             const uint32_t slot = prog->ubus_slot[u];

@@ -14,7 +14,7 @@ struct InterpArgs {
     const DevEvent *events; // device, sorted per voice in processing order; NULL if none this launch
     const uint32_t *ev_off; // [n_voices+1]
     uint32_t n_frames;
-    uint32_t chunk;         // frames per interpreter chunk (divides block_size, <= 16)
+    uint32_t chunk;         // frames per interpreter chunk (power of two <= 64 that divides block_size, capi.cpp pick_chunk)
     float *partials;        // [rows][n_frames]
     uint32_t row0;          // first partial row of this group
     const DevTap *taps;
