@@ -119,11 +119,15 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             // below cost more than the arithmetic and serialise it), and the wrapper is "times g_" with
             // g_ = 1 when there is none (x * 1 == x exactly).
             const uint32_t n_post_ = dn.n_post, o0_ = dn.out_slot[0];
-            const bool plain = !evc && dn.n_ar == 0 && nf == CH && (CH & 15u) == 0 && (n_post_ == 0 || (n_post_ == 1 && dn.post_op[0] == PO_MUL));
-            const float g_ = n_post_ ? pv[0] : 1.0f;
+            const bool plain_ok = dn.n_ar == 0 && (CH & 15u) == 0 && (n_post_ == 0 || (n_post_ == 1 && dn.post_op[0] == PO_MUL));
+            // a chunk is walked in groups of 16 frames; a group takes the fast path unless an event of this node
+            // falls into it (warp-uniform test on the lanes' event cursors) or it is a partial group
+#define FOR_GROUPS for (uint32_t g0_ = 0, fe_ = min(nf, 16u); g0_ < nf; g0_ += 16, fe_ = min(nf, g0_ + 16u))
+#define GROUP_PLAIN (plain_ok && fe_ - g0_ == 16 && !(evc && __any_sync(0xFFFFFFFFu, L.next_node == n && L.next_frame < c0 + fe_)))
 #define PLAIN16(EXPR_)                                                                 \
     {                                                                                  \
         float y_[16];                                                                  \
+        const float g_ = n_post_ ? pv[0] : 1.0f; /* an event in an earlier group of the chunk may have changed it */ \
         _Pragma("unroll") for (int k = 0; k < 16; k++) y_[k] = (EXPR_);                \
         _Pragma("unroll") for (int k = 0; k < 16; k++) sval[(o0_ * CH + g0_ + k) * 32] = y_[k] * g_; \
     }
@@ -151,12 +155,12 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             switch (dn.kind) {
             case DK_SINWT: {
                 uint32_t phase = sreg[rb * 32], off = sreg[(rb + 1) * 32], inc = sreg[(rb + 2) * 32];
-                if (plain) {
-                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) PLAIN16(sinwt_tick(phase, off, inc, a.sine_table))
-                    sreg[rb * 32] = phase;
-                    break;
-                }
-                for (uint32_t f = 0; f < nf; f++) {
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
+                        PLAIN16(sinwt_tick(phase, off, inc, a.sine_table))
+                        continue;
+                    }
+                    for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = phase, (phase = sreg[rb * 32], off = sreg[(rb + 1) * 32], inc = sreg[(rb + 2) * 32]))
                     for (int ai = 0; ai < dn.n_ar; ai++) {
                         float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
@@ -167,6 +171,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     float y = sinwt_tick(phase, off, inc, a.sine_table);
                     EMIT(f, 0, y)
                 }
+                }
                 sreg[rb * 32] = phase;
                 // audio-rate routes leave their last value in the ugen, like param_apply does
                 if (dn.n_ar) { sreg[(rb + 1) * 32] = off; sreg[(rb + 2) * 32] = inc; }
@@ -175,12 +180,12 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             case DK_SINNUM: {
                 float phase = __uint_as_float(sreg[rb * 32]), off = __uint_as_float(sreg[(rb + 1) * 32]),
                       inc = __uint_as_float(sreg[(rb + 2) * 32]);
-                if (plain) {
-                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) PLAIN16(sinnum_tick(phase, off, inc))
-                    sreg[rb * 32] = __float_as_uint(phase);
-                    break;
-                }
-                for (uint32_t f = 0; f < nf; f++) {
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
+                        PLAIN16(sinnum_tick(phase, off, inc))
+                        continue;
+                    }
+                    for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(phase),
                               (phase = __uint_as_float(sreg[rb * 32]), off = __uint_as_float(sreg[(rb + 1) * 32]),
                                inc = __uint_as_float(sreg[(rb + 2) * 32])))
@@ -193,6 +198,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     float y = sinnum_tick(phase, off, inc);
                     EMIT(f, 0, y)
                 }
+                }
                 sreg[rb * 32] = __float_as_uint(phase);
                 if (dn.n_ar) { sreg[(rb + 1) * 32] = __float_as_uint(off); sreg[(rb + 2) * 32] = __float_as_uint(inc); }
                 break;
@@ -202,16 +208,13 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 uint32_t use_sin = sreg[(rb + 2) * 32];
                 float pw = __uint_as_float(sreg[(rb + 3) * 32]);
                 uint32_t wf = sreg[(rb + 4) * 32];
-                if (plain) {
-                    if (__all_sync(0xFFFFFFFFu, wf == 0u && !use_sin)) { // every lane a sawtooth below sr/4: no waveform switch per frame
-                        for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) PLAIN16(polyblep_saw_tick_sel(t, dt))
-                    } else {
-                        for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) PLAIN16(polyblep_tick(t, dt, use_sin, pw, wf))
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
+                        if (__all_sync(0xFFFFFFFFu, wf == 0u && !use_sin)) PLAIN16(polyblep_saw_tick_sel(t, dt)) // every lane a sawtooth below sr/4
+                        else PLAIN16(polyblep_tick(t, dt, use_sin, pw, wf))
+                        continue;
                     }
-                    sreg[rb * 32] = __float_as_uint(t);
-                    break;
-                }
-                for (uint32_t f = 0; f < nf; f++) {
+                    for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(t),
                               (t = __uint_as_float(sreg[rb * 32]), dt = __uint_as_float(sreg[(rb + 1) * 32]), use_sin = sreg[(rb + 2) * 32],
                                pw = __uint_as_float(sreg[(rb + 3) * 32]), wf = sreg[(rb + 4) * 32]))
@@ -226,6 +229,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     }
                     float y = polyblep_tick(t, dt, use_sin, pw, wf);
                     EMIT(f, 0, y)
+                }
                 }
                 sreg[rb * 32] = __float_as_uint(t);
                 if (dn.n_ar) {
@@ -244,20 +248,19 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
 #define SVF_STORE (sreg[rb * 32] = __float_as_uint(ic1), sreg[(rb + 1) * 32] = __float_as_uint(ic2))
                 SVF_LOAD;
                 const int is = dn.in_slot[0];
-                if (plain) {
-                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) {
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
                         LOAD16(x_, is)
                         PLAIN16(svf_tick(x_[k], ic1, ic2, a1, a2, a3, m0, m1, m2))
+                        continue;
                     }
-                    SVF_STORE;
-                    break;
-                }
-                for (uint32_t f = 0; f < nf; f++) {
+                    for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, SVF_STORE, SVF_LOAD)
                     AR_POST_ROUTES(f)
                     float x = is >= 0 ? sval[(is * CH + f) * 32] : 0.f;
                     float y = svf_tick(x, ic1, ic2, a1, a2, a3, m0, m1, m2);
                     EMIT(f, 0, y)
+                }
                 }
                 SVF_STORE;
                 break;
@@ -267,22 +270,21 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 float y1 = __uint_as_float(sreg[rb * 32]), a0 = __uint_as_float(sreg[(rb + 1) * 32]), b1 = __uint_as_float(sreg[(rb + 2) * 32]);
                 const int is = dn.in_slot[0];
                 const bool hp = dn.kind == DK_ONEPOLE_HP;
-                if (plain) {
-                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) {
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
                         LOAD16(x_, is)
                         if (hp) PLAIN16(onepole_hp_tick(x_[k], y1, a0, b1))
                         else PLAIN16(onepole_lp_tick(x_[k], y1, a0, b1))
+                        continue;
                     }
-                    sreg[rb * 32] = __float_as_uint(y1);
-                    break;
-                }
-                for (uint32_t f = 0; f < nf; f++) {
+                    for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(y1),
                               (y1 = __uint_as_float(sreg[rb * 32]), a0 = __uint_as_float(sreg[(rb + 1) * 32]), b1 = __uint_as_float(sreg[(rb + 2) * 32])))
                     AR_POST_ROUTES(f)
                     float x = is >= 0 ? sval[(is * CH + f) * 32] : 0.f;
                     float y = hp ? onepole_hp_tick(x, y1, a0, b1) : onepole_lp_tick(x, y1, a0, b1);
                     EMIT(f, 0, y)
+                }
                 }
                 sreg[rb * 32] = __float_as_uint(y1);
                 break;
@@ -296,19 +298,18 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
 #define ENV_STORE (sreg[rb * 32] = st, sreg[(rb + 1) * 32] = __float_as_uint(t), sreg[(rb + 4) * 32] = __float_as_uint(sc))
                 ENV_LOAD;
                 const bool asr = dn.kind == DK_ENVASR;
-                if (plain) {
-                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) {
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
                         if (asr) PLAIN16(envasr_tick_sel(st, t, ar, rr, sc))
                         else PLAIN16(envar_tick(st, t, ar, rr, sc))
+                        continue;
                     }
-                    ENV_STORE;
-                    break;
-                }
-                for (uint32_t f = 0; f < nf; f++) {
+                    for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, ENV_STORE, ENV_LOAD)
                     AR_POST_ROUTES(f)
                     float y = asr ? envasr_tick(st, t, ar, rr, sc) : envar_tick(st, t, ar, rr, sc);
                     EMIT(f, 0, y)
+                }
                 }
                 ENV_STORE;
                 break;
@@ -353,9 +354,9 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             }
             case DK_MATH: {
                 const uint32_t nch = dn.n_out;
-                if (plain && nch == 1) {
-                    const int sa = dn.in_slot[0], sb = dn.in_slot[1];
-                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) {
+                FOR_GROUPS {
+                    if (GROUP_PLAIN && nch == 1) {
+                        const int sa = dn.in_slot[0], sb = dn.in_slot[1];
                         LOAD16(a_, sa)
                         LOAD16(b_, sb)
                         switch (dn.mode) { // the operation is chosen once per group, not once per frame
@@ -365,10 +366,9 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                         case 3: PLAIN16(a_[k] / b_[k]) break;
                         default: PLAIN16(math_apply(4, a_[k], b_[k])) break;
                         }
+                        continue;
                     }
-                    break;
-                }
-                for (uint32_t f = 0; f < nf; f++) {
+                    for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, (void)0, (void)0)
                     AR_POST_ROUTES(f)
                     float ain[MAX_IN];
@@ -380,6 +380,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                             float y = math_apply(dn.mode, ain[c], ain[c + nch]);
                             EMIT(f, c, y)
                         }
+                }
                 }
                 break;
             }
@@ -466,18 +467,17 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             case DK_INPLUS: {
                 float val = __uint_as_float(sreg[rb * 32]);
                 const int is = dn.kind == DK_INPLUS ? dn.in_slot[0] : -1;
-                if (plain) {
-                    for (uint32_t g0_ = 0; g0_ < CH; g0_ += 16) {
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
                         if (dn.kind == DK_INPLUS) {
                             LOAD16(x_, is)
                             PLAIN16(val + x_[k])
                         } else {
                             PLAIN16(val)
                         }
+                        continue;
                     }
-                    break;
-                }
-                for (uint32_t f = 0; f < nf; f++) {
+                    for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, (void)0, val = __uint_as_float(sreg[rb * 32]))
                     for (int ai = 0; ai < dn.n_ar; ai++) {
                         float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
@@ -487,6 +487,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     float y = val;
                     if (dn.kind == DK_INPLUS) y = val + (is >= 0 ? sval[(is * CH + f) * 32] : 0.f);
                     EMIT(f, 0, y)
+                }
                 }
                 if (dn.n_ar) sreg[rb * 32] = __float_as_uint(val);
                 break;
