@@ -321,9 +321,8 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
 #define ENVL_STORE (sreg[rb * 32] = running, sreg[(rb + 1) * 32] = seg, st_d(sreg, rb + 2, time), st_d(sreg, rb + 4, from))
                 ENVL_LOAD;
                 const uint32_t n_seg = dn.n_seg;
-                for (uint32_t f = 0; f < nf; f++) {
-                    EVENTS_AT(f, ENVL_STORE, ENVL_LOAD)
-                    AR_POST_ROUTES(f)
+                const bool looping = dn.looping;
+                auto env_tick = [&]() -> float {
                     float y;
                     if (!running) {
                         y = (float)from;
@@ -341,13 +340,25 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                         } else {
                             from = val;
                             y = (float)from;
-                            if (dn.looping) {
+                            if (looping) {
                                 seg = 0;
                                 time = 0.0;
                             } else running = 0;
                         }
                     }
-                    EMIT(f, 0, y)
+                    return y;
+                };
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
+                        PLAIN16(env_tick())
+                        continue;
+                    }
+                    for (uint32_t f = g0_; f < fe_; f++) {
+                        EVENTS_AT(f, ENVL_STORE, ENVL_LOAD)
+                        AR_POST_ROUTES(f)
+                        float y = env_tick();
+                        EMIT(f, 0, y)
+                    }
                 }
                 ENVL_STORE;
                 break;
@@ -386,21 +397,35 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             }
             case DK_MATH1: {
                 const int is = dn.in_slot[0];
-                for (uint32_t f = 0; f < nf; f++) {
-                    EVENTS_AT(f, (void)0, (void)0)
-                    AR_POST_ROUTES(f)
-                    float y = math1_apply(dn.mode, is >= 0 ? sval[(is * CH + f) * 32] : 0.f);
-                    EMIT(f, 0, y)
+                const uint32_t op1 = dn.mode;
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
+                        LOAD16(x_, is)
+                        PLAIN16(math1_apply(op1, x_[k]))
+                        continue;
+                    }
+                    for (uint32_t f = g0_; f < fe_; f++) {
+                        EVENTS_AT(f, (void)0, (void)0)
+                        AR_POST_ROUTES(f)
+                        float y = math1_apply(op1, is >= 0 ? sval[(is * CH + f) * 32] : 0.f);
+                        EMIT(f, 0, y)
+                    }
                 }
                 break;
             }
             case DK_PHASOR: {
                 double phase = ld_d(sreg, rb), step = ld_d(sreg, rb + 2);
-                for (uint32_t f = 0; f < nf; f++) {
-                    EVENTS_AT(f, st_d(sreg, rb, phase), (phase = ld_d(sreg, rb), step = ld_d(sreg, rb + 2)))
-                    AR_POST_ROUTES(f)
-                    float y = phasor_tick(phase, step);
-                    EMIT(f, 0, y)
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
+                        PLAIN16(phasor_tick(phase, step))
+                        continue;
+                    }
+                    for (uint32_t f = g0_; f < fe_; f++) {
+                        EVENTS_AT(f, st_d(sreg, rb, phase), (phase = ld_d(sreg, rb), step = ld_d(sreg, rb + 2)))
+                        AR_POST_ROUTES(f)
+                        float y = phasor_tick(phase, step);
+                        EMIT(f, 0, y)
+                    }
                 }
                 st_d(sreg, rb, phase);
                 break;
@@ -409,11 +434,19 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             case DK_BROWN: { // noise.rs:26-46,122-153 (no parameters: only wrapper events can be due)
                 uint64_t rng = ((uint64_t)sreg[(rb + 1) * 32] << 32) | sreg[rb * 32];
                 float last = dn.kind == DK_BROWN ? __uint_as_float(sreg[(rb + 2) * 32]) : 0.f;
-                for (uint32_t f = 0; f < nf; f++) {
-                    EVENTS_AT(f, (void)0, (void)0)
-                    AR_POST_ROUTES(f)
-                    float y = dn.kind == DK_BROWN ? brown_tick(rng, last) : white_sample(rng);
-                    EMIT(f, 0, y)
+                const bool brown = dn.kind == DK_BROWN;
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
+                        if (brown) PLAIN16(brown_tick(rng, last))
+                        else PLAIN16(white_sample(rng))
+                        continue;
+                    }
+                    for (uint32_t f = g0_; f < fe_; f++) {
+                        EVENTS_AT(f, (void)0, (void)0)
+                        AR_POST_ROUTES(f)
+                        float y = brown ? brown_tick(rng, last) : white_sample(rng);
+                        EMIT(f, 0, y)
+                    }
                 }
                 sreg[rb * 32] = (uint32_t)rng;
                 sreg[(rb + 1) * 32] = (uint32_t)(rng >> 32);
@@ -424,9 +457,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 uint64_t rng = ((uint64_t)sreg[(rb + 1) * 32] << 32) | sreg[rb * 32];
                 uint32_t counter = sreg[(rb + 12) * 32];
                 float pink = __uint_as_float(sreg[(rb + 13) * 32]), always = __uint_as_float(sreg[(rb + 11) * 32]);
-                for (uint32_t f = 0; f < nf; f++) {
-                    EVENTS_AT(f, (void)0, (void)0)
-                    AR_POST_ROUTES(f)
+                auto pink_tick = [&]() -> float {
                     const uint32_t idx = (uint32_t)(__ffs((int)counter) - 1); // counter.trailing_zeros(), 0..8
                     pink = pink - __uint_as_float(sreg[(rb + 2 + idx) * 32]);
                     const float w = white_sample(rng);
@@ -436,8 +467,19 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     always = white_sample(rng);
                     pink = pink + always;
                     counter = (counter & 255u) + 1u;                           // mask = 2^(9-1) = 256
-                    float y = pink / 10.0f;                                    // PINK_NOISE_OCTAVES + 1
-                    EMIT(f, 0, y)
+                    return pink / 10.0f;                                       // PINK_NOISE_OCTAVES + 1
+                };
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
+                        PLAIN16(pink_tick())
+                        continue;
+                    }
+                    for (uint32_t f = g0_; f < fe_; f++) {
+                        EVENTS_AT(f, (void)0, (void)0)
+                        AR_POST_ROUTES(f)
+                        float y = pink_tick();
+                        EMIT(f, 0, y)
+                    }
                 }
                 sreg[rb * 32] = (uint32_t)rng;
                 sreg[(rb + 1) * 32] = (uint32_t)(rng >> 32);
@@ -450,11 +492,17 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 uint64_t rng = ((uint64_t)sreg[(rb + 1) * 32] << 32) | sreg[rb * 32];
                 float cur = __uint_as_float(sreg[(rb + 2) * 32]), width = __uint_as_float(sreg[(rb + 3) * 32]),
                       phase = __uint_as_float(sreg[(rb + 4) * 32]), step = __uint_as_float(sreg[(rb + 5) * 32]);
-                for (uint32_t f = 0; f < nf; f++) {
-                    EVENTS_AT(f, (void)0, step = __uint_as_float(sreg[(rb + 5) * 32]))
-                    AR_POST_ROUTES(f)
-                    float y = randlin_tick(rng, cur, width, phase, step);
-                    EMIT(f, 0, y)
+                FOR_GROUPS {
+                    if (GROUP_PLAIN) {
+                        PLAIN16(randlin_tick(rng, cur, width, phase, step))
+                        continue;
+                    }
+                    for (uint32_t f = g0_; f < fe_; f++) {
+                        EVENTS_AT(f, (void)0, step = __uint_as_float(sreg[(rb + 5) * 32]))
+                        AR_POST_ROUTES(f)
+                        float y = randlin_tick(rng, cur, width, phase, step);
+                        EMIT(f, 0, y)
+                    }
                 }
                 sreg[rb * 32] = (uint32_t)rng;
                 sreg[(rb + 1) * 32] = (uint32_t)(rng >> 32);
