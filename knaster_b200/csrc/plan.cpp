@@ -1370,10 +1370,13 @@ struct StreamState {
 };
 
 #ifdef KGPU_PROFILE_HOST
+// cycle counters of the control simulation, summed over the worker threads and printed by stream_end
 #include <x86intrin.h>
-namespace { thread_local uint64_t g_prof[8]; struct ProfDump { ~ProfDump() { fprintf(stderr, "[prof] select %.1f gather %.1f nodes %.1f (process_node %.1f) merge %.1f split %.1f Mcycles\n", g_prof[0]/1e6, g_prof[1]/1e6, g_prof[2]/1e6, g_prof[3]/1e6, g_prof[4]/1e6, g_prof[5]/1e6); } }; thread_local ProfDump g_prof_dump; }
+#include <atomic>
+namespace { std::atomic<uint64_t> g_prof[8]; uint64_t g_prof_voices, g_prof_events;
+void prof_dump() { fprintf(stderr, "[prof] select %.1f gather %.1f nodes %.1f (process_node %.1f) merge %.1f split %.1f Mcycles (thread-summed)\n", g_prof[0].load()/1e6, g_prof[1].load()/1e6, g_prof[2].load()/1e6, g_prof[3].load()/1e6, g_prof[4].load()/1e6, g_prof[5].load()/1e6); for (auto &x : g_prof) x = 0; } }
 #define PROF_T(var) const uint64_t var = __rdtsc()
-#define PROF_ADD(i, a, b) g_prof[i] += (b) - (a)
+#define PROF_ADD(i, a, b) g_prof[i].fetch_add((b) - (a), std::memory_order_relaxed)
 #else
 #define PROF_T(var)
 #define PROF_ADD(i, a, b)
@@ -1412,9 +1415,10 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     PROF_ADD(0, p0, p1);
     if (e0 == e1 && !P.voice_ramps[gv] && !has_later && !has_carry) return;
 
+    const uint32_t chunk_shift = (uint32_t)__builtin_ctz(chunk); // chunk is a power of two (capi.cpp pick_chunk; recipes: 1)
     auto key_less = [&](const VoiceEvent &a, const VoiceEvent &b) {
         const uint64_t fa = a.frame < t0 ? t0 : a.frame, fb = b.frame < t0 ? t0 : b.frame;
-        const uint64_t ca = fa / chunk, cb = fb / chunk;
+        const uint64_t ca = fa >> chunk_shift, cb = fb >> chunk_shift;
         if (ca != cb) return ca < cb;
         if (a.ev.node != b.ev.node) return a.ev.node < b.ev.node;
         if (fa != fb) return fa < fb;
@@ -1440,16 +1444,35 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     for (uint32_t k = e0; k < e1; k++) evp.push_back(&P.pending[P.vorder[k]]);
     PROF_T(p2);
     PROF_ADD(1, p1, p2);
+    // the window's events bucketed by node: one stable counting sort instead of a filtering pass per node
+    uint32_t nstart[MAX_NODES + 1] = {0};
+    if (!evp.empty()) {
+        uint8_t loc[64];
+        std::vector<uint8_t> loc_big;
+        uint8_t *lp = loc;
+        if (evp.size() > 64) {
+            loc_big.resize(evp.size());
+            lp = loc_big.data();
+        }
+        for (size_t k = 0; k < evp.size(); k++) {
+            lp[k] = (uint8_t)P.node_ref[evp[k]->node].local;
+            nstart[lp[k] + 1]++;
+        }
+        for (uint32_t li = 0; li < nn; li++) nstart[li + 1] += nstart[li];
+        node_ev.resize(evp.size());
+        uint32_t fill[MAX_NODES];
+        for (uint32_t li = 0; li < nn; li++) fill[li] = nstart[li];
+        for (size_t k = 0; k < evp.size(); k++) node_ev[fill[lp[k]]++] = evp[k];
+    }
     for (uint32_t li = 0; li < nn; li++) {
         HostNode &hn = g.host[(size_t)v * nn + li];
-        node_ev.clear();
-        for (const RawEvent *r : evp)
-            if (P.node_ref[r->node].local == li) node_ev.push_back(r);
-        if (node_ev.empty() && !hn.ramp_active) continue;
+        const RawEvent *const *nev = node_ev.data() + nstart[li];
+        const size_t n_nev = nstart[li + 1] - nstart[li];
+        if (n_nev == 0 && !hn.ramp_active) continue;
         const bool was = hn.ramp_active;
         if (sk.run_start.back() != sk.buf.size()) sk.run_start.push_back((uint32_t)sk.buf.size());
         PROF_T(q0);
-        hn.ramp_active = process_node(P, sk, gi, v, li, node_ev.data(), node_ev.size(), wb0, wb1);
+        hn.ramp_active = process_node(P, sk, gi, v, li, nev, n_nev, wb0, wb1);
         PROF_T(q1);
         PROF_ADD(3, q0, q1);
         if (hn.ramp_active != was) {
@@ -1710,8 +1733,7 @@ void HostPlan::stream_end() {
     if (!S) return;
     if (S->pooled) workers().wait();
 #ifdef KGPU_PROFILE_HOST
-    fprintf(stderr, "[prof] select %.1f gather %.1f nodes %.1f (process_node %.1f) merge %.1f split %.1f Mcycles\n", g_prof[0]/1e6, g_prof[1]/1e6, g_prof[2]/1e6, g_prof[3]/1e6, g_prof[4]/1e6, g_prof[5]/1e6);
-    memset(g_prof, 0, sizeof g_prof);
+    prof_dump();
 #endif
     stream = nullptr;
     std::unique_ptr<StreamState> guard(S);
