@@ -210,7 +210,12 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 uint32_t wf = sreg[(rb + 4) * 32];
                 FOR_GROUPS {
                     if (GROUP_PLAIN) {
-                        if (__all_sync(0xFFFFFFFFu, wf == 0u && !use_sin)) PLAIN16(polyblep_saw_tick_sel(t, dt)) // every lane a sawtooth below sr/4
+                        if (__all_sync(0xFFFFFFFFu, wf == 0u && !use_sin)) { // every lane a sawtooth below sr/4
+                            if (__all_sync(0xFFFFFFFFu, saw_domain(t, dt))) { // the fused recipe's 15-instruction form (hoisted reciprocal)
+                                const float omd = 1.0f - dt, rc = div_prep(dt);
+                                PLAIN16(saw_fast_tick(t, dt, omd, rc))
+                            } else PLAIN16(polyblep_saw_tick_sel(t, dt))
+                        }
                         else PLAIN16(polyblep_tick(t, dt, use_sin, pw, wf))
                         continue;
                     }
