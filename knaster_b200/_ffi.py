@@ -76,7 +76,7 @@ class DebugNode(C.Structure):
 
 def build(verbose: bool = False) -> None:
     """Compile libknaster_gpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    r = subprocess.run(["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC], capture_output=True, text=True)
     if verbose:
         print(r.stdout)
     if r.returncode != 0:
