@@ -1529,7 +1529,14 @@ void stream_worker(HostPlan &P, StreamState &S, unsigned ti) {
             for (uint32_t gi = 0; gi < P.groups.size(); gi++) {
                 StreamState::PerGroup &pg = tc.g[gi];
                 size_t carry_pos = 0;
-                for (uint32_t v = pg.v_begin; v < pg.v_end; v++) simulate_voice_window(P, S, tc, gi, v, L, evp, node_ev, carry_pos);
+                // one-launch calls without active ramps or leftovers (block-by-block rendering): a voice without a
+                // ready event has nothing to do -- skip it on two loads instead of entering the simulation
+                const bool quick = S.n_launch == 1 && P.n_active_ramps == 0 && (S.lat_start[gi].empty());
+                const uint32_t *vc = P.vcount.data() + P.voice_base[gi];
+                for (uint32_t v = pg.v_begin; v < pg.v_end; v++) {
+                    if (quick && vc[v] == vc[v + 1]) continue;
+                    simulate_voice_window(P, S, tc, gi, v, L, evp, node_ev, carry_pos);
+                }
                 pg.carry.swap(pg.carry_next);
                 pg.carry_next.clear();
             }
@@ -1554,6 +1561,54 @@ HostPlan::~HostPlan() {
     delete pool;
 }
 
+// Keeps `pending` short for small render windows.  Invariant while active: every event of `pending` is due
+// before block far_horizon, every event of `pending_far` at or after it; both in arrival order.  Moving
+// events between the two never reorders events that become ready in the same block: the two sets are
+// separated by due block, moves are stable, and an event is due no earlier than the frame clock at which
+// it was pushed (HostPlan::push clamps), so "due block" IS the block in which it becomes ready.
+void HostPlan::calendar_update(uint64_t b0, uint64_t b1) {
+    constexpr uint64_t H = 64; // blocks of look-ahead kept in `pending`
+    const uint64_t bs = block_size;
+    if (far_horizon == UINT64_MAX) {
+        // switch on when a short window faces a long queue (one block at a time under seconds of schedule)
+        if (pending.size() < 16384 || b1 - b0 > H / 4) return;
+        far_horizon = b1 + H;
+        pending_clean = 0;
+    }
+    // first: newly pushed events that lie beyond the horizon go to the END of the far queue
+    size_t w = pending_clean;
+    for (size_t i = pending_clean; i < pending.size(); i++) {
+        if (pending[i].due_frame / bs >= far_horizon) pending_far.push_back(pending[i]);
+        else {
+            if (w != i) pending[w] = pending[i];
+            w++;
+        }
+    }
+    pending.resize(w);
+    pending_clean = w;
+    if (b1 > far_horizon || (b1 + H / 4 > far_horizon && !pending_far.empty())) {
+        // the window comes close to the horizon: pull the next stretch in (one scan of the far queue per ~H blocks)
+        const uint64_t nh = b1 + H;
+        size_t w = 0;
+        for (size_t i = 0; i < pending_far.size(); i++) {
+            if (pending_far[i].due_frame / bs < nh) pending.push_back(pending_far[i]);
+            else {
+                if (w != i) pending_far[w] = pending_far[i];
+                w++;
+            }
+        }
+        pending_far.resize(w);
+        // (events pushed since the last call that lie beyond the OLD horizon were appended to the far queue just
+        // above, behind everything that arrived before them, and come back in that order)
+        far_horizon = nh;
+        pending_clean = pending.size();
+    }
+    if (pending_far.empty()) { // nothing left to hold back
+        far_horizon = UINT64_MAX;
+        pending_clean = 0;
+    }
+}
+
 void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vector<uint32_t> &chunk_of_group) {
     PhaseTimer pt("stream_begin");
     if (stream) KGPU_THROW(KGPU_ERR_STATE, "stream_begin: a render call is already in progress");
@@ -1562,6 +1617,7 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
     const uint64_t b0 = t0 / bs, b1 = t1 / bs;
     const size_t n_launch = bounds.size() - 1, n_groups = groups.size();
     if (n_launch > 4096) KGPU_THROW(KGPU_ERR_INVALID, "too many launches in one render call (%zu)", n_launch);
+    calendar_update(b0, b1);
     if (voice_base.size() != n_groups + 1) {
         voice_base.assign(n_groups + 1, 0);
         for (size_t gi = 0; gi < n_groups; gi++) voice_base[gi + 1] = voice_base[gi] + groups[gi].n_voices;
@@ -1726,6 +1782,7 @@ void HostPlan::consume_ready(uint64_t b1) {
             w++;
         }
     pending.resize(w);
+    if (far_horizon != UINT64_MAX) pending_clean = w; // what is left was checked against the horizon by calendar_update
 }
 
 void HostPlan::stream_end() {

@@ -157,7 +157,14 @@ struct HostPlan {
     std::vector<NodeRef> node_ref; // per graph node
     uint32_t n_mix_nodes = 0;
     uint64_t dropped_changes = 0, ignored_delays = 0, device_events = 0;
-    std::vector<RawEvent, DefaultInitAllocator<RawEvent>> pending; // not yet simulated
+    std::vector<RawEvent, DefaultInitAllocator<RawEvent>> pending; // not yet simulated, arrival order
+    // Calendar for block-by-block rendering under a large backlog of scheduled events: while it is active
+    // `pending` only holds events due before block `far_horizon`, the rest waits in `pending_far` (arrival
+    // order too), so that a render call scans what can become ready soon instead of everything queued.
+    std::vector<RawEvent, DefaultInitAllocator<RawEvent>> pending_far;
+    uint64_t far_horizon = UINT64_MAX; // UINT64_MAX: calendar inactive (everything is in `pending`)
+    size_t pending_clean = 0;          // leading events of `pending` already known to be due before far_horizon
+    void calendar_update(uint64_t b0, uint64_t b1);
 
     // caches / scratch of the hot host path (push / compile_events)
     struct Rule { char want; uint8_t smooth_ok, polyblep_wave, svf_type; };

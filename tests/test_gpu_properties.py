@@ -421,3 +421,47 @@ def test_readme_shape_bank_runs_the_time_parallel_wavetable_kernel():
     assert np.array_equal(taps, ref_taps)          # integer phase, one f32 product
     assert np.abs(out - ref).max() <= 1e-6
     assert np.abs(ref).max() > 0.05
+
+
+def test_block_by_block_under_a_large_event_backlog_equals_batched():
+    # run_without_inputs() once per block with seconds of schedule queued: the host keeps a calendar (only the
+    # events that can become ready soon are scanned per call, plan.cpp calendar_update).  Same result as batched
+    # renders, including events pushed while the calendar is active: near ones, ones beyond its horizon, a late
+    # one, and two for the same frame whose arrival order matters.
+    n_voices, n_blocks = 600, 750
+
+    def extra(graph, ids_saw, clock):
+        with graph.edit() as g:
+            g.set(ids_saw[5], "freq", 333.0, kn.Time.at(at(clock + 10)))
+            g.set(ids_saw[6], "freq", 444.0, kn.Time.at(at(clock + 64 * 200)))       # beyond the horizon
+            g.set(ids_saw[6], "freq", 555.0, kn.Time.at(at(clock + 64 * 200)))       # same frame: the later push wins
+            g.set(ids_saw[7], "freq", 222.0, kn.Time.at(at(max(0, clock - 500))))    # late: next block
+            g.set(ids_saw[8], "freq", 111.0, kn.Time.at(at(clock + 64 * 70 + 3)))    # just beyond the look-ahead
+
+    def saws(graph):
+        from knaster_b200 import ugens as U
+        return [i for i, n in enumerate(graph.nodes) if n.ugen.kind == U.KIND_POLYBLEP]
+
+    g1, p1 = AudioProcessor.new(0, 2, AudioProcessorOptions(sample_rate=SR))
+    banks.subtractive_bank(g1, n_voices, 1.0, n_notes=16)
+    assert sum(len(a) for a in g1.pending_event_arrays) + len(g1.pending_events) > 16384
+    s1 = saws(g1)
+    blocks = []
+    for b in range(n_blocks):
+        if b in (100, 300):
+            extra(g1, s1, b * 64)
+        p1.run_without_inputs()
+        blocks.append(p1.output_block())
+    per_block = np.stack(blocks)
+
+    g2, p2 = AudioProcessor.new(0, 2, AudioProcessorOptions(sample_rate=SR))
+    banks.subtractive_bank(g2, n_voices, 1.0, n_notes=16)
+    s2 = saws(g2)
+    parts = [p2.render(100)]
+    extra(g2, s2, 100 * 64)
+    parts.append(p2.render(200))
+    extra(g2, s2, 300 * 64)
+    parts.append(p2.render(450))
+    batched = np.concatenate(parts)
+    assert np.abs(batched).max() > 1e-3
+    assert np.array_equal(per_block, batched)
