@@ -58,7 +58,10 @@ typedef enum {
     KGPU_WHITE_NOISE = 16,       /* noise.rs:26-46       no params; args[0] = seed                          */
     KGPU_PINK_NOISE = 17,        /* noise.rs:53-115      no params; args[0] = seed                          */
     KGPU_BROWN_NOISE = 18,       /* noise.rs:122-153     no params; args[0] = seed                          */
-    KGPU_RANDOM_LIN = 19         /* noise.rs:156-217     params: 0 freq; args[0] = freq, args[1] = seed (already *94+53) */
+    KGPU_RANDOM_LIN = 19,        /* noise.rs:156-217     params: 0 freq; args[0] = freq, args[1] = seed (already *94+53) */
+    /* pan.rs: the gains are fastapprox 0.3.1's fast::cos / fast::sin (a crate that is NOT under the reference
+       tree; restated from its published source, parity unpinned); 1 input, 2 outputs                     */
+    KGPU_PAN2 = 20               /* pan.rs:12-38         params: 0 pan; args[0] = pan (-1..1)                */
 } kgpu_ugen_kind;
 
 /* kgpu_node_desc.mode for KGPU_MATH (math.rs:22-85) */

@@ -15,7 +15,7 @@ CUDA library is missing.
 from .graph import (Graph, GraphEdit, GraphError, Parameter, ParameterError, ParameterSmoothing, PTrigger,
                     SchedulingEvent, Seconds, SH, Time)
 from .ugens import (BrownNoise, Constant, EnvAr, EnvAsr, Envelope, EnvelopeSegment, Math1Op, Math1UGen, MathOp, MathUGen,
-                    OnePoleHpf, OnePoleLpf, Phasor, PinkNoise, PolyBlep, RandomLin, SinNumeric, SinWt, SvfFilter,
+                    OnePoleHpf, OnePoleLpf, Pan2, Phasor, PinkNoise, PolyBlep, RandomLin, SinNumeric, SinWt, SvfFilter,
                     SvfFilterType, TestInPlusParamUGen, TestNumUGen, UGen, Waveform, WhiteNoise,
                     next_randomness_seed, reset_randomness_seed)
 

@@ -27,10 +27,11 @@ enum DevKind : uint8_t {
     DK_PINK = 16,    // regs: 0,1 rng 2..10 white_noises[9] 11 always_on 12 counter(u32) 13 pink  noise.rs:53-115
     DK_BROWN = 17,   // regs: 0,1 rng 2 last_output                                        noise.rs:122-153
     DK_RANDLIN = 18, // regs: 0,1 rng 2 current_value 3 current_change_width 4 phase 5 phase_step  noise.rs:156-217
+    DK_PAN2 = 19,    // regs: 0 left_gain 1 right_gain (the host evaluates fast::cos / fast::sin when pan changes)  pan.rs:12-38
 };
 enum { REGS_SINWT = 3, REGS_SINNUM = 3, REGS_POLYBLEP = 5, REGS_SVF = 8, REGS_ONEPOLE = 3, REGS_ENV = 5,
        REGS_ENVELOPE_BASE = 8, REGS_ENVELOPE_PER_SEG = 6, REGS_CONST = 1, REGS_PHASOR = 4,
-       REGS_WHITE = 2, REGS_PINK = 14, REGS_BROWN = 3, REGS_RANDLIN = 6 };
+       REGS_WHITE = 2, REGS_PINK = 14, REGS_BROWN = 3, REGS_RANDLIN = 6, REGS_PAN2 = 2 };
 enum { ASR_STOPPED = 0, ASR_ATTACKING = 1, ASR_SUSTAINING = 2, ASR_RELEASING = 3 };
 
 // arithmetic wrappers applied to a node's outputs, innermost first (wrappers_core/math.rs)

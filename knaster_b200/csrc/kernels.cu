@@ -516,6 +516,18 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 sreg[(rb + 4) * 32] = __float_as_uint(phase);
                 break;
             }
+            case DK_PAN2: { // pan.rs:31-36: [signal * left_gain, signal * right_gain]
+                float gl = __uint_as_float(sreg[rb * 32]), gr = __uint_as_float(sreg[(rb + 1) * 32]);
+                const int is = dn.in_slot[0];
+                for (uint32_t f = 0; f < nf; f++) {
+                    EVENTS_AT(f, (void)0, (gl = __uint_as_float(sreg[rb * 32]), gr = __uint_as_float(sreg[(rb + 1) * 32])))
+                    AR_POST_ROUTES(f)
+                    const float x = is >= 0 ? sval[(is * CH + f) * 32] : 0.f;
+                    EMIT(f, 0, x * gl)
+                    EMIT(f, 1, x * gr)
+                }
+                break;
+            }
             case DK_CONST:
             case DK_INPLUS: {
                 float val = __uint_as_float(sreg[rb * 32]);

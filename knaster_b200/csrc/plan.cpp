@@ -81,6 +81,33 @@ inline float wy_f32(uint64_t &state) {
     return f - 1.0f;
 }
 
+// fastapprox 0.3.1 (fast::sin / fast::cos: Paul Mineiro's fastsin / fastcos), restated for Pan2 (pan.rs:31-36).
+// The crate is not under the reference tree: parity of these two functions is unpinned.
+inline float fa_from_bits(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline float fa_sin(float x) {
+    const float FOUROVERPI = 1.2732395447351627f, FOUROVERPISQ = 0.40528473456935109f, Q = 0.78444488374548933f;
+    uint32_t p = fbits(0.20363937680730309f), r = fbits(0.015124940802184233f), s = fbits(-0.0032225901625579573f);
+    uint32_t v = fbits(x);
+    const uint32_t sign = v & 0x80000000u;
+    v &= 0x7FFFFFFFu;
+    const float qpprox = FOUROVERPI * x - FOUROVERPISQ * x * fa_from_bits(v);
+    const float qpproxsq = qpprox * qpprox;
+    p |= sign;
+    r |= sign;
+    s ^= sign;
+    return Q * qpprox + qpproxsq * (fa_from_bits(p) + qpproxsq * (fa_from_bits(r) + qpproxsq * fa_from_bits(s)));
+}
+inline float fa_cos(float x) {
+    const float HALFPI = 1.5707963267948966f, HALFPIMINUSTWOPI = -4.7123889803846899f;
+    return fa_sin(x + (x > HALFPI ? HALFPIMINUSTWOPI : HALFPI));
+}
+// Pan2::process's two gains for a stored pan position (pan.rs:31-35)
+inline void pan2_gains(float pan01, float &gl, float &gr) {
+    const float rad = pan01 * 1.57079632679489661923f; // core::f32::consts::FRAC_PI_2
+    gl = fa_cos(rad);
+    gr = fa_sin(rad);
+}
+
 // ---- static facts about node kinds ------------------------------------------------------
 struct KindInfo {
     int n_in, n_out, n_params, dev_kind, n_regs;
@@ -106,6 +133,7 @@ KindInfo kind_info(const kgpu_node_desc &d) {
     case KGPU_PINK_NOISE: return {0, 1, 0, DK_PINK, REGS_PINK};
     case KGPU_BROWN_NOISE: return {0, 1, 0, DK_BROWN, REGS_BROWN};
     case KGPU_RANDOM_LIN: return {0, 1, 1, DK_RANDLIN, REGS_RANDLIN};
+    case KGPU_PAN2: return {1, 2, 1, DK_PAN2, REGS_PAN2};
     default: KGPU_THROW(KGPU_ERR_UNSUPPORTED, "unknown ugen kind %u", d.kind);
     }
 }
@@ -119,7 +147,7 @@ const char *param_types(uint32_t kind) {
     case KGPU_ENV_ASR: return "fftt";
     case KGPU_ENV_AR: return "fft";
     case KGPU_ENVELOPE: return "fitt";
-    case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: case KGPU_PHASOR: case KGPU_RANDOM_LIN: return "f";
+    case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: case KGPU_PHASOR: case KGPU_RANDOM_LIN: case KGPU_PAN2: return "f";
     default: return "";
     }
 }
@@ -268,6 +296,14 @@ void ugen_param_apply(Sim &s, uint32_t param, const PV &v, uint64_t frame) {
         break;
     case KGPU_PHASOR: // osc.rs:191-197
         if (param == 0) s.set_d(frame, r + 2, v.f * h.d0);
+        break;
+    case KGPU_PAN2: // pan.rs:26-29: self.pan = pan * 0.5 + 0.5 (f32), gains re-evaluated per sample from it
+        if (param == 0) {
+            float gl, gr;
+            pan2_gains((float)v.f * 0.5f + 0.5f, gl, gr);
+            s.set_f(frame, r + 0, gl);
+            s.set_f(frame, r + 1, gr);
+        }
         break;
     case KGPU_RANDOM_LIN: // noise.rs:206-213 (after init(): phase_step = F::new(value) * freq_to_phase_inc)
         if (param == 0) s.set_f(frame, r + 5, (float)v.f * h.f0);
@@ -955,6 +991,13 @@ void HostPlan::build(const kgpu_graph_desc &d) {
                     const uint64_t seed = (uint64_t)nd.args[0];    // fastrand::Rng::with_seed(seed): the state IS the seed
                     R(r + 0, v) = (uint32_t)seed; R(r + 1, v) = (uint32_t)(seed >> 32);
                     if (nd.kind == KGPU_PINK_NOISE) R(r + 12, v) = 1u; // counter: 1 (noise.rs:74)
+                    break;
+                }
+                case KGPU_PAN2: { // pan.rs:19-24
+                    float gl, gr;
+                    pan2_gains((float)nd.args[0] * 0.5f + 0.5f, gl, gr);
+                    R(r + 0, v) = fbits(gl);
+                    R(r + 1, v) = fbits(gr);
                     break;
                 }
                 case KGPU_RANDOM_LIN: { // noise.rs:170-185: new() draws current_value, init() scales the step and calls new_value()

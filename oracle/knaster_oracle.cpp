@@ -990,6 +990,48 @@ struct RandomLin : UGenT<RandomLin, 0, 1, 1> {
     }
 };
 
+// ---------------------------------------------------------------- Pan2
+// knaster_core_dsp/src/ugens/pan.rs:12-38.  The gains come from the `fastapprox` crate, pinned at 0.3.1
+// (knaster_core_dsp/Cargo.toml:35) and NOT vendored under the reference: PARITY UNPINNED for fast::sin /
+// fast::cos, restated here from the crate's published source (a port of Paul Mineiro's fastsin / fastcos).
+namespace fastapprox_fast {
+inline uint32_t to_bits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float from_bits(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline float sin(float x) {
+    const float FOUROVERPI = 1.2732395447351627f, FOUROVERPISQ = 0.40528473456935109f, Q = 0.78444488374548933f;
+    uint32_t p = to_bits(0.20363937680730309f), r = to_bits(0.015124940802184233f), s = to_bits(-0.0032225901625579573f);
+    uint32_t v = to_bits(x);
+    const uint32_t sign = v & 0x80000000u;
+    v &= 0x7FFFFFFFu;
+    const float qpprox = FOUROVERPI * x - FOUROVERPISQ * x * from_bits(v);
+    const float qpproxsq = qpprox * qpprox;
+    p |= sign;
+    r |= sign;
+    s ^= sign;
+    return Q * qpprox + qpproxsq * (from_bits(p) + qpproxsq * (from_bits(r) + qpproxsq * from_bits(s)));
+}
+inline float cos(float x) {
+    const float HALFPI = 1.5707963267948966f, HALFPIMINUSTWOPI = -4.7123889803846899f;
+    const float offset = x > HALFPI ? HALFPIMINUSTWOPI : HALFPI;
+    return sin(x + offset);
+}
+} // namespace fastapprox_fast
+struct Pan2 : UGenT<Pan2, 1, 2, 1> {
+    float pan;
+    explicit Pan2(float p) : pan(p * 0.5f + 0.5f) {}                          // :19-24
+    inline void tick(Ctx &, const F *in, F *out) {                            // :31-36
+        const F signal = in[0];
+        const float pan_pos_radians = pan * 1.57079632679489661923f;          // core::f32::consts::FRAC_PI_2
+        const F left_gain = (F)fastapprox_fast::cos(pan_pos_radians);
+        const F right_gain = (F)fastapprox_fast::sin(pan_pos_radians);
+        out[0] = signal * left_gain;
+        out[1] = signal * right_gain;
+    }
+    void param_apply(Ctx &, size_t index, const ParamValue &v) override {    // :26-29
+        if (index == 0 && v.kind == PK::Float) pan = (float)v.f * 0.5f + 0.5f;
+    }
+};
+
 struct Constant : UGenT<Constant, 0, 1, 1> {
     F value;
     explicit Constant(F v) : value(v) {}
@@ -1314,6 +1356,7 @@ std::unique_ptr<UGen> make_ugen(const ko_node_desc &d) {
     case KO_PINK_NOISE: u.reset(new PinkNoise((uint64_t)d.args[0])); break;
     case KO_BROWN_NOISE: u.reset(new BrownNoise((uint64_t)d.args[0])); break;
     case KO_RANDOM_LIN: u.reset(new RandomLin((F)d.args[0], (uint64_t)d.args[1])); break;
+    case KO_PAN2: u.reset(new Pan2((float)d.args[0])); break;
     default: g_last_error = "oracle: unknown ugen kind"; return nullptr;
     }
     for (uint32_t i = 0; i < d.n_wrappers; i++) {

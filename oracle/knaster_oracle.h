@@ -52,6 +52,7 @@ enum {
     KO_PINK_NOISE = 17,
     KO_BROWN_NOISE = 18,
     KO_RANDOM_LIN = 19,  /* args[0] = freq, args[1] = seed */
+    KO_PAN2 = 20,        /* pan.rs; args[0] = pan */
 };
 /* MathUGen ops */
 enum { KO_OP_ADD = 0, KO_OP_SUB = 1, KO_OP_MUL = 2, KO_OP_DIV = 3, KO_OP_POW = 4 };

@@ -85,7 +85,20 @@ def cases():
                 ids.append(n.id())
         return ids
 
+    def many_sines(g):  # knaster/examples/many_sines.rs:51-60: (EnvAr * SinWt.wr_mul) >> Pan2 -> stereo out
+        ids = []
+        with g.edit() as e:
+            for i in range(6):
+                env = e.push(kn.EnvAr(0.01, 0.05))
+                sine = e.push(kn.SinWt(400.0 + 111.0 * i).wr_mul(0.05))
+                pan = e.push(kn.Pan2(-1.0 + 0.4 * i))
+                ((env * sine) >> pan).to_graph_out()
+                env.param("t_restart").trig_at(kn.Seconds.from_samples(50 + 30 * i, SR))
+                ids.append(pan.id())
+        return ids
+
     return {
+        "many_sines_pan2": (many_sines, 40),
         "readme_sine": (banks.readme_sine, 8),
         "additive_4": (lambda g: banks.additive_bank(g, 4, 0.05), 37),
         "subtractive_asr_3": (lambda g: banks.subtractive_bank(g, 3, 0.15, n_notes=2), 112),

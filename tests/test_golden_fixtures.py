@@ -53,7 +53,7 @@ def test_engine_matches_the_committed_cases(name):
     out = proc.render(n_blocks)
     taps = proc.read_taps()
     ref_out, ref_taps = FIX[name + "/bus"], FIX[name + "/taps"]
-    exact = name in ("readme_sine", "additive_4", "noise_4")      # integer phase / integer RNG + single f32 ops
+    exact = name in ("readme_sine", "additive_4", "noise_4", "many_sines_pan2")      # integer phase / integer RNG + single f32 ops
     if exact:
         assert np.array_equal(taps, ref_taps)
     else:
