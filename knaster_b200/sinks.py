@@ -35,3 +35,18 @@ def save_to_disk(audio: np.ndarray, path: str, sample_rate: int) -> None:
     with open(path, "wb") as f:
         f.write(header)
         f.write(data)
+
+
+def save_stems(taps: np.ndarray, path_pattern: str, sample_rate: int) -> list:
+    """Per-voice stem dumps: `taps` is what ``AudioProcessor.read_taps()`` returns, [n_taps, frames] f32 (one
+    pre-mix signal per ``add_tap``); tap i goes to ``path_pattern.format(i)`` as a mono 16-bit WAVE file in
+    the same sample format as ``save_to_disk``.  Returns the paths written."""
+    t = np.asarray(taps, dtype=np.float32)
+    if t.ndim != 2:
+        raise ValueError("expected [n_taps, frames]")
+    paths = []
+    for i in range(t.shape[0]):
+        path = path_pattern.format(i)
+        save_to_disk(t[i].reshape(1, 1, -1), path, sample_rate)
+        paths.append(path)
+    return paths

@@ -29,3 +29,15 @@ def test_wave_file_round_trip(tmp_path):
     right = audio[:, 1, :].reshape(-1)
     assert np.array_equal(pcm[:, 0], np.trunc(left * np.float32(32767.0)).astype(np.int16))
     assert np.array_equal(pcm[:, 1], np.trunc(right * np.float32(32767.0)).astype(np.int16))
+
+
+def test_stem_dumps_one_mono_file_per_tap(tmp_path):
+    rng = np.random.Generator(np.random.PCG64(6))
+    taps = rng.uniform(-1.0, 1.0, (3, 500)).astype(np.float32)
+    paths = sinks.save_stems(taps, str(tmp_path / "voice_{:03d}.wav"), 48000)
+    assert [p.split("/")[-1] for p in paths] == ["voice_000.wav", "voice_001.wav", "voice_002.wav"]
+    for i, p in enumerate(paths):
+        with wave.open(p, "rb") as w:
+            assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 48000, 500)
+            pcm = np.frombuffer(w.readframes(500), dtype="<i2")
+        assert np.array_equal(pcm, sinks.to_pcm16(taps[i].reshape(1, 1, -1)))
