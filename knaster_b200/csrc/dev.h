@@ -89,6 +89,11 @@ enum DevOp : uint16_t {
     OP_SET = 0,          // regs[reg] = value
     OP_ASR_RELEASE = 1,  // EnvAsr::t_release (envelopes.rs:112-128); reg = node base
     OP_ENV_STOP = 2,     // Envelope t_stop   (envelopes.rs:511-523); reg = node base
+    // Envelope triggers as ONE event each instead of a register write per (half) field; the node's register
+    // base comes from `node` (interpreter) or is fixed by the recipe (render_sub_seg):
+    OP_ENV_RESTART = 3,  // t_restart (envelopes.rs:504-510): running, segment 0, time 0, from_value = the f64 in (reg = lo, value = hi)
+    OP_ENV_JUMP = 4,     // jump_to_segment (envelopes.rs:480-503): running, segment = value (already clamped), time 0; reg = node base
+    OP_ENV_STEP = 5,     // time_scale (envelopes.rs:477-479): step = time_scale * (1 / sr) = the f64 in (reg = lo, value = hi)
 };
 struct DevEvent {
     uint32_t frame;  // relative to the first frame of the render call

@@ -136,8 +136,8 @@ struct AsrEnv {
         default: break;
         }
     }
-    KN_DEV void op(uint32_t o) {
-        if (o == OP_ASR_RELEASE) envasr_release(est, et, sc);
+    KN_DEV void op(const DevEvent &e) {
+        if (e.op == OP_ASR_RELEASE) envasr_release(est, et, sc);
     }
     KN_DEV void derive(D &d) const {
         d.att = est == ASR_ATTACKING;
@@ -279,10 +279,27 @@ struct SegEnv {
     KN_DEV double level() const { // from_value + (t * reciprocal_duration) * (value - from_value), envelopes.rs:425-429
         return __dadd_rn(from, __dmul_rn(__dmul_rn(time, recip), __dsub_rn(val, from)));
     }
-    KN_DEV void op(uint32_t o) {
-        if (o == OP_ENV_STOP) { // t_stop, envelopes.rs:511-523
+    KN_DEV void op(const DevEvent &e) {
+        if (e.op == OP_ENV_STOP) {           // t_stop, envelopes.rs:511-523
             if (running) from = level();
             running = 0;
+        } else if (e.op == OP_ENV_RESTART) { // t_restart, envelopes.rs:504-510; (reg, value) = from_value
+            running = 1;
+            time = 0.0;
+            from = mk(e.reg, e.value);
+            if (seg != 0) {
+                seg = 0;
+                reload();
+            }
+        } else if (e.op == OP_ENV_JUMP) {    // jump_to_segment, envelopes.rs:480-503
+            running = 1;
+            time = 0.0;
+            if (seg != e.value) {
+                seg = e.value;
+                reload();
+            }
+        } else if (e.op == OP_ENV_STEP) {    // time_scale, envelopes.rs:477-479; (reg, value) = step
+            step = mk(e.reg, e.value);
         }
     }
     KN_DEV void derive(D &d) const {
@@ -591,7 +608,7 @@ KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
             bool touched = false;
             while (ec.next_frame <= f) { // events are sorted by (frame, node, arrival)
                 if (ec.e0.op == OP_SET) s.set(ec.e0.reg, ec.e0.value);
-                else s.e.op(ec.e0.op);
+                else s.e.op(ec.e0);
                 ec.pop();
                 touched = true;
             }

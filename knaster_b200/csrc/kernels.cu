@@ -46,7 +46,7 @@ KN_DEV void st_d(uint32_t *sreg, uint32_t r, double v) {
 }
 
 // apply every event of `node` due at or before `frame` to the lane's registers (in shared memory)
-KN_DEV void apply_events(LaneEv &L, uint32_t node, uint32_t frame, uint32_t *sreg) {
+KN_DEV void apply_events(LaneEv &L, uint32_t node, uint32_t node_reg, uint32_t frame, uint32_t *sreg) {
     while (L.next_node == node && L.next_frame <= frame) {
         const DevEvent e = L.ev[L.cur];
         if (e.op == OP_SET) {
@@ -69,6 +69,21 @@ KN_DEV void apply_events(LaneEv &L, uint32_t node, uint32_t frame, uint32_t *sre
                 st_d(sreg, e.reg + 4, from);
             }
             sreg[e.reg * 32] = 0;
+        } else if (e.op == OP_ENV_RESTART) { // envelopes.rs:504-510; (reg, value) = from_value
+            sreg[node_reg * 32] = 1;
+            sreg[(node_reg + 1) * 32] = 0;
+            sreg[(node_reg + 2) * 32] = 0;
+            sreg[(node_reg + 3) * 32] = 0;
+            sreg[(node_reg + 4) * 32] = e.reg;
+            sreg[(node_reg + 5) * 32] = e.value;
+        } else if (e.op == OP_ENV_JUMP) {    // envelopes.rs:480-503
+            sreg[e.reg * 32] = 1;
+            sreg[(e.reg + 1) * 32] = e.value;
+            sreg[(e.reg + 2) * 32] = 0;
+            sreg[(e.reg + 3) * 32] = 0;
+        } else if (e.op == OP_ENV_STEP) {    // envelopes.rs:477-479; (reg, value) = step
+            sreg[(node_reg + 6) * 32] = e.reg;
+            sreg[(node_reg + 7) * 32] = e.value;
         }
         L.cur++;
         L.fetch();
@@ -137,7 +152,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
 #define EVENTS_AT(f_, STORE_, LOAD_)                                                   \
     if (evc && L.next_node == n && L.next_frame <= c0 + (f_)) {                        \
         STORE_;                                                                        \
-        apply_events(L, n, c0 + (f_), sreg);                                           \
+        apply_events(L, n, rb, c0 + (f_), sreg);                                       \
         LOAD_;                                                                         \
         _Pragma("unroll") for (int k = 0; k < MAX_POST; k++) if (k < dn.n_post)        \
             pv[k] = __uint_as_float(sreg[dn.post_reg[k] * 32]);                        \

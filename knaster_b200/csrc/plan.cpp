@@ -357,21 +357,20 @@ void ugen_param_apply(Sim &s, uint32_t param, const PV &v, uint64_t frame) {
         else if ((h.kind == KGPU_ENV_ASR && param == 3) || (h.kind == KGPU_ENV_AR && param == 2))
             s.set_u(frame, r + 0, ASR_ATTACKING);
         break;
-    case KGPU_ENVELOPE: // envelopes.rs:476-526
+    case KGPU_ENVELOPE: // envelopes.rs:476-526; one compound device event per trigger (dev.h OP_ENV_*)
         if (param == 0) {
             double ts = (double)(float)v.f;
-            s.set_d(frame, r + 6, ts * (1.0 / (double)s.P.sample_rate));
+            uint32_t lo, hi;
+            dbits(ts * (1.0 / (double)s.P.sample_rate), lo, hi);
+            s.emit(frame, OP_ENV_STEP, lo, hi);
         } else if (param == 1) {
             uint64_t j = sat_usize(v.f);
             if (j >= h.n_seg) j = h.n_seg - 1;
-            s.set_u(frame, r + 1, (uint32_t)j);
-            s.set_d(frame, r + 2, 0.0);
-            s.set_u(frame, r + 0, 1);
+            s.emit(frame, OP_ENV_JUMP, r, (uint32_t)j);
         } else if (param == 2) {
-            s.set_u(frame, r + 0, 1);
-            s.set_u(frame, r + 1, 0);
-            s.set_d(frame, r + 2, 0.0);
-            s.set_d(frame, r + 4, h.d0);
+            uint32_t lo, hi;
+            dbits(h.d0, lo, hi);
+            s.emit(frame, OP_ENV_RESTART, lo, hi);
         } else if (param == 3) s.emit(frame, OP_ENV_STOP, r, 0);
         break;
     case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: // util.rs:45-48
