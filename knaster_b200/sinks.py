@@ -50,3 +50,41 @@ def save_stems(taps: np.ndarray, path_pattern: str, sample_rate: int) -> list:
         save_to_disk(t[i].reshape(1, 1, -1), path, sample_rate)
         paths.append(path)
     return paths
+
+
+class WavStream:
+    """Streaming form of ``save_to_disk``: append rendered audio ([n_blocks, channels, block] f32) call by call
+    -- e.g. one ``AudioProcessor.render(n)`` at a time for renders that do not fit in memory -- and patch the
+    RIFF sizes on ``close()``.  Same sample format (16-bit PCM, ``(x * i16::MAX) as i16``)."""
+
+    def __init__(self, path: str, channels: int, sample_rate: int):
+        self.channels, self.sample_rate, self._bytes = int(channels), int(sample_rate), 0
+        self._f = open(path, "wb")
+        self._f.write(self._header(0))
+
+    def _header(self, n: int) -> bytes:
+        block_align = self.channels * 2
+        return (b"RIFF" + struct.pack("<I", 36 + n) + b"WAVE" + b"fmt "
+                + struct.pack("<IHHIIHH", 16, 1, self.channels, self.sample_rate, self.sample_rate * block_align, block_align, 16)
+                + b"data" + struct.pack("<I", n))
+
+    def write(self, audio: np.ndarray) -> None:
+        a = np.asarray(audio)
+        if a.ndim != 3 or a.shape[1] != self.channels:
+            raise ValueError(f"expected [n_blocks, {self.channels}, block_size]")
+        data = to_pcm16(a).astype("<i2").tobytes()
+        self._f.write(data)
+        self._bytes += len(data)
+
+    def close(self) -> None:
+        if self._f:
+            self._f.seek(0)
+            self._f.write(self._header(self._bytes))
+            self._f.close()
+            self._f = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

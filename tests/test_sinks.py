@@ -41,3 +41,14 @@ def test_stem_dumps_one_mono_file_per_tap(tmp_path):
             assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 48000, 500)
             pcm = np.frombuffer(w.readframes(500), dtype="<i2")
         assert np.array_equal(pcm, sinks.to_pcm16(taps[i].reshape(1, 1, -1)))
+
+
+def test_streamed_wave_equals_the_one_shot_file(tmp_path):
+    rng = np.random.Generator(np.random.PCG64(7))
+    audio = rng.uniform(-1.0, 1.0, (9, 2, 64)).astype(np.float32)
+    sinks.save_to_disk(audio, str(tmp_path / "a.wav"), 44100)
+    with sinks.WavStream(str(tmp_path / "b.wav"), 2, 44100) as w:
+        w.write(audio[:4])
+        w.write(audio[4:5])
+        w.write(audio[5:])
+    assert (tmp_path / "a.wav").read_bytes() == (tmp_path / "b.wav").read_bytes()
