@@ -1441,13 +1441,18 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     uint32_t &cur = pg.cursor[v - pg.v_begin];
     const uint32_t e0 = cur, vend = P.vcount[gv + 1];
     if (L == 0 && vend - e0 > 1) { // first visit: (ready block, arrival) order
-        auto rb = [&](uint32_t idx) { return std::max(P.pending[idx].due_frame / bs, S.b0); };
+        // events that arrive in frame order (the usual case) are in block order: checked without a division
         bool sorted = true;
-        for (uint32_t k = e0 + 1; k < vend && sorted; k++) sorted = rb(P.vorder[k - 1]) <= rb(P.vorder[k]);
-        if (!sorted) std::stable_sort(P.vorder.begin() + e0, P.vorder.begin() + vend, [&](uint32_t x, uint32_t y) { return rb(x) < rb(y); });
+        for (uint32_t k = e0 + 1; k < vend && sorted; k++) sorted = P.pending[P.vorder[k - 1]].due_frame <= P.pending[P.vorder[k]].due_frame;
+        if (!sorted) {
+            auto rb = [&](uint32_t idx) { return std::max(P.pending[idx].due_frame / bs, S.b0); };
+            sorted = true;
+            for (uint32_t k = e0 + 1; k < vend && sorted; k++) sorted = rb(P.vorder[k - 1]) <= rb(P.vorder[k]);
+            if (!sorted) std::stable_sort(P.vorder.begin() + e0, P.vorder.begin() + vend, [&](uint32_t x, uint32_t y) { return rb(x) < rb(y); });
+        }
     }
     uint32_t e1 = e0;
-    while (e1 < vend && std::max(P.pending[P.vorder[e1]].due_frame / bs, S.b0) < wb1) e1++;
+    while (e1 < vend && P.pending[P.vorder[e1]].due_frame < t1) e1++; // t1 is a block boundary: same as due block < wb1
     cur = e1;
     const std::vector<uint32_t> &ls = S.lat_start[gi];
     const bool has_later = L == 0 && !ls.empty() && ls[v + 1] > ls[v];
