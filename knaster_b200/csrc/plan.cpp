@@ -1572,6 +1572,9 @@ void stream_worker(HostPlan &P, StreamState &S, unsigned ti) {
     StreamState::ThreadCtx &tc = *S.th[ti];
     try {
         std::vector<const RawEvent *> evp, node_ev;
+        if (ti < 3 && S.n_launch > 2 && getenv("KGPU_TIMING"))
+            fprintf(stderr, "[kgpu timing]     worker %u started at +%.2f ms\n", ti,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S.t_begin).count());
         for (size_t L = 0; L < S.n_launch; L++) {
             for (uint32_t gi = 0; gi < P.groups.size(); gi++) {
                 StreamState::PerGroup &pg = tc.g[gi];
