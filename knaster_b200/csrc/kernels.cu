@@ -137,6 +137,17 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
             const bool plain_ok = dn.n_ar == 0 && (CH & 15u) == 0 && (n_post_ == 0 || (n_post_ == 1 && dn.post_op[0] == PO_MUL));
             // a chunk is walked in groups of 16 frames; a group takes the fast path unless an event of this node
             // falls into it (warp-uniform test on the lanes' event cursors) or it is a partial group
+            // the same with audio-rate routes into the node's own parameters (not into a wrapper value): SinWt,
+            // SinNumeric and PolyBlep read the routed samples 16 at a time and update the parameter per frame
+            bool plain_ar_ok = dn.n_ar > 0 && (CH & 15u) == 0 && (n_post_ == 0 || (n_post_ == 1 && dn.post_op[0] == PO_MUL));
+            int ar_s0 = -1, ar_s1 = -1; // value slots of the routes into parameter 0 (freq) / parameter 1 (phase_offset, pulse_width)
+            for (int ai = 0; ai < dn.n_ar; ai++) {
+                const uint32_t code = dn.ar_code[ai];
+                if (code == AR_SINWT_FREQ || code == AR_SINNUM_FREQ || code == AR_POLYBLEP_FREQ) ar_s0 = dn.ar_slot[ai];
+                else if (code == AR_SINWT_OFFSET || code == AR_SINNUM_OFFSET || code == AR_POLYBLEP_PW) ar_s1 = dn.ar_slot[ai];
+                else plain_ar_ok = false;
+            }
+#define GROUP_PLAIN_AR (plain_ar_ok && fe_ - g0_ == 16 && !(evc && __any_sync(0xFFFFFFFFu, L.next_node == n && L.next_frame < c0 + fe_)))
 #define FOR_GROUPS for (uint32_t g0_ = 0, fe_ = min(nf, 16u); g0_ < nf; g0_ += 16, fe_ = min(nf, g0_ + 16u))
 #define GROUP_PLAIN (plain_ok && fe_ - g0_ == 16 && !(evc && __any_sync(0xFFFFFFFFu, L.next_node == n && L.next_frame < c0 + fe_)))
 #define PLAIN16(EXPR_)                                                                 \
@@ -175,6 +186,17 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                         PLAIN16(sinwt_tick(phase, off, inc, a.sine_table))
                         continue;
                     }
+                    if (GROUP_PLAIN_AR) {
+                        LOAD16(xf_, ar_s0)
+                        LOAD16(xo_, ar_s1)
+                        auto tk = [&](int k) {
+                            if (ar_s0 >= 0) inc = kn_sat_u32(__dmul_rn((double)xf_[k], sinwt_k));
+                            if (ar_s1 >= 0) off = kn_sat_u32(__dmul_rn((double)xo_[k], 65536.0));
+                            return sinwt_tick(phase, off, inc, a.sine_table);
+                        };
+                        PLAIN16(tk(k))
+                        continue;
+                    }
                     for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = phase, (phase = sreg[rb * 32], off = sreg[(rb + 1) * 32], inc = sreg[(rb + 2) * 32]))
                     for (int ai = 0; ai < dn.n_ar; ai++) {
@@ -198,6 +220,17 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 FOR_GROUPS {
                     if (GROUP_PLAIN) {
                         PLAIN16(sinnum_tick(phase, off, inc))
+                        continue;
+                    }
+                    if (GROUP_PLAIN_AR) {
+                        LOAD16(xf_, ar_s0)
+                        LOAD16(xo_, ar_s1)
+                        auto tk = [&](int k) {
+                            if (ar_s0 >= 0) inc = xf_[k] / sr; // osc.rs:240-242
+                            if (ar_s1 >= 0) off = xo_[k];
+                            return sinnum_tick(phase, off, inc);
+                        };
+                        PLAIN16(tk(k))
                         continue;
                     }
                     for (uint32_t f = g0_; f < fe_; f++) {
@@ -232,6 +265,20 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                             } else PLAIN16(polyblep_saw_tick_sel(t, dt))
                         }
                         else PLAIN16(polyblep_tick(t, dt, use_sin, pw, wf))
+                        continue;
+                    }
+                    if (GROUP_PLAIN_AR) {
+                        LOAD16(xf_, ar_s0)
+                        LOAD16(xo_, ar_s1)
+                        auto tk = [&](int k) {
+                            if (ar_s0 >= 0) {
+                                dt = xf_[k] / sr;
+                                use_sin = (dt * sr >= sr / 4.0f) ? 1u : 0u;
+                            }
+                            if (ar_s1 >= 0) pw = xo_[k];
+                            return polyblep_tick(t, dt, use_sin, pw, wf);
+                        };
+                        PLAIN16(tk(k))
                         continue;
                     }
                     for (uint32_t f = g0_; f < fe_; f++) {
