@@ -235,6 +235,17 @@ uint64_t kgpu_plan_last_upload_bytes(kgpu_plan *plan);
 /* K = blocks rendered per kernel launch (default: as many as fit a 256 MiB partial-sum buffer,
  * at most 2048).  K = 1 reproduces "one launch per 64-frame block". */
 int kgpu_plan_set_blocks_per_launch(kgpu_plan *plan, uint64_t blocks);
+/* ---- snapshot / restore (no counterpart in the reference: knaster cannot rewind a running graph) ------------
+ * kgpu_plan_snapshot copies the whole render state of the plan -- the voices' registers (device -> host), the
+ * control-side state of every node of every voice, the queued events, the frame clock and the counters -- into
+ * an object owned by the caller; kgpu_plan_restore puts it back (events pushed after the snapshot are gone,
+ * the next render continues from the snapshot's frame clock).  Not valid between kgpu_plan_prepare and its
+ * render.  With a peer bus every rank snapshots / restores at the same point. */
+typedef struct kgpu_snapshot kgpu_snapshot;
+int kgpu_plan_snapshot(kgpu_plan *plan, kgpu_snapshot **out);
+int kgpu_plan_restore(kgpu_plan *plan, const kgpu_snapshot *snapshot);
+void kgpu_snapshot_destroy(kgpu_snapshot *snapshot);
+
 /* ---- multi-GPU mix bus over peer memory -------------------------------------------------------
  * One process per GPU, voices sharded across ranks.  Instead of reducing the rank-local
  * buses with a collective afterwards, every rank's bus-reduction kernel stores straight into its slot

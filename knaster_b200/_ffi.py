@@ -128,6 +128,10 @@ def lib() -> C.CDLL:
     L.kgpu_plan_last_upload_bytes.restype = u64
     L.kgpu_plan_set_blocks_per_launch.argtypes = [vp, u64]
     L.kgpu_plan_set_host_threads.argtypes = [vp, u32]
+    L.kgpu_plan_snapshot.argtypes = [vp, C.POINTER(vp)]
+    L.kgpu_plan_restore.argtypes = [vp, vp]
+    L.kgpu_snapshot_destroy.argtypes = [vp]
+    L.kgpu_snapshot_destroy.restype = None
     L.kgpu_plan_set_peer_bus.argtypes = [vp, u32, u32, vp, u64]
     L.kgpu_plan_peer_bus_timed_out.argtypes = [vp]
     L.kgpu_peer_bus_header_bytes.argtypes = [u32]

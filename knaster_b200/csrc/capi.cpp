@@ -791,6 +791,98 @@ int kgpu_plan_set_blocks_per_launch(kgpu_plan *p, uint64_t blocks) {
     return KGPU_OK;
 }
 
+// ---- snapshot / restore of the whole render state ---------------------------
+// Everything a later render depends on: the voices' registers on the device, the control-side state of every
+// node of every voice (wrapper queues, smoothing ramps, setters' cached fields), the queued events (near and
+// far), the simulated events that lie beyond the last render's end, the frame clock and the counters.
+struct kgpu_snapshot {
+    std::vector<std::vector<uint32_t>> regs;       // per group: [n_regs][n_voices]
+    std::vector<std::vector<HostNode>> host;       // per group
+    decltype(HostPlan::pending) pending, pending_far;
+    uint64_t far_horizon = UINT64_MAX;
+    size_t pending_clean = 0;
+    std::vector<std::vector<VoiceEvent>> later;
+    std::vector<int32_t> voice_ramps;
+    std::vector<uint64_t> voice_base;
+    uint64_t n_active_ramps = 0, dropped_changes = 0, ignored_delays = 0, device_events = 0, frame_clock = 0;
+    bool rendered = false;
+};
+
+int kgpu_plan_snapshot(kgpu_plan *p, kgpu_snapshot **out) {
+    if (!p || !out) return fail(KGPU_ERR_INVALID, "kgpu_plan_snapshot: NULL argument");
+    *out = nullptr;
+    try {
+        if (p->prepared) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_snapshot: a prepared render is pending");
+        if (p->host.stream) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_snapshot: a render call is in progress");
+        CUDA_TRY(cudaSetDevice(p->device));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        std::unique_ptr<kgpu_snapshot> s(new kgpu_snapshot());
+        for (size_t gi = 0; gi < p->gd.size(); gi++) {
+            const Group &g = p->host.groups[gi];
+            s->regs.emplace_back((size_t)g.prog.n_regs * g.n_voices);
+            if (!s->regs.back().empty())
+                CUDA_TRY(cudaMemcpy(s->regs.back().data(), p->gd[gi].regs.p, s->regs.back().size() * 4, cudaMemcpyDeviceToHost));
+            s->host.push_back(g.host);
+        }
+        s->pending = p->host.pending;
+        s->pending_far = p->host.pending_far;
+        s->far_horizon = p->host.far_horizon;
+        s->pending_clean = p->host.pending_clean;
+        s->later = p->host.later;
+        s->voice_ramps = p->host.voice_ramps;
+        s->voice_base = p->host.voice_base;
+        s->n_active_ramps = p->host.n_active_ramps;
+        s->dropped_changes = p->host.dropped_changes;
+        s->ignored_delays = p->host.ignored_delays;
+        s->device_events = p->host.device_events;
+        s->frame_clock = p->frame_clock;
+        s->rendered = p->rendered;
+        *out = s.release();
+        return KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
+int kgpu_plan_restore(kgpu_plan *p, const kgpu_snapshot *s) {
+    if (!p || !s) return fail(KGPU_ERR_INVALID, "kgpu_plan_restore: NULL argument");
+    try {
+        if (p->host.stream) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_restore: a render call is in progress");
+        if (s->regs.size() != p->gd.size()) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_plan_restore: the snapshot belongs to another plan");
+        for (size_t gi = 0; gi < p->gd.size(); gi++) {
+            const Group &g = p->host.groups[gi];
+            if (s->regs[gi].size() != (size_t)g.prog.n_regs * g.n_voices || s->host[gi].size() != g.host.size())
+                KGPU_THROW(KGPU_ERR_INVALID, "kgpu_plan_restore: the snapshot belongs to another plan");
+        }
+        CUDA_TRY(cudaSetDevice(p->device));
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        for (size_t gi = 0; gi < p->gd.size(); gi++) {
+            if (!s->regs[gi].empty())
+                CUDA_TRY(cudaMemcpy(p->gd[gi].regs.p, s->regs[gi].data(), s->regs[gi].size() * 4, cudaMemcpyHostToDevice));
+            p->host.groups[gi].host = s->host[gi];
+        }
+        p->host.pending = s->pending;
+        p->host.pending_far = s->pending_far;
+        p->host.far_horizon = s->far_horizon;
+        p->host.pending_clean = s->pending_clean;
+        p->host.later = s->later;
+        p->host.voice_ramps = s->voice_ramps;
+        p->host.voice_base = s->voice_base;
+        p->host.n_active_ramps = s->n_active_ramps;
+        p->host.dropped_changes = s->dropped_changes;
+        p->host.ignored_delays = s->ignored_delays;
+        p->host.device_events = s->device_events;
+        p->frame_clock = s->frame_clock;
+        p->rendered = s->rendered;
+        p->prepared = false;
+        return KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
+void kgpu_snapshot_destroy(kgpu_snapshot *s) { delete s; }
+
 float kgpu_plan_last_render_ms(kgpu_plan *p) {
     if (!p || !p->timed) return -1.f;
     if (cudaEventSynchronize(p->ev1) != cudaSuccess) return -1.f;

@@ -205,6 +205,20 @@ class AudioProcessor:
     def peer_bus_timed_out(self) -> bool:
         return bool(self._plan) and int(self._lib.kgpu_plan_peer_bus_timed_out(self._plan)) != 0
 
+    def snapshot(self) -> "Snapshot":
+        """Copy of the whole render state (voice registers, control-side state, queued events, frame clock):
+        ``restore()`` rewinds the processor to it.  Events must be pushed first, so the graph's pending ones are."""
+        self._ensure_plan()
+        self._push_events()
+        h = C.c_void_p()
+        _ffi.check(self._lib.kgpu_plan_snapshot(self._plan, C.byref(h)))
+        return Snapshot(self._lib, h)
+
+    def restore(self, snap: "Snapshot") -> None:
+        self._ensure_plan()
+        self._push_events()          # what the graph still holds belongs to "before the restore": queued, then discarded
+        _ffi.check(self._lib.kgpu_plan_restore(self._plan, snap._h))
+
     def set_host_threads(self, n_threads: int) -> None:
         """Worker threads of the host event pipeline (0 = hardware threads - 1, at most 16)."""
         self._ensure_plan()
@@ -212,3 +226,15 @@ class AudioProcessor:
 
     def last_render_ms(self) -> float:
         return float(self._lib.kgpu_plan_last_render_ms(self._plan))
+
+
+class Snapshot:
+    """Owner of a ``kgpu_snapshot`` (include/knaster_gpu.h)."""
+
+    def __init__(self, lib, handle):
+        self._lib, self._h = lib, handle
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.kgpu_snapshot_destroy(self._h)
+            self._h = None

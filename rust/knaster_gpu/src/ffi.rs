@@ -26,6 +26,7 @@ use std::os::raw::{c_char, c_int, c_void};
     pub dropped_changes: u64, pub ignored_delays: u64, pub device_events: u64, pub kernel_launches: u64,
 }
 #[repr(C)] pub struct kgpu_plan { _private: [u8; 0] }
+#[repr(C)] pub struct kgpu_snapshot { _private: [u8; 0] }
 
 extern "C" {
     pub fn kgpu_plan_create(desc: *const kgpu_graph_desc, out: *mut *mut kgpu_plan) -> c_int;
@@ -48,6 +49,10 @@ extern "C" {
     pub fn kgpu_peer_bus_bytes(world: u32, floats_per_rank: u64) -> u64;
     pub fn kgpu_plan_set_peer_bus(plan: *mut kgpu_plan, rank: u32, world: u32, root_buffer: *mut c_void, buffer_bytes: u64) -> c_int;
     pub fn kgpu_plan_peer_bus_timed_out(plan: *mut kgpu_plan) -> c_int;
+    // snapshot / restore of the whole render state
+    pub fn kgpu_plan_snapshot(plan: *mut kgpu_plan, out: *mut *mut kgpu_snapshot) -> c_int;
+    pub fn kgpu_plan_restore(plan: *mut kgpu_plan, snapshot: *const kgpu_snapshot) -> c_int;
+    pub fn kgpu_snapshot_destroy(snapshot: *mut kgpu_snapshot);
     // introspection / measurement
     pub fn kgpu_plan_get_info(plan: *mut kgpu_plan, info: *mut kgpu_plan_info) -> c_int;
     pub fn kgpu_plan_group_kernel(plan: *mut kgpu_plan, group: u32) -> *const c_char;

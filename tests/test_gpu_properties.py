@@ -465,3 +465,39 @@ def test_block_by_block_under_a_large_event_backlog_equals_batched():
     batched = np.concatenate(parts)
     assert np.abs(batched).max() > 1e-3
     assert np.array_equal(per_block, batched)
+
+
+@pytest.mark.parametrize("bank", ["asr", "segments", "additive", "fm", "interp"])
+def test_snapshot_restore_rewinds_the_render(bank):
+    # kgpu_plan_snapshot / kgpu_plan_restore: voice registers, control-side state (smoothing ramps, precise-timing
+    # queues), queued events and the frame clock all come back; what was pushed after the snapshot does not
+    def build(graph):
+        if bank == "additive":
+            return banks.additive_bank(graph, 70, 1.0)
+        if bank == "fm":
+            return banks.fm_bank(graph, 40)
+        return banks.subtractive_bank(graph, 70, 1.0, n_notes=6, envelope="segments" if bank == "segments" else "asr")
+
+    graph, proc = AudioProcessor.new(0, 2, AudioProcessorOptions(sample_rate=SR, force_interpreter=bank == "interp"))
+    build(graph)
+    first = proc.render(130)                      # stops in the middle of notes / smoothing ramps
+    snap = proc.snapshot()
+    a = proc.render(400)
+    assert proc.frame_clock() == 530 * 64
+    proc.restore(snap)
+    assert proc.frame_clock() == 130 * 64
+    b = proc.render(400)
+    assert np.array_equal(a, b)
+    assert np.abs(a).max() > 1e-3
+    # an event pushed after the snapshot changes the render, and is gone after the next restore
+    with graph.edit() as g:
+        g.set(0, 0, 987.0, kn.Time.asap())        # node 0 / parameter 0 is a frequency in every bank
+    c = proc.render(60)
+    assert not np.array_equal(c, a[:60])
+    proc.restore(snap)
+    d = proc.render(400)
+    assert np.array_equal(d, a)
+    # the whole run equals an uninterrupted one
+    g2, p2 = AudioProcessor.new(0, 2, AudioProcessorOptions(sample_rate=SR, force_interpreter=bank == "interp"))
+    build(g2)
+    assert np.array_equal(p2.render(530), np.concatenate([first, a]))
