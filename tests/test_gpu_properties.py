@@ -501,3 +501,26 @@ def test_snapshot_restore_rewinds_the_render(bank):
     g2, p2 = AudioProcessor.new(0, 2, AudioProcessorOptions(sample_rate=SR, force_interpreter=bank == "interp"))
     build(g2)
     assert np.array_equal(p2.render(530), np.concatenate([first, a]))
+
+
+@pytest.mark.parametrize("bank,voices", [("segments", 16384), ("fm", 8192), ("fm", 9600)])
+def test_full_size_launch_split_invariance_of_the_other_recipes(bank, voices):
+    # BASELINE.json sizes for configs[2] variant B and configs[3] (and the one-lane FM form above 9472 voices):
+    # one launch against 97-block and 5-block launches -- the f64 envelope state, the FM kernel's drained carrier
+    # pipeline and the partial-row layout must make the split invisible, bit for bit
+    def run(bpl):
+        graph, proc = AudioProcessor.new(0, 2, AudioProcessorOptions(sample_rate=SR))
+        if bank == "fm":
+            banks.fm_bank(graph, voices)
+        else:
+            banks.subtractive_bank(graph, voices, 0.5, envelope="segments")
+        if bpl:
+            proc.set_blocks_per_launch(bpl)
+        return proc.render(375), proc.info()["kernels"]
+
+    whole, kernels = run(0)
+    assert kernels == ["render_fm2" if bank == "fm" else "render_sub_seg"]
+    assert np.isfinite(whole).all() and np.abs(whole).max() > 1e-4
+    for bpl in (97, 5):
+        out, _ = run(bpl)
+        assert np.array_equal(out, whole), f"{bank}: render differs with {bpl} blocks per launch"
