@@ -346,3 +346,41 @@ def test_sinf_restatement_matches_libm():
     inside = np.abs(xs) < 120.0
     assert np.array_equal(ys[inside].view(np.uint32), ref[inside].view(np.uint32))
     assert np.abs(ys[~inside] - ref[~inside]).max() <= 1.2e-7   # fallback path: f64 sine rounded once
+
+
+def test_event_calendar_does_not_change_what_the_device_sees():
+    # Block-by-block calls under a long queue of scheduled events switch the host's calendar on (plan.cpp
+    # calendar_update: near / far queues).  The device event stream must be the one a single call produces --
+    # including same-frame events whose arrival order decides the final value, and events due far ahead.
+    n_nodes, n_blocks = 48, 400
+    rng = np.random.Generator(np.random.PCG64(9))
+    g = Graph(0, 1, 16, SR)
+    ids = []
+    with g.edit() as e:
+        for i in range(n_nodes):
+            n = e.push(kn.Constant(float(i)).precise_timing(8))
+            n.to_graph_out()
+            ids.append(n.id())
+    frames = rng.integers(0, n_blocks * 16, (n_nodes, 420))
+    frames[:, :40] = frames[:, 40:80]                     # same-frame pairs: the later arrival must win
+    order = rng.permutation(n_nodes * 420)                # arrival order unrelated to due time
+    nodes = np.repeat(np.asarray(ids, dtype=np.uint32), 420)[order]
+    fr = frames.reshape(-1)[order].astype(np.uint64)
+    vals = rng.uniform(-1.0, 1.0, len(fr))
+    g.schedule_bulk(nodes, np.zeros(len(fr)), np.ones(len(fr)), vals, fr)
+    ev = g.take_events()
+    assert len(ev) > 16384
+    one, _, info1 = _ffi.debug_simulate(g, ev, n_blocks, 0)
+    per_block, _, info2 = _ffi.debug_simulate(g, ev, n_blocks, 1)
+    assert info1["device_events"] == info2["device_events"] and info1["dropped_changes"] == info2["dropped_changes"]
+
+    def per_voice(evs):
+        d = {}
+        for (grp, voice, node, op, reg, val, frame) in evs:
+            d.setdefault((grp, voice), []).append((frame, node, op, reg, val))
+        return d
+
+    a, b = per_voice(one), per_voice(per_block)
+    assert a.keys() == b.keys()
+    for k in a:
+        assert a[k] == b[k], f"voice {k}: device events differ between one call and block-by-block calls"
