@@ -245,6 +245,11 @@ typedef struct kgpu_snapshot kgpu_snapshot;
 int kgpu_plan_snapshot(kgpu_plan *plan, kgpu_snapshot **out);
 int kgpu_plan_restore(kgpu_plan *plan, const kgpu_snapshot *snapshot);
 void kgpu_snapshot_destroy(kgpu_snapshot *snapshot);
+/* A snapshot as bytes (checkpoint on disk; restore into a plan created from the same graph description, in
+ * this or another process).  Serialize: call with buf == NULL to get the size, then with a buffer of at least
+ * that many bytes.  Deserialize rejects truncated, foreign or other-version images with KGPU_ERR_INVALID. */
+int kgpu_snapshot_serialize(const kgpu_snapshot *snapshot, void *buf, uint64_t cap, uint64_t *size);
+int kgpu_snapshot_deserialize(const void *buf, uint64_t size, kgpu_snapshot **out);
 
 /* ---- multi-GPU mix bus over peer memory -------------------------------------------------------
  * One process per GPU, voices sharded across ranks.  Instead of reducing the rank-local

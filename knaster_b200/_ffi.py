@@ -132,6 +132,8 @@ def lib() -> C.CDLL:
     L.kgpu_plan_restore.argtypes = [vp, vp]
     L.kgpu_snapshot_destroy.argtypes = [vp]
     L.kgpu_snapshot_destroy.restype = None
+    L.kgpu_snapshot_serialize.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.kgpu_snapshot_deserialize.argtypes = [vp, u64, C.POINTER(vp)]
     L.kgpu_plan_set_peer_bus.argtypes = [vp, u32, u32, vp, u64]
     L.kgpu_plan_peer_bus_timed_out.argtypes = [vp]
     L.kgpu_peer_bus_header_bytes.argtypes = [u32]

@@ -883,6 +883,188 @@ int kgpu_plan_restore(kgpu_plan *p, const kgpu_snapshot *s) {
 
 void kgpu_snapshot_destroy(kgpu_snapshot *s) { delete s; }
 
+// ---- a snapshot as bytes (checkpoint on disk, resume in another process on the same graph) ------------
+// Flat little-endian image: magic, version, then every field length-prefixed.  The leaf structs are plain data
+// and are written field by field (no padding bytes, no pointers), so the image depends on this file's version
+// number only.
+extern "C++" {
+namespace {
+constexpr uint64_t SNAP_MAGIC = 0x50414E5355504B47ull; // "GKPUSNAP"
+constexpr uint32_t SNAP_VERSION = 1;
+struct Writer {
+    uint8_t *buf;
+    uint64_t cap, pos = 0;
+    void raw(const void *p, size_t n) {
+        if (buf && pos + n <= cap) std::memcpy(buf + pos, p, n);
+        pos += n;
+    }
+    template <class T> void pod(const T &v) { static_assert(std::is_trivially_copyable<T>::value, "pod"); raw(&v, sizeof v); }
+    template <class V> void pods(const V &v) { // vector of padding-free scalars
+        pod<uint64_t>(v.size());
+        if (!v.empty()) raw(v.data(), v.size() * sizeof(v[0]));
+    }
+};
+struct Reader {
+    const uint8_t *buf;
+    uint64_t size, pos = 0;
+    void raw(void *p, size_t n) {
+        if (pos + n > size) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: truncated image");
+        std::memcpy(p, buf + pos, n);
+        pos += n;
+    }
+    template <class T> T pod() { T v; raw(&v, sizeof v); return v; }
+    template <class V> void pods(V &v) {
+        const uint64_t n = pod<uint64_t>();
+        if (n > (size - pos) / sizeof(v[0])) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad length");
+        v.resize(n);
+        if (n) raw(v.data(), n * sizeof(v[0]));
+    }
+};
+void put_pv(Writer &w, const PV &v) { w.pod<uint8_t>(v.kind); w.pod(v.f); w.pod(v.smoothing); w.pod(v.smooth_seconds); }
+void get_pv(Reader &r, PV &v) { v.kind = (PV::Kind)r.pod<uint8_t>(); v.f = r.pod<double>(); v.smoothing = r.pod<uint8_t>(); v.smooth_seconds = r.pod<float>(); }
+void put_raw_events(Writer &w, const decltype(HostPlan::pending) &v) {
+    w.pod<uint64_t>(v.size());
+    for (const RawEvent &e : v) { w.pod(e.node); w.pod(e.param); w.pod(e.value_kind); w.pod(e.smoothing_kind); w.pod(e.timed); w.pod(e.smooth_seconds); w.pod(e.value); w.pod(e.due_frame); }
+}
+void get_raw_events(Reader &r, decltype(HostPlan::pending) &v) {
+    const uint64_t n = r.pod<uint64_t>();
+    if (n > (r.size - r.pos) / 29) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad length");
+    v.resize(n);
+    for (RawEvent &e : v) {
+        std::memset(&e, 0, sizeof e);
+        e.node = r.pod<uint32_t>(); e.param = r.pod<uint16_t>(); e.value_kind = r.pod<uint8_t>(); e.smoothing_kind = r.pod<uint8_t>();
+        e.timed = r.pod<uint8_t>(); e.smooth_seconds = r.pod<float>(); e.value = r.pod<double>(); e.due_frame = r.pod<uint64_t>();
+    }
+}
+void put_node(Writer &w, const HostNode &h) {
+    w.pod(h.kind); w.pod(h.dev_kind); w.pod(h.mode); w.pod(h.reg); w.pod(h.n_seg); w.pod(h.base_params);
+    w.pod(h.f0); w.pod(h.f1); w.pod(h.f2); w.pod(h.d0);
+    for (float c : h.svf_coef) w.pod(c);
+    w.pod<uint8_t>(h.has_smooth); w.pod<uint8_t>(h.has_precise); w.pod(h.smooth_level); w.pod(h.precise_level);
+    w.pod<uint8_t>(h.ramp_active); w.pod(h.ramp_list_pos);
+    w.pod<uint64_t>(h.wr.size());
+    for (const WrapSim &x : h.wr) {
+        w.pod(x.kind); w.pod(x.capacity); w.pod(x.reg); w.pod(x.inner_params);
+        w.pod<uint64_t>(x.smooth.size());
+        for (const SmoothState &m : x.smooth) {
+            w.pod<uint8_t>(m.linear); w.pod(m.current_value); w.pod(m.start_value); w.pod(m.end_value);
+            w.pod(m.duration_frames); w.pod(m.frames_elapsed); w.pod<uint8_t>(m.done);
+        }
+        w.pods(x.next_delay);
+        w.pod<uint64_t>(x.queue.size());
+        for (const QueuedChange &q : x.queue) { w.pod(q.delay); w.pod(q.param); put_pv(w, q.value); }
+        w.pods(x.ar_bound);
+    }
+}
+void get_node(Reader &r, HostNode &h) {
+    h.kind = r.pod<uint8_t>(); h.dev_kind = r.pod<uint8_t>(); h.mode = r.pod<uint32_t>(); h.reg = r.pod<uint16_t>(); h.n_seg = r.pod<uint16_t>();
+    h.base_params = r.pod<uint32_t>();
+    h.f0 = r.pod<float>(); h.f1 = r.pod<float>(); h.f2 = r.pod<float>(); h.d0 = r.pod<double>();
+    for (float &c : h.svf_coef) c = r.pod<float>();
+    h.has_smooth = r.pod<uint8_t>() != 0; h.has_precise = r.pod<uint8_t>() != 0; h.smooth_level = r.pod<int8_t>(); h.precise_level = r.pod<int8_t>();
+    h.ramp_active = r.pod<uint8_t>() != 0; h.ramp_list_pos = r.pod<uint32_t>();
+    const uint64_t nw = r.pod<uint64_t>();
+    if (nw > 64) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad wrapper count");
+    h.wr.resize(nw);
+    for (WrapSim &x : h.wr) {
+        x.kind = r.pod<uint8_t>(); x.capacity = r.pod<uint32_t>(); x.reg = r.pod<uint16_t>(); x.inner_params = r.pod<uint32_t>();
+        const uint64_t ns = r.pod<uint64_t>();
+        if (ns > 4096) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad length");
+        x.smooth.resize(ns);
+        for (SmoothState &m : x.smooth) {
+            m.linear = r.pod<uint8_t>() != 0; m.current_value = r.pod<double>(); m.start_value = r.pod<double>(); m.end_value = r.pod<double>();
+            m.duration_frames = r.pod<uint64_t>(); m.frames_elapsed = r.pod<uint64_t>(); m.done = r.pod<uint8_t>() != 0;
+        }
+        r.pods(x.next_delay);
+        const uint64_t nq = r.pod<uint64_t>();
+        if (nq > (1u << 20)) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad length");
+        x.queue.resize(nq);
+        for (QueuedChange &q : x.queue) { q.delay = r.pod<uint16_t>(); q.param = r.pod<uint32_t>(); get_pv(r, q.value); }
+        r.pods(x.ar_bound);
+    }
+}
+void put_voice_events(Writer &w, const std::vector<VoiceEvent> &v) {
+    w.pod<uint64_t>(v.size());
+    for (const VoiceEvent &e : v) { w.pod(e.voice); w.pod(e.seq); w.pod(e.frame); w.pod(e.ev.frame); w.pod(e.ev.node); w.pod(e.ev.op); w.pod(e.ev.reg); w.pod(e.ev.value); }
+}
+void get_voice_events(Reader &r, std::vector<VoiceEvent> &v) {
+    const uint64_t n = r.pod<uint64_t>();
+    if (n > (r.size - r.pos) / 32) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad length");
+    v.resize(n);
+    for (VoiceEvent &e : v) {
+        e.voice = r.pod<uint32_t>(); e.seq = r.pod<uint32_t>(); e.frame = r.pod<uint64_t>();
+        e.ev.frame = r.pod<uint32_t>(); e.ev.node = r.pod<uint16_t>(); e.ev.op = r.pod<uint16_t>(); e.ev.reg = r.pod<uint32_t>(); e.ev.value = r.pod<uint32_t>();
+    }
+}
+void write_snapshot(Writer &w, const kgpu_snapshot &s) {
+    w.pod(SNAP_MAGIC); w.pod(SNAP_VERSION);
+    w.pod<uint64_t>(s.regs.size());
+    for (size_t gi = 0; gi < s.regs.size(); gi++) {
+        w.pods(s.regs[gi]);
+        w.pod<uint64_t>(s.host[gi].size());
+        for (const HostNode &h : s.host[gi]) put_node(w, h);
+    }
+    put_raw_events(w, s.pending); put_raw_events(w, s.pending_far);
+    w.pod(s.far_horizon); w.pod<uint64_t>(s.pending_clean);
+    w.pod<uint64_t>(s.later.size());
+    for (const auto &l : s.later) put_voice_events(w, l);
+    w.pods(s.voice_ramps); w.pods(s.voice_base);
+    w.pod(s.n_active_ramps); w.pod(s.dropped_changes); w.pod(s.ignored_delays); w.pod(s.device_events); w.pod(s.frame_clock);
+    w.pod<uint8_t>(s.rendered);
+}
+} // namespace
+} // extern "C++"
+
+/* Size query: buf == NULL.  Returns KGPU_ERR_INVALID if cap is too small (*size still receives the need). */
+int kgpu_snapshot_serialize(const kgpu_snapshot *s, void *buf, uint64_t cap, uint64_t *size) {
+    if (!s || !size) return fail(KGPU_ERR_INVALID, "kgpu_snapshot_serialize: NULL argument");
+    Writer w{static_cast<uint8_t *>(buf), buf ? cap : 0};
+    write_snapshot(w, *s);
+    *size = w.pos;
+    if (buf && w.pos > cap) return fail(KGPU_ERR_INVALID, "kgpu_snapshot_serialize: buffer too small");
+    return KGPU_OK;
+}
+
+int kgpu_snapshot_deserialize(const void *buf, uint64_t size, kgpu_snapshot **out) {
+    if (!buf || !out) return fail(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: NULL argument");
+    *out = nullptr;
+    try {
+        Reader r{static_cast<const uint8_t *>(buf), size};
+        if (r.pod<uint64_t>() != SNAP_MAGIC) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: not a snapshot image");
+        if (r.pod<uint32_t>() != SNAP_VERSION) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: unsupported image version");
+        std::unique_ptr<kgpu_snapshot> s(new kgpu_snapshot());
+        const uint64_t ng = r.pod<uint64_t>();
+        if (ng > (1u << 20)) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad group count");
+        s->regs.resize(ng);
+        s->host.resize(ng);
+        for (uint64_t gi = 0; gi < ng; gi++) {
+            r.pods(s->regs[gi]);
+            const uint64_t nh = r.pod<uint64_t>();
+            if (nh > (size - r.pos)) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad length");
+            s->host[gi].resize(nh);
+            for (HostNode &h : s->host[gi]) get_node(r, h);
+        }
+        get_raw_events(r, s->pending);
+        get_raw_events(r, s->pending_far);
+        s->far_horizon = r.pod<uint64_t>();
+        s->pending_clean = (size_t)r.pod<uint64_t>();
+        const uint64_t nl = r.pod<uint64_t>();
+        if (nl > (1u << 20)) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad length");
+        s->later.resize(nl);
+        for (auto &l : s->later) get_voice_events(r, l);
+        r.pods(s->voice_ramps);
+        r.pods(s->voice_base);
+        s->n_active_ramps = r.pod<uint64_t>(); s->dropped_changes = r.pod<uint64_t>(); s->ignored_delays = r.pod<uint64_t>();
+        s->device_events = r.pod<uint64_t>(); s->frame_clock = r.pod<uint64_t>();
+        s->rendered = r.pod<uint8_t>() != 0;
+        if (r.pos != size) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: trailing bytes");
+        *out = s.release();
+        return KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
 float kgpu_plan_last_render_ms(kgpu_plan *p) {
     if (!p || !p->timed) return -1.f;
     if (cudaEventSynchronize(p->ev1) != cudaSuccess) return -1.f;

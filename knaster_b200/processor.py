@@ -238,3 +238,18 @@ class Snapshot:
         if getattr(self, "_h", None):
             self._lib.kgpu_snapshot_destroy(self._h)
             self._h = None
+
+    def to_bytes(self) -> bytes:
+        """The snapshot as a flat byte image (kgpu_snapshot_serialize): a checkpoint that can be written to disk."""
+        n = C.c_uint64(0)
+        _ffi.check(self._lib.kgpu_snapshot_serialize(self._h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _ffi.check(self._lib.kgpu_snapshot_serialize(self._h, buf, n.value, C.byref(n)))
+        return buf.raw[: n.value]
+
+    @staticmethod
+    def from_bytes(data: bytes) -> "Snapshot":
+        lib = _ffi.lib()
+        h = C.c_void_p()
+        _ffi.check(lib.kgpu_snapshot_deserialize(data, len(data), C.byref(h)))
+        return Snapshot(lib, h)

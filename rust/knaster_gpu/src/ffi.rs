@@ -53,6 +53,8 @@ extern "C" {
     pub fn kgpu_plan_snapshot(plan: *mut kgpu_plan, out: *mut *mut kgpu_snapshot) -> c_int;
     pub fn kgpu_plan_restore(plan: *mut kgpu_plan, snapshot: *const kgpu_snapshot) -> c_int;
     pub fn kgpu_snapshot_destroy(snapshot: *mut kgpu_snapshot);
+    pub fn kgpu_snapshot_serialize(snapshot: *const kgpu_snapshot, buf: *mut c_void, cap: u64, size: *mut u64) -> c_int;
+    pub fn kgpu_snapshot_deserialize(buf: *const c_void, size: u64, out: *mut *mut kgpu_snapshot) -> c_int;
     // introspection / measurement
     pub fn kgpu_plan_get_info(plan: *mut kgpu_plan, info: *mut kgpu_plan_info) -> c_int;
     pub fn kgpu_plan_group_kernel(plan: *mut kgpu_plan, group: u32) -> *const c_char;

@@ -501,6 +501,20 @@ def test_snapshot_restore_rewinds_the_render(bank):
     g2, p2 = AudioProcessor.new(0, 2, AudioProcessorOptions(sample_rate=SR, force_interpreter=bank == "interp"))
     build(g2)
     assert np.array_equal(p2.render(530), np.concatenate([first, a]))
+    # the snapshot as bytes, restored into ANOTHER processor built from the same graph (checkpoint / resume)
+    from knaster_b200.processor import Snapshot
+
+    image = snap.to_bytes()
+    g3, p3 = AudioProcessor.new(0, 2, AudioProcessorOptions(sample_rate=SR, force_interpreter=bank == "interp"))
+    build(g3)
+    g3.take_events()                                  # its events are inside the image
+    p3.restore(Snapshot.from_bytes(image))
+    assert p3.frame_clock() == 130 * 64
+    assert np.array_equal(p3.render(400), a)
+    with pytest.raises(Exception):
+        Snapshot.from_bytes(image[:-3])
+    with pytest.raises(Exception):
+        Snapshot.from_bytes(b"x" * 64)
 
 
 @pytest.mark.parametrize("bank,voices", [("segments", 16384), ("fm", 8192), ("fm", 9600)])
