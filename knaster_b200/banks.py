@@ -143,3 +143,22 @@ def fm_bank(graph: Graph, n_voices: int, seed: int = 3003, voice_offset: int = 0
             sig.out([0, 0]).to_graph_out()
             out_ids.append(sig._outputs[0][0])
     return out_ids
+
+
+def bank_builder(workload: str, seconds: float, seed=None):
+    """The bench / parity workloads of BASELINE.json by name: returns build(graph, n_voices, voice_offset,
+    total_voices) -> one tap node id per voice (the voice's pre-mix signal).  voice_offset / total_voices select a
+    slice of a larger bank (a GPU rank's share of configs[4], or a checker thread's shard) from the same random stream."""
+
+    def build(graph, nv, offset, total):
+        kw = {} if seed is None else {"seed": seed}
+        if workload in ("subtractive", "subtractive_seg"):
+            return subtractive_bank(graph, nv, seconds, voice_offset=offset, total_voices=total,
+                                    envelope="asr" if workload == "subtractive" else "segments", **kw)
+        if workload == "additive":
+            return additive_bank(graph, nv, seconds, voice_offset=offset, total_voices=total, **kw)
+        if workload == "fm":
+            return fm_bank(graph, nv, voice_offset=offset, total_voices=total, **kw)
+        raise ValueError(f"unknown workload {workload}")
+
+    return build

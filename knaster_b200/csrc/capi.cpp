@@ -132,6 +132,7 @@ struct kgpu_plan {
     size_t kev_used = 0;
     bool prepared = false;                 // phase 1 already done for `prepared_blocks`
     uint64_t prepared_blocks = 0;
+    uint64_t prepared_bpl = 0;             // launch split the prepared events were compiled for
 
     uint64_t last_h2d_bytes = 0;
     // pipelined render (kgpu_render without a prior kgpu_plan_prepare): launch L's events are
@@ -309,8 +310,13 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
         p->tap_out.ensure((size_t)p->n_taps * total_frames);
         p->tap_frames = total_frames;
     }
-    const uint64_t bpl = blocks_per_launch(p);
-    const bool was_prepared = p->prepared && p->prepared_blocks == n_blocks;
+    // kgpu_plan_prepare(N) has already consumed the queued events and advanced every ramp / queue by N blocks: the
+    // only valid continuation is the render of exactly those N blocks, with the launch split they were compiled for
+    if (p->prepared && p->prepared_blocks != n_blocks)
+        KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_prepare(%llu) must be followed by a render of %llu blocks, not %llu",
+                   (unsigned long long)p->prepared_blocks, (unsigned long long)p->prepared_blocks, (unsigned long long)n_blocks);
+    const bool was_prepared = p->prepared;
+    const uint64_t bpl = was_prepared ? p->prepared_bpl : blocks_per_launch(p);
     p->prepared = false;
     if (!was_prepared) p->last_h2d_bytes = 0;
     p->partials.ensure((size_t)std::max(1u, p->n_rows) * std::min<uint64_t>(bpl, n_blocks) * bs);
@@ -577,6 +583,7 @@ void kgpu_plan_destroy(kgpu_plan *p) {
 
 int kgpu_plan_push_events(kgpu_plan *p, const kgpu_event *events, size_t n) {
     if (!p || (n && !events)) return fail(KGPU_ERR_INVALID, "kgpu_plan_push_events: NULL argument");
+    if (p->prepared) return fail(KGPU_ERR_STATE, "kgpu_plan_push_events: a prepared render is pending (its range is already simulated)");
     try {
         p->host.push(events, n, p->frame_clock);
         return KGPU_OK;
@@ -587,6 +594,7 @@ int kgpu_plan_push_events(kgpu_plan *p, const kgpu_event *events, size_t n) {
 
 int kgpu_render_device(kgpu_plan *p, uint64_t n_blocks, float *device_out, void *cuda_stream) {
     if (!p || !device_out) return fail(KGPU_ERR_INVALID, "kgpu_render_device: NULL argument");
+    if (n_blocks == 0) return KGPU_OK;
     try {
         CUDA_TRY(cudaSetDevice(p->device));
         p->timed = true;
@@ -615,8 +623,12 @@ int kgpu_render(kgpu_plan *p, uint64_t n_blocks, float *host_out) {
             const auto t1 = now();
             CUDA_TRY(cudaStreamSynchronize(p->stream));
             const auto t2 = now();
-            std::memcpy(host_out, p->out_pinned.p, per_block * n_blocks * 4);
-            std::memcpy(p->last_block.data(), host_out + per_block * (n_blocks - 1), per_block * 4);
+            // with a peer bus only rank 0 receives audio (the sum over all ranks): the other ranks' host buffers and
+            // kgpu_output_block stay untouched, as the header says
+            if (!(p->peer_world > 1 && p->peer_rank != 0)) {
+                std::memcpy(host_out, p->out_pinned.p, per_block * n_blocks * 4);
+                std::memcpy(p->last_block.data(), host_out + per_block * (n_blocks - 1), per_block * 4);
+            }
             if (timing && n_blocks > 100) {
                 float span = 0.f, kern = 0.f, red = 0.f;
                 cudaEventElapsedTime(&span, p->ev0, p->ev1);
@@ -631,7 +643,8 @@ int kgpu_render(kgpu_plan *p, uint64_t n_blocks, float *host_out) {
                 fprintf(stderr, "[kgpu timing] kgpu_render: host loop %.1f ms, device tail %.1f ms, copy out %.1f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, now()));
         } else {
             render_range(p, n_blocks, p->out.p, p->stream);
-            CUDA_TRY(cudaMemcpyAsync(p->last_block.data(), p->out.p + per_block * (n_blocks - 1), per_block * 4, cudaMemcpyDeviceToHost, p->stream));
+            if (!(p->peer_world > 1 && p->peer_rank != 0))
+                CUDA_TRY(cudaMemcpyAsync(p->last_block.data(), p->out.p + per_block * (n_blocks - 1), per_block * 4, cudaMemcpyDeviceToHost, p->stream));
             CUDA_TRY(cudaStreamSynchronize(p->stream));
         }
         return KGPU_OK;
@@ -656,7 +669,7 @@ uint64_t kgpu_plan_frame_clock(const kgpu_plan *p) { return p ? p->frame_clock :
 
 int kgpu_plan_add_tap(kgpu_plan *p, uint32_t node, uint32_t channel) {
     if (!p) return fail(KGPU_ERR_INVALID, "NULL plan");
-    if (p->rendered) return fail(KGPU_ERR_STATE, "kgpu_plan_add_tap must be called before the first render");
+    if (p->rendered || p->prepared) return fail(KGPU_ERR_STATE, "kgpu_plan_add_tap must be called before the first render / prepare");
     try {
         if (node >= p->host.node_ref.size()) KGPU_THROW(KGPU_ERR_INVALID, "tap: NodeNotFound (%u)", node);
         const NodeRef &nr = p->host.node_ref[node];
@@ -717,10 +730,13 @@ int kgpu_plan_prepare(kgpu_plan *p, uint64_t n_blocks) {
     if (!p || n_blocks == 0) return fail(KGPU_ERR_INVALID, "kgpu_plan_prepare: bad argument");
     try {
         CUDA_TRY(cudaSetDevice(p->device));
-        prepare_range(p, n_blocks, blocks_per_launch(p), p->stream);
+        if (p->prepared) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_prepare: a prepared render is already pending");
+        const uint64_t bpl = blocks_per_launch(p);
+        prepare_range(p, n_blocks, bpl, p->stream);
         CUDA_TRY(cudaStreamSynchronize(p->stream));
         p->prepared = true;
         p->prepared_blocks = n_blocks;
+        p->prepared_bpl = bpl;
         return KGPU_OK;
     } catch (const Error &e) {
         return fail(e.code, e.msg);
@@ -787,6 +803,7 @@ int kgpu_plan_set_host_threads(kgpu_plan *p, uint32_t n_threads) {
 
 int kgpu_plan_set_blocks_per_launch(kgpu_plan *p, uint64_t blocks) {
     if (!p || blocks == 0) return fail(KGPU_ERR_INVALID, "kgpu_plan_set_blocks_per_launch: bad argument");
+    if (p->prepared) return fail(KGPU_ERR_STATE, "kgpu_plan_set_blocks_per_launch: a prepared render is pending");
     p->max_blocks_per_launch = blocks;
     return KGPU_OK;
 }

@@ -21,6 +21,8 @@
 //
 // Per voice-sample: 1 IMAD + 1 IADD + 1 shift/mask + 1 LDS + 1 FMUL + 1 FADD (+ 1/32 LDG.128).
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 
 #include "dev.h"
@@ -218,12 +220,17 @@ cudaError_t launch_add_wt(const FusedArgs &a, cudaStream_t stream) {
     const uint32_t n_tiles = (a.n_frames + WT_THREADS - 1) / WT_THREADS;
     const dim3 grid((n_tiles + WT_TILES_PER_CTA - 1) / WT_TILES_PER_CTA, n_slices);
     const size_t smem = SINE_TABLE_SIZE * sizeof(float) + (size_t)WT_MAX_TILE_BLOCKS * WT_VCHUNK * sizeof(uint4);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(add_wt_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the opt-in above 48 KB of dynamic shared memory is a PER-DEVICE function attribute: one flag per device, so
+    // that a second plan on another GPU of the same process (INTEGRATION.md "Several GPUs") gets it too
+    static std::atomic<bool> attr_set[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
+        e = cudaFuncSetAttribute(add_wt_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(add_wt_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
     if (a.n_taps) add_wt_render<true><<<grid, WT_THREADS, smem, stream>>>(a, table, n_slices, n_tiles);
     else add_wt_render<false><<<grid, WT_THREADS, smem, stream>>>(a, table, n_slices, n_tiles);

@@ -17,3 +17,23 @@ def pytest_sessionstart(session):
 
     if not os.path.exists(_ffi.LIB_PATH):
         _ffi.build()
+
+
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` tests need a CUDA device: on a box without one they are skipped, not failed (the engine has no CPU
+    fallback, so every call would raise KGPU_ERR_CUDA and bury real CPU-side regressions)."""
+    import pytest
+
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if not gpu_items:
+        return
+    from knaster_b200 import _ffi
+
+    try:
+        n = int(_ffi.lib().kgpu_device_count())
+    except Exception:
+        n = 0
+    if n == 0:
+        skip = pytest.mark.skip(reason="no CUDA device on this box (kgpu_device_count() == 0)")
+        for it in gpu_items:
+            it.add_marker(skip)

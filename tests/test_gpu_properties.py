@@ -538,3 +538,29 @@ def test_full_size_launch_split_invariance_of_the_other_recipes(bank, voices):
     for bpl in (97, 5):
         out, _ = run(bpl)
         assert np.array_equal(out, whole), f"{bank}: render differs with {bpl} blocks per launch"
+
+
+def test_prepare_must_be_followed_by_the_render_it_prepared():
+    # kgpu_plan_prepare(N) consumes the queued events and advances every ramp / queue by N blocks: any other call
+    # in between is KGPU_ERR_STATE instead of a silently wrong render
+    from knaster_b200 import _ffi
+
+    graph, proc = AudioProcessor.new(0, 2, AudioProcessorOptions())
+    banks.subtractive_bank(graph, 40, 0.5, n_notes=3)
+    ev = graph.take_events()
+    graph.pending_event_arrays = [ev.copy()]
+    proc.prepare(100)
+    for call in (lambda: proc.render(50), lambda: proc.set_blocks_per_launch(7), lambda: proc.prepare(100),
+                 lambda: proc.add_tap(0, 0)):
+        with pytest.raises(_ffi.KgpuError) as e:
+            call()
+        assert e.value.code == _ffi.KGPU_ERR_STATE
+    graph.pending_event_arrays = [ev[:1].copy()]
+    with pytest.raises(_ffi.KgpuError) as e:
+        proc.render(100)            # pushes the pending event first: refused, nothing rendered
+    assert e.value.code == _ffi.KGPU_ERR_STATE
+    graph.take_events()
+    a = proc.render(100)            # the prepared render itself is still valid ...
+    g2, p2 = AudioProcessor.new(0, 2, AudioProcessorOptions())
+    banks.subtractive_bank(g2, 40, 0.5, n_notes=3)
+    assert np.array_equal(a, p2.render(100))   # ... and equals the unprepared one
