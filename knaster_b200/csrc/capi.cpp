@@ -140,6 +140,11 @@ struct kgpu_plan {
     Staging staging[3];
     uint32_t staging_next = 0;
     PinBuf<float> out_pinned;
+    // pieces of out_pinned in the order their downloads were enqueued, each with the event recorded behind its copy:
+    // kgpu_render hands a piece to the caller's buffer as soon as it has landed, while later launches still render
+    struct OutPiece { size_t off, n; };
+    std::vector<OutPiece> out_pieces;
+    std::vector<cudaEvent_t> out_ev;
     // copies of the streaming path run beside the kernels: events of launch L+1 go up (h2d_stream,
     // device buffers ping-pong) and the bus of launch L-1 comes down (d2h_stream) while launch L renders
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -339,6 +344,16 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
     }
     if (p->timed) CUDA_TRY(cudaEventRecord(p->ev0, stream));
     size_t piece = 0;
+    p->out_pieces.clear();
+    auto piece_landed = [&](size_t off, size_t n, cudaStream_t s) { // call right after the D2H copy of out_pinned[off, off + n) was enqueued on s
+        if (p->out_pieces.size() == p->out_ev.size()) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            p->out_ev.push_back(e);
+        }
+        CUDA_TRY(cudaEventRecord(p->out_ev[p->out_pieces.size()], s));
+        p->out_pieces.push_back({off, n});
+    };
     p->kev_used = 0;
     p->kev_class.clear();
     auto mark = [&](int cls, bool begin) {
@@ -363,7 +378,8 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
     // than its predecessor renders, below that the device waits for the host (ramp from 128: 1.7 ms idle).
     std::vector<uint64_t> sizes;
     {
-        uint64_t left = n_blocks, next = was_prepared || bpl < 32 || n_blocks < 2 * bpl ? bpl : bpl / 8;
+        // (the ramp starts at bpl / 64: the device is busy ~0.1 ms after the host has its first 32 blocks, and a launch costs ~25 us)
+        uint64_t left = n_blocks, next = was_prepared || bpl < 64 || n_blocks < 2 * bpl ? bpl : std::max<uint64_t>(32, bpl / 64);
         while (left) {
             const uint64_t nb = std::min(next, left);
             sizes.push_back(nb);
@@ -453,8 +469,10 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
                 CUDA_TRY(launch_sum_slots(p->peer_slots + (size_t)done * n_out * bs, p->peer_slot_floats, p->peer_world, p->peer_flags + launch,
                                           KGPU_PEER_MAX_LAUNCHES, p->peer_epoch, dst, (size_t)nf * n_out, p->peer_timeout, p->aux_stream));
                 p->kernel_launches++;
-                if (pinned_out)
+                if (pinned_out) {
                     CUDA_TRY(cudaMemcpyAsync(pinned_out + (size_t)done * n_out * bs, dst, (size_t)nf * n_out * 4, cudaMemcpyDeviceToHost, p->aux_stream));
+                    piece_landed((size_t)done * n_out * bs, (size_t)nf * n_out, p->aux_stream);
+                }
             }
         } else if (pinned_out) {
             cudaStream_t cs = was_prepared ? stream : p->d2h_stream;
@@ -463,6 +481,7 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
                 CUDA_TRY(cudaStreamWaitEvent(cs, p->red_done[launch & 1], 0));
             }
             CUDA_TRY(cudaMemcpyAsync(pinned_out + (size_t)done * n_out * bs, dst, (size_t)nf * n_out * 4, cudaMemcpyDeviceToHost, cs));
+            piece_landed((size_t)done * n_out * bs, (size_t)nf * n_out, cs);
         }
     }
     if (peer) {
@@ -575,6 +594,7 @@ void kgpu_plan_destroy(kgpu_plan *p) {
     p->scratch.release();
     p->partials.release(); p->row_mask.release(); p->out.release(); p->sine.release(); p->tap_out.release();
     for (cudaEvent_t e : p->kev) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->out_ev) cudaEventDestroy(e);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -621,12 +641,16 @@ int kgpu_render(kgpu_plan *p, uint64_t n_blocks, float *host_out) {
             p->out_pinned.ensure(per_block * n_blocks);
             render_range(p, n_blocks, p->out.p, p->stream, p->out_pinned.p);
             const auto t1 = now();
+            // hand the audio over piece by piece, each as soon as its download has landed (the rest still renders)
+            for (size_t i = 0; i < p->out_pieces.size(); i++) {
+                CUDA_TRY(cudaEventSynchronize(p->out_ev[i]));
+                std::memcpy(host_out + p->out_pieces[i].off, p->out_pinned.p + p->out_pieces[i].off, p->out_pieces[i].n * 4);
+            }
             CUDA_TRY(cudaStreamSynchronize(p->stream));
             const auto t2 = now();
             // with a peer bus only rank 0 receives audio (the sum over all ranks): the other ranks' host buffers and
             // kgpu_output_block stay untouched, as the header says
             if (!(p->peer_world > 1 && p->peer_rank != 0)) {
-                std::memcpy(host_out, p->out_pinned.p, per_block * n_blocks * 4);
                 std::memcpy(p->last_block.data(), host_out + per_block * (n_blocks - 1), per_block * 4);
             }
             if (timing && n_blocks > 100) {
@@ -830,7 +854,7 @@ int kgpu_plan_snapshot(kgpu_plan *p, kgpu_snapshot **out) {
     *out = nullptr;
     try {
         if (p->prepared) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_snapshot: a prepared render is pending");
-        if (p->host.stream) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_snapshot: a render call is in progress");
+        if (p->host.stream_active) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_snapshot: a render call is in progress");
         CUDA_TRY(cudaSetDevice(p->device));
         CUDA_TRY(cudaStreamSynchronize(p->stream));
         std::unique_ptr<kgpu_snapshot> s(new kgpu_snapshot());
@@ -864,7 +888,7 @@ int kgpu_plan_snapshot(kgpu_plan *p, kgpu_snapshot **out) {
 int kgpu_plan_restore(kgpu_plan *p, const kgpu_snapshot *s) {
     if (!p || !s) return fail(KGPU_ERR_INVALID, "kgpu_plan_restore: NULL argument");
     try {
-        if (p->host.stream) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_restore: a render call is in progress");
+        if (p->host.stream_active) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_restore: a render call is in progress");
         if (s->regs.size() != p->gd.size()) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_plan_restore: the snapshot belongs to another plan");
         for (size_t gi = 0; gi < p->gd.size(); gi++) {
             const Group &g = p->host.groups[gi];
@@ -907,7 +931,7 @@ void kgpu_snapshot_destroy(kgpu_snapshot *s) { delete s; }
 extern "C++" {
 namespace {
 constexpr uint64_t SNAP_MAGIC = 0x50414E5355504B47ull; // "GKPUSNAP"
-constexpr uint32_t SNAP_VERSION = 1;
+constexpr uint32_t SNAP_VERSION = 2;
 struct Writer {
     uint8_t *buf;
     uint64_t cap, pos = 0;
@@ -941,16 +965,16 @@ void put_pv(Writer &w, const PV &v) { w.pod<uint8_t>(v.kind); w.pod(v.f); w.pod(
 void get_pv(Reader &r, PV &v) { v.kind = (PV::Kind)r.pod<uint8_t>(); v.f = r.pod<double>(); v.smoothing = r.pod<uint8_t>(); v.smooth_seconds = r.pod<float>(); }
 void put_raw_events(Writer &w, const decltype(HostPlan::pending) &v) {
     w.pod<uint64_t>(v.size());
-    for (const RawEvent &e : v) { w.pod(e.node); w.pod(e.param); w.pod(e.value_kind); w.pod(e.smoothing_kind); w.pod(e.timed); w.pod(e.smooth_seconds); w.pod(e.value); w.pod(e.due_frame); }
+    for (const RawEvent &e : v) { w.pod(e.node); w.pod(e.gvoice); w.pod(e.param); w.pod(e.local); w.pod(e.kinds); w.pod(e.smooth_seconds); w.pod(e.value); w.pod(e.due_frame); }
 }
 void get_raw_events(Reader &r, decltype(HostPlan::pending) &v) {
     const uint64_t n = r.pod<uint64_t>();
-    if (n > (r.size - r.pos) / 29) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad length");
+    if (n > (r.size - r.pos) / 32) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad length");
     v.resize(n);
     for (RawEvent &e : v) {
         std::memset(&e, 0, sizeof e);
-        e.node = r.pod<uint32_t>(); e.param = r.pod<uint16_t>(); e.value_kind = r.pod<uint8_t>(); e.smoothing_kind = r.pod<uint8_t>();
-        e.timed = r.pod<uint8_t>(); e.smooth_seconds = r.pod<float>(); e.value = r.pod<double>(); e.due_frame = r.pod<uint64_t>();
+        e.node = r.pod<uint32_t>(); e.gvoice = r.pod<uint32_t>(); e.param = r.pod<uint16_t>(); e.local = r.pod<uint8_t>(); e.kinds = r.pod<uint8_t>();
+        e.smooth_seconds = r.pod<float>(); e.value = r.pod<double>(); e.due_frame = r.pod<uint64_t>();
     }
 }
 void put_node(Writer &w, const HostNode &h) {
@@ -959,6 +983,7 @@ void put_node(Writer &w, const HostNode &h) {
     for (float c : h.svf_coef) w.pod(c);
     w.pod<uint8_t>(h.has_smooth); w.pod<uint8_t>(h.has_precise); w.pod(h.smooth_level); w.pod(h.precise_level);
     w.pod<uint8_t>(h.ramp_active); w.pod(h.ramp_list_pos);
+    for (uint16_t d : h.nd) w.pod(d);
     w.pod<uint64_t>(h.wr.size());
     for (const WrapSim &x : h.wr) {
         w.pod(x.kind); w.pod(x.capacity); w.pod(x.reg); w.pod(x.inner_params);
@@ -980,6 +1005,7 @@ void get_node(Reader &r, HostNode &h) {
     for (float &c : h.svf_coef) c = r.pod<float>();
     h.has_smooth = r.pod<uint8_t>() != 0; h.has_precise = r.pod<uint8_t>() != 0; h.smooth_level = r.pod<int8_t>(); h.precise_level = r.pod<int8_t>();
     h.ramp_active = r.pod<uint8_t>() != 0; h.ramp_list_pos = r.pod<uint32_t>();
+    for (uint16_t &d : h.nd) d = r.pod<uint16_t>();
     const uint64_t nw = r.pod<uint64_t>();
     if (nw > 64) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad wrapper count");
     h.wr.resize(nw);
@@ -1160,6 +1186,63 @@ int kgpu_debug_simulate(const kgpu_graph_desc *desc, const kgpu_event *events, s
             info->device_events = hp.device_events;
         }
         return n > cap ? KGPU_ERR_INVALID : KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
+/* Times the host half of `n_steps` render calls of n_blocks blocks each the way kgpu_render drives it (launch sizes
+ * ramping 1/8, 1/4, 1/2, 1, 1, ... of `bpl` blocks; stream_begin, then stream_launch per launch), without a device.
+ * The event schedule repeats every step (whole seconds per step).  out_ms: [n_steps][4] = push, stream_begin,
+ * first launch ready (since the start of the call), all launches fetched. */
+int kgpu_debug_host_bench(const kgpu_graph_desc *desc, const kgpu_event *events, size_t n_events, uint64_t n_blocks, uint64_t bpl,
+                          uint32_t n_steps, uint32_t n_threads, double *out_ms) {
+    try {
+        HostPlan hp;
+        hp.build(*desc);
+        hp.pool_threads = n_threads;
+        const uint64_t bs = hp.block_size;
+        const uint64_t step_frames = n_blocks * bs;
+        if (step_frames % hp.sample_rate) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_debug_host_bench: a step must be a whole number of seconds");
+        const uint32_t step_seconds = (uint32_t)(step_frames / hp.sample_rate);
+        std::vector<kgpu_event> ev(events, events + n_events);
+        std::vector<uint32_t> chunks(hp.groups.size(), 1);
+        HostPlan::CompiledEvents ce;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        uint64_t clock = 0;
+        size_t total_ev = 0;
+        for (uint32_t s = 0; s < n_steps; s++) {
+            std::vector<uint64_t> bounds{clock};
+            uint64_t left = n_blocks, next = bpl < 32 || n_blocks < 2 * bpl ? bpl : bpl / 8;
+            while (left) {
+                const uint64_t nb = std::min(next, left);
+                bounds.push_back(bounds.back() + nb * bs);
+                left -= nb;
+                next = std::min(bpl, next * 2);
+            }
+            const auto t0 = now();
+            hp.push(ev.data(), ev.size(), clock);
+            const auto t1 = now();
+            hp.stream_begin(bounds, chunks);
+            const auto t2 = now();
+            auto t3 = t2;
+            for (size_t L = 0; L + 1 < bounds.size(); L++) {
+                hp.stream_launch(L, ce);
+                total_ev += ce.events.size();
+                if (L == 0) t3 = now();
+            }
+            const auto t4 = now();
+            hp.stream_end();
+            out_ms[4 * s + 0] = ms(t0, t1);
+            out_ms[4 * s + 1] = ms(t1, t2);
+            out_ms[4 * s + 2] = ms(t0, t3);
+            out_ms[4 * s + 3] = ms(t0, t4);
+            clock += step_frames;
+            for (kgpu_event &e : ev)
+                if (e.time_kind == 1) e.seconds += step_seconds;
+        }
+        return total_ev ? KGPU_OK : KGPU_OK;
     } catch (const Error &e) {
         return fail(e.code, e.msg);
     }

@@ -25,6 +25,9 @@ typedef struct {
 int kgpu_debug_simulate(const kgpu_graph_desc *desc, const kgpu_event *events, size_t n_events,
                         uint64_t n_blocks, uint64_t blocks_per_call, kgpu_debug_event *out, size_t cap,
                         size_t *n_out, kgpu_debug_node *nodes_out, kgpu_plan_info *info);
+/* Times the host half of n_steps render calls (no device): see capi.cpp.  out_ms: [n_steps][4]. */
+int kgpu_debug_host_bench(const kgpu_graph_desc *desc, const kgpu_event *events, size_t n_events, uint64_t n_blocks, uint64_t bpl,
+                          uint32_t n_steps, uint32_t n_threads, double *out_ms);
 /* initial register value of a node register after init() */
 int kgpu_debug_init_reg(const kgpu_graph_desc *desc, uint32_t node, uint32_t reg_offset, uint32_t *value);
 

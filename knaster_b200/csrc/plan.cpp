@@ -237,32 +237,26 @@ void svf_coeffs(uint32_t ty, float cutoff, float q, float gain_db, float sr, flo
 }
 
 // ---- control simulation ------------------------------------------------------------------
-// per-thread sink of the control simulation
+// per-thread sink of the control simulation: the device events of the block being simulated, in emission order
+// (node-major; inside a node by frame, then arrival), frames relative to the launch window's first frame
 struct Sink {
-    std::vector<VoiceEvent> buf; // device events of the voice being processed, one run per node
-    std::vector<uint32_t> run_start; // start of each node's run in buf (frames non-decreasing inside a run)
-    std::vector<VoiceEvent> merged;
-    uint32_t seq = 0;
+    std::vector<DevEvent> blk;
+    uint64_t t0 = 0;
     uint64_t dropped = 0, ignored = 0, devev = 0;
 };
 struct Sim {
     HostPlan &P;
     Sink &out;
-    uint32_t gi;
-    uint32_t voice;
     uint32_t local;
     HostNode &hn;
     void emit(uint64_t frame, uint16_t op, uint32_t reg, uint32_t value) {
-        VoiceEvent ve;
-        ve.voice = voice;
-        ve.frame = frame;
-        ve.seq = out.seq++;
-        ve.ev.frame = 0;
-        ve.ev.node = (uint16_t)local;
-        ve.ev.op = op;
-        ve.ev.reg = reg;
-        ve.ev.value = value;
-        out.buf.push_back(ve);
+        DevEvent d;
+        d.frame = (uint32_t)(frame - out.t0);
+        d.node = (uint16_t)local;
+        d.op = op;
+        d.reg = reg;
+        d.value = value;
+        out.blk.push_back(d);
         out.devev++;
     }
     void set_f(uint64_t frame, uint32_t reg, float v) { emit(frame, OP_SET, reg, fbits(v)); }
@@ -764,6 +758,8 @@ void HostPlan::build(const kgpu_graph_desc &d) {
         KGPU_THROW(KGPU_ERR_INVALID, "NULL array in graph description");
     sample_rate = d.sample_rate;
     block_size = d.block_size;
+    bs_pow2 = (block_size & (block_size - 1)) == 0;
+    bs_shift = bs_pow2 ? (uint32_t)__builtin_ctz(block_size) : 0;
     n_outputs = d.n_outputs;
     const uint32_t N = d.n_nodes;
     for (uint32_t i = 0; i < N; i++) validate_node(d.nodes[i], i);
@@ -875,7 +871,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
         } else it->second.push_back(lf);
     }
     node_ref.assign(N, NodeRef{});
-    for (uint32_t i = 0; i < N; i++) node_ref[i].n_params = total_params(d.nodes[i]);
+    for (uint32_t i = 0; i < N; i++) node_ref[i].n_params = (uint16_t)total_params(d.nodes[i]);
     std::unordered_map<uint64_t, std::vector<uint32_t>> by_hash;
     std::vector<int> local_of(N, -1);
     groups.clear();
@@ -944,7 +940,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
         for (size_t li = 0; li < order.size(); li++) {
             node_ref[order[li]].group = gi;
             node_ref[order[li]].voice = voice;
-            node_ref[order[li]].local = (uint32_t)li;
+            node_ref[order[li]].local = (uint16_t)li;
         }
     }
     // initial registers + control state: Node::init (graph.rs:462-475) of every node of every voice
@@ -953,6 +949,53 @@ void HostPlan::build(const kgpu_graph_desc &d) {
         const uint32_t V = g.n_voices, nn = (uint32_t)g.tpl.nodes.size();
         g.init_regs.assign((size_t)g.prog.n_regs * V, 0u);
         g.host.assign((size_t)V * nn, HostNode{});
+        // the template's wrapper stacks, once per group
+        g.nstat.assign(nn, NodeStatic{});
+        for (uint32_t li = 0; li < nn; li++) {
+            const TemplateNode &tn = g.tpl.nodes[li];
+            const DevNode &dn = g.prog.nodes[li];
+            NodeStatic &ns = g.nstat[li];
+            kgpu_node_desc tmp{};
+            tmp.kind = tn.kind; tmp.channels = tn.channels; tmp.n_segments = tn.n_segments;
+            ns.kind = (uint8_t)tn.kind;
+            ns.base_params = (uint32_t)kind_info(tmp).n_params;
+            uint32_t inner = ns.base_params;
+            int post_i = 0;
+            bool only_math_above = true; // walking inwards from the top is done below; here: innermost first
+            ns.n_levels = (uint8_t)std::min<size_t>(tn.wrappers.size(), MAX_WRAP_LEVELS);
+            for (size_t l = 0; l < tn.wrappers.size(); l++) {
+                const uint32_t k = tn.wrappers[l].kind;
+                if (l < (size_t)MAX_WRAP_LEVELS) {
+                    ns.lv_kind[l] = (uint8_t)k;
+                    ns.lv_inner[l] = inner;
+                }
+                if (is_math_wrapper(k)) {
+                    if (l < (size_t)MAX_WRAP_LEVELS) ns.lv_reg[l] = dn.post_reg[post_i];
+                    post_i++;
+                    if (k == KGPU_WR_MUL) inner++;
+                } else if (k == KGPU_WR_SMOOTH_PARAMS) ns.smooth_level = (int8_t)l;
+                else if (k == KGPU_WR_PRECISE_TIMING) {
+                    ns.precise_level = (int8_t)l;
+                    ns.capacity = tn.wrappers[l].capacity;
+                    ns.nd_size = inner;
+                } else if (k == KGPU_WR_AR_PARAMS && l < (size_t)MAX_WRAP_LEVELS) {
+                    for (auto &pe : tn.par)
+                        if (std::get<0>(pe) < inner && std::get<0>(pe) < 32) ns.lv_ar_mask[l] |= 1u << std::get<0>(pe);
+                }
+            }
+            ns.total_params = inner;
+            (void)only_math_above;
+            // set_delay walks inwards from the outermost wrapper: math wrappers forward, the first WrPreciseTiming takes it,
+            // WrSmoothParams / WrArParams swallow it (trait default, ugen.rs:339-341)
+            ns.delay_reaches = false;
+            for (int l = (int)tn.wrappers.size() - 1; l >= 0; l--) {
+                const uint32_t k = tn.wrappers[l].kind;
+                if (k == KGPU_WR_PRECISE_TIMING) { ns.delay_reaches = true; break; }
+                if (!is_math_wrapper(k)) break;
+            }
+            ns.fast = ns.smooth_level < 0 && tn.wrappers.size() <= (size_t)MAX_WRAP_LEVELS && ns.total_params <= 8 && ns.capacity <= 32;
+            if (getenv("KGPU_HOST_GENERIC")) ns.fast = false; // tests: the block-by-block model for every node
+        }
         auto R = [&](uint32_t reg, uint32_t v) -> uint32_t & { return g.init_regs[(size_t)reg * V + v]; };
         for (uint32_t v = 0; v < V; v++)
             for (uint32_t li = 0; li < nn; li++) {
@@ -1065,6 +1108,11 @@ void HostPlan::build(const kgpu_graph_desc &d) {
                 // wrappers
                 uint32_t inner = h.base_params;
                 int post_i = 0;
+                if (g.nstat[li].fast) { // everything but the wrapper VALUES is static (NodeStatic); next_delay lives in h.nd
+                    for (uint32_t l = 0; l < nd.n_wrappers; l++)
+                        if (is_math_wrapper(nd.wrappers[l].kind)) R(dn.post_reg[post_i++], v) = fbits((float)nd.wrappers[l].value);
+                    continue;
+                }
                 h.wr.resize(nd.n_wrappers);
                 for (uint32_t l = 0; l < nd.n_wrappers; l++) {
                     WrapSim &w = h.wr[l];
@@ -1092,6 +1140,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
                 }
             }
     }
+    finish_build();
 }
 
 // Validation of an event only depends on (group, node-in-template, parameter): cache it.
@@ -1100,21 +1149,47 @@ struct ParamRule {
     bool smooth_ok = false;
     bool polyblep_wave = false, svf_type = false;
 };
-static ParamRule param_rule(const HostNode &h, uint32_t p) {
+static ParamRule param_rule(const TemplateNode &tn, uint32_t base_params, uint32_t p) {
     ParamRule r;
     bool wr_mul_target = false;
-    for (int l = (int)h.wr.size() - 1; l >= 0; l--) { // outermost -> innermost, like param_apply
-        const WrapSim &w = h.wr[l];
-        if (w.kind == KGPU_WR_MUL && p == w.inner_params) { wr_mul_target = true; break; }
-        if (w.kind == KGPU_WR_SMOOTH_PARAMS && p < w.smooth.size()) r.smooth_ok = true;
+    std::vector<uint32_t> inner(tn.wrappers.size() + 1, base_params); // parameters visible below wrapper l
+    for (size_t l = 0; l < tn.wrappers.size(); l++) inner[l + 1] = inner[l] + (tn.wrappers[l].kind == KGPU_WR_MUL ? 1u : 0u);
+    for (int l = (int)tn.wrappers.size() - 1; l >= 0; l--) { // outermost -> innermost, like param_apply
+        const uint32_t k = tn.wrappers[l].kind;
+        if (k == KGPU_WR_MUL && p == inner[l]) { wr_mul_target = true; break; }
+        if (k == KGPU_WR_SMOOTH_PARAMS && p < inner[l]) r.smooth_ok = true;
     }
     if (!wr_mul_target) {
-        const char *types = param_types(h.kind);
+        const char *types = param_types(tn.kind);
         r.want = p < std::strlen(types) ? types[p] : 'f';
-        r.polyblep_wave = h.kind == KGPU_POLYBLEP && p == 2;
-        r.svf_type = h.kind == KGPU_SVF && p == 3;
+        r.polyblep_wave = tn.kind == KGPU_POLYBLEP && p == 2;
+        r.svf_type = tn.kind == KGPU_SVF && p == 3;
     }
     return r;
+}
+
+void HostPlan::finish_build() {
+    const size_t n_groups = groups.size();
+    voice_base.assign(n_groups + 1, 0);
+    for (size_t gi = 0; gi < n_groups; gi++) voice_base[gi + 1] = voice_base[gi] + groups[gi].n_voices;
+    voice_ramps.assign(voice_base.back(), 0);
+    later.assign(n_groups, {});
+    // validation rules, flat: [group][local][param] -> rule_base of the (group, local) + param
+    rules.clear();
+    std::vector<std::vector<uint32_t>> base(n_groups);
+    for (size_t gi = 0; gi < n_groups; gi++) {
+        const Group &g = groups[gi];
+        base[gi].resize(g.tpl.nodes.size());
+        for (size_t li = 0; li < g.tpl.nodes.size(); li++) {
+            base[gi][li] = (uint32_t)rules.size();
+            for (uint32_t p = 0; p < g.nstat[li].total_params; p++) {
+                ParamRule pr = param_rule(g.tpl.nodes[li], g.nstat[li].base_params, p);
+                rules.push_back({pr.want, (uint8_t)pr.smooth_ok, (uint8_t)pr.polyblep_wave, (uint8_t)pr.svf_type});
+            }
+        }
+    }
+    for (NodeRef &nr : node_ref)
+        if (nr.group >= 0) nr.rule_base = base[nr.group][nr.local];
 }
 
 // ---- WorkPool -----------------------------------------------------------------------------------
@@ -1204,104 +1279,74 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
         }
     } push_timer;
     push_timer.n = n;
-    if (rules.empty()) { // [group][local][param], built from voice 0 of each group
-        rules.resize(groups.size());
-        for (size_t gi = 0; gi < groups.size(); gi++) {
-            const Group &g = groups[gi];
-            const size_t nn = g.tpl.nodes.size();
-            rules[gi].resize(nn);
-            for (size_t li = 0; li < nn; li++) {
-                const HostNode &h = g.host[li];
-                uint32_t np = h.base_params;
-                for (const WrapSim &w : h.wr)
-                    if (w.kind == KGPU_WR_MUL) np++;
-                for (uint32_t p = 0; p < np; p++) {
-                    ParamRule pr = param_rule(h, p);
-                    rules[gi][li].push_back({pr.want, (uint8_t)pr.smooth_ok, (uint8_t)pr.polyblep_wave, (uint8_t)pr.svf_type});
-                }
-            }
-        }
-    }
-    // validate everything first so that a failing call queues nothing; large batches are split
-    // over the pool (the first failing event, in event order, is the one reported)
-    auto validate = [&](size_t i) -> bool { // returns whether the event is queued
+    // One pass: every event is validated and converted into its own position of `pending` (grown uninitialised).
+    // A failing call queues nothing: `pending` is cut back and the first failing event, in event order, is reported.
+    // Events of unreachable nodes are rare and are squeezed out afterwards.
+    const NodeRef *nref = node_ref.data();
+    const size_t n_nodes = node_ref.size();
+    const Rule *rl = rules.data();
+    const uint64_t *vbase = voice_base.data();
+    const uint64_t sr = sample_rate;
+    auto one = [&](size_t i, RawEvent &r) -> bool { // false: dropped (the node reaches no output)
         const kgpu_event &e = evs[i];
-        if (e.node >= node_ref.size()) KGPU_THROW(KGPU_ERR_INVALID, "event %zu: NodeNotFound (%u)", i, e.node);
-        const NodeRef &nr = node_ref[e.node];
+        if (e.node >= n_nodes) KGPU_THROW(KGPU_ERR_INVALID, "event %zu: NodeNotFound (%u)", i, e.node);
+        const NodeRef nr = nref[e.node];
         if (e.param >= nr.n_params) KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: ParameterIndexOutOfBounds (node %u param %u)", i, e.node, e.param);
         if (e.value_kind > 4 || e.smoothing_kind > 2 || e.time_kind > 2) KGPU_THROW(KGPU_ERR_INVALID, "event %zu: bad enum field", i);
         if (e.smoothing_kind != 0 && e.smooth_rate != 0)
             KGPU_THROW(KGPU_ERR_UNSUPPORTED, "event %zu: Rate::AudioRate smoothing is not supported (its branch is unreachable in knaster, "
                        "smooth_params.rs:140-146)", i);
         if (nr.group < 0) return false; // unreachable node: knaster would run it, but nothing can hear it
-        const Rule &r = rules[nr.group][nr.local][e.param];
-        if (e.smoothing_kind != 0 && !r.smooth_ok)
+        const Rule &ru = rl[nr.rule_base + e.param];
+        if (e.smoothing_kind != 0 && !ru.smooth_ok)
             KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: smoothing sent to node %u param %u which has no WrSmoothParams around it "
                        "(knaster would panic: parameter value is expected to be a float)", i, e.node, e.param);
         if (e.value_kind != 0) {
-            const char want = r.want;
-            bool ok = want == 't' || (want == 'f' && e.value_kind == 1) || (want == 'i' && e.value_kind == 3) || (want == 'b' && e.value_kind == 4);
+            const char want = ru.want;
+            const bool ok = want == 't' || (want == 'f' && e.value_kind == 1) || (want == 'i' && e.value_kind == 3) || (want == 'b' && e.value_kind == 4);
             if (!ok) KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: wrong value type for node %u param %u", i, e.node, e.param);
-            if (r.polyblep_wave && ((int64_t)e.value < 0 || (int64_t)e.value > 13))
+            if (ru.polyblep_wave && ((int64_t)e.value < 0 || (int64_t)e.value > 13))
                 KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: bad PolyBlep Waveform %lld", i, (long long)e.value);
-            if (r.svf_type && ((int64_t)e.value < 0 || (int64_t)e.value > 8))
+            if (ru.svf_type && ((int64_t)e.value < 0 || (int64_t)e.value > 8))
                 KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: bad SvfFilterType", i);
         }
-        return true;
-    };
-    auto convert = [&](size_t i) {
-        const kgpu_event &e = evs[i];
-        RawEvent r;
         r.node = e.node;
+        r.gvoice = (uint32_t)(vbase[nr.group] + nr.voice);
         r.param = (uint16_t)e.param;
-        r.value_kind = (uint8_t)e.value_kind;
-        r.smoothing_kind = (uint8_t)e.smoothing_kind;
-        r.timed = e.time_kind != 0;
+        r.local = (uint8_t)nr.local;
+        r.kinds = (uint8_t)(e.value_kind | (e.smoothing_kind << 3) | ((e.time_kind != 0 ? 1u : 0u) << 5));
         r.smooth_seconds = e.smooth_seconds;
         r.value = e.value_kind == 3 ? (double)(int64_t)e.value : e.value;
-        uint64_t samples = (uint64_t)e.seconds * sample_rate + ((uint64_t)e.subsec * sample_rate) / 282240000ull; // time.rs:86-90
-        if (e.time_kind == 1) r.due_frame = samples;                    // scheduling.rs:102-108
-        else if (e.time_kind == 2) r.due_frame = frame_clock + samples; // scheduling.rs:110-119
-        else r.due_frame = frame_clock;
-        if (r.due_frame < frame_clock) r.due_frame = frame_clock;       // late: saturating_sub -> delay 0
-        return r;
+        const uint64_t samples = (uint64_t)e.seconds * sr + ((uint64_t)e.subsec * sr) / 282240000ull; // time.rs:86-90
+        uint64_t due;
+        if (e.time_kind == 1) due = samples;                    // scheduling.rs:102-108
+        else if (e.time_kind == 2) due = frame_clock + samples; // scheduling.rs:110-119
+        else due = frame_clock;
+        r.due_frame = due < frame_clock ? frame_clock : due;    // late: saturating_sub -> delay 0
+        return true;
     };
-    const unsigned T = n >= 65536 ? workers().size() : 1u;
-    if (T == 1) {
-        size_t kept = 0;
-        for (size_t i = 0; i < n; i++) kept += validate(i);
-        pending.reserve(pending.size() + kept);
-        for (size_t i = 0; i < n; i++)
-            if (node_ref[evs[i].node].group >= 0) pending.push_back(convert(i));
-        return;
-    }
-    // One parallel pass: every chunk validates and converts into its own positions of `pending` (grown
-    // uninitialised); events of unreachable nodes are rare and are squeezed out afterwards.  A failing call
-    // queues nothing: `pending` is cut back before the first failing event (in event order) is reported.
+    const unsigned T = n >= 32768 ? std::min<unsigned>(workers().size(), (unsigned)(n / 8192)) : 1u;
     std::vector<size_t> dropped(T, 0);
     std::vector<Error> errs(T, Error{0, ""});
-    static const bool ptime = getenv("KGPU_TIMING") != nullptr;
-    auto tp0 = std::chrono::steady_clock::now();
     const size_t base = pending.size();
     pending.resize(base + n);
-    auto tp1 = std::chrono::steady_clock::now();
-    workers().run(T, [&](unsigned c) {
+    auto chunk = [&](unsigned c) {
         const size_t i0 = n * c / T, i1 = n * (c + 1) / T;
         size_t d = 0;
+        RawEvent *dst = pending.data() + base;
         try {
-            for (size_t i = i0; i < i1; i++) {
-                if (validate(i)) {
-                    pending[base + i] = convert(i);
-                } else {
-                    pending[base + i].node = 0xFFFFFFFFu; // dropped
+            for (size_t i = i0; i < i1; i++)
+                if (!one(i, dst[i])) {
+                    dst[i].node = 0xFFFFFFFFu; // dropped
                     d++;
                 }
-            }
         } catch (const Error &e) {
             errs[c] = e;
         }
         dropped[c] = d;
-    });
+    };
+    if (T == 1) chunk(0);
+    else workers().run(T, chunk);
     for (unsigned c = 0; c < T; c++)
         if (errs[c].code) {
             pending.resize(base);
@@ -1314,11 +1359,6 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
         for (size_t i = base; i < base + n; i++)
             if (pending[i].node != 0xFFFFFFFFu) pending[w++] = pending[i];
         pending.resize(w);
-    }
-    if (ptime) {
-        auto tp2 = std::chrono::steady_clock::now();
-        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "[kgpu timing]     push: grow %.2f ms, validate+convert %.2f ms (%u threads)\n", ms(tp0, tp1), ms(tp1, tp2), T);
     }
 }
 
@@ -1335,44 +1375,92 @@ struct PhaseTimer {
     }
 };
 
-// one node of one voice: replay its ready events block by block (graph_gen.rs:111-166,269-305)
-bool process_node(HostPlan &P, Sink &out, uint32_t gi, uint32_t voice, uint32_t local, const RawEvent *const *ev, size_t n,
-                  uint64_t b0, uint64_t b1) {
-    Group &g = P.groups[gi];
-    const uint64_t bs = P.block_size;
-    HostNode &hn = g.host[(size_t)voice * g.tpl.nodes.size() + local];
-    Sim s{P, out, gi, voice, local, hn};
+inline PV pv_of(const RawEvent &r) {
+    PV pv;
+    pv.kind = (PV::Kind)r.value_kind();
+    pv.f = r.value;
+    return pv;
+}
+
+// ---- one node, one block, block-by-block model (any wrapper stack): what GraphGen does with the node's ready events at
+// the top of the block (graph_gen.rs:269-305) and what the wrapper stack's process_block then does at control rate.
+// ev[0..n): the voice's ready events of this block in arrival order; only those of node `local` are this node's.
+void generic_node_block(Sim &s, const RawEvent *const *ev, size_t n, uint32_t local, uint64_t block_start, uint64_t bs) {
+    HostNode &hn = s.hn;
     const int top = (int)hn.wr.size() - 1;
-    auto blk = [&](size_t i) { return std::max(ev[i]->due_frame / bs, b0); };
-    size_t ei = 0;
-    uint64_t b = needs_processing(hn) ? b0 : (n ? blk(0) : b1);
-    while (b < b1) {
-        const uint64_t block_start = b * bs;
-        while (ei < n && blk(ei) == b) { // apply_parameter_change, graph_gen.rs:269-305
-            const RawEvent &r = *ev[ei];
-            uint64_t delay = r.timed && r.due_frame > block_start ? r.due_frame - block_start : 0;
-            if (delay > 0) wr_set_delay(s, top, r.param, (uint16_t)delay);
-            if (r.smoothing_kind) {
-                PV pv;
-                pv.kind = PV::Smoothing;
-                pv.smoothing = r.smoothing_kind == 2 ? 1 : 0;
-                pv.smooth_seconds = r.smooth_seconds;
-                wr_param_apply(s, top, r.param, pv, block_start);
-            }
-            if (r.value_kind) {
-                PV pv;
-                pv.kind = (PV::Kind)r.value_kind;
-                pv.f = r.value;
-                wr_param_apply(s, top, r.param, pv, block_start);
-            }
-            ei++;
+    for (size_t i = 0; i < n; i++) { // apply_parameter_change, graph_gen.rs:269-305
+        const RawEvent &r = *ev[i];
+        if (r.local != local) continue;
+        const uint64_t delay = r.timed() && r.due_frame > block_start ? r.due_frame - block_start : 0;
+        if (delay > 0) wr_set_delay(s, top, r.param, (uint16_t)delay);
+        if (r.smoothing_kind()) {
+            PV pv;
+            pv.kind = PV::Smoothing;
+            pv.smoothing = r.smoothing_kind() == 2 ? 1 : 0;
+            pv.smooth_seconds = r.smooth_seconds;
+            wr_param_apply(s, top, r.param, pv, block_start);
         }
-        if (needs_processing(hn)) wr_process_block(s, top, block_start, 0, (uint32_t)bs);
-        if (needs_processing(hn)) b++;
-        else if (ei < n) b = blk(ei);
-        else break;
+        if (r.value_kind()) wr_param_apply(s, top, r.param, pv_of(r), block_start);
     }
-    return needs_processing(hn);
+    if (needs_processing(hn)) wr_process_block(s, top, block_start, 0, (uint32_t)bs);
+}
+
+// ---- the same for a node WITHOUT WrSmoothParams (NodeStatic::fast), in closed form.  Such a node's wrapper stack has no
+// control-rate state besides WrPreciseTiming's sticky next_delay[]: its queue is filled by the block's events and drained
+// by the same block's process_block, which applies queued change k at the frame of the largest delay among changes
+// 0..k (the scan stops at the first change that is not due yet and resumes there, precise_timing.rs:82-101).  Changes
+// that are not delayed apply at the block start, before every queued one.  Device events come out in the order the
+// block-by-block model emits them.
+inline bool route_levels(Sim &s, const NodeStatic &ns, int from, int stop, const RawEvent &r, uint64_t frame) {
+    for (int l = from; l > stop; l--) {
+        const uint8_t k = ns.lv_kind[l];
+        if (k == KGPU_WR_MUL) {
+            if (r.param == ns.lv_inner[l]) { // the wrapper's own parameter, wrappers_core/math.rs:92-98
+                if (r.value_kind() == PV::Float) s.set_f(frame, ns.lv_reg[l], (float)r.value);
+                return false;
+            }
+        } else if (k == KGPU_WR_AR_PARAMS) { // audio_rate.rs:70-74: ignored while a buffer is set
+            if (r.param < 32 && ((ns.lv_ar_mask[l] >> r.param) & 1u)) return false;
+        }
+    }
+    return true;
+}
+void fast_node_block(Sim &s, const NodeStatic &ns, const RawEvent *const *ev, size_t n, uint32_t local, uint64_t block_start) {
+    HostNode &hn = s.hn;
+    const int top = (int)ns.n_levels - 1, pl = ns.precise_level;
+    const RawEvent *queue[32];
+    uint16_t qdelay[32];
+    uint32_t nq = 0;
+    for (size_t i = 0; i < n; i++) {
+        const RawEvent &r = *ev[i];
+        if (r.local != local) continue;
+        const uint64_t delay = r.timed() && r.due_frame > block_start ? r.due_frame - block_start : 0;
+        if (delay > 0) { // set_delay_within_block_for_param through the stack
+            if (ns.delay_reaches) {
+                if (r.param < ns.nd_size) hn.nd[r.param] = (uint16_t)delay; // precise_timing.rs:146-148
+            } else s.out.ignored++;                                         // ugen.rs:339-341: warning, no effect
+        }
+        if (!r.value_kind()) continue; // (smoothing settings never reach a node without WrSmoothParams: rejected at push time)
+        if (pl < 0) {
+            if (route_levels(s, ns, top, -1, r, block_start)) ugen_param_apply(s, r.param, pv_of(r), block_start);
+            continue;
+        }
+        if (!route_levels(s, ns, top, pl, r, block_start)) continue;
+        if (r.param >= ns.nd_size) continue;                     // would index out of bounds in knaster
+        const uint16_t nd = hn.nd[r.param];
+        if (nd == 0) {                                           // precise_timing.rs:127-128: apply now
+            if (route_levels(s, ns, pl - 1, -1, r, block_start)) ugen_param_apply(s, r.param, pv_of(r), block_start);
+        } else if (nq < ns.capacity) {                           // :129-131
+            queue[nq] = &r;
+            qdelay[nq++] = nd;
+        } else s.out.dropped++;                                  // :132-134
+    }
+    uint32_t run_max = 0;
+    for (uint32_t k = 0; k < nq; k++) {
+        run_max = std::max<uint32_t>(run_max, qdelay[k]);
+        const uint64_t frame = block_start + run_max;
+        if (route_levels(s, ns, pl - 1, -1, *queue[k], frame)) ugen_param_apply(s, queue[k]->param, pv_of(*queue[k]), frame);
+    }
 }
 } // namespace
 
@@ -1382,20 +1470,22 @@ bool process_node(HostPlan &P, Sink &out, uint32_t gi, uint32_t voice, uint32_t 
 // worker threads that each own a slice of every group's voices and walk the launches IN ORDER,
 // publishing how many launches they have finished: the caller can upload launch L and start its
 // kernels while the workers are already simulating launch L+1 (stream_begin / stream_launch /
-// stream_end).  Each voice's events are ordered the way its kernel consumes them:
-// (frame / chunk, node, frame, arrival).
+// stream_end).  A voice is walked block by block over the blocks in which something happens (a ready
+// event, an active smoothing ramp); the device events of a block are ordered the way the kernels
+// consume them -- (frame / chunk, node, frame, arrival) -- and appended to the launch's list.
 struct StreamState {
     struct PerGroup {
         uint32_t v_begin = 0, v_end = 0;
-        std::vector<std::vector<DevEvent>> ev;   // per launch
+        std::vector<std::vector<DevEvent>> ev;   // per launch (capacity kept from call to call)
         std::vector<std::vector<uint32_t>> cnt;  // per launch, per voice of the slice
-        std::vector<uint32_t> cursor;            // per voice of the slice: next unconsumed entry of vorder
-        std::vector<VoiceEvent> carry, carry_next, later; // events beyond the window / beyond the call
+        std::vector<uint32_t> cursor;            // per voice of the slice: next unconsumed ready event
     };
     struct alignas(128) ThreadCtx {
         std::vector<PerGroup> g;
         Sink sink;
+        std::vector<const RawEvent *> evp;
         int64_t ramp_delta = 0;
+        uint64_t prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         std::atomic<uint32_t> done{0};           // launches finished
         std::string error;
         int error_code = 0;
@@ -1405,8 +1495,10 @@ struct StreamState {
     size_t n_launch = 0, n_ready = 0;
     uint64_t b0 = 0;
     bool any_work = false;
-    std::vector<std::vector<uint32_t>> lat_start; // per group: CSR of HostPlan::later by voice
+    bool identity = false;                       // the ready events are `pending` itself, already grouped by voice: vorder unused
+    unsigned n_threads = 0;                      // contexts of this call: th[0..n_threads)
     std::vector<std::unique_ptr<ThreadCtx>> th;
+    std::vector<std::vector<uint32_t>> hist;     // bucketing scratch
     bool pooled = false; // workers run on HostPlan::pool
     std::chrono::steady_clock::time_point t_begin = std::chrono::steady_clock::now();
 };
@@ -1414,11 +1506,8 @@ struct StreamState {
 #ifdef KGPU_PROFILE_HOST
 // cycle counters of the control simulation, summed over the worker threads and printed by stream_end
 #include <x86intrin.h>
-#include <atomic>
-namespace { std::atomic<uint64_t> g_prof[8]; uint64_t g_prof_voices, g_prof_events;
-void prof_dump() { fprintf(stderr, "[prof] select %.1f gather %.1f nodes %.1f (process_node %.1f) merge %.1f split %.1f Mcycles (thread-summed)\n", g_prof[0].load()/1e6, g_prof[1].load()/1e6, g_prof[2].load()/1e6, g_prof[3].load()/1e6, g_prof[4].load()/1e6, g_prof[5].load()/1e6); for (auto &x : g_prof) x = 0; } }
 #define PROF_T(var) const uint64_t var = __rdtsc()
-#define PROF_ADD(i, a, b) g_prof[i].fetch_add((b) - (a), std::memory_order_relaxed)
+#define PROF_ADD(i, a, b) tc.prof[i] += (b) - (a)
 #else
 #define PROF_T(var)
 #define PROF_ADD(i, a, b)
@@ -1426,172 +1515,128 @@ void prof_dump() { fprintf(stderr, "[prof] select %.1f gather %.1f nodes %.1f (p
 
 namespace {
 // one voice, one launch window: what a separate render call over that window would do
-void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &tc, uint32_t gi, uint32_t v, size_t L,
-                           std::vector<const RawEvent *> &evp, std::vector<const RawEvent *> &node_ev, size_t &carry_pos) {
+void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &tc, uint32_t gi, uint32_t v, size_t L) {
     Group &g = P.groups[gi];
     StreamState::PerGroup &pg = tc.g[gi];
     const uint64_t bs = P.block_size;
     const uint32_t nn = (uint32_t)g.tpl.nodes.size();
-    const uint32_t chunk = S.chunks[gi];
     const uint64_t t0 = S.bounds[L], t1 = S.bounds[L + 1];
     const uint64_t wb0 = t0 / bs, wb1 = t1 / bs;
     const size_t gv = P.voice_base[gi] + v;
+    const RawEvent *pend = P.pending.data();
     PROF_T(p0);
-    // ready events of this voice inside the window (vorder is sorted by ready block inside a voice)
+    // ready events of this voice inside the window (sorted by ready block inside a voice)
     uint32_t &cur = pg.cursor[v - pg.v_begin];
     const uint32_t e0 = cur, vend = P.vcount[gv + 1];
+    const uint32_t *vo = S.identity ? nullptr : P.vorder.data();
+    auto ev_at = [&](uint32_t k) -> const RawEvent & { return pend[vo ? vo[k] : k]; };
     if (L == 0 && vend - e0 > 1) { // first visit: (ready block, arrival) order
         // events that arrive in frame order (the usual case) are in block order: checked without a division
         bool sorted = true;
-        for (uint32_t k = e0 + 1; k < vend && sorted; k++) sorted = P.pending[P.vorder[k - 1]].due_frame <= P.pending[P.vorder[k]].due_frame;
+        for (uint32_t k = e0 + 1; k < vend && sorted; k++) sorted = ev_at(k - 1).due_frame <= ev_at(k).due_frame;
         if (!sorted) {
-            auto rb = [&](uint32_t idx) { return std::max(P.pending[idx].due_frame / bs, S.b0); };
+            auto rb = [&](const RawEvent &r) { return std::max(r.due_frame / bs, S.b0); };
             sorted = true;
-            for (uint32_t k = e0 + 1; k < vend && sorted; k++) sorted = rb(P.vorder[k - 1]) <= rb(P.vorder[k]);
-            if (!sorted) std::stable_sort(P.vorder.begin() + e0, P.vorder.begin() + vend, [&](uint32_t x, uint32_t y) { return rb(x) < rb(y); });
+            for (uint32_t k = e0 + 1; k < vend && sorted; k++) sorted = rb(ev_at(k - 1)) <= rb(ev_at(k));
+            if (!sorted) {
+                if (S.identity) KGPU_THROW(KGPU_ERR_STATE, "internal: identity bucketing with unsorted events"); // stream_begin checks
+                std::stable_sort(P.vorder.begin() + e0, P.vorder.begin() + vend, [&](uint32_t x, uint32_t y) { return rb(pend[x]) < rb(pend[y]); });
+            }
         }
     }
     uint32_t e1 = e0;
-    while (e1 < vend && P.pending[P.vorder[e1]].due_frame < t1) e1++; // t1 is a block boundary: same as due block < wb1
+    while (e1 < vend && ev_at(e1).due_frame < t1) e1++; // t1 is a block boundary: same as due block < wb1
     cur = e1;
-    const std::vector<uint32_t> &ls = S.lat_start[gi];
-    const bool has_later = L == 0 && !ls.empty() && ls[v + 1] > ls[v];
-    while (carry_pos < pg.carry.size() && pg.carry[carry_pos].voice < v) carry_pos++;
-    const bool has_carry = carry_pos < pg.carry.size() && pg.carry[carry_pos].voice == v;
     PROF_T(p1);
     PROF_ADD(0, p0, p1);
-    if (e0 == e1 && !P.voice_ramps[gv] && !has_later && !has_carry) return;
+    if (e0 == e1 && !P.voice_ramps[gv]) return;
 
-    const uint32_t chunk_shift = (uint32_t)__builtin_ctz(chunk); // chunk is a power of two (capi.cpp pick_chunk; recipes: 1)
-    auto key_less = [&](const VoiceEvent &a, const VoiceEvent &b) {
-        const uint64_t fa = a.frame < t0 ? t0 : a.frame, fb = b.frame < t0 ? t0 : b.frame;
-        const uint64_t ca = fa >> chunk_shift, cb = fb >> chunk_shift;
-        if (ca != cb) return ca < cb;
-        if (a.ev.node != b.ev.node) return a.ev.node < b.ev.node;
-        if (fa != fb) return fa < fb;
-        return a.seq < b.seq;
-    };
+    const uint32_t chunk_shift = (uint32_t)__builtin_ctz(S.chunks[gi]); // chunk is a power of two (capi.cpp pick_chunk; recipes: 1)
     Sink &sk = tc.sink;
-    sk.buf.clear();
-    sk.run_start.clear();
-    sk.seq = 0;
-    sk.run_start.push_back(0);
-    if (has_later)
-        for (uint32_t k = ls[v]; k < ls[v + 1]; k++) {
-            VoiceEvent ve = P.later[gi][k];
-            ve.seq = sk.seq++;
-            sk.buf.push_back(ve);
-        }
-    while (carry_pos < pg.carry.size() && pg.carry[carry_pos].voice == v) {
-        VoiceEvent ve = pg.carry[carry_pos++];
-        ve.seq = sk.seq++;
-        sk.buf.push_back(ve);
-    }
-    evp.clear();
-    for (uint32_t k = e0; k < e1; k++) evp.push_back(&P.pending[P.vorder[k]]);
-    PROF_T(p2);
-    PROF_ADD(1, p1, p2);
-    // the window's events bucketed by node: one stable counting sort instead of a filtering pass per node
-    uint32_t nstart[MAX_NODES + 1] = {0};
-    if (!evp.empty()) {
-        uint8_t loc[64];
-        std::vector<uint8_t> loc_big;
-        uint8_t *lp = loc;
-        if (evp.size() > 64) {
-            loc_big.resize(evp.size());
-            lp = loc_big.data();
-        }
-        for (size_t k = 0; k < evp.size(); k++) {
-            lp[k] = (uint8_t)P.node_ref[evp[k]->node].local;
-            nstart[lp[k] + 1]++;
-        }
-        for (uint32_t li = 0; li < nn; li++) nstart[li + 1] += nstart[li];
-        node_ev.resize(evp.size());
-        uint32_t fill[MAX_NODES];
-        for (uint32_t li = 0; li < nn; li++) fill[li] = nstart[li];
-        for (size_t k = 0; k < evp.size(); k++) node_ev[fill[lp[k]]++] = evp[k];
-    }
-    for (uint32_t li = 0; li < nn; li++) {
-        HostNode &hn = g.host[(size_t)v * nn + li];
-        const RawEvent *const *nev = node_ev.data() + nstart[li];
-        const size_t n_nev = nstart[li + 1] - nstart[li];
-        if (n_nev == 0 && !hn.ramp_active) continue;
-        const bool was = hn.ramp_active;
-        if (sk.run_start.back() != sk.buf.size()) sk.run_start.push_back((uint32_t)sk.buf.size());
+    sk.t0 = t0;
+    std::vector<DevEvent> &out = pg.ev[L];
+    const size_t out0 = out.size();
+    auto ready_block = [&](uint32_t k) { return std::max(P.block_of(ev_at(k).due_frame), wb0); };
+    uint32_t ei = e0;
+    uint64_t b = P.voice_ramps[gv] ? wb0 : ready_block(ei);
+    std::vector<const RawEvent *> &evp = tc.evp;
+    while (b < wb1) {
+        const uint64_t block_start = b * bs;
+        // this block's ready events, arrival order
         PROF_T(q0);
-        hn.ramp_active = process_node(P, sk, gi, v, li, nev, n_nev, wb0, wb1);
+        evp.clear();
+        uint32_t mask = 0;
+        while (ei < e1 && ready_block(ei) == b) {
+            const RawEvent &r = ev_at(ei++);
+            evp.push_back(&r);
+            mask |= 1u << r.local;
+        }
+        sk.blk.clear();
         PROF_T(q1);
-        PROF_ADD(3, q0, q1);
-        if (hn.ramp_active != was) {
-            tc.ramp_delta += hn.ramp_active ? 1 : -1;
-            P.voice_ramps[gv] += hn.ramp_active ? 1 : -1;
-        }
-    }
-    PROF_T(p3);
-    PROF_ADD(2, p2, p3);
-    // order for the device: k-way merge of the per-node runs (each already in time order)
-    sk.run_start.push_back((uint32_t)sk.buf.size());
-    std::vector<VoiceEvent> *bufp = &sk.buf;
-    const size_t n_runs = sk.run_start.size() - 1;
-    if (n_runs > 1 && !std::is_sorted(sk.buf.begin(), sk.buf.end(), key_less)) {
-        sk.merged.clear();
-        uint32_t head[MAX_NODES + 2];
-        if (n_runs > (size_t)MAX_NODES + 1) {
-            std::sort(sk.buf.begin(), sk.buf.end(), key_less);
-        } else {
-            for (size_t r = 0; r < n_runs; r++) head[r] = sk.run_start[r];
-            for (size_t done_n = 0; done_n < sk.buf.size(); done_n++) {
-                int best = -1;
-                for (size_t r = 0; r < n_runs; r++) {
-                    if (head[r] == sk.run_start[r + 1]) continue;
-                    if (best < 0 || key_less(sk.buf[head[r]], sk.buf[head[best]])) best = (int)r;
+        PROF_ADD(1, q0, q1);
+        for (uint32_t li = 0; li < nn; li++) {
+            const NodeStatic &ns = g.nstat[li];
+            HostNode &hn = g.host[(size_t)v * nn + li];
+            if (!((mask >> li) & 1u) && !hn.ramp_active) continue;
+            Sim s{P, sk, li, hn};
+            if (ns.fast) {
+                fast_node_block(s, ns, evp.data(), evp.size(), li, block_start);
+            } else {
+                const bool was = hn.ramp_active;
+                generic_node_block(s, evp.data(), evp.size(), li, block_start, bs);
+                hn.ramp_active = needs_processing(hn);
+                if (hn.ramp_active != was) {
+                    tc.ramp_delta += hn.ramp_active ? 1 : -1;
+                    P.voice_ramps[gv] += hn.ramp_active ? 1 : -1;
                 }
-                sk.merged.push_back(sk.buf[head[best]++]);
             }
-            bufp = &sk.merged;
         }
-    }
-    PROF_T(p4);
-    PROF_ADD(4, p3, p4);
-    const bool last = L + 1 == S.n_launch;
-    for (const VoiceEvent &ve : *bufp) {
-        if (ve.frame >= t1) {
-            (last ? pg.later : pg.carry_next).push_back(ve);
-            continue;
+        // device order inside the block: (frame / chunk, node, frame, arrival).  Emission order is (node, frame, arrival),
+        // so a stable sort by chunk is all that is left (insertion sort: a block holds a handful of events)
+        const size_t nb = sk.blk.size();
+        PROF_T(q2);
+        PROF_ADD(2, q1, q2);
+        if (nb) {
+            DevEvent *be = sk.blk.data();
+            for (size_t i = 1; i < nb; i++) {
+                const DevEvent x = be[i];
+                const uint32_t kx = x.frame >> chunk_shift;
+                size_t j = i;
+                while (j > 0 && (be[j - 1].frame >> chunk_shift) > kx) {
+                    be[j] = be[j - 1];
+                    j--;
+                }
+                be[j] = x;
+            }
+            out.insert(out.end(), be, be + nb);
         }
-        DevEvent d = ve.ev;
-        d.frame = (uint32_t)(ve.frame < t0 ? 0 : ve.frame - t0); // late events: relative frame 0
-        pg.ev[L].push_back(d);
-        pg.cnt[L][v - pg.v_begin]++;
+        PROF_T(q3);
+        PROF_ADD(3, q2, q3);
+        if (P.voice_ramps[gv]) b++;
+        else if (ei < e1) b = ready_block(ei);
+        else break;
     }
-    PROF_T(p5);
-    PROF_ADD(5, p4, p5);
+    pg.cnt[L][v - pg.v_begin] = (uint32_t)(out.size() - out0);
 }
 
 void stream_worker(HostPlan &P, StreamState &S, unsigned ti) {
     StreamState::ThreadCtx &tc = *S.th[ti];
+    static const bool timing = getenv("KGPU_TIMING") != nullptr;
     try {
-        std::vector<const RawEvent *> evp, node_ev;
-        if (ti < 3 && S.n_launch > 2 && getenv("KGPU_TIMING"))
-            fprintf(stderr, "[kgpu timing]     worker %u started at +%.2f ms\n", ti,
-                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S.t_begin).count());
         for (size_t L = 0; L < S.n_launch; L++) {
             for (uint32_t gi = 0; gi < P.groups.size(); gi++) {
                 StreamState::PerGroup &pg = tc.g[gi];
-                size_t carry_pos = 0;
-                // one-launch calls without active ramps or leftovers (block-by-block rendering): a voice without a
+                // calls without active ramps (block-by-block rendering, banks without smoothing): a voice without a
                 // ready event has nothing to do -- skip it on two loads instead of entering the simulation
-                const bool quick = S.n_launch == 1 && P.n_active_ramps == 0 && (S.lat_start[gi].empty());
+                const bool quick = P.n_active_ramps == 0 && tc.ramp_delta == 0;
                 const uint32_t *vc = P.vcount.data() + P.voice_base[gi];
                 for (uint32_t v = pg.v_begin; v < pg.v_end; v++) {
-                    if (quick && vc[v] == vc[v + 1]) continue;
-                    simulate_voice_window(P, S, tc, gi, v, L, evp, node_ev, carry_pos);
+                    if (quick && pg.cursor[v - pg.v_begin] == vc[v + 1]) continue;
+                    simulate_voice_window(P, S, tc, gi, v, L);
                 }
-                pg.carry.swap(pg.carry_next);
-                pg.carry_next.clear();
             }
             tc.done.store((uint32_t)L + 1, std::memory_order_release);
-            if (L < 2 && ti < 3 && getenv("KGPU_TIMING"))
+            if (timing && L < 2 && ti < 3 && S.n_launch > 2)
                 fprintf(stderr, "[kgpu timing]     worker %u finished launch %zu at +%.2f ms\n", ti, L,
                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - S.t_begin).count());
         }
@@ -1605,7 +1650,7 @@ void stream_worker(HostPlan &P, StreamState &S, unsigned ti) {
 
 HostPlan::~HostPlan() {
     if (stream) {
-        if (stream->pooled && pool) pool->wait();
+        if (stream_active && stream->pooled && pool) pool->wait();
         delete stream;
     }
     delete pool;
@@ -1661,19 +1706,12 @@ void HostPlan::calendar_update(uint64_t b0, uint64_t b1) {
 
 void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vector<uint32_t> &chunk_of_group) {
     PhaseTimer pt("stream_begin");
-    if (stream) KGPU_THROW(KGPU_ERR_STATE, "stream_begin: a render call is already in progress");
+    if (stream_active) KGPU_THROW(KGPU_ERR_STATE, "stream_begin: a render call is already in progress");
     const uint64_t bs = block_size;
     const uint64_t t0 = bounds.front(), t1 = bounds.back();
     const uint64_t b0 = t0 / bs, b1 = t1 / bs;
     const size_t n_launch = bounds.size() - 1, n_groups = groups.size();
-    if (n_launch > 4096) KGPU_THROW(KGPU_ERR_INVALID, "too many launches in one render call (%zu)", n_launch);
     calendar_update(b0, b1);
-    if (voice_base.size() != n_groups + 1) {
-        voice_base.assign(n_groups + 1, 0);
-        for (size_t gi = 0; gi < n_groups; gi++) voice_base[gi + 1] = voice_base[gi] + groups[gi].n_voices;
-        voice_ramps.assign(voice_base.back(), 0);
-        later.assign(n_groups, {});
-    }
     // ---- ready events: due block < b1 (graph_gen.rs:283: ready iff delay < block_size).
     // `pending` stays in arrival order.  Inside a voice the workers need (block in which the event
     // becomes ready, arrival) order -- late events become ready in block b0 whatever their due time
@@ -1681,25 +1719,56 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
     // block, which is the order knaster's waiting queue applies them in.  Bucketing by voice keeps
     // arrival order; each worker then stable-sorts the (rare) voices whose events did not arrive
     // in time order.
-    size_t n_ready = 0;
     const size_t NV = voice_base.back();
     const size_t NP = pending.size();
-    // per-chunk histograms over the voices (chunks in arrival order => a stable bucket sort)
+    const uint64_t t_ready = b1 * bs; // ready iff due_frame < t_ready
+    if (!stream) stream = new StreamState();
+    StreamState *S = stream;
+    S->t_begin = std::chrono::steady_clock::now();
+    // per-chunk histograms over the voices (chunks in arrival order => a stable bucket sort).  The same pass notices
+    // when there is nothing to sort: every queued event is ready and the events already arrive grouped by voice, voices
+    // ascending (a schedule written voice by voice) -- then `pending` itself is the bucketed list.
     const unsigned TB = NP >= 65536 ? workers().size() : 1u;
-    std::vector<std::vector<uint32_t>> hist(TB);
+    std::vector<std::vector<uint32_t>> &hist = S->hist;
+    hist.resize(std::max<size_t>(hist.size(), TB));
+    std::vector<uint8_t> mono(TB, 1);
+    std::vector<uint32_t> first_v(TB, 0xFFFFFFFFu), last_v(TB, 0);
+    std::vector<uint64_t> first_due(TB, 0), last_due(TB, 0);
     auto count_chunk = [&](unsigned c) {
         std::vector<uint32_t> &hc = hist[c];
         hc.assign(NV, 0);
         const size_t i0 = NP * c / TB, i1 = NP * (c + 1) / TB;
+        uint32_t prev = 0;
+        uint64_t prev_due = 0;
+        bool m = true;
         for (size_t i = i0; i < i1; i++) {
             const RawEvent &r = pending[i];
-            if (r.due_frame / bs >= b1) continue;
-            const NodeRef &nr = node_ref[r.node];
-            hc[voice_base[nr.group] + nr.voice]++;
+            if (r.due_frame >= t_ready) {
+                m = false;
+                continue;
+            }
+            if (i == i0) {
+                first_v[c] = r.gvoice;
+                first_due[c] = r.due_frame;
+            }
+            // voices ascending, and inside a voice in time order (then also in ready-block order)
+            m &= r.gvoice > prev || (r.gvoice == prev && r.due_frame >= prev_due) || i == i0;
+            prev = r.gvoice;
+            prev_due = r.due_frame;
+            hc[r.gvoice]++;
         }
+        last_v[c] = prev;
+        last_due[c] = prev_due;
+        mono[c] = m;
     };
     if (TB == 1) count_chunk(0);
     else workers().run(TB, count_chunk);
+    bool identity = NP > 0;
+    for (unsigned c = 0; c < TB && identity; c++) {
+        identity = mono[c] != 0;
+        if (c > 0 && NP * c / TB < NP * (c + 1) / TB && first_v[c] != 0xFFFFFFFFu)
+            identity &= first_v[c] > last_v[c - 1] || (first_v[c] == last_v[c - 1] && first_due[c] >= last_due[c - 1]);
+    }
     vcount.assign(NV + 1, 0);
     for (size_t v = 0; v < NV; v++) { // hist[c][v] becomes chunk c's first slot for voice v
         uint32_t run = vcount[v];
@@ -1710,64 +1779,61 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
         }
         vcount[v + 1] = run;
     }
-    n_ready = vcount[NV];
+    const size_t n_ready = vcount[NV];
     bool any_work = n_ready > 0 || n_active_ramps > 0;
-    size_t n_later = 0;
-    for (auto &l : later) n_later += l.size();
-    any_work |= n_later > 0;
-
-    StreamState *S = new StreamState();
-    stream = S;
     S->bounds = bounds;
     S->chunks = chunk_of_group;
     S->n_launch = n_launch;
     S->n_ready = n_ready;
     S->b0 = b0;
     S->any_work = any_work;
+    S->identity = identity;
+    S->pooled = false;
+    S->n_threads = 0;
+    stream_active = true;
     if (!any_work) return;
     // bucket by global voice (arrival order inside a voice)
-    vorder.resize(n_ready);
-    {
+    if (!identity) {
+        vorder.resize(n_ready);
         auto scatter_chunk = [&](unsigned c) {
             std::vector<uint32_t> &hc = hist[c];
             const size_t i0 = NP * c / TB, i1 = NP * (c + 1) / TB;
             for (size_t i = i0; i < i1; i++) {
                 const RawEvent &r = pending[i];
-                if (r.due_frame / bs >= b1) continue;
-                const NodeRef &nr = node_ref[r.node];
-                vorder[hc[voice_base[nr.group] + nr.voice]++] = (uint32_t)i;
+                if (r.due_frame >= t_ready) continue;
+                vorder[hc[r.gvoice]++] = (uint32_t)i;
             }
         };
         if (TB == 1) scatter_chunk(0);
         else workers().run(TB, scatter_chunk);
     }
-    // leftovers of the previous call (events at/after its end), bucketed by voice
-    S->lat_start.assign(n_groups, {});
-    for (size_t gi = 0; gi < n_groups; gi++) {
-        std::vector<VoiceEvent> &lat = later[gi];
-        if (lat.empty()) continue;
-        const uint32_t V = groups[gi].n_voices;
-        std::stable_sort(lat.begin(), lat.end(), [](const VoiceEvent &a, const VoiceEvent &b) { return a.voice < b.voice; });
-        S->lat_start[gi].assign(V + 1, 0);
-        for (auto &ve : lat) S->lat_start[gi][ve.voice + 1]++;
-        for (uint32_t v = 0; v < V; v++) S->lat_start[gi][v + 1] += S->lat_start[gi][v];
-    }
     pt.lap("bucket");
-    const size_t work = n_ready + n_later + n_active_ramps;
+    const size_t work = n_ready + n_active_ramps;
     unsigned T = work > 20000 ? workers().size() : 1u;
     T = std::min<unsigned>(T, std::max<unsigned>(1u, (unsigned)(NV / 64)));
+    S->n_threads = T;
+    while (S->th.size() < T) S->th.emplace_back(new StreamState::ThreadCtx());
     for (unsigned ti = 0; ti < T; ti++) {
-        S->th.emplace_back(new StreamState::ThreadCtx());
-        StreamState::ThreadCtx &tc = *S->th.back();
+        StreamState::ThreadCtx &tc = *S->th[ti];
         tc.g.resize(n_groups);
+        tc.ramp_delta = 0;
+        tc.sink.dropped = tc.sink.ignored = tc.sink.devev = 0;
+        tc.done.store(0, std::memory_order_relaxed);
+        tc.error.clear();
+        tc.error_code = 0;
         for (size_t gi = 0; gi < n_groups; gi++) {
             StreamState::PerGroup &pg = tc.g[gi];
             const uint32_t V = groups[gi].n_voices;
             pg.v_begin = (uint32_t)((uint64_t)V * ti / T);
             pg.v_end = (uint32_t)((uint64_t)V * (ti + 1) / T);
-            pg.ev.assign(n_launch, {});
-            pg.cnt.assign(n_launch, std::vector<uint32_t>(pg.v_end - pg.v_begin, 0));
-            pg.cursor.resize(pg.v_end - pg.v_begin);
+            const uint32_t nv = pg.v_end - pg.v_begin;
+            if (pg.ev.size() < n_launch) pg.ev.resize(n_launch);
+            if (pg.cnt.size() < n_launch) pg.cnt.resize(n_launch);
+            for (size_t L = 0; L < n_launch; L++) {
+                pg.ev[L].clear();
+                pg.cnt[L].assign(nv, 0);
+            }
+            pg.cursor.resize(nv);
             for (uint32_t v = pg.v_begin; v < pg.v_end; v++) pg.cursor[v - pg.v_begin] = vcount[voice_base[gi] + v];
         }
     }
@@ -1783,7 +1849,7 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
 // voice order + CSR offsets (n_voices + 1), pieces indexed by group.
 void HostPlan::stream_launch(size_t L, CompiledEvents &out) {
     StreamState *S = stream;
-    if (!S) KGPU_THROW(KGPU_ERR_STATE, "stream_launch without stream_begin");
+    if (!S || !stream_active) KGPU_THROW(KGPU_ERR_STATE, "stream_launch without stream_begin");
     const size_t n_groups = groups.size();
     out.events.clear();
     out.offsets.clear();
@@ -1792,7 +1858,8 @@ void HostPlan::stream_launch(size_t L, CompiledEvents &out) {
     out.piece_any.assign(n_groups, 0);
     if (!S->any_work) return;
     PhaseTimer pt("stream_launch");
-    for (auto &tc : S->th) {
+    for (unsigned ti = 0; ti < S->n_threads; ti++) {
+        StreamState::ThreadCtx *tc = S->th[ti].get();
         unsigned spins = 0;
         while (tc->done.load(std::memory_order_acquire) <= L) {
             if (++spins < 64) std::this_thread::yield();
@@ -1803,22 +1870,25 @@ void HostPlan::stream_launch(size_t L, CompiledEvents &out) {
     pt.lap("wait");
     for (size_t gi = 0; gi < n_groups; gi++) {
         size_t total = 0;
-        for (auto &tc : S->th) total += tc->g[gi].ev[L].size();
+        for (unsigned ti = 0; ti < S->n_threads; ti++) total += S->th[ti]->g[gi].ev[L].size();
         out.piece_ev[gi] = out.events.size();
         if (!total) continue;
         out.piece_any[gi] = 1;
         out.piece_off[gi] = out.offsets.size();
+        const size_t ev0 = out.events.size(), off0 = out.offsets.size();
+        out.events.resize(ev0 + total);
+        out.offsets.resize(off0 + groups[gi].n_voices + 1);
         uint32_t run_off = 0;
-        for (auto &tc : S->th) {
-            StreamState::PerGroup &pg = tc->g[gi];
-            out.events.insert(out.events.end(), pg.ev[L].begin(), pg.ev[L].end());
+        uint32_t *off = out.offsets.data() + off0;
+        for (unsigned ti = 0; ti < S->n_threads; ti++) {
+            StreamState::PerGroup &pg = S->th[ti]->g[gi];
+            if (!pg.ev[L].empty()) std::memcpy(out.events.data() + ev0 + run_off, pg.ev[L].data(), pg.ev[L].size() * sizeof(DevEvent));
             for (uint32_t c : pg.cnt[L]) {
-                out.offsets.push_back(run_off);
+                *off++ = run_off;
                 run_off += c;
             }
-            std::vector<DevEvent>().swap(pg.ev[L]);
         }
-        out.offsets.push_back(run_off);
+        *off = run_off;
     }
 }
 
@@ -1837,21 +1907,21 @@ void HostPlan::consume_ready(uint64_t b1) {
 
 void HostPlan::stream_end() {
     StreamState *S = stream;
-    if (!S) return;
+    if (!S || !stream_active) return;
     if (S->pooled) workers().wait();
 #ifdef KGPU_PROFILE_HOST
-    prof_dump();
+    {
+        uint64_t t[8] = {0};
+        for (unsigned ti = 0; ti < S->n_threads; ti++)
+            for (int i = 0; i < 8; i++) { t[i] += S->th[ti]->prof[i]; S->th[ti]->prof[i] = 0; }
+        fprintf(stderr, "[prof] select %.1f gather %.1f nodes %.1f sort+append %.1f Mcycles (thread-summed)\n", t[0] / 1e6, t[1] / 1e6, t[2] / 1e6, t[3] / 1e6);
+    }
 #endif
-    stream = nullptr;
-    std::unique_ptr<StreamState> guard(S);
+    stream_active = false;
     if (!S->any_work) return;
-    for (size_t gi = 0; gi < groups.size(); gi++) later[gi].clear();
     Error err{0, ""};
-    for (auto &tc : S->th) {
-        for (size_t gi = 0; gi < groups.size(); gi++) {
-            StreamState::PerGroup &pg = tc->g[gi];
-            later[gi].insert(later[gi].end(), pg.later.begin(), pg.later.end());
-        }
+    for (unsigned ti = 0; ti < S->n_threads; ti++) {
+        StreamState::ThreadCtx *tc = S->th[ti].get();
         dropped_changes += tc->sink.dropped;
         ignored_delays += tc->sink.ignored;
         device_events += tc->sink.devev;

@@ -71,6 +71,29 @@ struct HostNode {
     int8_t smooth_level = -1, precise_level = -1;
     bool ramp_active = false;
     uint32_t ramp_list_pos = 0;
+    // WrPreciseTiming::next_delay of a node on the fast path (NodeStatic::fast): sticky, App. B1.  Such a node keeps
+    // no WrapSim at all -- everything else about its wrapper stack is static and lives in the template's NodeStatic.
+    uint16_t nd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+// What the control simulation needs to know about one node of a voice TEMPLATE (the same for every voice of the
+// group): its wrapper stack, innermost first.  A node without WrSmoothParams takes the fast path: parameter changes
+// have no effect outside the block they become ready in, so the block-by-block model of the wrapper stack
+// collapses to "apply now, or at block_start + running maximum of the queued delays" (precise_timing.rs:65-114).
+constexpr int MAX_WRAP_LEVELS = 8;
+struct NodeStatic {
+    uint8_t kind = 0;            // kgpu_ugen_kind
+    uint8_t n_levels = 0;
+    bool fast = false;
+    bool delay_reaches = false;  // set_delay_within_block_for_param reaches a WrPreciseTiming (only math wrappers above it)
+    int8_t precise_level = -1, smooth_level = -1;
+    uint32_t base_params = 0, total_params = 0;
+    uint32_t capacity = 0;       // of the WrPreciseTiming
+    uint32_t nd_size = 0;        // parameters visible at the WrPreciseTiming (its next_delay array)
+    uint8_t lv_kind[MAX_WRAP_LEVELS] = {0};
+    uint16_t lv_reg[MAX_WRAP_LEVELS] = {0};
+    uint32_t lv_inner[MAX_WRAP_LEVELS] = {0};
+    uint32_t lv_ar_mask[MAX_WRAP_LEVELS] = {0}; // WrArParams: parameters that have a buffer (audio_rate.rs:70-74)
 };
 
 struct TemplateNode {
@@ -94,16 +117,18 @@ struct Group {
     uint32_t n_voices = 0;
     std::vector<uint32_t> init_regs;                // [reg][voice]
     std::vector<HostNode> host;                     // [voice * n_nodes + local]
+    std::vector<NodeStatic> nstat;                  // [local]
     std::vector<std::vector<uint16_t>> slot_of;     // [local][channel] -> value slot
     int fused_recipe = -1;                          // index into the fused-kernel table, -1 = interpreter
     std::string kernel_name;
 };
 
-struct NodeRef {
+struct NodeRef { // 16 bytes
     int32_t group = -1; // -1: mix-bus Add node or unreachable node
     uint32_t voice = 0;
-    uint32_t local = 0;
-    uint32_t n_params = 0;
+    uint16_t local = 0;
+    uint16_t n_params = 0;
+    uint32_t rule_base = 0; // first validation rule of this node's parameters in HostPlan::rules
 };
 
 // std::allocator whose value-less construct() default-initialises: vector::resize() of a POD then leaves
@@ -116,13 +141,17 @@ template <class T> struct DefaultInitAllocator : std::allocator<T> {
 
 struct RawEvent { // 32 bytes
     uint32_t node;
+    uint32_t gvoice;        // global voice index (voice_base[group] + voice), resolved once at push time
     uint16_t param;
-    uint8_t value_kind;     // 0 none, 1 float, 2 trigger, 3 integer, 4 bool
-    uint8_t smoothing_kind; // 0 none, 1 ParameterSmoothing::None, 2 Linear
-    uint8_t timed;          // 0: `time: None` (delay 0 by construction)
+    uint8_t local;          // node index inside the voice template
+    uint8_t kinds;          // value_kind (0 none, 1 float, 2 trigger, 3 integer, 4 bool) | smoothing_kind << 3 (0 none,
+                            // 1 ParameterSmoothing::None, 2 Linear) | timed << 5 (0: `time: None`, delay 0 by construction)
     float smooth_seconds;
     double value;
     uint64_t due_frame;     // absolute; events without time: frame clock at push
+    uint8_t value_kind() const { return kinds & 7u; }
+    uint8_t smoothing_kind() const { return (kinds >> 3) & 3u; }
+    bool timed() const { return (kinds >> 5) & 1u; }
 };
 
 struct VoiceEvent { // a device event tagged with its destination
@@ -153,6 +182,9 @@ class WorkPool {
 
 struct HostPlan {
     uint32_t sample_rate = 48000, block_size = 64, n_outputs = 2;
+    uint32_t bs_shift = 6;
+    bool bs_pow2 = true;
+    uint64_t block_of(uint64_t frame) const { return bs_pow2 ? frame >> bs_shift : frame / block_size; }
     std::vector<Group> groups;
     std::vector<NodeRef> node_ref; // per graph node
     uint32_t n_mix_nodes = 0;
@@ -168,7 +200,7 @@ struct HostPlan {
 
     // caches / scratch of the hot host path (push / compile_events)
     struct Rule { char want; uint8_t smooth_ok, polyblep_wave, svf_type; };
-    std::vector<std::vector<std::vector<Rule>>> rules;   // [group][local][param]
+    std::vector<Rule> rules;                             // flat: NodeRef::rule_base + param
     uint64_t n_active_ramps = 0;
     std::vector<uint64_t> voice_base;                    // prefix sum of voices per group
     std::vector<int32_t> voice_ramps;                    // per global voice: nodes with active ramps / queues
@@ -176,13 +208,14 @@ struct HostPlan {
     std::vector<uint32_t> vcount, vfill, vorder;
 
     struct CompiledEvents {
-        std::vector<DevEvent> events;      // concatenated pieces
-        std::vector<uint32_t> offsets;     // concatenated CSR offset arrays (n_voices+1 each)
+        std::vector<DevEvent, DefaultInitAllocator<DevEvent>> events;   // concatenated pieces
+        std::vector<uint32_t, DefaultInitAllocator<uint32_t>> offsets;  // concatenated CSR offset arrays (n_voices+1 each)
         std::vector<uint64_t> piece_ev, piece_off; // [launch * n_groups + group]
         std::vector<uint8_t> piece_any;
     };
 
     void build(const kgpu_graph_desc &d);
+    void finish_build();
     // push_events: validate + timestamp (frame_clock = next block to render)
     void push(const kgpu_event *ev, size_t n, uint64_t frame_clock);
     // host half of a render call, see plan.cpp
@@ -194,7 +227,8 @@ struct HostPlan {
     void stream_launch(size_t launch, CompiledEvents &out);
     void stream_end();
     void consume_ready(uint64_t b1);
-    StreamState *stream = nullptr;
+    StreamState *stream = nullptr;       // kept between calls (its buffers are reused); valid while stream_active
+    bool stream_active = false;
     WorkPool *pool = nullptr;            // created on first use
     uint32_t pool_threads = 0;           // 0: hardware threads - 1, at most 16
     WorkPool &workers();
