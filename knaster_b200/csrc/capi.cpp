@@ -384,7 +384,7 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             const uint64_t nb = std::min(next, left);
             sizes.push_back(nb);
             left -= nb;
-            next = std::min(bpl, next * 2);
+            next = std::min(bpl, next + next / 2); // x1.5: the host stays ahead of the device with a 1.6x margin (3 workers per GPU)
         }
     }
     if (peer && sizes.size() > KGPU_PEER_MAX_LAUNCHES)
@@ -846,8 +846,57 @@ struct kgpu_snapshot {
     std::vector<int32_t> voice_ramps;
     std::vector<uint64_t> voice_base;
     uint64_t n_active_ramps = 0, dropped_changes = 0, ignored_delays = 0, device_events = 0, frame_clock = 0;
+    uint64_t graph_hash = 0; // HostPlan::graph_hash of the plan the snapshot was taken from
     bool rendered = false;
 };
+
+namespace {
+// A snapshot may come from a byte image (kgpu_snapshot_deserialize): before any of it is used as an index, everything
+// that is immutable in a plan must equal the plan's own, and every index it carries must be in range.
+void validate_snapshot(const kgpu_plan *p, const kgpu_snapshot *s) {
+    const HostPlan &H = p->host;
+    auto bad = [](const char *what) { KGPU_THROW(KGPU_ERR_INVALID, "kgpu_plan_restore: the snapshot does not fit this plan (%s)", what); };
+    if (s->graph_hash != H.graph_hash) bad("it was taken from another graph");
+    if (s->regs.size() != p->gd.size() || s->host.size() != p->gd.size()) bad("group count");
+    if (s->voice_base != H.voice_base) bad("voices per group");
+    if (s->voice_ramps.size() != H.voice_ramps.size()) bad("voice count");
+    if (s->pending_clean > s->pending.size()) bad("pending_clean");
+    for (const auto &l : s->later)
+        if (!l.empty()) bad("leftover device events");
+    for (size_t gi = 0; gi < p->gd.size(); gi++) {
+        const Group &g = H.groups[gi];
+        if (s->regs[gi].size() != (size_t)g.prog.n_regs * g.n_voices || s->host[gi].size() != g.host.size()) bad("group size");
+        for (size_t i = 0; i < g.host.size(); i++) {
+            const HostNode &a = s->host[gi][i], &b = g.host[i];
+            if (a.kind != b.kind || a.dev_kind != b.dev_kind || a.reg != b.reg || a.n_seg != b.n_seg || a.base_params != b.base_params ||
+                a.has_smooth != b.has_smooth || a.has_precise != b.has_precise || a.smooth_level != b.smooth_level ||
+                a.precise_level != b.precise_level || a.wr.size() != b.wr.size())
+                bad("node layout");
+            if (a.kind == KGPU_SVF ? a.mode > 8 : a.mode != b.mode) bad("node mode");
+            for (size_t l = 0; l < a.wr.size(); l++) {
+                const WrapSim &x = a.wr[l], &y = b.wr[l];
+                if (x.kind != y.kind || x.capacity != y.capacity || x.reg != y.reg || x.inner_params != y.inner_params ||
+                    x.smooth.size() != y.smooth.size() || x.next_delay.size() != y.next_delay.size() || x.ar_bound.size() != y.ar_bound.size())
+                    bad("wrapper layout");
+                if (x.queue.size() > x.capacity) bad("WrPreciseTiming queue longer than its capacity");
+                for (const QueuedChange &q : x.queue)
+                    if (q.param >= x.next_delay.size() || q.value.kind > PV::Smoothing) bad("queued change");
+            }
+        }
+    }
+    auto check_events = [&](const decltype(HostPlan::pending) &v) {
+        for (const RawEvent &e : v) {
+            if (e.node >= H.node_ref.size()) bad("event node");
+            const NodeRef &nr = H.node_ref[e.node];
+            if (nr.group < 0 || e.param >= nr.n_params || e.local != nr.local || e.gvoice != H.voice_base[nr.group] + nr.voice ||
+                e.value_kind() > 4 || e.smoothing_kind() > 2)
+                bad("queued event");
+        }
+    };
+    check_events(s->pending);
+    check_events(s->pending_far);
+}
+} // namespace
 
 int kgpu_plan_snapshot(kgpu_plan *p, kgpu_snapshot **out) {
     if (!p || !out) return fail(KGPU_ERR_INVALID, "kgpu_plan_snapshot: NULL argument");
@@ -878,6 +927,7 @@ int kgpu_plan_snapshot(kgpu_plan *p, kgpu_snapshot **out) {
         s->device_events = p->host.device_events;
         s->frame_clock = p->frame_clock;
         s->rendered = p->rendered;
+        s->graph_hash = p->host.graph_hash;
         *out = s.release();
         return KGPU_OK;
     } catch (const Error &e) {
@@ -889,12 +939,8 @@ int kgpu_plan_restore(kgpu_plan *p, const kgpu_snapshot *s) {
     if (!p || !s) return fail(KGPU_ERR_INVALID, "kgpu_plan_restore: NULL argument");
     try {
         if (p->host.stream_active) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_restore: a render call is in progress");
-        if (s->regs.size() != p->gd.size()) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_plan_restore: the snapshot belongs to another plan");
-        for (size_t gi = 0; gi < p->gd.size(); gi++) {
-            const Group &g = p->host.groups[gi];
-            if (s->regs[gi].size() != (size_t)g.prog.n_regs * g.n_voices || s->host[gi].size() != g.host.size())
-                KGPU_THROW(KGPU_ERR_INVALID, "kgpu_plan_restore: the snapshot belongs to another plan");
-        }
+        if (p->prepared) KGPU_THROW(KGPU_ERR_STATE, "kgpu_plan_restore: a prepared render is pending");
+        validate_snapshot(p, s);
         CUDA_TRY(cudaSetDevice(p->device));
         CUDA_TRY(cudaStreamSynchronize(p->stream));
         for (size_t gi = 0; gi < p->gd.size(); gi++) {
@@ -907,18 +953,28 @@ int kgpu_plan_restore(kgpu_plan *p, const kgpu_snapshot *s) {
         p->host.far_horizon = s->far_horizon;
         p->host.pending_clean = s->pending_clean;
         p->host.later = s->later;
-        p->host.voice_ramps = s->voice_ramps;
-        p->host.voice_base = s->voice_base;
-        p->host.n_active_ramps = s->n_active_ramps;
+        // the ramp bookkeeping is derived state: rebuilt from the nodes' flags rather than trusted
+        p->host.voice_ramps.assign(p->host.voice_base.back(), 0);
+        p->host.n_active_ramps = 0;
+        for (size_t gi = 0; gi < p->gd.size(); gi++) {
+            const Group &g = p->host.groups[gi];
+            const size_t nn = g.tpl.nodes.size();
+            for (size_t i = 0; i < g.host.size(); i++)
+                if (g.host[i].ramp_active) {
+                    p->host.voice_ramps[p->host.voice_base[gi] + i / nn]++;
+                    p->host.n_active_ramps++;
+                }
+        }
         p->host.dropped_changes = s->dropped_changes;
         p->host.ignored_delays = s->ignored_delays;
         p->host.device_events = s->device_events;
         p->frame_clock = s->frame_clock;
         p->rendered = s->rendered;
-        p->prepared = false;
         return KGPU_OK;
     } catch (const Error &e) {
         return fail(e.code, e.msg);
+    } catch (const std::exception &e) {
+        return fail(KGPU_ERR_INVALID, std::string("kgpu_plan_restore: ") + e.what());
     }
 }
 
@@ -1040,7 +1096,7 @@ void get_voice_events(Reader &r, std::vector<VoiceEvent> &v) {
     }
 }
 void write_snapshot(Writer &w, const kgpu_snapshot &s) {
-    w.pod(SNAP_MAGIC); w.pod(SNAP_VERSION);
+    w.pod(SNAP_MAGIC); w.pod(SNAP_VERSION); w.pod(s.graph_hash);
     w.pod<uint64_t>(s.regs.size());
     for (size_t gi = 0; gi < s.regs.size(); gi++) {
         w.pods(s.regs[gi]);
@@ -1076,6 +1132,7 @@ int kgpu_snapshot_deserialize(const void *buf, uint64_t size, kgpu_snapshot **ou
         if (r.pod<uint64_t>() != SNAP_MAGIC) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: not a snapshot image");
         if (r.pod<uint32_t>() != SNAP_VERSION) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: unsupported image version");
         std::unique_ptr<kgpu_snapshot> s(new kgpu_snapshot());
+        s->graph_hash = r.pod<uint64_t>();
         const uint64_t ng = r.pod<uint64_t>();
         if (ng > (1u << 20)) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad group count");
         s->regs.resize(ng);
@@ -1105,6 +1162,8 @@ int kgpu_snapshot_deserialize(const void *buf, uint64_t size, kgpu_snapshot **ou
         return KGPU_OK;
     } catch (const Error &e) {
         return fail(e.code, e.msg);
+    } catch (const std::exception &e) { // bad_alloc / length_error from a hostile length field
+        return fail(KGPU_ERR_INVALID, std::string("kgpu_snapshot_deserialize: ") + e.what());
     }
 }
 
@@ -1214,12 +1273,12 @@ int kgpu_debug_host_bench(const kgpu_graph_desc *desc, const kgpu_event *events,
         size_t total_ev = 0;
         for (uint32_t s = 0; s < n_steps; s++) {
             std::vector<uint64_t> bounds{clock};
-            uint64_t left = n_blocks, next = bpl < 32 || n_blocks < 2 * bpl ? bpl : bpl / 8;
+            uint64_t left = n_blocks, next = bpl < 64 || n_blocks < 2 * bpl ? bpl : std::max<uint64_t>(32, bpl / 64);
             while (left) {
                 const uint64_t nb = std::min(next, left);
                 bounds.push_back(bounds.back() + nb * bs);
                 left -= nb;
-                next = std::min(bpl, next * 2);
+                next = std::min(bpl, next + next / 2);
             }
             const auto t0 = now();
             hp.push(ev.data(), ev.size(), clock);

@@ -763,6 +763,24 @@ void HostPlan::build(const kgpu_graph_desc &d) {
     n_outputs = d.n_outputs;
     const uint32_t N = d.n_nodes;
     for (uint32_t i = 0; i < N; i++) validate_node(d.nodes[i], i);
+    {
+        auto hd = [](double x) { uint64_t u; std::memcpy(&u, &x, 8); return u; };
+        uint64_t h = hash_mix(0x6b67707573ull, ((uint64_t)d.sample_rate << 32) | d.block_size);
+        h = hash_mix(h, ((uint64_t)d.n_outputs << 32) | d.n_nodes);
+        for (uint32_t i = 0; i < N; i++) {
+            const kgpu_node_desc &n = d.nodes[i];
+            h = hash_mix(h, n.kind | ((uint64_t)n.mode << 8) | ((uint64_t)n.channels << 24) | ((uint64_t)n.flags << 32) | ((uint64_t)n.n_wrappers << 40) | ((uint64_t)n.n_segments << 48));
+            for (double a : n.args) h = hash_mix(h, hd(a));
+            for (uint32_t w = 0; w < n.n_wrappers; w++) h = hash_mix(hash_mix(h, n.wrappers[w].kind | ((uint64_t)n.wrappers[w].capacity << 8)), hd(n.wrappers[w].value));
+            if (n.kind == KGPU_ENVELOPE)
+                for (uint32_t k = 0; k < 2 * n.n_segments; k++) h = hash_mix(h, hd(n.segments[k]));
+        }
+        for (uint32_t e = 0; e < d.n_edges; e++)
+            h = hash_mix(h, (uint64_t)(uint32_t)d.edges[e].source_node | ((uint64_t)d.edges[e].source_channel << 32)), h = hash_mix(h, (uint64_t)(uint32_t)d.edges[e].sink_node | ((uint64_t)d.edges[e].sink_channel << 32));
+        for (uint32_t e = 0; e < d.n_param_edges; e++)
+            h = hash_mix(h, (uint64_t)(uint32_t)d.param_edges[e].source_node | ((uint64_t)d.param_edges[e].source_channel << 32)), h = hash_mix(h, (uint64_t)(uint32_t)d.param_edges[e].sink_node | ((uint64_t)d.param_edges[e].param_index << 32));
+        graph_hash = h;
+    }
 
     // adjacency
     std::vector<uint32_t> in_off(N + 1, 0);
@@ -1330,20 +1348,52 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
     std::vector<Error> errs(T, Error{0, ""});
     const size_t base = pending.size();
     pending.resize(base + n);
+    // A large batch pushed into an empty queue is bucketed by voice while it is converted (the per-chunk histograms
+    // stream_begin needs, and whether the events already arrive grouped by voice and in time order): the render call
+    // that follows then has no pass of its own over the events before its first launch.
+    BucketPrep &bp = bucket_prep;
+    const bool track = base == 0 && n >= 32768 && far_horizon == UINT64_MAX;
+    bp.valid = false;
+    if (track) bp.reset(T, voice_base.back());
     auto chunk = [&](unsigned c) {
         const size_t i0 = n * c / T, i1 = n * (c + 1) / T;
         size_t d = 0;
         RawEvent *dst = pending.data() + base;
+        uint32_t *hc = track ? bp.hist[c].data() : nullptr;
+        uint32_t prev = 0;
+        uint64_t prev_due = 0, max_due = 0;
+        bool mono = true;
         try {
-            for (size_t i = i0; i < i1; i++)
+            for (size_t i = i0; i < i1; i++) {
                 if (!one(i, dst[i])) {
                     dst[i].node = 0xFFFFFFFFu; // dropped
                     d++;
+                    continue;
                 }
+                if (track) {
+                    const RawEvent &r = dst[i];
+                    if (i == i0) {
+                        bp.first_v[c] = r.gvoice;
+                        bp.first_due[c] = r.due_frame;
+                    }
+                    // voices ascending, and inside a voice in time order (then also in ready-block order)
+                    mono &= r.gvoice > prev || (r.gvoice == prev && r.due_frame >= prev_due) || i == i0;
+                    prev = r.gvoice;
+                    prev_due = r.due_frame;
+                    max_due = std::max(max_due, r.due_frame);
+                    hc[r.gvoice]++;
+                }
+            }
         } catch (const Error &e) {
             errs[c] = e;
         }
         dropped[c] = d;
+        if (track) {
+            bp.last_v[c] = prev;
+            bp.last_due[c] = prev_due;
+            bp.mono[c] = mono;
+            bp.max_due[c] = max_due;
+        }
     };
     if (T == 1) chunk(0);
     else workers().run(T, chunk);
@@ -1359,6 +1409,9 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
         for (size_t i = base; i < base + n; i++)
             if (pending[i].node != 0xFFFFFFFFu) pending[w++] = pending[i];
         pending.resize(w);
+    } else if (track) {
+        bp.valid = true;
+        bp.n = n;
     }
 }
 
@@ -1479,6 +1532,7 @@ struct StreamState {
         std::vector<std::vector<DevEvent>> ev;   // per launch (capacity kept from call to call)
         std::vector<std::vector<uint32_t>> cnt;  // per launch, per voice of the slice
         std::vector<uint32_t> cursor;            // per voice of the slice: next unconsumed ready event
+        std::vector<uint64_t> next_due;          // ... and its due frame (UINT64_MAX: none left): the per-window skip test
     };
     struct alignas(128) ThreadCtx {
         std::vector<PerGroup> g;
@@ -1530,7 +1584,7 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     const uint32_t e0 = cur, vend = P.vcount[gv + 1];
     const uint32_t *vo = S.identity ? nullptr : P.vorder.data();
     auto ev_at = [&](uint32_t k) -> const RawEvent & { return pend[vo ? vo[k] : k]; };
-    if (L == 0 && vend - e0 > 1) { // first visit: (ready block, arrival) order
+    if (L == 0 && vend - e0 > 1 && !S.identity) { // first visit: (ready block, arrival) order; identity bucketing has checked it
         // events that arrive in frame order (the usual case) are in block order: checked without a division
         bool sorted = true;
         for (uint32_t k = e0 + 1; k < vend && sorted; k++) sorted = ev_at(k - 1).due_frame <= ev_at(k).due_frame;
@@ -1539,7 +1593,6 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
             sorted = true;
             for (uint32_t k = e0 + 1; k < vend && sorted; k++) sorted = rb(ev_at(k - 1)) <= rb(ev_at(k));
             if (!sorted) {
-                if (S.identity) KGPU_THROW(KGPU_ERR_STATE, "internal: identity bucketing with unsorted events"); // stream_begin checks
                 std::stable_sort(P.vorder.begin() + e0, P.vorder.begin() + vend, [&](uint32_t x, uint32_t y) { return rb(pend[x]) < rb(pend[y]); });
             }
         }
@@ -1547,6 +1600,7 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     uint32_t e1 = e0;
     while (e1 < vend && ev_at(e1).due_frame < t1) e1++; // t1 is a block boundary: same as due block < wb1
     cur = e1;
+    pg.next_due[v - pg.v_begin] = e1 < vend ? ev_at(e1).due_frame : UINT64_MAX;
     PROF_T(p1);
     PROF_ADD(0, p0, p1);
     if (e0 == e1 && !P.voice_ramps[gv]) return;
@@ -1630,8 +1684,11 @@ void stream_worker(HostPlan &P, StreamState &S, unsigned ti) {
                 // ready event has nothing to do -- skip it on two loads instead of entering the simulation
                 const bool quick = P.n_active_ramps == 0 && tc.ramp_delta == 0;
                 const uint32_t *vc = P.vcount.data() + P.voice_base[gi];
+                const uint64_t t1 = S.bounds[L + 1];
+                const uint64_t *nd = pg.next_due.data();
+                (void)vc;
                 for (uint32_t v = pg.v_begin; v < pg.v_end; v++) {
-                    if (quick && pg.cursor[v - pg.v_begin] == vc[v + 1]) continue;
+                    if (quick && nd[v - pg.v_begin] >= t1) continue; // nothing of this voice becomes ready in this window
                     simulate_voice_window(P, S, tc, gi, v, L);
                 }
             }
@@ -1728,12 +1785,22 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
     // per-chunk histograms over the voices (chunks in arrival order => a stable bucket sort).  The same pass notices
     // when there is nothing to sort: every queued event is ready and the events already arrive grouped by voice, voices
     // ascending (a schedule written voice by voice) -- then `pending` itself is the bucketed list.
-    const unsigned TB = NP >= 65536 ? workers().size() : 1u;
-    std::vector<std::vector<uint32_t>> &hist = S->hist;
+    BucketPrep &bp = bucket_prep;
+    bool prepped = bp.valid && bp.n == NP && far_horizon == UINT64_MAX && bp.hist.size() >= bp.T && NP > 0;
+    if (prepped)
+        for (unsigned c = 0; c < bp.T; c++) prepped &= bp.max_due[c] < t_ready; // every queued event is ready
+    bp.valid = false; // one use: the queue changes below / at the end of the call
+    const unsigned TB = prepped ? bp.T : (NP >= 65536 ? workers().size() : 1u);
+    std::vector<std::vector<uint32_t>> &hist = prepped ? bp.hist : S->hist;
     hist.resize(std::max<size_t>(hist.size(), TB));
     std::vector<uint8_t> mono(TB, 1);
     std::vector<uint32_t> first_v(TB, 0xFFFFFFFFu), last_v(TB, 0);
     std::vector<uint64_t> first_due(TB, 0), last_due(TB, 0);
+    if (prepped) {
+        mono = bp.mono;
+        first_v = bp.first_v; last_v = bp.last_v;
+        first_due = bp.first_due; last_due = bp.last_due;
+    }
     auto count_chunk = [&](unsigned c) {
         std::vector<uint32_t> &hc = hist[c];
         hc.assign(NV, 0);
@@ -1761,7 +1828,8 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
         last_due[c] = prev_due;
         mono[c] = m;
     };
-    if (TB == 1) count_chunk(0);
+    if (prepped) {}
+    else if (TB == 1) count_chunk(0);
     else workers().run(TB, count_chunk);
     bool identity = NP > 0;
     for (unsigned c = 0; c < TB && identity; c++) {
@@ -1834,7 +1902,15 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
                 pg.cnt[L].assign(nv, 0);
             }
             pg.cursor.resize(nv);
-            for (uint32_t v = pg.v_begin; v < pg.v_end; v++) pg.cursor[v - pg.v_begin] = vcount[voice_base[gi] + v];
+            pg.next_due.resize(nv);
+            const uint32_t *vo = identity ? nullptr : vorder.data();
+            for (uint32_t v = pg.v_begin; v < pg.v_end; v++) {
+                const uint32_t c0 = vcount[voice_base[gi] + v], c1 = vcount[voice_base[gi] + v + 1];
+                pg.cursor[v - pg.v_begin] = c0;
+                // events of a voice are in ready-block order only after the first visit's sort: until then the skip test
+                // must let every voice with events through (0), afterwards it is exact
+                pg.next_due[v - pg.v_begin] = c0 == c1 ? UINT64_MAX : (identity ? pending[vo ? vo[c0] : c0].due_frame : 0);
+            }
         }
     }
     pt.lap("contexts");

@@ -188,6 +188,7 @@ struct HostPlan {
     std::vector<Group> groups;
     std::vector<NodeRef> node_ref; // per graph node
     uint32_t n_mix_nodes = 0;
+    uint64_t graph_hash = 0;       // of the whole graph description (snapshots only restore into the same graph)
     uint64_t dropped_changes = 0, ignored_delays = 0, device_events = 0;
     std::vector<RawEvent, DefaultInitAllocator<RawEvent>> pending; // not yet simulated, arrival order
     // Calendar for block-by-block rendering under a large backlog of scheduled events: while it is active
@@ -227,6 +228,24 @@ struct HostPlan {
     void stream_launch(size_t launch, CompiledEvents &out);
     void stream_end();
     void consume_ready(uint64_t b1);
+    // what HostPlan::push learns about a large batch while converting it (see push / stream_begin)
+    struct BucketPrep {
+        bool valid = false;
+        size_t n = 0;
+        unsigned T = 0;
+        std::vector<std::vector<uint32_t>> hist; // [chunk][global voice]
+        std::vector<uint8_t> mono;
+        std::vector<uint32_t> first_v, last_v;
+        std::vector<uint64_t> first_due, last_due, max_due;
+        void reset(unsigned t, size_t n_voices) {
+            T = t;
+            if (hist.size() < t) hist.resize(t);
+            for (unsigned c = 0; c < t; c++) hist[c].assign(n_voices, 0);
+            mono.assign(t, 1);
+            first_v.assign(t, 0xFFFFFFFFu); last_v.assign(t, 0);
+            first_due.assign(t, 0); last_due.assign(t, 0); max_due.assign(t, 0);
+        }
+    } bucket_prep;
     StreamState *stream = nullptr;       // kept between calls (its buffers are reused); valid while stream_active
     bool stream_active = false;
     WorkPool *pool = nullptr;            // created on first use

@@ -564,3 +564,43 @@ def test_prepare_must_be_followed_by_the_render_it_prepared():
     g2, p2 = AudioProcessor.new(0, 2, AudioProcessorOptions())
     banks.subtractive_bank(g2, 40, 0.5, n_notes=3)
     assert np.array_equal(a, p2.render(100))   # ... and equals the unprepared one
+
+
+def test_restore_rejects_foreign_and_corrupt_snapshots():
+    # a deserialized image is checked against the plan before any of it is used as an index --
+    # another graph of the same shape, flipped bytes and hostile lengths all come back as KGPU_ERR_INVALID
+    from knaster_b200 import _ffi
+    from knaster_b200.processor import Snapshot
+
+    def make(seed):
+        graph, proc = AudioProcessor.new(0, 2, AudioProcessorOptions(sample_rate=SR))
+        banks.additive_bank(graph, 40, 1.0, seed=seed)          # smoothing ramps + queued events: every table is non-trivial
+        proc.render(20)
+        return graph, proc
+
+    g1, p1 = make(1001)
+    image = p1.snapshot().to_bytes()
+    g2, p2 = make(1002)                                          # same shape, other frequencies / gains
+    with pytest.raises(_ffi.KgpuError) as e:
+        p2.restore(Snapshot.from_bytes(image))
+    assert e.value.code == _ffi.KGPU_ERR_INVALID
+    ref = p1.render(50)
+    r = np.random.Generator(np.random.PCG64(5))
+    rejected = 0
+    for trial in range(300):
+        bad = bytearray(image)
+        for _ in range(int(r.integers(1, 4))):
+            pos = int(r.integers(12, len(bad)))                  # keep magic + version intact: the interesting paths lie behind them
+            bad[pos] = int(r.integers(0, 256)) if r.random() < 0.5 else 0xFF
+        try:
+            snap = Snapshot.from_bytes(bytes(bad))
+            p1.restore(snap)
+        except _ffi.KgpuError as err:
+            assert err.code == _ffi.KGPU_ERR_INVALID
+            rejected += 1
+            continue
+        out = p1.render(5)                                       # accepted images differ in values only: rendering must not fault
+        assert out.shape == (5, 2, 64)
+    assert rejected > 30
+    p1.restore(Snapshot.from_bytes(image))                       # and the pristine image still restores exactly
+    assert np.array_equal(p1.render(50), ref)

@@ -24,7 +24,7 @@ L = _ffi.lib()
 L.kgpu_debug_host_bench.argtypes = [C.POINTER(_ffi.GraphDesc), C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]
 gd, keep = _ffi.graph_desc(g)
 out = np.zeros((steps, 4))
-_ffi.check(L.kgpu_debug_host_bench(C.byref(gd), ev.ctypes.data, len(ev), n_blocks, 2048, steps, threads, out.ctypes.data))
+_ffi.check(L.kgpu_debug_host_bench(C.byref(gd), ev.ctypes.data, len(ev), n_blocks, int(os.environ.get("BPL", "2048")), steps, threads, out.ctypes.data))
 print(f"{workload} {voices} voices x {seconds:g} s, {len(ev)} events/step, {threads} worker threads; ms per step:")
 print("   push   begin  first-launch-ready  all-launches")
 for r in out:
