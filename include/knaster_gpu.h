@@ -146,6 +146,8 @@ typedef struct {
 } kgpu_graph_desc;
 
 #define KGPU_PLAN_FORCE_INTERPRETER 1u /* use the generic plan interpreter even if a fused kernel matches */
+#define KGPU_PLAN_NO_SCAN 2u           /* small saw -> SVF -> EnvAsr banks: keep the bit-exact one-lane-per-voice kernel instead of
+                                          the time-parallel scan kernel (render_sub_scan, <= 1e-4 on the filter) */
 
 /* SchedulingEvent (scheduling.rs:29-36) + Time (scheduling.rs:73-92) + ParameterValue
  * (parameters/types.rs:25-37).  Tokens are not supported (SchedulingToken::activate is

@@ -19,6 +19,7 @@ KGPU_OK = 0
 KGPU_ERR_INVALID, KGPU_ERR_UNSUPPORTED, KGPU_ERR_CUDA, KGPU_ERR_PARAMETER, KGPU_ERR_STATE = -1, -2, -3, -4, -5
 KGPU_GRAPH = -2
 KGPU_PLAN_FORCE_INTERPRETER = 1
+KGPU_PLAN_NO_SCAN = 2
 
 
 class KgpuError(RuntimeError):

@@ -119,6 +119,7 @@ struct kgpu_plan {
     uint64_t frame_clock = 0;
     bool rendered = false;
     bool force_interp = false;
+    bool no_scan = false;                   // KGPU_PLAN_NO_SCAN: keep small banks on the bit-exact one-lane-per-voice kernel
     std::vector<float> last_block;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
@@ -205,6 +206,7 @@ void choose_kernels(kgpu_plan *p) {
         Group &g = p->host.groups[gi];
         GroupDev &d = p->gd[gi];
         int recipe = p->force_interp ? -1 : match_fused_recipe(g.prog, p->host.block_size);
+        if (recipe == 0 && !p->no_scan && sub_scan_applies(g.n_voices, p->host.block_size)) recipe = 4;
         if (recipe == 2) // the block-table recipe needs every parameter change on a block boundary
             for (const TemplateNode &tn : g.tpl.nodes)
                 for (const kgpu_wrapper_desc &w : tn.wrappers)
@@ -525,6 +527,7 @@ int kgpu_plan_create(const kgpu_graph_desc *desc, kgpu_plan **out) {
         p = new kgpu_plan();
         p->host.build(*desc);
         p->force_interp = (desc->flags & KGPU_PLAN_FORCE_INTERPRETER) != 0;
+        p->no_scan = (desc->flags & KGPU_PLAN_NO_SCAN) != 0;
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
             cudaGetLastError();

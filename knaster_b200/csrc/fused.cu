@@ -87,7 +87,11 @@ template <class ENV> struct SubVoice {
 // wrap01, div_prep, div_rc, saw_eval: csrc/nodes.cuh (shared with the interpreter's fast path)
 
 #ifndef SUB_SUB
-#define SUB_SUB 16 // frames per straight-line group (16 or 32; 32 measured 1 % faster for twice the code)
+#define SUB_SUB 8 // frames per straight-line group (8, 16 or 32).  Measured, 16 384 voices x 10 s: 8 -> 13.65 ms, 16 -> 14.47 ms,
+                  // 32 -> 14.85 ms: the 8-frame group (~300 instructions, 4.8 KB) stays in the instruction cache
+#endif
+#ifndef SUB_MINB
+#define SUB_MINB 8 // __launch_bounds__ minimum CTAs per SM of the one-warp kernels (caps the registers per thread)
 #endif
 constexpr int SUBW_TILE = 2 * SUB_SUB; // render_sub_asr staging tile: two halves of SUB_SUB frames
 
@@ -496,6 +500,8 @@ struct EvCursor {
     }
 };
 
+#include "fused_scan.cuh" // recipe 4 "render_sub_scan": the same voice, one warp per voice, for small banks
+
 // The body of render_sub_asr / render_sub_seg: ENV = AsrEnv or SegEnv.
 template <class ENV, bool TAPS>
 KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
@@ -669,7 +675,7 @@ KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
 }
 
 template <bool TAPS>
-__global__ void __launch_bounds__(32, 8) render_sub_asr(FusedArgs a) {
+__global__ void __launch_bounds__(32, SUB_MINB) render_sub_asr(FusedArgs a) {
     __shared__ __align__(16) float st[SUBW_TILE * SUBW_PAD];
     render_sub_body<AsrEnv, TAPS>(a, st);
 }
@@ -1429,12 +1435,23 @@ const char *fused_recipe_name(int recipe) {
     case 1: return "render_fm2";
     case 2: return "render_add_wt";
     case 3: return "render_sub_seg";
+    case 4: return "render_sub_scan";
     default: return "render_interp";
     }
 }
 // recipe 1: two lanes per voice while that still leaves at most one warp per SM sub-partition (148 x 4)
 bool fm_two_lanes(uint32_t n_voices) { return (n_voices + FM_VPW - 1) / FM_VPW <= 148u * 4u; }
+// recipe 0 -> 4: a bank this small leaves most schedulers without a warp under one-lane-per-voice; one warp per voice
+// with the frames of a chunk across the lanes is faster up to ~4800 voices.  Chunks of 32 frames
+// must tile the block grid, so that a render is identical however it is split into launches.
+bool sub_scan_applies(uint32_t n_voices, uint32_t block_size) {
+    static const int force = [] { const char *e = getenv("KGPU_SUB_SCAN"); return e ? atoi(e) : -1; }(); // 0 never, 1 always (tests / measurements)
+    if (block_size % SCAN_CHUNK) return false;
+    if (force >= 0) return force != 0;
+    return n_voices <= 4096;
+}
 uint32_t fused_rows(int recipe, uint32_t n_voices, uint32_t n_ubus) {
+    if (recipe == 4) return n_voices * n_ubus;                // one partial row per voice
     if (recipe == 2) return add_wt_slices(n_voices) * n_ubus; // one partial row per voice slice
     if (recipe == 1 && fm_two_lanes(n_voices)) return ((n_voices + FM_VPW - 1) / FM_VPW) * n_ubus;
     return ((n_voices + 31) / 32) * n_ubus;                   // one partial row per warp
@@ -1456,6 +1473,18 @@ cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream) {
         return cudaGetLastError();
     }
     if (recipe == 2) return launch_add_wt(a, stream);
+    if (recipe == 4) {
+        // KGPU_SCAN_PIPE=0: the unpipelined form (pre-pass, then the frame-parallel half), kept for measurements
+        static const bool pipe = [] { const char *e = getenv("KGPU_SCAN_PIPE"); return !(e && *e == '0'); }();
+        if (pipe) {
+            if (a.n_taps) render_sub_scan<true, true><<<a.n_voices, 32, 0, stream>>>(a);
+            else render_sub_scan<false, true><<<a.n_voices, 32, 0, stream>>>(a);
+        } else {
+            if (a.n_taps) render_sub_scan<true, false><<<a.n_voices, 32, 0, stream>>>(a);
+            else render_sub_scan<false, false><<<a.n_voices, 32, 0, stream>>>(a);
+        }
+        return cudaGetLastError();
+    }
     if (recipe == 3) {
         const uint32_t nw = (a.n_voices + 31) / 32;
         if (a.n_taps) render_sub_seg<true><<<nw, 32, 0, stream>>>(a);

@@ -809,6 +809,7 @@ int match_fused_recipe(const DevProgram &, uint32_t) { return -1; }
 size_t fused_scratch_bytes(int, uint32_t, uint32_t, uint32_t) { return 0; }
 const char *fused_recipe_name(int) { return "render_interp"; }
 uint32_t fused_rows(int, uint32_t, uint32_t) { return 0; }
+bool sub_scan_applies(uint32_t, uint32_t) { return false; }
 cudaError_t launch_fused(int, const FusedArgs &, cudaStream_t) { return cudaErrorNotSupported; }
 #endif
 

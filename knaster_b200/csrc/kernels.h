@@ -56,6 +56,8 @@ struct FusedArgs {
     void *scratch;               // fused_scratch_bytes() bytes of device memory, private to the launch
     uint32_t *regs_out;          // recipe-internal: where a kernel leaves the launch-end registers (default: regs)
 };
+// recipe 0 (render_sub_asr) is replaced by recipe 4 (render_sub_scan) for banks this small (fused.cu)
+bool sub_scan_applies(uint32_t n_voices, uint32_t block_size);
 // number of partial rows a fused recipe produces for n_voices voices
 uint32_t fused_rows(int recipe, uint32_t n_voices, uint32_t n_ubus);
 cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream);

@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def render_bank(n_voices, seconds, n_blocks, blocks_per_launch=0, gain_scale=1.0, n_notes=8, seed=2002):
-    graph, proc = AudioProcessor.new(0, 2, AudioProcessorOptions())
+    graph, proc = AudioProcessor.new(0, 2, AudioProcessorOptions(no_scan=True))
     banks.subtractive_bank(graph, n_voices, seconds, seed=seed, n_notes=n_notes)
     if gain_scale != 1.0:  # WrMul's parameter ("wr_mul", index 4 of EnvAsr.wr_mul) on every envelope node
         from knaster_b200 import ugens as U
@@ -51,7 +51,9 @@ def oracle_render(build, n_blocks, outputs=1, block_size=64, taps=()):
 
 
 def gpu_render(build, n_blocks, outputs=1, block_size=64, blocks_per_launch=0, taps=True):
-    graph, proc = AudioProcessor.new(0, outputs, AudioProcessorOptions(block_size=block_size, sample_rate=SR))
+    # no_scan: the small banks of this file are edge cases of the one-lane-per-voice kernels (bit-exact); the scan kernel
+    # that small subtractive banks take by default has its own file, test_gpu_scan.py
+    graph, proc = AudioProcessor.new(0, outputs, AudioProcessorOptions(block_size=block_size, sample_rate=SR, no_scan=True))
     ids = build(graph)
     if taps:
         for i in ids:
@@ -252,7 +254,7 @@ def test_late_events_keep_arrival_order():
             env.param("t_restart").trig_at(at(0))
         return proc.render(20)
 
-    graph, proc = AudioProcessor.new(0, 1, AudioProcessorOptions())
+    graph, proc = AudioProcessor.new(0, 1, AudioProcessorOptions(no_scan=True))
     with graph.edit() as g:
         handles = _voice(g)
     gpu = run(proc, graph, handles)
@@ -278,7 +280,7 @@ def test_two_warp_kernel_variant_matches():
     outs = []
     for flag in ("0", "1"):
         path = os.path.join(ROOT, "gpurun_out", f"_two_warp_{flag}.npy") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else f"/tmp/_two_warp_{flag}.npy"
-        env = dict(os.environ, KGPU_SUB_TWO_WARPS=flag)
+        env = dict(os.environ, KGPU_SUB_TWO_WARPS=flag, KGPU_SUB_SCAN="0")
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
         outs.append(np.load(path))
         os.remove(path)
