@@ -8,8 +8,11 @@ pub mod ffi;
 
 use std::ffi::CStr;
 use std::os::raw::c_int;
+use std::sync::{Arc, Mutex};
 
+use knaster_core::{ParameterSmoothing, ParameterValue, Rate};
 use knaster_graph::graph::{Graph, GraphError, NodeKey};
+use knaster_graph::scheduling::{SchedulingEvent, Time};
 use slotmap::SecondaryMap;
 
 /// source index of an edge: a node, or the graph's own inputs (-2 = KGPU_GRAPH in include/knaster_gpu.h)
@@ -20,7 +23,47 @@ fn src(index: &SecondaryMap<NodeKey, i32>, source: knaster_graph::graph::NodeOrG
     }
 }
 
-pub struct GpuProcessor { plan: *mut ffi::kgpu_plan, block: usize, outputs: usize }
+/// The event path (knaster_graph/src/handle.rs:38-73): `SchedulingChannelSender::send` pushes a `SchedulingEvent` into an
+/// `rtrb` ring that GraphGen drains at the top of every block (graph_gen.rs:143-166).  `GpuEventSink` is the second sink
+/// INTEGRATION.md asks `SchedulingChannelSender` to carry: `send` converts the event to a `kgpu_event` (scheduling.rs:29-36
+/// field by field) and appends it to a vector that `GpuProcessor::run* / render` hands to `kgpu_plan_push_events` before
+/// rendering -- arrival order is kept, nothing is dropped for a full ring.  Any number of control threads
+/// may hold a clone, exactly like `Arc<Mutex<rtrb::Producer>>` today.
+#[derive(Clone)]
+pub struct GpuEventSink { queue: Arc<Mutex<Vec<ffi::kgpu_event>>>, index: Arc<SecondaryMap<NodeKey, i32>> }
+
+impl GpuEventSink {
+    /// `SchedulingChannelSender::send` for the GPU engine.
+    pub fn send(&self, ev: SchedulingEvent) -> Result<(), GraphError> {
+        if ev.token.is_some() { return Err(GraphError::UnsupportedOnGpu); }   // SchedulingToken::activate is todo!() (scheduling.rs:175-178)
+        let node = *self.index.get(ev.node_key).ok_or(GraphError::NodeNotFound)? as u32;
+        let (value_kind, value) = match ev.value {                            // parameters/types.rs:25-37
+            None => (0, 0.0),
+            Some(ParameterValue::Float(v)) => (1, v),
+            Some(ParameterValue::Trigger) => (2, 0.0),
+            Some(ParameterValue::Integer(i)) => (3, i.0 as f64),
+            Some(ParameterValue::Bool(b)) => (4, if b { 1.0 } else { 0.0 }),
+            Some(ParameterValue::Smoothing(..)) => return Err(GraphError::UnsupportedOnGpu), // travels in `smoothing`
+        };
+        let (smoothing_kind, smooth_seconds) = match ev.smoothing {           // parameters/types.rs:108-119
+            None => (0, 0.0),
+            Some(ParameterSmoothing::None) => (1, 0.0),
+            Some(ParameterSmoothing::Linear(s)) => (2, s),
+        };
+        let (time_kind, seconds, subsec) = match ev.time {                    // scheduling.rs:73-92, time.rs:25-28
+            None => (0, 0, 0),
+            Some(Time::At(s)) => (1, s.seconds(), s.subsecond_tesimals()),
+            Some(Time::After(s)) => (2, s.seconds(), s.subsecond_tesimals()),
+        };
+        let e = ffi::kgpu_event { node, param: ev.parameter as u32, value_kind, smoothing_kind, value, smooth_seconds,
+                                  smooth_rate: Rate::BlockRate as u32, time_kind, seconds, subsec, _pad: 0 };
+        self.queue.lock().unwrap_or_else(|p| p.into_inner()).push(e);
+        Ok(())
+    }
+}
+
+pub struct GpuProcessor { plan: *mut ffi::kgpu_plan, block: usize, outputs: usize,
+                          queue: Arc<Mutex<Vec<ffi::kgpu_event>>>, index: Arc<SecondaryMap<NodeKey, i32>> }
 
 impl GpuProcessor {
     /// Call after `graph.edit(..)` / `commit_changes()`; the graph must stay static afterwards.
@@ -50,15 +93,28 @@ impl GpuProcessor {
             nodes: nodes.as_ptr(), edges: edges.as_ptr(), param_edges: pedges.as_ptr() };
         let mut plan = std::ptr::null_mut();
         check(unsafe { ffi::kgpu_plan_create(&desc, &mut plan) })?;
-        Ok(Self { plan, block: graph.block_size(), outputs: graph.outputs() as usize })
+        Ok(Self { plan, block: graph.block_size(), outputs: graph.outputs() as usize,
+                  queue: Arc::new(Mutex::new(Vec::new())), index: Arc::new(index) })
+    }
+    /// The sender control threads use instead of (or beside) the rtrb producer; see `GpuEventSink`.
+    pub fn event_sink(&self) -> GpuEventSink { GpuEventSink { queue: self.queue.clone(), index: self.index.clone() } }
+    /// What GraphGen does at the top of a block (graph_gen.rs:143-166): everything sent so far reaches the engine, in send order.
+    fn drain_events(&mut self) -> Result<(), GraphError> {
+        let batch = std::mem::take(&mut *self.queue.lock().unwrap_or_else(|p| p.into_inner()));
+        if batch.is_empty() { return Ok(()); }
+        check(unsafe { ffi::kgpu_plan_push_events(self.plan, batch.as_ptr(), batch.len()) })
     }
     /// AudioProcessor::run_without_inputs (processor.rs:142-148)
-    pub fn run_without_inputs(&mut self) -> Result<(), GraphError> { check(unsafe { ffi::kgpu_render_block(self.plan) }) }
+    pub fn run_without_inputs(&mut self) -> Result<(), GraphError> {
+        self.drain_events()?;
+        check(unsafe { ffi::kgpu_render_block(self.plan) })
+    }
     /// AudioProcessor::output_block (processor.rs:182-184): [outputs][block] f32
     pub fn output_block(&mut self) -> &[f32] { unsafe { std::slice::from_raw_parts(ffi::kgpu_output_block(self.plan), self.block * self.outputs) } }
     /// Non-realtime render of n blocks: [n_blocks][outputs][block]
     pub fn render(&mut self, n_blocks: u64, out: &mut [f32]) -> Result<(), GraphError> {
         assert_eq!(out.len() as u64, n_blocks * (self.block * self.outputs) as u64);
+        self.drain_events()?;
         check(unsafe { ffi::kgpu_render(self.plan, n_blocks, out.as_mut_ptr()) })
     }
 }
