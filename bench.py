@@ -32,14 +32,15 @@ sys.path.insert(0, ROOT)
 
 SR, BLOCK = 48000, 64
 # algorithmic ops per voice-sample (Envelope: 7 f64 + cvt in place of EnvAsr's 5 + scale)
-W_FLOPS = {"subtractive": 40.0, "subtractive_seg": 42.0, "additive": 6.0, "fm": 15.0}
+W_FLOPS = {"subtractive": 40.0, "subtractive_seg": 42.0, "additive": 6.0, "fm": 15.0, "chain": 43.0}  # chain: + OnePoleLpf 3
 N_SM, FP32_LANES, XU_LANES, LDS_BANKS = 148, 128, 16, 32
-DEFAULT_VOICES = {"subtractive": 16384, "subtractive_seg": 16384, "additive": 4096, "fm": 8192}
+DEFAULT_VOICES = {"subtractive": 16384, "subtractive_seg": 16384, "additive": 4096, "fm": 8192, "chain": 16384}
 WORKLOAD_NAMES = {
     "subtractive": "subtractive polysynth: saw -> SvfFilter lowpass -> EnvAsr -> VCA, sample-accurate note events",
     "subtractive_seg": "subtractive polysynth, Envelope variant: saw -> SvfFilter lowpass -> Envelope (A/D/R segments) -> VCA, sample-accurate note events",
     "additive": "additive bank: SinWt partials with per-partial amp smoothing",
     "fm": "FM bank: SinNumeric -> SinNumeric audio-rate freq",
+    "chain": "a voice shape without a hand-written recipe: saw -> SvfFilter lowpass -> OnePoleLpf -> EnvAsr -> VCA, on the kernel generated for its template",
 }
 
 
@@ -120,7 +121,7 @@ def workload_config(args, world):
     `cpu_baseline.sample` / `sample_seconds_per_step`)."""
     return {"workload": WORKLOAD_NAMES[args.workload], "voices_per_gpu": args.voices, "total_voices": args.voices * world,
             "seconds_per_step": args.seconds, "blocks_per_step": int(round(args.seconds * SR)) // BLOCK, "block_size": BLOCK,
-            "sample_rate": SR, "notes_per_voice_per_step": 8 if args.workload.startswith("subtractive") else 0,
+            "sample_rate": SR, "notes_per_voice_per_step": 8 if args.workload.startswith("subtractive") or args.workload == "chain" else 0,
             "l2": "per-voice state + events stream once per launch; working set changes every launch (no L2 reuse to flush)"}
 
 
@@ -474,7 +475,7 @@ def parity_and_bus_check(env, args, n_taps=64):
 def other_workloads(env, args, peaks, peak_src):
     """N = 1: the other BASELINE configs, 3 device-resident steps each, every one against its own bound."""
     out = {}
-    for wl in ("additive", "fm", "subtractive_seg", "subtractive"):
+    for wl in ("additive", "fm", "subtractive_seg", "subtractive", "chain"):
         if wl == args.workload:
             continue
         r = measure(env, args, wl, DEFAULT_VOICES[wl], args.seconds, steps=3, warmup=3, with_e2e=True)
@@ -510,7 +511,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="subtractive", choices=["subtractive", "subtractive_seg", "additive", "fm"])
+    ap.add_argument("--workload", default="subtractive", choices=["subtractive", "subtractive_seg", "additive", "fm", "chain"])
     ap.add_argument("--voices", type=int, default=0, help="voices per GPU (default: the BASELINE config's)")
     ap.add_argument("--seconds", type=float, default=10.0, help="audio seconds per step")
     ap.add_argument("--chunks", type=int, default=10, help="NCCL reduce chunks per step (N>1, --bus nccl)")

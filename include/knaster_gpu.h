@@ -146,6 +146,8 @@ typedef struct {
 } kgpu_graph_desc;
 
 #define KGPU_PLAN_FORCE_INTERPRETER 1u /* use the generic plan interpreter even if a fused kernel matches */
+#define KGPU_PLAN_FORCE_JIT 4u         /* generate a kernel per voice template (csrc/jit.cpp) even for banks below the size at which the
+                                          compilation pays for itself (default: >= 256 voices; KGPU_JIT=0 turns generation off) */
 #define KGPU_PLAN_NO_SCAN 2u           /* small saw -> SVF -> EnvAsr banks: keep the bit-exact one-lane-per-voice kernel instead of
                                           the time-parallel scan kernel (render_sub_scan, <= 1e-4 on the filter) */
 

@@ -20,6 +20,7 @@ KGPU_ERR_INVALID, KGPU_ERR_UNSUPPORTED, KGPU_ERR_CUDA, KGPU_ERR_PARAMETER, KGPU_
 KGPU_GRAPH = -2
 KGPU_PLAN_FORCE_INTERPRETER = 1
 KGPU_PLAN_NO_SCAN = 2
+KGPU_PLAN_FORCE_JIT = 4
 
 
 class KgpuError(RuntimeError):
@@ -144,6 +145,7 @@ def lib() -> C.CDLL:
     L.kgpu_debug_simulate.argtypes = [C.POINTER(GraphDesc), vp, C.c_size_t, u64, u64, vp, C.c_size_t,
                                       C.POINTER(C.c_size_t), vp, C.POINTER(PlanInfo)]
     L.kgpu_debug_init_reg.argtypes = [C.POINTER(GraphDesc), u32, u32, C.POINTER(u32)]
+    L.kgpu_debug_jit_compile.argtypes = [C.POINTER(GraphDesc), u32, C.POINTER(u32), C.POINTER(u32)]
     _lib = L
     return L
 
@@ -217,3 +219,13 @@ def debug_simulate(graph, events: np.ndarray, n_blocks: int, blocks_per_call: in
     evs = [(e.group, e.voice, e.node, e.op, e.reg, e.value, e.frame) for e in out[: n.value]]
     nds = [(d.group, d.voice, d.local, d.reg_base) for d in nodes[: gd.n_nodes]]
     return evs, nds, info.as_dict()
+
+
+def jit_compile(graph, tap_outputs: bool = False):
+    """Host-only: generate + compile (NVRTC -> the cubin cache next to the library; no GPU needed) the kernels of every voice
+    template of `graph` that has no hand-written recipe.  Returns (generated, already cached)."""
+    L = lib()
+    gd, _keep = graph_desc(graph)
+    a, b = C.c_uint32(0), C.c_uint32(0)
+    check(L.kgpu_debug_jit_compile(C.byref(gd), 1 if tap_outputs else 0, C.byref(a), C.byref(b)))
+    return a.value, b.value

@@ -145,6 +145,54 @@ def fm_bank(graph: Graph, n_voices: int, seed: int = 3003, voice_offset: int = 0
     return out_ids
 
 
+def chain_bank(graph: Graph, n_voices: int, seconds: float, seed: int = 5005, n_notes: int = 8, voice_offset: int = 0,
+               total_voices: int = 0) -> List[int]:
+    """A voice shape NO hand-written recipe matches: PolyBlep(Sawtooth) -> SvfFilter(Low) -> OnePoleLpf -> * EnvAsr.wr_mul(1/N),
+    note events like subtractive_bank.  What renders it is the kernel generated for its template (csrc/jit.cpp)."""
+    total = total_voices or n_voices
+    sr = graph.sample_rate
+    n_frames = int(round(seconds * sr))
+    r = _rng(seed)
+    midi = r.integers(36, 85, total)
+    fc = r.uniform(200.0, 8000.0, total)
+    q = r.uniform(0.5, 8.0, total)
+    lp = r.uniform(1000.0, 12000.0, total)
+    att = r.uniform(0.002, 0.05, total)
+    rel = r.uniform(0.05, 0.5, total)
+    on = np.sort(r.integers(0, max(1, n_frames), (total, n_notes)), axis=1)
+    note_midi = r.integers(36, 85, (total, n_notes))
+    note_fc = r.uniform(200.0, 8000.0, (total, n_notes))
+    off = on + (r.uniform(0.1, 0.4, (total, n_notes)) * sr).astype(np.int64)
+    sl = slice(voice_offset, voice_offset + n_voices)
+    midi, fc, q, lp, att, rel, on, note_midi, note_fc, off = (x[sl] for x in (midi, fc, q, lp, att, rel, on, note_midi, note_fc, off))
+    f0 = 440.0 * 2.0 ** ((midi - 69) / 12.0)
+    note_f = 440.0 * 2.0 ** ((note_midi - 69) / 12.0)
+    saw_ids, svf_ids, env_ids, out_ids = [], [], [], []
+    with graph.edit() as g:
+        for i in range(n_voices):
+            saw = g.push(U.PolyBlep(U.Waveform.Sawtooth, float(f0[i])).precise_timing(8))
+            svf = g.push(U.SvfFilter(U.SvfFilterType.Low, float(fc[i]), float(q[i]), 0.0).precise_timing(8))
+            opl = g.push(U.OnePoleLpf(float(lp[i])))
+            env = g.push(U.EnvAsr(float(att[i]), float(rel[i])).wr_mul(1.0 / total).precise_timing(8))
+            sig = (saw >> svf >> opl) * env
+            sig.out([0, 0]).to_graph_out()
+            saw_ids.append(saw.id()); svf_ids.append(svf.id()); env_ids.append(env.id()); out_ids.append(sig._outputs[0][0])
+    saw_a, svf_a, env_a = (np.asarray(x, dtype=np.uint32) for x in (saw_ids, svf_ids, env_ids))
+    V, K = n_voices, n_notes
+    rep = lambda a: np.repeat(a, K)
+    FLOAT, TRIG = 1, 2
+    nodes = np.stack([rep(env_a), rep(saw_a), rep(svf_a), rep(env_a)], 1).reshape(V, K * 4)
+    params = np.tile(np.array([3, 0, 0, 2]), (V, K, 1)).reshape(V, K * 4)
+    kinds = np.tile(np.array([TRIG, FLOAT, FLOAT, TRIG]), (V, K, 1)).reshape(V, K * 4)
+    vals = np.stack([np.zeros(V * K), note_f.reshape(-1), note_fc.reshape(-1), np.zeros(V * K)], 1).reshape(V, K * 4)
+    frames = np.stack([on.reshape(-1), on.reshape(-1), on.reshape(-1), off.reshape(-1)], 1).reshape(V, K * 4)
+    order = np.argsort(frames, axis=1, kind="stable")
+    tk = lambda x: np.take_along_axis(x, order, 1).reshape(-1)
+    keep = tk(frames) < n_frames
+    graph.schedule_bulk(tk(nodes)[keep], tk(params)[keep], tk(kinds)[keep], tk(vals)[keep], tk(frames)[keep].astype(np.uint64))
+    return out_ids
+
+
 def bank_builder(workload: str, seconds: float, seed=None):
     """The bench / parity workloads of BASELINE.json by name: returns build(graph, n_voices, voice_offset,
     total_voices) -> one tap node id per voice (the voice's pre-mix signal).  voice_offset / total_voices select a
@@ -159,6 +207,8 @@ def bank_builder(workload: str, seconds: float, seed=None):
             return additive_bank(graph, nv, seconds, voice_offset=offset, total_voices=total, **kw)
         if workload == "fm":
             return fm_bank(graph, nv, voice_offset=offset, total_voices=total, **kw)
+        if workload == "chain":
+            return chain_bank(graph, nv, seconds, voice_offset=offset, total_voices=total, **kw)
         raise ValueError(f"unknown workload {workload}")
 
     return build

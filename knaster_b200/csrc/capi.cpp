@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/knaster_gpu.h"
+#include "jit.hpp"
 #include "kernels.h"
 #include "plan.hpp"
 
@@ -99,8 +100,10 @@ struct GroupDev {
     std::vector<std::pair<uint32_t, uint32_t>> pinned; // (local node, channel) kept live for taps
     uint32_t rows = 0, row0 = 0;
     uint32_t chunk = 1;
-    int recipe = -1;
+    int recipe = -1;   // fused.cu recipes 0..4, RECIPE_JIT, or -1 = the plan interpreter
+    JitKernel jit;     // RECIPE_JIT: the kernel generated for this group's voice template (jit.cpp)
 };
+constexpr int RECIPE_JIT = 5;
 } // namespace
 
 struct kgpu_plan {
@@ -119,6 +122,8 @@ struct kgpu_plan {
     uint64_t frame_clock = 0;
     bool rendered = false;
     bool force_interp = false;
+    bool force_jit = false;                 // KGPU_PLAN_FORCE_JIT
+    std::string jit_note;                   // why the last template that could have been generated was not (diagnostics)
     bool no_scan = false;                   // KGPU_PLAN_NO_SCAN: keep small banks on the bit-exact one-lane-per-voice kernel
     std::vector<float> last_block;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -219,10 +224,27 @@ void choose_kernels(kgpu_plan *p) {
                     if ((uint32_t)std::get<0>(o) == pin.first && std::get<1>(o) == pin.second) on_bus = true;
                 if (!on_bus) recipe = -1;
             }
+        // no hand-written recipe: a kernel generated for this voice template (register-resident, bit-identical to the
+        // interpreter); banks too small to pay for a compilation stay on the interpreter
+        jit_unload(d.jit);
+        static const bool jit_on = [] { const char *e = getenv("KGPU_JIT"); return !(e && *e == '0'); }();
+        static const uint32_t jit_min = [] { const char *e = getenv("KGPU_JIT_MIN_VOICES"); return e ? (uint32_t)atoi(e) : 256u; }();
+        if (recipe < 0 && !p->force_interp && jit_on && (g.n_voices >= jit_min || p->force_jit)) {
+            std::vector<uint16_t> tapped;
+            for (auto &pin : d.pinned) {
+                const uint16_t slot = g.slot_of[pin.first][pin.second];
+                if (std::find(tapped.begin(), tapped.end(), slot) == tapped.end()) tapped.push_back(slot);
+            }
+            const std::string src = jit_source(g.prog, tapped);
+            std::vector<char> cubin;
+            std::string err;
+            if (!src.empty() && jit_cubin(src, cubin, err) && jit_load(cubin, d.jit, err)) recipe = RECIPE_JIT;
+            else if (!err.empty()) p->jit_note = err;
+        }
         d.recipe = recipe;
         d.chunk = recipe >= 0 ? 1 : pick_chunk(p->host.block_size, g.prog.n_regs, g.prog.n_slots);
         g.fused_recipe = recipe;
-        g.kernel_name = recipe >= 0 ? fused_recipe_name(recipe) : "render_interp";
+        g.kernel_name = recipe == RECIPE_JIT ? "render_jit" : recipe >= 0 ? fused_recipe_name(recipe) : "render_interp";
     }
     layout_rows(p);
 }
@@ -436,7 +458,10 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
                     p->scratch.ensure(sb);
                 }
                 a.scratch = p->scratch.p;
-                CUDA_TRY(launch_fused(d.recipe, a, stream));
+                if (d.recipe == RECIPE_JIT) {
+                    void *args[] = {&a};
+                    CUDA_TRY(cudaLaunchKernel((const void *)d.jit.kernel, dim3((g.n_voices + 31) / 32), dim3(32), args, 0, stream));
+                } else CUDA_TRY(launch_fused(d.recipe, a, stream));
             } else {
                 InterpArgs a{};
                 a.prog = d.prog.p; a.regs = d.regs.p; a.n_voices = g.n_voices; a.events = d_ev; a.ev_off = d_off;
@@ -528,6 +553,7 @@ int kgpu_plan_create(const kgpu_graph_desc *desc, kgpu_plan **out) {
         p->host.build(*desc);
         p->force_interp = (desc->flags & KGPU_PLAN_FORCE_INTERPRETER) != 0;
         p->no_scan = (desc->flags & KGPU_PLAN_NO_SCAN) != 0;
+        p->force_jit = (desc->flags & KGPU_PLAN_FORCE_JIT) != 0;
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
             cudaGetLastError();
@@ -576,6 +602,7 @@ void kgpu_plan_destroy(kgpu_plan *p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     for (GroupDev &d : p->gd) {
         d.prog.release(); d.regs.release(); d.events.release(); d.ev_off.release(); d.taps.release();
+        jit_unload(d.jit);
     }
     p->d_events_all.release(); p->d_off_all.release();
     for (Staging &sg : p->staging) {
@@ -1305,6 +1332,45 @@ int kgpu_debug_host_bench(const kgpu_graph_desc *desc, const kgpu_event *events,
                 if (e.time_kind == 1) e.seconds += step_seconds;
         }
         return total_ev ? KGPU_OK : KGPU_OK;
+    } catch (const Error &e) {
+        return fail(e.code, e.msg);
+    }
+}
+
+/* Host-only: generate and compile (NVRTC -> cubin cache, no device needed) the kernel of every voice template of `desc`
+ * that has no hand-written recipe.  *n_generated / *n_cached count them; fails with the compiler's log otherwise. */
+int kgpu_debug_jit_compile(const kgpu_graph_desc *desc, uint32_t tap_outputs, uint32_t *n_generated, uint32_t *n_cached) {
+    try {
+        HostPlan hp;
+        hp.build(*desc);
+        uint32_t ng = 0, nc = 0;
+        for (Group &g : hp.groups) {
+            if (match_fused_recipe(g.prog, hp.block_size) >= 0) continue;
+            std::vector<uint16_t> tapped;
+            if (tap_outputs) { // what kgpu_plan_add_tap on a voice's bus output does: keep that value slot live to the end of the frame
+                std::vector<std::pair<uint32_t, uint32_t>> pinned;
+                for (auto &o : g.tpl.outs) {
+                    std::pair<uint32_t, uint32_t> pin{(uint32_t)std::get<0>(o), std::get<1>(o)};
+                    if (std::find(pinned.begin(), pinned.end(), pin) == pinned.end()) pinned.push_back(pin);
+                }
+                recompile_group_slots(g, hp.sample_rate, pinned);
+                for (auto &pin : pinned) {
+                    const uint16_t slot = g.slot_of[pin.first][pin.second];
+                    if (std::find(tapped.begin(), tapped.end(), slot) == tapped.end()) tapped.push_back(slot);
+                }
+            }
+            const std::string src = jit_source(g.prog, tapped);
+            if (src.empty()) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "jit: the generator does not cover a node of this template");
+            std::vector<char> cubin;
+            std::string err;
+            bool cached = false;
+            if (!jit_cubin(src, cubin, err, &cached)) KGPU_THROW(KGPU_ERR_INVALID, "%s", err.c_str());
+            ng++;
+            nc += cached;
+        }
+        if (n_generated) *n_generated = ng;
+        if (n_cached) *n_cached = nc;
+        return KGPU_OK;
     } catch (const Error &e) {
         return fail(e.code, e.msg);
     }

@@ -28,6 +28,8 @@ int kgpu_debug_simulate(const kgpu_graph_desc *desc, const kgpu_event *events, s
 /* Times the host half of n_steps render calls (no device): see capi.cpp.  out_ms: [n_steps][4]. */
 int kgpu_debug_host_bench(const kgpu_graph_desc *desc, const kgpu_event *events, size_t n_events, uint64_t n_blocks, uint64_t bpl,
                           uint32_t n_steps, uint32_t n_threads, double *out_ms);
+/* Generate + compile (NVRTC, cubin cache) the kernels of the voice templates of `desc` that have no hand-written recipe. */
+int kgpu_debug_jit_compile(const kgpu_graph_desc *desc, uint32_t tap_outputs, uint32_t *n_generated, uint32_t *n_cached);
 /* initial register value of a node register after init() */
 int kgpu_debug_init_reg(const kgpu_graph_desc *desc, uint32_t node, uint32_t reg_offset, uint32_t *value);
 

@@ -20,6 +20,7 @@
 #include "dev.h"
 #include "kernels.h"
 #include "nodes.cuh"
+#include "evcursor.cuh"
 #include "plan.hpp"
 
 namespace kgpu {
@@ -89,6 +90,14 @@ template <class ENV> struct SubVoice {
 #ifndef SUB_SUB
 #define SUB_SUB 8 // frames per straight-line group (8, 16 or 32).  Measured, 16 384 voices x 10 s: 8 -> 13.65 ms, 16 -> 14.47 ms,
                   // 32 -> 14.85 ms: the 8-frame group (~300 instructions, 4.8 KB) stays in the instruction cache
+#endif
+#ifndef SUB_ROT
+#define SUB_ROT 1     // rotated main loop: filter(group g) beside oscillator + envelope(group g + 1), see sub_produce / sub_consume
+#endif
+#ifndef SUB_COMPACT
+#define SUB_COMPACT 0 // (measured: slower, 14.7 ms against 14.1 -- an exact frame costs more than a 4- / 1-frame group) the frames between the last whole group and the limit frame run through ONE rolled exact-frame loop
+                      // instead of 4- and 1-frame straight-line groups: a limit costs ~1900 cycles of mostly instruction
+                      // fetch (r2a profile: 2.7 % of the instructions, 9.8 % of the time), so the path is kept small
 #endif
 #ifndef SUB_MINB
 #define SUB_MINB 8 // __launch_bounds__ minimum CTAs per SM of the one-warp kernels (caps the registers per thread)
@@ -443,62 +452,64 @@ KN_DEV void sub_group_fast(SubVoice<ENV> &s, const typename ENV::D &d, float omd
     }
 }
 
+// The same group cut where no state crosses, for the rotated main loop (SUB_ROT): sub_produce advances the phase and the
+// envelope by N frames and leaves the N saw samples and envelope gains in registers; sub_consume runs the filter, the VCA
+// and the staging stores on them (and the previous group's mix-bus sum).  The loop body is consume(group g) followed by
+// produce(group g + 1): the filter's dependency chain starts at the top of the basic block on operands that are already
+// there, and the independent work of the next group fills its latency gaps up to the last instruction -- the one-piece
+// group spent 8 % of its cycles waiting at its head (first saw sample) and tail (last filter steps, r2a profile).
+template <class ENV, int N>
+KN_DEV void sub_produce(SubVoice<ENV> &s, const typename ENV::D &d, float omd, float rc, float (&x)[N], float (&env)[N]) {
+    float ph[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        ph[k] = s.t;
+        s.t = wrap01(s.t + s.dt); // inc(), polyblep.rs:232-235
+    }
+    s.e.template group<N>(d, env);
+#pragma unroll
+    for (int k = 0; k < N; k++) x[k] = saw_eval(ph[k], s.dt, omd, rc);
+}
+template <class ENV, bool LP, int N, bool TAPS>
+KN_DEV void sub_consume(SubVoice<ENV> &s, const float (&x)[N], const float (&env)[N], float *strow, float *tap,
+                        const float *sum_src, float *sum_dst, bool sum_store) {
+    float tot;
+    if (N == 32) {
+        tot = sum16(sum_src) + sum16(sum_src + 16);
+    } else if (N == 16) {
+        const float h = sum16(sum_src);
+        tot = h + __shfl_xor_sync(0xFFFFFFFFu, h, 16);
+    } else {
+        const float q = sum8(sum_src);
+        const float h = q + __shfl_xor_sync(0xFFFFFFFFu, q, 8);
+        tot = h + __shfl_xor_sync(0xFFFFFFFFu, h, 16);
+    }
+    if (sum_store) *sum_dst = tot;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        const float v0 = x[k];
+        float y;
+        if (LP) {
+            const float v3 = v0 - s.ic2;
+            const float v1 = s.a1 * s.ic1 + s.a2 * v3;
+            const float v2 = (s.ic2 + s.a2 * s.ic1) + s.a3 * v3;
+            s.ic1 = __fmaf_rn(2.0f, v1, -s.ic1);
+            s.ic2 = __fmaf_rn(2.0f, v2, -s.ic2);
+            y = v2;
+        } else {
+            y = svf_tick(v0, s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2);
+        }
+        const float o = y * env[k];
+        strow[k * SUBW_PAD] = o;
+        if (TAPS && tap) tap[k] = o;
+    }
+}
+
 // per-lane validity of the straight-line formulation
 template <class ENV> KN_DEV bool sub_lane_fast(const SubVoice<ENV> &s) {
     return s.dt >= 9.5367431640625e-7f && s.dt < 0.25f && s.t >= 0.0f && s.t < 1.0f && !s.use_sin && s.wf == 0u;
 }
 template <class ENV> KN_DEV bool sub_lane_lp(const SubVoice<ENV> &s) { return s.m0 == 0.0f && s.m1 == 0.0f && s.m2 == 1.0f; }
-
-// one parameter event (16 B) through the read-only path
-KN_DEV DevEvent ldg_event(const DevEvent *p) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p));
-    DevEvent e;
-    e.frame = q.x;
-    e.node = (uint16_t)(q.y & 0xFFFFu);
-    e.op = (uint16_t)(q.y >> 16);
-    e.reg = q.z;
-    e.value = q.w;
-    return e;
-}
-
-// Per-lane event cursor with the next FOUR events in registers.  e[0] is complete by construction;
-// the slot freed by a pop is refilled at once, so a load has four pops (or thousands of frames) to
-// land -- a scheduler that holds a single warp has nothing else to hide a load behind.  Events
-// arrive by H2D copy, i.e. from DRAM: the 32-byte sectors 16 events ahead are pulled into L2 early.
-struct EvCursor {
-    const DevEvent *events;
-    uint32_t cur, end, next_frame;
-    DevEvent e0, e1, e2, e3;
-    static constexpr uint32_t AHEAD = 16;
-    KN_DEV void prefetch(uint32_t i) const {
-        if (i < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(events + i));
-    }
-    KN_DEV void init(const DevEvent *ev, const uint32_t *off, uint32_t v, bool on) {
-        events = ev;
-        cur = end = 0;
-        next_frame = 0xFFFFFFFFu;
-        e0 = e1 = e2 = e3 = DevEvent{};
-        if (ev && on) {
-            cur = off[v];
-            end = off[v + 1];
-            if (cur < end) e0 = ldg_event(events + cur);
-            if (cur + 1 < end) e1 = ldg_event(events + cur + 1);
-            if (cur + 2 < end) e2 = ldg_event(events + cur + 2);
-            if (cur + 3 < end) e3 = ldg_event(events + cur + 3);
-            for (uint32_t i = 4; i < AHEAD; i += 2) prefetch(cur + i);
-            if (cur < end) next_frame = e0.frame;
-        }
-    }
-    KN_DEV void pop() {
-        cur++;
-        e0 = e1;
-        e1 = e2;
-        e2 = e3;
-        next_frame = cur < end ? e0.frame : 0xFFFFFFFFu;
-        if (cur + 3 < end) e3 = ldg_event(events + cur + 3);
-        prefetch(cur + AHEAD);
-    }
-};
 
 #include "fused_scan.cuh" // recipe 4 "render_sub_scan": the same voice, one warp per voice, for small banks
 
@@ -588,6 +599,25 @@ KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
             bool pending = false;
             // lane = (staged frame r, voice group c of 32 / (32 / SUB_SUB) voices)
             const uint32_t r = lane & (SUB_SUB - 1u), c = lane / SUB_SUB, cw = SUB_SUB == 32 ? 32u : (SUB_SUB == 16 ? 16u : 8u);
+#if SUB_ROT
+            float gx[SUB_SUB], ge[SUB_SUB];
+            sub_produce<ENV, SUB_SUB>(s, d, omd, rc, gx, ge);      // the group at f; the oscillator / envelope state is now at f + SUB_SUB
+#pragma unroll 1
+            while (f + 2 * SUB_SUB <= lim) {
+                __syncwarp();
+                sub_consume<ENV, LP, SUB_SUB, TAPS>(s, gx, ge, st + (half * SUB_SUB) * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr,
+                                                    st + ((half ^ 1u) * SUB_SUB + r) * SUBW_PAD + c * cw, prow + (f - SUB_SUB + r), pending && c == 0);
+                sub_produce<ENV, SUB_SUB>(s, d, omd, rc, gx, ge);
+                pending = true;
+                half ^= 1u;
+                f += SUB_SUB;
+            }
+            __syncwarp();
+            sub_consume<ENV, LP, SUB_SUB, TAPS>(s, gx, ge, st + (half * SUB_SUB) * SUBW_PAD + lane, TAPS && tap ? tap + f : nullptr,
+                                                st + ((half ^ 1u) * SUB_SUB + r) * SUBW_PAD + c * cw, prow + (f - SUB_SUB + r), pending && c == 0);
+            half ^= 1u;
+            f += SUB_SUB;
+#else
 #pragma unroll 1
             do {
                 __syncwarp();
@@ -598,18 +628,24 @@ KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
                 half ^= 1u;
                 f += SUB_SUB;
             } while (f + SUB_SUB <= lim);
+#endif
             rbase = (half ^ 1u) * SUB_SUB;
             rows = SUB_SUB;
         }
+#if !SUB_COMPACT
         run_groups(lp_tag, std::integral_constant<int, 4>{}, lim);
         run_groups(lp_tag, std::integral_constant<int, 1>{}, lim);
+#endif
     };
     for (;;) {
         const uint32_t lim = min(limit, NF);
         if (all_lp) run_fast(std::true_type{}, lim);
         else run_fast(std::false_type{}, lim);
         if (f >= NF) break;
-        // frame `limit`: events are applied, then the frame runs with the envelope state machine checked
+        // frame `limit`: events are applied, then the frame runs with the envelope state machine checked.  (SUB_COMPACT: the
+        // frames between the last whole group and `limit` come through here as well -- nothing is due in them and the
+        // envelope cannot move, the exact frame is simply the general one -- and keep `limit` as it is.)
+        const bool at_limit = f >= limit;
         if (f >= next_ev) {
             bool touched = false;
             while (ec.next_frame <= f) { // events are sorted by (frame, node, arrival)
@@ -651,8 +687,10 @@ KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
         }
         rows += 1;
         f += 1;
-        s.e.derive(d);
-        limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(f));
+        if (at_limit) {
+            s.e.derive(d);
+            limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(f));
+        }
     }
     if (rows) flush();
     if (active) {

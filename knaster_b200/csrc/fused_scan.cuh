@@ -98,22 +98,43 @@ __global__ void __launch_bounds__(32, 16) render_sub_scan(FusedArgs a) {
     const uint32_t NF = a.n_frames;
     const bool writer = lane == 0;
 
-    // the pre-pass of one chunk: the two f32 recurrences, sequentially, in the reference's rounding order.  Every lane
+    // The pre-pass of one chunk: the two f32 recurrences, sequentially, in the reference's rounding order.  Every lane
     // runs the same chain (the stores are predicated); lane 0 leaves (t_k, et_k) in `dst`.
-    auto prepass = [&](float2 *dst) {
+    // The phase step t' = wrap01(t + dt) is three dependent instructions (add, compare, subtract the 0/1 flag: ~16
+    // cycles of latency per frame, and latency is all a one-voice warp has).  A wrap happens once per 1/dt frames, so
+    // the chain is first run WITHOUT the wrap -- 32 dependent adds -- and accepted if its last value is still below 1:
+    // then no step wrapped (dt > 0 in the straight-line domain), `x - 0` is `x`, and the values are the reference's to the
+    // bit.  Otherwise (a wrap inside the chunk) prepass_exact redoes the chunk with the wrap.  Returns whether accepted.
+    float pre_t0 = 0.0f;   // the phase at the first frame of the chunk prepass_spec ran on (for prepass_exact)
+    auto prepass_spec = [&](float2 *dst) -> bool {
         float t = s.t, et = s.e.et;
+        pre_t0 = t;
 #pragma unroll
         for (int k = 0; k < SCAN_CHUNK; k++) {
             if (writer) dst[k] = make_float2(t, et);
-            t = wrap01(t + s.dt);      // inc(), polyblep.rs:232-235
+            t = t + s.dt;              // inc() without its wrap, polyblep.rs:232-235
             et = et + d.delta;         // envelopes.rs:58-66 with the state fixed over the chunk
         }
         s.t = t;
         s.e.et = (d.att || d.rel) ? et : s.e.et;
+        return t < 1.0f;
     };
-    // whether the chunk starting at f0 can take the scan path, given the state at its first frame
+    auto prepass_exact = [&](float2 *dst) { // the phase column again, with the wrap; the envelope column is already right
+        float t = pre_t0;
+#pragma unroll 8
+        for (int k = 0; k < SCAN_CHUNK; k++) {
+            if (writer) dst[k].x = t;
+            t = wrap01(t + s.dt);
+        }
+        s.t = t;
+    };
+    // Whether the chunk starting at f0 takes the scan path: a function of the state at its first frame and of the events
+    // inside it only, so that a render is identical however it is split into launches (the scan path and the exact path
+    // round the filter differently).  lane_fast: the straight-line domain (sawtooth below sr / 4, dt in range) -- moves
+    // with parameter events only; t stays in [0, 1).
+    bool lane_fast = sub_lane_fast(s);
     auto chunk_fast = [&](uint32_t f0) {
-        return f0 + SCAN_CHUNK <= NF && next_frame >= f0 + SCAN_CHUNK && sub_lane_fast(s) && s.e.safe_frames() >= (uint32_t)SCAN_CHUNK;
+        return lane_fast && f0 + SCAN_CHUNK <= NF && next_frame >= f0 + SCAN_CHUNK && s.e.safe_frames() >= (uint32_t)SCAN_CHUNK;
     };
     // the frame-parallel half of a chunk: lane k renders frame f0 + k from (t_k, et_k)
     auto parallel = [&](const float2 pk, uint32_t f0) {
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(32, 16) render_sub_scan(FusedArgs a) {
     for (uint32_t f0 = 0; f0 < NF; f0 += SCAN_CHUNK) {
         if (have || chunk_fast(f0)) {
             if (!have) {
-                prepass(pre[buf]);
+                if (!prepass_spec(pre[buf])) prepass_exact(pre[buf]);
                 __syncwarp();
             }
             const float2 pk = pre[buf][lane];
@@ -167,8 +188,9 @@ __global__ void __launch_bounds__(32, 16) render_sub_scan(FusedArgs a) {
             // basic block as this chunk's frame-parallel half (shuffle latencies): each fills the other's stalls.  Its
             // inputs are all known here -- the state at the next chunk's first frame is where this chunk's pre-pass ended.
             if (PIPE && chunk_fast(f0 + SCAN_CHUNK)) {
-                prepass(pre[buf ^ 1]);
+                const bool ok = prepass_spec(pre[buf ^ 1]);
                 parallel(pk, f0);
+                if (!ok) prepass_exact(pre[buf ^ 1]);
                 have = true;
             } else {
                 parallel(pk, f0);
@@ -200,6 +222,7 @@ __global__ void __launch_bounds__(32, 16) render_sub_scan(FusedArgs a) {
                 rc = div_prep(s.dt);
             }
             s.e.derive(d);
+            lane_fast = sub_lane_fast(s);
             if (f0 + lane < NF) {
                 prow[f0 + lane] = out;
                 if (TAPS && tap) tap[f0 + lane] = out;

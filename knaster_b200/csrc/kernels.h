@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "dev.h"
+#include "launch_args.h" // struct FusedArgs (also compiled by NVRTC for the generated kernels, jit.cpp)
 
 namespace kgpu {
 
@@ -35,27 +36,7 @@ cudaError_t launch_wait_flag(const uint32_t *flag, uint32_t value, uint32_t *tim
 cudaError_t launch_sum_slots(const float *slots, size_t slot_stride, uint32_t world, const uint32_t *flags, uint32_t flag_stride, uint32_t epoch,
                              float *out, size_t n, uint32_t *timeout_flag, cudaStream_t stream);
 
-// fused bank kernels (fused.cu)
-struct FusedArgs {
-    const DevProgram *prog;
-    uint32_t *regs;
-    uint32_t n_voices;
-    const DevEvent *events;
-    const uint32_t *ev_off;
-    uint32_t n_frames;
-    float *partials;
-    uint32_t row0;
-    const DevTap *taps;
-    uint32_t n_taps;
-    float *tap_out;
-    uint64_t tap_stride;
-    uint64_t tap_frame0;
-    const float *sine_table;
-    const DevProgram *host_prog; // host copy of *prog (launch-time decisions)
-    uint32_t block_size;
-    void *scratch;               // fused_scratch_bytes() bytes of device memory, private to the launch
-    uint32_t *regs_out;          // recipe-internal: where a kernel leaves the launch-end registers (default: regs)
-};
+// fused bank kernels (fused.cu): struct FusedArgs is in launch_args.h
 // recipe 0 (render_sub_asr) is replaced by recipe 4 (render_sub_scan) for banks this small (fused.cu)
 bool sub_scan_applies(uint32_t n_voices, uint32_t block_size);
 // number of partial rows a fused recipe produces for n_voices voices

@@ -31,6 +31,7 @@ class AudioProcessorOptions:
     log_channel_capacity: int = 100   # kept for source compatibility
     device: int = -1                  # CUDA device ordinal, -1 = current
     force_interpreter: bool = False   # render with the generic plan interpreter only
+    force_jit: bool = False           # generate a kernel per voice template even for small banks (default: >= 256 voices)
     no_scan: bool = False             # small saw -> SVF -> EnvAsr banks: bit-exact one-lane-per-voice kernel instead of the scan kernel
 
 
@@ -80,6 +81,8 @@ class AudioProcessor:
         flags = _ffi.KGPU_PLAN_FORCE_INTERPRETER if self.options.force_interpreter else 0
         if self.options.no_scan:
             flags |= _ffi.KGPU_PLAN_NO_SCAN
+        if self.options.force_jit:
+            flags |= _ffi.KGPU_PLAN_FORCE_JIT
         gd, _keep = _ffi.graph_desc(g, self.options.device, flags)
         plan = C.c_void_p(None)
         _ffi.check(self._lib.kgpu_plan_create(C.byref(gd), C.byref(plan)))
