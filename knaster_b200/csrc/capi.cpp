@@ -900,7 +900,7 @@ void validate_snapshot(const kgpu_plan *p, const kgpu_snapshot *s) {
             const HostNode &a = s->host[gi][i], &b = g.host[i];
             if (a.kind != b.kind || a.dev_kind != b.dev_kind || a.reg != b.reg || a.n_seg != b.n_seg || a.base_params != b.base_params ||
                 a.has_smooth != b.has_smooth || a.has_precise != b.has_precise || a.smooth_level != b.smooth_level ||
-                a.precise_level != b.precise_level || a.wr.size() != b.wr.size())
+                a.precise_level != b.precise_level || a.wr.size() != b.wr.size() || a.ar_regs != b.ar_regs)
                 bad("node layout");
             if (a.kind == KGPU_SVF ? a.mode > 8 : a.mode != b.mode) bad("node mode");
             for (size_t l = 0; l < a.wr.size(); l++) {
@@ -1017,7 +1017,7 @@ void kgpu_snapshot_destroy(kgpu_snapshot *s) { delete s; }
 extern "C++" {
 namespace {
 constexpr uint64_t SNAP_MAGIC = 0x50414E5355504B47ull; // "GKPUSNAP"
-constexpr uint32_t SNAP_VERSION = 2;
+constexpr uint32_t SNAP_VERSION = 3;
 struct Writer {
     uint8_t *buf;
     uint64_t cap, pos = 0;
@@ -1068,7 +1068,7 @@ void put_node(Writer &w, const HostNode &h) {
     w.pod(h.f0); w.pod(h.f1); w.pod(h.f2); w.pod(h.d0);
     for (float c : h.svf_coef) w.pod(c);
     w.pod<uint8_t>(h.has_smooth); w.pod<uint8_t>(h.has_precise); w.pod(h.smooth_level); w.pod(h.precise_level);
-    w.pod<uint8_t>(h.ramp_active); w.pod(h.ramp_list_pos);
+    w.pod<uint8_t>(h.ramp_active); w.pod<uint8_t>(h.ar_regs); w.pod(h.ramp_list_pos);
     for (uint16_t d : h.nd) w.pod(d);
     w.pod<uint64_t>(h.wr.size());
     for (const WrapSim &x : h.wr) {
@@ -1090,7 +1090,7 @@ void get_node(Reader &r, HostNode &h) {
     h.f0 = r.pod<float>(); h.f1 = r.pod<float>(); h.f2 = r.pod<float>(); h.d0 = r.pod<double>();
     for (float &c : h.svf_coef) c = r.pod<float>();
     h.has_smooth = r.pod<uint8_t>() != 0; h.has_precise = r.pod<uint8_t>() != 0; h.smooth_level = r.pod<int8_t>(); h.precise_level = r.pod<int8_t>();
-    h.ramp_active = r.pod<uint8_t>() != 0; h.ramp_list_pos = r.pod<uint32_t>();
+    h.ramp_active = r.pod<uint8_t>() != 0; h.ar_regs = r.pod<uint8_t>() != 0; h.ramp_list_pos = r.pod<uint32_t>();
     for (uint16_t &d : h.nd) d = r.pod<uint16_t>();
     const uint64_t nw = r.pod<uint64_t>();
     if (nw > 64) KGPU_THROW(KGPU_ERR_INVALID, "kgpu_snapshot_deserialize: bad wrapper count");

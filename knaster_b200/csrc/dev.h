@@ -11,6 +11,7 @@ enum DevKind : uint8_t {
     DK_SINNUM = 2,   // regs: 0 phase 1 phase_offset 2 phase_increment (f32)               osc.rs:222-226
     DK_POLYBLEP = 3, // regs: 0 t 1 dt 2 use_sin(u32) 3 pulse_width 4 waveform(u32)        polyblep.rs:128-135
     DK_SVF = 4,      // regs: 0 ic1eq 1 ic2eq 2 a1 3 a2 4 a3 5 m0 6 m1 7 m2                svf.rs:44-59
+                     //       with an audio-rate route into cutoff / q / gain also: 8 cutoff 9 q 10 gain_db 11 type(u32)
     DK_ONEPOLE_LP = 5, // regs: 0 last_output 1 a0 2 b1                                    onepole.rs:13-17
     DK_ONEPOLE_HP = 6,
     DK_ENVASR = 7,   // regs: 0 state(u32) 1 t 2 attack_rate 3 release_rate 4 release_scale envelopes.rs:19-28
@@ -29,7 +30,7 @@ enum DevKind : uint8_t {
     DK_RANDLIN = 18, // regs: 0,1 rng 2 current_value 3 current_change_width 4 phase 5 phase_step  noise.rs:156-217
     DK_PAN2 = 19,    // regs: 0 left_gain 1 right_gain (the host evaluates fast::cos / fast::sin when pan changes)  pan.rs:12-38
 };
-enum { REGS_SINWT = 3, REGS_SINNUM = 3, REGS_POLYBLEP = 5, REGS_SVF = 8, REGS_ONEPOLE = 3, REGS_ENV = 5,
+enum { REGS_SINWT = 3, REGS_SINNUM = 3, REGS_POLYBLEP = 5, REGS_SVF = 8, REGS_SVF_AR = 12, REGS_ONEPOLE = 3, REGS_ENV = 5,
        REGS_ENVELOPE_BASE = 8, REGS_ENVELOPE_PER_SEG = 6, REGS_CONST = 1, REGS_PHASOR = 4,
        REGS_WHITE = 2, REGS_PINK = 14, REGS_BROWN = 3, REGS_RANDLIN = 6, REGS_PAN2 = 2 };
 enum { ASR_STOPPED = 0, ASR_ATTACKING = 1, ASR_SUSTAINING = 2, ASR_RELEASING = 3 };
@@ -47,7 +48,12 @@ enum ArCode : uint8_t {
     AR_POLYBLEP_FREQ = 5, // dt = v / sr                       polyblep.rs:163-165,181-184
     AR_REG0 = 6,          // regs[0] = v (Constant.value, TestInPlusParam.number)
     AR_POLYBLEP_PW = 7,   // pulse_width = v                   polyblep.rs:167-170
-    AR_POST = 8,          // AR_POST + k: value of arithmetic wrapper k = v (wr_mul)   math.rs:92-98
+    // routes into filter parameters: the coefficients are recomputed every frame, as knaster's per-frame param_apply does
+    AR_SVF_CUTOFF = 8,    // cutoff = v; set_coeffs            svf.rs:81-89,146-242
+    AR_SVF_Q = 9,         // q = v; set_coeffs                 svf.rs:91-99
+    AR_SVF_GAIN = 10,     // gain_db = v; set_coeffs           svf.rs:101-109
+    AR_ONEPOLE_CUTOFF = 11, // b1 = exp(-2 pi v / sr), a0 = 1 - b1   onepole.rs:35-46,135-139
+    AR_POST = 32,         // AR_POST + k: value of arithmetic wrapper k = v (wr_mul)   math.rs:92-98
 };
 
 constexpr int MAX_NODES = 24;   // nodes per voice template

@@ -324,12 +324,28 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, SVF_STORE, SVF_LOAD)
                     AR_POST_ROUTES(f)
+                    // audio-rate routes into cutoff / q / gain (regs 8..10, type in 11): set_coeffs every frame, svf.rs:81-109
+                    bool recalc = false;
+                    for (int ai = 0; ai < dn.n_ar; ai++) {
+                        const uint32_t code = dn.ar_code[ai];
+                        if (code >= AR_SVF_CUTOFF && code <= AR_SVF_GAIN) {
+                            sreg[(rb + 8 + (code - AR_SVF_CUTOFF)) * 32] = __float_as_uint(sval[(dn.ar_slot[ai] * CH + f) * 32]);
+                            recalc = true;
+                        }
+                    }
+                    if (recalc)
+                        svf_coeffs_dev(sreg[(rb + 11) * 32], __uint_as_float(sreg[(rb + 8) * 32]), __uint_as_float(sreg[(rb + 9) * 32]),
+                                       __uint_as_float(sreg[(rb + 10) * 32]), sr, a1, a2, a3, m0, m1, m2);
                     float x = is >= 0 ? sval[(is * CH + f) * 32] : 0.f;
                     float y = svf_tick(x, ic1, ic2, a1, a2, a3, m0, m1, m2);
                     EMIT(f, 0, y)
                 }
                 }
                 SVF_STORE;
+                if (dn.n_ar) { // routed coefficients persist like a param_apply would
+                    sreg[(rb + 2) * 32] = __float_as_uint(a1); sreg[(rb + 3) * 32] = __float_as_uint(a2); sreg[(rb + 4) * 32] = __float_as_uint(a3);
+                    sreg[(rb + 5) * 32] = __float_as_uint(m0); sreg[(rb + 6) * 32] = __float_as_uint(m1); sreg[(rb + 7) * 32] = __float_as_uint(m2);
+                }
                 break;
             }
             case DK_ONEPOLE_LP:
@@ -348,12 +364,15 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     EVENTS_AT(f, sreg[rb * 32] = __float_as_uint(y1),
                               (y1 = __uint_as_float(sreg[rb * 32]), a0 = __uint_as_float(sreg[(rb + 1) * 32]), b1 = __uint_as_float(sreg[(rb + 2) * 32])))
                     AR_POST_ROUTES(f)
+                    for (int ai = 0; ai < dn.n_ar; ai++)
+                        if (dn.ar_code[ai] == AR_ONEPOLE_CUTOFF) onepole_coeffs_dev(sval[(dn.ar_slot[ai] * CH + f) * 32], sr, a0, b1); // onepole.rs:135-139
                     float x = is >= 0 ? sval[(is * CH + f) * 32] : 0.f;
                     float y = hp ? onepole_hp_tick(x, y1, a0, b1) : onepole_lp_tick(x, y1, a0, b1);
                     EMIT(f, 0, y)
                 }
                 }
                 sreg[rb * 32] = __float_as_uint(y1);
+                if (dn.n_ar) { sreg[(rb + 1) * 32] = __float_as_uint(a0); sreg[(rb + 2) * 32] = __float_as_uint(b1); }
                 break;
             }
             case DK_ENVASR:

@@ -317,6 +317,10 @@ void ugen_param_apply(Sim &s, uint32_t param, const PV &v, uint64_t frame) {
         else if (param == 2) h.f2 = (float)v.f;
         else if (param == 3) h.mode = (uint32_t)(int64_t)v.f;
         else if (param != 4) break;
+        if (h.ar_regs && param < 4) { // the device recomputes the coefficients from these every frame (audio-rate route)
+            if (param == 3) s.set_u(frame, r + 11, h.mode);
+            else s.set_f(frame, r + 8 + param, param == 0 ? h.f0 : (param == 1 ? h.f1 : h.f2));
+        }
         float c[6];
         svf_coeffs(h.mode, h.f0, h.f1, h.f2, sr, c);
         for (int i = 0; i < 6; i++)
@@ -617,6 +621,12 @@ uint8_t ar_code_for(const TemplateNode &tn, uint32_t param, int ar_level) {
         if (param == 1) return AR_POLYBLEP_PW;
         break;
     case KGPU_CONSTANT: case KGPU_TEST_IN_PLUS_PARAM: if (param == 0) return AR_REG0; break;
+    case KGPU_SVF:
+        if (param == 0) return AR_SVF_CUTOFF;
+        if (param == 1) return AR_SVF_Q;
+        if (param == 2) return AR_SVF_GAIN;
+        break;
+    case KGPU_ONEPOLE_LPF: case KGPU_ONEPOLE_HPF: if (param == 0) return AR_ONEPOLE_CUTOFF; break;
     default: break;
     }
     KGPU_THROW(KGPU_ERR_UNSUPPORTED, "audio-rate route to parameter %u of ugen kind %u is not supported yet", param, tn.kind);
@@ -651,6 +661,15 @@ void compile_template(Group &g, uint32_t sample_rate, const std::vector<std::pai
         dn.n_seg = (uint16_t)tn.n_segments;
         dn.looping = (uint8_t)(tn.flags & 1);
         reg += (uint32_t)ki.n_regs;
+        // an SvfFilter whose cutoff / q / gain is driven at audio rate keeps those parameters (and its type) in registers
+        // too: the device recomputes the coefficients every frame
+        {
+            bool has_ar = false;
+            for (auto &w : tn.wrappers) has_ar |= w.kind == KGPU_WR_AR_PARAMS;
+            bool svf_route = false;
+            for (auto &pe : tn.par) svf_route |= std::get<0>(pe) <= 2;
+            if (tn.kind == KGPU_SVF && has_ar && svf_route) reg += REGS_SVF_AR - REGS_SVF;
+        }
         int ar_level = -1;
         for (size_t l = 0; l < tn.wrappers.size(); l++) {
             uint32_t k = tn.wrappers[l].kind;
@@ -1087,6 +1106,11 @@ void HostPlan::build(const kgpu_graph_desc &d) {
                     h.f0 = (float)nd.args[0]; h.f1 = (float)nd.args[1]; h.f2 = (float)nd.args[2];
                     svf_coeffs(h.mode, h.f0, h.f1, h.f2, sr, h.svf_coef);
                     for (int i = 0; i < 6; i++) R(r + 2 + i, v) = fbits(h.svf_coef[i]);
+                    for (int k = 0; k < dn.n_ar; k++)
+                        if (dn.ar_code[k] >= AR_SVF_CUTOFF && dn.ar_code[k] <= AR_SVF_GAIN) h.ar_regs = true;
+                    if (h.ar_regs) {
+                        R(r + 8, v) = fbits(h.f0); R(r + 9, v) = fbits(h.f1); R(r + 10, v) = fbits(h.f2); R(r + 11, v) = h.mode;
+                    }
                     break;
                 }
                 case KGPU_ONEPOLE_LPF: case KGPU_ONEPOLE_HPF: { // onepole.rs:118-129,157-167,35-46

@@ -70,6 +70,7 @@ struct HostNode {
     bool has_smooth = false, has_precise = false;
     int8_t smooth_level = -1, precise_level = -1;
     bool ramp_active = false;
+    bool ar_regs = false;    // SvfFilter with an audio-rate route into cutoff / q / gain: the parameters live on the device too
     uint32_t ramp_list_pos = 0;
     // WrPreciseTiming::next_delay of a node on the fast path (NodeStatic::fast): sticky, App. B1.  Such a node keeps
     // no WrapSim at all -- everything else about its wrapper stack is static and lives in the template's NodeStatic.
