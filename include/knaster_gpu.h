@@ -270,7 +270,7 @@ int kgpu_snapshot_deserialize(const void *buf, uint64_t size, kgpu_snapshot **ou
  * Every rank must make the same sequence of kgpu_render* calls.  Only rank 0's output buffer
  * receives audio (the sum over all ranks); the other ranks' output buffers are left untouched.
  * world <= 1 or root_buffer == NULL detaches. */
-#define KGPU_PEER_MAX_LAUNCHES 4096
+#define KGPU_PEER_MAX_LAUNCHES 16384 /* 10 s at one launch per 64-frame block (configs[4] read literally) is 7500 */
 uint64_t kgpu_peer_bus_header_bytes(uint32_t world);
 uint64_t kgpu_peer_bus_bytes(uint32_t world, uint64_t floats_per_rank);
 int kgpu_plan_set_peer_bus(kgpu_plan *plan, uint32_t rank, uint32_t world, void *root_buffer, uint64_t buffer_bytes);
