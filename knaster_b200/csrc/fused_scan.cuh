@@ -19,6 +19,13 @@
 //       <= 1e-4 against the reference (BASELINE.json's budget for scan-reordered IIR filters; measured
 //       ~1e-6), where render_sub_asr is bit-identical.
 //
+// Measured (256 voices x 10 s, one warp per scheduler): 6.7 ms against 13.0 ms for render_sub_asr.  The chunk is latency-bound:
+// the frame-parallel half is a ~320-cycle dependent path (saw, 5 shuffle rounds, state fix-up) and the pre-pass a ~530-cycle
+// one (32 x add / compare / subtract); software-pipelining them against each other (PIPE) took 8.1 -> 6.7 ms.  Tried and
+// reverted, both parity-clean: running the phase chain without its wrap and redoing only the chunks (later: only the
+// frames) behind a wrap -- 7.1 ms, the redo's extra branches and barriers cost what the shorter chain saved; two chunks
+// per iteration with independent scans -- 10.0 ms.
+//
 // Chunks that hold a parameter event, may move the envelope's state machine, or lie outside the
 // straight-line domain (other waveforms, dt >= 1/4, ...) run the reference-order per-frame code on
 // all lanes instead (a few per note), so events and envelope transitions stay sample-exact.
@@ -98,43 +105,22 @@ __global__ void __launch_bounds__(32, 16) render_sub_scan(FusedArgs a) {
     const uint32_t NF = a.n_frames;
     const bool writer = lane == 0;
 
-    // The pre-pass of one chunk: the two f32 recurrences, sequentially, in the reference's rounding order.  Every lane
+    // the pre-pass of one chunk: the two f32 recurrences, sequentially, in the reference's rounding order.  Every lane
     // runs the same chain (the stores are predicated); lane 0 leaves (t_k, et_k) in `dst`.
-    // The phase step t' = wrap01(t + dt) is three dependent instructions (add, compare, subtract the 0/1 flag: ~16
-    // cycles of latency per frame, and latency is all a one-voice warp has).  A wrap happens once per 1/dt frames, so
-    // the chain is first run WITHOUT the wrap -- 32 dependent adds -- and accepted if its last value is still below 1:
-    // then no step wrapped (dt > 0 in the straight-line domain), `x - 0` is `x`, and the values are the reference's to the
-    // bit.  Otherwise (a wrap inside the chunk) prepass_exact redoes the chunk with the wrap.  Returns whether accepted.
-    float pre_t0 = 0.0f;   // the phase at the first frame of the chunk prepass_spec ran on (for prepass_exact)
-    auto prepass_spec = [&](float2 *dst) -> bool {
+    auto prepass = [&](float2 *dst) {
         float t = s.t, et = s.e.et;
-        pre_t0 = t;
 #pragma unroll
         for (int k = 0; k < SCAN_CHUNK; k++) {
             if (writer) dst[k] = make_float2(t, et);
-            t = t + s.dt;              // inc() without its wrap, polyblep.rs:232-235
+            t = wrap01(t + s.dt);      // inc(), polyblep.rs:232-235
             et = et + d.delta;         // envelopes.rs:58-66 with the state fixed over the chunk
         }
         s.t = t;
         s.e.et = (d.att || d.rel) ? et : s.e.et;
-        return t < 1.0f;
     };
-    auto prepass_exact = [&](float2 *dst) { // the phase column again, with the wrap; the envelope column is already right
-        float t = pre_t0;
-#pragma unroll 8
-        for (int k = 0; k < SCAN_CHUNK; k++) {
-            if (writer) dst[k].x = t;
-            t = wrap01(t + s.dt);
-        }
-        s.t = t;
-    };
-    // Whether the chunk starting at f0 takes the scan path: a function of the state at its first frame and of the events
-    // inside it only, so that a render is identical however it is split into launches (the scan path and the exact path
-    // round the filter differently).  lane_fast: the straight-line domain (sawtooth below sr / 4, dt in range) -- moves
-    // with parameter events only; t stays in [0, 1).
-    bool lane_fast = sub_lane_fast(s);
+    // whether the chunk starting at f0 can take the scan path, given the state at its first frame
     auto chunk_fast = [&](uint32_t f0) {
-        return lane_fast && f0 + SCAN_CHUNK <= NF && next_frame >= f0 + SCAN_CHUNK && s.e.safe_frames() >= (uint32_t)SCAN_CHUNK;
+        return f0 + SCAN_CHUNK <= NF && next_frame >= f0 + SCAN_CHUNK && sub_lane_fast(s) && s.e.safe_frames() >= (uint32_t)SCAN_CHUNK;
     };
     // the frame-parallel half of a chunk: lane k renders frame f0 + k from (t_k, et_k)
     auto parallel = [&](const float2 pk, uint32_t f0) {
@@ -180,7 +166,7 @@ __global__ void __launch_bounds__(32, 16) render_sub_scan(FusedArgs a) {
     for (uint32_t f0 = 0; f0 < NF; f0 += SCAN_CHUNK) {
         if (have || chunk_fast(f0)) {
             if (!have) {
-                if (!prepass_spec(pre[buf])) prepass_exact(pre[buf]);
+                prepass(pre[buf]);
                 __syncwarp();
             }
             const float2 pk = pre[buf][lane];
@@ -188,9 +174,8 @@ __global__ void __launch_bounds__(32, 16) render_sub_scan(FusedArgs a) {
             // basic block as this chunk's frame-parallel half (shuffle latencies): each fills the other's stalls.  Its
             // inputs are all known here -- the state at the next chunk's first frame is where this chunk's pre-pass ended.
             if (PIPE && chunk_fast(f0 + SCAN_CHUNK)) {
-                const bool ok = prepass_spec(pre[buf ^ 1]);
+                prepass(pre[buf ^ 1]);
                 parallel(pk, f0);
-                if (!ok) prepass_exact(pre[buf ^ 1]);
                 have = true;
             } else {
                 parallel(pk, f0);
@@ -222,7 +207,6 @@ __global__ void __launch_bounds__(32, 16) render_sub_scan(FusedArgs a) {
                 rc = div_prep(s.dt);
             }
             s.e.derive(d);
-            lane_fast = sub_lane_fast(s);
             if (f0 + lane < NF) {
                 prow[f0 + lane] = out;
                 if (TAPS && tap) tap[f0 + lane] = out;
