@@ -276,10 +276,19 @@ def test_unsupported_shapes_are_rejected_not_faked():
     g = Graph(0, 1, 64, SR)
     with g.edit() as e:
         lfo = e.push(kn.SinWt(3.0))
+        env = e.push(kn.EnvAsr(0.01, 0.1).ar_params())
+        env.link("attack_time", lfo * 0.001 + 0.01)
+        (e.push(kn.SinWt(100.0)) * env).to_graph_out()
+    expect_error(g, _ffi.KGPU_ERR_UNSUPPORTED)          # audio-rate route into an envelope time: not built
+
+    g = Graph(0, 1, 64, SR)                             # ... into filter parameters it is (round 2): the plan compiles
+    with g.edit() as e:
+        lfo = e.push(kn.SinWt(3.0))
         f = e.push(kn.SvfFilter(kn.SvfFilterType.Low, 500.0, 1.0, 0.0).ar_params())
         f.link("cutoff_freq", lfo * 100.0 + 500.0)
         e.push(kn.SinWt(100.0)).to(f).to_graph_out()
-    expect_error(g, _ffi.KGPU_ERR_UNSUPPORTED)          # audio-rate route into filter coefficients: not built yet
+    _evs, _nodes, info = _ffi.debug_simulate(g, g.take_events(), 4)
+    assert info["n_voices"] == 1
 
     g = Graph(0, 1, 64, SR)
     with g.edit() as e:
