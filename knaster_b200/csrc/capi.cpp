@@ -116,6 +116,11 @@ struct kgpu_plan {
     DevBuf<float> out;
     DevBuf<float> sine;
     DevBuf<float> tap_out;
+    // internal signals (plan.hpp HostPlan::signal_level): [signal][frames of the launch], reduced level by level
+    DevBuf<float> signals;
+    DevBuf<uint32_t> sig_which;             // device: the signals of level 0, then level 1, ... (sig_level_off indexes it)
+    std::vector<uint32_t> sig_level_off;    // [max_level + 2]
+    std::vector<uint32_t> level_rows_end;   // [max_level + 1]: partial rows of the groups up to and including that level
     DevBuf<uint8_t> scratch;               // fused_scratch_bytes() of the largest group, reused launch after launch
     uint32_t n_rows = 0, n_taps = 0;
     uint64_t tap_frames = 0;
@@ -201,6 +206,22 @@ void layout_rows(kgpu_plan *p) {
         row += d.rows;
     }
     p->n_rows = row;
+    // groups are sorted by level: the rows of the levels <= L are a prefix
+    const int max_level = p->host.max_level;
+    p->level_rows_end.assign((size_t)max_level + 1, 0);
+    for (uint32_t gi = 0; gi < p->gd.size(); gi++) {
+        const int lv = p->host.groups[gi].tpl.level;
+        for (int l = lv; l <= max_level; l++) p->level_rows_end[l] = std::max(p->level_rows_end[l], p->gd[gi].row0 + p->gd[gi].rows);
+    }
+    std::vector<uint32_t> which;
+    p->sig_level_off.assign((size_t)max_level + 2, 0);
+    for (int l = 0; l <= max_level; l++) {
+        for (uint32_t sg = 0; sg < p->host.signal_level.size(); sg++)
+            if (p->host.signal_level[sg] == l) which.push_back(sg);
+        p->sig_level_off[l + 1] = (uint32_t)which.size();
+    }
+    p->sig_which.ensure(std::max<size_t>(1, which.size()));
+    if (!which.empty()) CUDA_TRY(cudaMemcpyAsync(p->sig_which.p, which.data(), which.size() * 4, cudaMemcpyHostToDevice, p->stream));
     p->row_mask.ensure(std::max<size_t>(1, mask.size()));
     if (!mask.empty()) CUDA_TRY(cudaMemcpyAsync(p->row_mask.p, mask.data(), mask.size() * 4, cudaMemcpyHostToDevice, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
@@ -354,6 +375,11 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
     for (GroupDev &d : p->gd) chunks.push_back(d.chunk);
 
     const bool peer = p->peer_world > 1;
+    const uint32_t n_signals = (uint32_t)p->host.signal_level.size();
+    if (n_signals) {
+        if (peer) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "a plan with internal signals (post-mix nodes, sources shared between voices) cannot be sharded over a peer bus");
+        p->signals.ensure((size_t)n_signals * std::min<uint64_t>(bpl, n_blocks) * bs);
+    }
     if (peer) {
         if ((uint64_t)total_frames * n_out > p->peer_slot_floats)
             KGPU_THROW(KGPU_ERR_INVALID, "peer bus holds %llu floats per rank, this render needs %llu", (unsigned long long)p->peer_slot_floats,
@@ -439,6 +465,17 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
         for (uint32_t gi = 0; gi < p->gd.size(); gi++, piece++) {
             Group &g = p->host.groups[gi];
             GroupDev &d = p->gd[gi];
+            // a level's groups are done: the signals they complete are reduced before the next level's voices read them
+            if (n_signals && gi > 0 && g.tpl.level != p->host.groups[gi - 1].tpl.level) {
+                const int lv = p->host.groups[gi - 1].tpl.level;
+                const uint32_t w0 = p->sig_level_off[lv], w1 = p->sig_level_off[lv + 1];
+                if (w1 > w0) {
+                    mark(1, true);
+                    CUDA_TRY(launch_reduce_signals(p->partials.p, p->row_mask.p, p->level_rows_end[lv], nf, p->signals.p, n_out, p->sig_which.p + w0, w1 - w0, stream));
+                    mark(1, false);
+                    p->kernel_launches++;
+                }
+            }
             const bool any = !p->ce.piece_any.empty() && p->ce.piece_any[piece];
             const DevEvent *ev_base = was_prepared ? p->d_events_all.p : p->d_events_pp[launch & 1].p;
             const uint32_t *off_base = was_prepared ? p->d_off_all.p : p->d_off_pp[launch & 1].p;
@@ -452,6 +489,7 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
                 a.taps = d.taps.p; a.n_taps = (uint32_t)d.host_taps.size(); a.tap_out = p->tap_out.p;
                 a.tap_stride = total_frames; a.tap_frame0 = done * bs; a.sine_table = p->sine.p;
                 a.host_prog = &g.prog; a.block_size = bs;
+                a.ext = n_signals ? p->signals.p : nullptr; a.ext_stride = nf;
                 const size_t sb = fused_scratch_bytes(d.recipe, g.n_voices, nf, bs);
                 if (sb > p->scratch.cap) {
                     CUDA_TRY(cudaStreamSynchronize(stream)); // a queued launch may still use the old buffer
@@ -468,6 +506,7 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
                 a.n_frames = nf; a.chunk = d.chunk; a.partials = p->partials.p; a.row0 = d.row0;
                 a.taps = d.taps.p; a.n_taps = (uint32_t)d.host_taps.size(); a.tap_out = p->tap_out.p;
                 a.tap_stride = total_frames; a.tap_frame0 = done * bs; a.sine_table = p->sine.p;
+                a.ext = n_signals ? p->signals.p : nullptr; a.ext_stride = nf;
                 CUDA_TRY(launch_interp(a, g.prog.n_regs, g.prog.n_slots, stream));
             }
             mark(0, false);
@@ -621,7 +660,7 @@ void kgpu_plan_destroy(kgpu_plan *p) {
         if (e) cudaEventDestroy(e);
     if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
     if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
-    p->scratch.release();
+    p->scratch.release(); p->signals.release(); p->sig_which.release();
     p->partials.release(); p->row_mask.release(); p->out.release(); p->sine.release(); p->tap_out.release();
     for (cudaEvent_t e : p->kev) cudaEventDestroy(e);
     for (cudaEvent_t e : p->out_ev) cudaEventDestroy(e);

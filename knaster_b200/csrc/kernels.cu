@@ -157,9 +157,12 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
         _Pragma("unroll") for (int k = 0; k < 16; k++) y_[k] = (EXPR_);                \
         _Pragma("unroll") for (int k = 0; k < 16; k++) sval[(o0_ * CH + g0_ + k) * 32] = y_[k] * g_; \
     }
+// the value a node reads: a value slot of the voice (>= 0), the permanent zero channel (-1), or an internal signal of the plan
+// (<= -2: sums of voices read by nodes, sources shared between voices -- a.ext[signal][frame of the launch], the same for every voice)
+#define RDV(slot_, f_) ((slot_) >= 0 ? sval[((slot_) * CH + (f_)) * 32] : ((slot_) == -1 ? 0.f : a.ext[(size_t)(-2 - (slot_)) * a.ext_stride + c0 + (f_)]))
 #define LOAD16(x_, slot_)                                                              \
     float x_[16];                                                                      \
-    _Pragma("unroll") for (int k = 0; k < 16; k++) x_[k] = (slot_) >= 0 ? sval[((slot_) * CH + g0_ + k) * 32] : 0.f;
+    _Pragma("unroll") for (int k = 0; k < 16; k++) x_[k] = RDV(slot_, g0_ + k);
 #define EVENTS_AT(f_, STORE_, LOAD_)                                                   \
     if (evc && L.next_node == n && L.next_frame <= c0 + (f_)) {                        \
         STORE_;                                                                        \
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
     }
 #define AR_POST_ROUTES(f_)                                                             \
     for (int ai = 0; ai < dn.n_ar; ai++)                                               \
-        if (dn.ar_code[ai] >= AR_POST) pv[dn.ar_code[ai] - AR_POST] = sval[(dn.ar_slot[ai] * CH + (f_)) * 32];
+        if (dn.ar_code[ai] >= AR_POST) pv[dn.ar_code[ai] - AR_POST] = RDV(dn.ar_slot[ai], f_);
 #define EMIT(f_, ch_, y_)                                                              \
     {                                                                                  \
         float _y = (y_);                                                               \
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, sreg[rb * 32] = phase, (phase = sreg[rb * 32], off = sreg[(rb + 1) * 32], inc = sreg[(rb + 2) * 32]))
                     for (int ai = 0; ai < dn.n_ar; ai++) {
-                        float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
+                        float x = RDV(dn.ar_slot[ai], f);
                         if (dn.ar_code[ai] == AR_SINWT_FREQ) inc = kn_sat_u32(__dmul_rn((double)x, sinwt_k));
                         else if (dn.ar_code[ai] == AR_SINWT_OFFSET) off = kn_sat_u32(__dmul_rn((double)x, 65536.0));
                         else pv[dn.ar_code[ai] - AR_POST] = x;
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                               (phase = __uint_as_float(sreg[rb * 32]), off = __uint_as_float(sreg[(rb + 1) * 32]),
                                inc = __uint_as_float(sreg[(rb + 2) * 32])))
                     for (int ai = 0; ai < dn.n_ar; ai++) {
-                        float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
+                        float x = RDV(dn.ar_slot[ai], f);
                         if (dn.ar_code[ai] == AR_SINNUM_FREQ) inc = x / sr; // osc.rs:240-242
                         else if (dn.ar_code[ai] == AR_SINNUM_OFFSET) off = x;
                         else pv[dn.ar_code[ai] - AR_POST] = x;
@@ -286,7 +289,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                               (t = __uint_as_float(sreg[rb * 32]), dt = __uint_as_float(sreg[(rb + 1) * 32]), use_sin = sreg[(rb + 2) * 32],
                                pw = __uint_as_float(sreg[(rb + 3) * 32]), wf = sreg[(rb + 4) * 32]))
                     for (int ai = 0; ai < dn.n_ar; ai++) {
-                        float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
+                        float x = RDV(dn.ar_slot[ai], f);
                         if (dn.ar_code[ai] == AR_POLYBLEP_FREQ) {
                             dt = x / sr;
                             use_sin = (dt * sr >= sr / 4.0f) ? 1u : 0u;
@@ -329,14 +332,14 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     for (int ai = 0; ai < dn.n_ar; ai++) {
                         const uint32_t code = dn.ar_code[ai];
                         if (code >= AR_SVF_CUTOFF && code <= AR_SVF_GAIN) {
-                            sreg[(rb + 8 + (code - AR_SVF_CUTOFF)) * 32] = __float_as_uint(sval[(dn.ar_slot[ai] * CH + f) * 32]);
+                            sreg[(rb + 8 + (code - AR_SVF_CUTOFF)) * 32] = __float_as_uint(RDV(dn.ar_slot[ai], f));
                             recalc = true;
                         }
                     }
                     if (recalc)
                         svf_coeffs_dev(sreg[(rb + 11) * 32], __uint_as_float(sreg[(rb + 8) * 32]), __uint_as_float(sreg[(rb + 9) * 32]),
                                        __uint_as_float(sreg[(rb + 10) * 32]), sr, a1, a2, a3, m0, m1, m2);
-                    float x = is >= 0 ? sval[(is * CH + f) * 32] : 0.f;
+                    float x = RDV(is, f);
                     float y = svf_tick(x, ic1, ic2, a1, a2, a3, m0, m1, m2);
                     EMIT(f, 0, y)
                 }
@@ -365,8 +368,8 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                               (y1 = __uint_as_float(sreg[rb * 32]), a0 = __uint_as_float(sreg[(rb + 1) * 32]), b1 = __uint_as_float(sreg[(rb + 2) * 32])))
                     AR_POST_ROUTES(f)
                     for (int ai = 0; ai < dn.n_ar; ai++)
-                        if (dn.ar_code[ai] == AR_ONEPOLE_CUTOFF) onepole_coeffs_dev(sval[(dn.ar_slot[ai] * CH + f) * 32], sr, a0, b1); // onepole.rs:135-139
-                    float x = is >= 0 ? sval[(is * CH + f) * 32] : 0.f;
+                        if (dn.ar_code[ai] == AR_ONEPOLE_CUTOFF) onepole_coeffs_dev(RDV(dn.ar_slot[ai], f), sr, a0, b1); // onepole.rs:135-139
+                    float x = RDV(is, f);
                     float y = hp ? onepole_hp_tick(x, y1, a0, b1) : onepole_lp_tick(x, y1, a0, b1);
                     EMIT(f, 0, y)
                 }
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     AR_POST_ROUTES(f)
                     float ain[MAX_IN];
 #pragma unroll
-                    for (int c = 0; c < MAX_IN; c++) ain[c] = (c < 2 * (int)nch && dn.in_slot[c] >= 0) ? sval[(dn.in_slot[c] * CH + f) * 32] : 0.f;
+                    for (int c = 0; c < MAX_IN; c++) ain[c] = c < 2 * (int)nch ? RDV(dn.in_slot[c], f) : 0.f;
 #pragma unroll
                     for (int c = 0; c < MAX_OUT; c++)
                         if (c < (int)nch) {
@@ -493,7 +496,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     for (uint32_t f = g0_; f < fe_; f++) {
                         EVENTS_AT(f, (void)0, (void)0)
                         AR_POST_ROUTES(f)
-                        float y = math1_apply(op1, is >= 0 ? sval[(is * CH + f) * 32] : 0.f);
+                        float y = math1_apply(op1, RDV(is, f));
                         EMIT(f, 0, y)
                     }
                 }
@@ -603,7 +606,7 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 for (uint32_t f = 0; f < nf; f++) {
                     EVENTS_AT(f, (void)0, (gl = __uint_as_float(sreg[rb * 32]), gr = __uint_as_float(sreg[(rb + 1) * 32])))
                     AR_POST_ROUTES(f)
-                    const float x = is >= 0 ? sval[(is * CH + f) * 32] : 0.f;
+                    const float x = RDV(is, f);
                     EMIT(f, 0, x * gl)
                     EMIT(f, 1, x * gr)
                 }
@@ -626,12 +629,12 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, (void)0, val = __uint_as_float(sreg[rb * 32]))
                     for (int ai = 0; ai < dn.n_ar; ai++) {
-                        float x = sval[(dn.ar_slot[ai] * CH + f) * 32];
+                        float x = RDV(dn.ar_slot[ai], f);
                         if (dn.ar_code[ai] == AR_REG0) val = x;
                         else pv[dn.ar_code[ai] - AR_POST] = x;
                     }
                     float y = val;
-                    if (dn.kind == DK_INPLUS) y = val + (is >= 0 ? sval[(is * CH + f) * 32] : 0.f);
+                    if (dn.kind == DK_INPLUS) y = val + RDV(is, f);
                     EMIT(f, 0, y)
                 }
                 }
@@ -748,6 +751,31 @@ __global__ void __launch_bounds__(RB_GROUPS *RB_FRAMES) reduce_bus(const float *
     }
 }
 
+// Internal signals (plan.hpp): sig[w][t] = sum, in row order, of the partial rows whose mask carries bit first_bit + which[w].
+// One thread per frame; a handful of signals, each summed by its own pass over the rows (deterministic).
+__global__ void reduce_signals(const float *__restrict__ partials, const uint32_t *__restrict__ row_mask, uint32_t n_rows, uint32_t n_frames,
+                               float *__restrict__ sig, uint32_t first_bit, const uint32_t *__restrict__ which, uint32_t n_which) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_frames) return;
+    for (uint32_t w = 0; w < n_which; w++) {
+        const uint32_t sgn = which[w], bit = 1u << (first_bit + sgn);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        uint32_t k = 0;
+        for (uint32_t r = 0; r < n_rows; r++) {
+            if (!(row_mask[r] & bit)) continue;
+            const float x = partials[(size_t)r * n_frames + t];
+            switch (k & 3u) {
+            case 0: a0 = a0 + x; break;
+            case 1: a1 = a1 + x; break;
+            case 2: a2 = a2 + x; break;
+            default: a3 = a3 + x; break;
+            }
+            k++;
+        }
+        sig[(size_t)sgn * n_frames + t] = (a0 + a1) + (a2 + a3);
+    }
+}
+
 // ---- multi-GPU mix bus over peer memory (NVLink) ------------------------------------------------
 // Every rank's reduce_bus writes its bus straight into its slot of a buffer in rank 0's memory;
 // signal_flag then publishes "launch L of epoch E is there" with a system-scope release store, and
@@ -805,6 +833,11 @@ cudaError_t launch_interp(const InterpArgs &a, uint32_t n_regs, uint32_t n_slots
 cudaError_t launch_reduce_bus(const float *partials, const uint32_t *row_mask, uint32_t n_rows, uint32_t n_frames, float *out,
                               uint32_t n_out, uint32_t block_size, cudaStream_t stream) {
     reduce_bus<<<(n_frames + RB_FRAMES - 1) / RB_FRAMES, RB_GROUPS * RB_FRAMES, 0, stream>>>(partials, row_mask, n_rows, n_frames, out, n_out, block_size);
+    return cudaGetLastError();
+}
+cudaError_t launch_reduce_signals(const float *partials, const uint32_t *row_mask, uint32_t n_rows, uint32_t n_frames, float *sig,
+                                  uint32_t first_bit, const uint32_t *which, uint32_t n_which, cudaStream_t stream) {
+    reduce_signals<<<(n_frames + 127) / 128, 128, 0, stream>>>(partials, row_mask, n_rows, n_frames, sig, first_bit, which, n_which);
     return cudaGetLastError();
 }
 cudaError_t launch_signal_flag(uint32_t *flag, uint32_t value, cudaStream_t stream) {

@@ -24,11 +24,18 @@ struct InterpArgs {
     uint64_t tap_stride;
     uint64_t tap_frame0;
     const float *sine_table; // device, 16384 f32 (wavetable.rs:130-139)
+    const float *ext;        // internal signals [signal][ext_stride] of this launch; NULL if none
+    uint32_t ext_stride;
 };
 
 cudaError_t launch_interp(const InterpArgs &a, uint32_t n_regs, uint32_t n_slots, cudaStream_t stream);
 cudaError_t launch_reduce_bus(const float *partials, const uint32_t *row_mask, uint32_t n_rows, uint32_t n_frames, float *out,
                               uint32_t n_out, uint32_t block_size, cudaStream_t stream);
+
+// internal signals (plan.hpp): signal s = sum of the partial rows [0, n_rows) whose mask has bit (first_bit + s), for the
+// signals listed in `which` (n_which of them), written to sig[s * n_frames + frame]
+cudaError_t launch_reduce_signals(const float *partials, const uint32_t *row_mask, uint32_t n_rows, uint32_t n_frames, float *sig,
+                                  uint32_t first_bit, const uint32_t *which, uint32_t n_which, cudaStream_t stream);
 
 // multi-GPU mix bus over peer memory (kernels.cu)
 cudaError_t launch_signal_flag(uint32_t *flag, uint32_t value, cudaStream_t stream);

@@ -26,6 +26,8 @@ struct FusedArgs {
     uint32_t block_size;
     void *scratch;               // fused_scratch_bytes() bytes of device memory, private to the launch
     uint32_t *regs_out;          // recipe-internal: where a kernel leaves the launch-end registers (default: regs)
+    const float *ext;            // internal signals [signal][ext_stride] of this launch (plan.hpp HostPlan::signal_level); NULL if none
+    uint32_t ext_stride;
 };
 
 } // namespace kgpu

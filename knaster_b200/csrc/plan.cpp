@@ -564,7 +564,7 @@ bool TemplateNode::same_shape(const TemplateNode &o) const {
     return true;
 }
 bool Template::same_shape(const Template &o) const {
-    if (nodes.size() != o.nodes.size() || outs != o.outs) return false;
+    if (nodes.size() != o.nodes.size() || outs != o.outs || level != o.level) return false;
     for (size_t i = 0; i < nodes.size(); i++)
         if (!nodes[i].same_shape(o.nodes[i])) return false;
     return true;
@@ -581,7 +581,7 @@ uint64_t template_hash(const Template &t) {
         for (auto &p : n.par) h = hash_mix(h, std::get<0>(p) | ((uint64_t)(uint32_t)std::get<1>(p) << 16) | ((uint64_t)std::get<2>(p) << 40));
     }
     for (auto &o : t.outs) h = hash_mix(h, (uint64_t)(uint32_t)std::get<0>(o) | ((uint64_t)std::get<1>(o) << 20) | ((uint64_t)std::get<2>(o) << 40));
-    return h;
+    return hash_mix(h, (uint64_t)t.level);
 }
 
 // resolve an audio-rate parameter route of a node to a device action
@@ -698,7 +698,8 @@ void compile_template(Group &g, uint32_t sample_rate, const std::vector<std::pai
     for (size_t i = 0; i < n; i++) {
         for (auto &e : t.nodes[i].in)
             if (e.first >= 0) last_use[e.first][e.second] = std::max(last_use[e.first][e.second], (int)i);
-        for (auto &pe : t.nodes[i].par) last_use[std::get<1>(pe)][std::get<2>(pe)] = std::max(last_use[std::get<1>(pe)][std::get<2>(pe)], (int)i);
+        for (auto &pe : t.nodes[i].par)
+            if (std::get<1>(pe) >= 0) last_use[std::get<1>(pe)][std::get<2>(pe)] = std::max(last_use[std::get<1>(pe)][std::get<2>(pe)], (int)i);
     }
     for (auto &o : t.outs) last_use[std::get<0>(o)][std::get<1>(o)] = INF;
     for (auto &pin : pinned) last_use[pin.first][pin.second] = INF;
@@ -713,6 +714,7 @@ void compile_template(Group &g, uint32_t sample_rate, const std::vector<std::pai
         for (int c = 0; c < MAX_IN; c++) dn.in_slot[c] = -1;
         for (size_t c = 0; c < tn.in.size(); c++) {
             auto &e = tn.in[c];
+            if (e.first <= EXT_BASE) dn.in_slot[c] = (int16_t)e.first; // an internal signal, read from its buffer
             if (e.first < 0) continue;
             dn.in_slot[c] = (int16_t)g.slot_of[e.first][e.second];
             if (last_use[e.first][e.second] == (int)i) dying.push_back(e);
@@ -723,6 +725,10 @@ void compile_template(Group &g, uint32_t sample_rate, const std::vector<std::pai
         for (auto &pe : tn.par) {
             int src = std::get<1>(pe);
             uint32_t ch = std::get<2>(pe);
+            if (src <= EXT_BASE) { // routed from an internal signal
+                if (has_ar) dn.ar_slot[ai++] = (int16_t)src;
+                continue;
+            }
             if (has_ar) dn.ar_slot[ai++] = (int16_t)g.slot_of[src][ch];
             if (last_use[src][ch] == (int)i) dying.push_back({src, ch});
         }
@@ -839,63 +845,152 @@ void HostPlan::build(const kgpu_graph_desc &d) {
     for (auto &pl : par_edges)
         for (auto &pe : pl) fanout[std::get<1>(pe)]++;
 
-    // mix-bus Add chains: ((v0+v1)+v2)+... per graph output (graph.rs:850-864)
-    auto is_mix = [&](int node) {
+    // ---- mix buses, internal signals, voices ---------------------------------------------------------------------------
+    // A graph output is the left fold ((v0+v1)+v2)+... of an Add chain (graph.rs:850-864): its leaves are voice outputs and
+    // the chain becomes the mix-bus reduction.  The same happens INSIDE the graph when a node reads the sum of many voices
+    // (post-mix processing) or when one source feeds many voices: such a source is an internal signal, reduced into its own
+    // buffer one level before the voices that read it, and what reads it is cut loose from what produces it -- otherwise
+    // the whole bank would be one connected "voice".  Thresholds: a sum of >= mix_min leaves, a node with >= shared_min
+    // consumers.  16 keeps every graph that fitted a voice before (MAX_NODES = 24) exactly as it was; if a component still
+    // outgrows a voice the discovery is repeated with 2 (every fan-in / fan-out point is a cut).
+    auto sum_like = [&](int node) {
         const kgpu_node_desc &nd = d.nodes[node];
         if (nd.kind != KGPU_MATH || nd.mode != KGPU_OP_ADD || nd.channels != 1 || nd.n_wrappers != 0) return false;
-        if (fanout[node] != 1) return false;
         return in_edges[in_off[node]].first >= 0 && in_edges[in_off[node] + 1].first >= 0;
     };
-    struct Leaf { int node; uint32_t ch; uint32_t out_ch; };
-    std::vector<Leaf> leaves;
-    std::vector<char> mix_node(N, 0);
-    n_mix_nodes = 0;
-    for (uint32_t oc = 0; oc < n_outputs; oc++) {
-        if (out_edges[oc].first < 0) continue;
-        std::vector<std::pair<int, uint32_t>> stack{out_edges[oc]};
-        while (!stack.empty()) {
-            auto cur = stack.back();
-            stack.pop_back();
-            if (is_mix(cur.first)) {
-                mix_node[cur.first] = 1;
-                n_mix_nodes++;
-                stack.push_back(in_edges[in_off[cur.first] + 1]); // right operand after ...
-                stack.push_back(in_edges[in_off[cur.first]]);     // ... the left one (in-order)
-            } else leaves.push_back({cur.first, cur.second, oc});
+    auto is_mix = [&](int node) { return sum_like(node) && fanout[node] == 1; };
+    struct Leaf { int node; uint32_t ch; uint32_t target; };
+    struct Discovery {
+        std::vector<Leaf> leaves;
+        std::vector<char> mix_node;
+        std::vector<int> in_ext;                               // per input edge: internal signal or -1
+        std::vector<std::vector<int>> par_ext;                 // per parameter edge likewise
+        std::vector<int> comp;
+        std::vector<int> uf;
+        uint32_t n_signals = 0, n_mix = 0;
+    };
+    auto discover = [&](uint32_t mix_min, uint32_t shared_min, Discovery &D) {
+        D = Discovery{};
+        D.mix_node.assign(N, 0);
+        D.in_ext.assign(in_off[N], -1);
+        D.par_ext.resize(N);
+        for (uint32_t i = 0; i < N; i++) D.par_ext[i].assign(par_edges[i].size(), -1);
+        D.comp.assign(N, -1);
+        // expands the Add chain rooted at `root` (the root itself may have any fan-out, inner Adds exactly one consumer)
+        auto expand = [&](std::pair<int, uint32_t> root, uint32_t target, bool root_any_fanout, bool commit, std::vector<Leaf> &out) {
+            std::vector<std::pair<int, uint32_t>> stack{root};
+            bool first = true;
+            while (!stack.empty()) {
+                auto cur = stack.back();
+                stack.pop_back();
+                const bool through = first && root_any_fanout ? sum_like(cur.first) : is_mix(cur.first);
+                first = false;
+                if (through) {
+                    if (commit && !D.mix_node[cur.first]) {
+                        D.mix_node[cur.first] = 1;
+                        D.n_mix++;
+                    }
+                    stack.push_back(in_edges[in_off[cur.first] + 1]); // right operand after ...
+                    stack.push_back(in_edges[in_off[cur.first]]);     // ... the left one (in-order)
+                } else out.push_back({cur.first, cur.second, target});
+            }
+        };
+        for (uint32_t oc = 0; oc < n_outputs; oc++) {
+            if (out_edges[oc].first < 0) continue;
+            // a large sum that feeds this output AND something else (the dry mix beside a master effect): its leaves go to the
+            // output directly, whatever else reads the sum gets it as an internal signal made of the same leaves
+            std::vector<Leaf> probe;
+            const bool shared_root = sum_like(out_edges[oc].first) && fanout[out_edges[oc].first] > 1;
+            if (shared_root) expand(out_edges[oc], oc, true, false, probe);
+            expand(out_edges[oc], oc, shared_root && probe.size() >= mix_min, true, D.leaves);
         }
+        std::unordered_map<uint64_t, int> sig_of; // (node, channel) -> signal
+        // what (src, ch) is to a consumer: the node itself (-1) or an internal signal
+        auto resolve = [&](int src, uint32_t ch) -> int {
+            const uint64_t key = ((uint64_t)(uint32_t)src << 8) | ch;
+            auto it = sig_of.find(key);
+            if (it != sig_of.end()) return it->second;
+            std::vector<Leaf> lv;
+            bool cut = false;
+            if (sum_like(src)) {
+                expand({src, ch}, 0, true, false, lv);
+                cut = lv.size() >= mix_min;
+            }
+            if (!cut && fanout[src] >= shared_min) {
+                lv.assign(1, Leaf{src, ch, 0});
+                cut = true;
+            }
+            if (!cut) return sig_of[key] = -1;
+            if (sum_like(src) && lv.size() > 1) {
+                lv.clear();
+                expand({src, ch}, 0, true, true, lv); // now for real: the chain's Adds disappear into the reduction
+            }
+            const int sidx = (int)D.n_signals++;
+            for (Leaf &l : lv) {
+                l.target = n_outputs + (uint32_t)sidx;
+                D.leaves.push_back(l);
+            }
+            return sig_of[key] = sidx;
+        };
+        auto find = [&](int x) {
+            while (D.uf[x] != x) x = D.uf[x] = D.uf[D.uf[x]];
+            return x;
+        };
+        std::vector<int> stack;
+        for (size_t li = 0; li < D.leaves.size(); li++) { // grows while signals are found
+            const Leaf lf = D.leaves[li];
+            if (D.mix_node[lf.node]) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %d is both summed into a mix and read on its own", lf.node);
+            if (D.comp[lf.node] >= 0) continue;
+            const int c = (int)D.uf.size();
+            D.uf.push_back(c);
+            D.comp[lf.node] = c;
+            stack.assign(1, lf.node);
+            while (!stack.empty()) {
+                const int nk = stack.back();
+                stack.pop_back();
+                auto visit = [&](int src, uint32_t ch, int &ext) {
+                    if (src < 0) return;
+                    ext = resolve(src, ch);
+                    if (ext >= 0) return; // read through the signal's buffer: no edge between the two voices
+                    if (D.mix_node[src]) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %d reads a node that is summed into a mix", nk);
+                    if (D.comp[src] < 0) {
+                        D.comp[src] = c;
+                        stack.push_back(src);
+                    } else {
+                        const int a = find(D.comp[src]), b = find(c);
+                        if (a != b) D.uf[std::max(a, b)] = std::min(a, b);
+                    }
+                };
+                for (uint32_t k = in_off[nk]; k < in_off[nk + 1]; k++) visit(in_edges[k].first, in_edges[k].second, D.in_ext[k]);
+                for (size_t k = 0; k < par_edges[nk].size(); k++) visit(std::get<1>(par_edges[nk][k]), std::get<2>(par_edges[nk][k]), D.par_ext[nk][k]);
+            }
+        }
+        // the largest component, in nodes
+        std::unordered_map<int, uint32_t> size;
+        uint32_t largest = 0;
+        for (uint32_t i = 0; i < N; i++)
+            if (D.comp[i] >= 0) largest = std::max(largest, ++size[find(D.comp[i])]);
+        return largest;
+    };
+    Discovery D;
+    if (discover(16, 16, D) > (uint32_t)MAX_NODES) {
+        Discovery D2;
+        bool ok = false;
+        try {
+            ok = discover(2, 2, D2) <= (uint32_t)MAX_NODES && n_outputs + D2.n_signals <= 32;
+        } catch (const Error &) {
+        }
+        if (ok) D = std::move(D2);
     }
-    // voices = connected components of the leaves' upstream closures
-    std::vector<int> comp(N, -1);
-    std::vector<int> uf;
+    if (n_outputs + D.n_signals > 32)
+        KGPU_THROW(KGPU_ERR_UNSUPPORTED, "%u internal signals (sums of voices read by nodes, sources shared between voices): at most %u", D.n_signals, 32 - n_outputs);
+    n_mix_nodes = D.n_mix;
+    std::vector<Leaf> &leaves = D.leaves;
+    std::vector<int> &comp = D.comp;
     auto find = [&](int x) {
-        while (uf[x] != x) x = uf[x] = uf[uf[x]];
+        while (D.uf[x] != x) x = D.uf[x] = D.uf[D.uf[x]];
         return x;
     };
-    std::vector<int> stack;
-    for (auto &lf : leaves) {
-        if (comp[lf.node] >= 0) continue;
-        int c = (int)uf.size();
-        uf.push_back(c);
-        comp[lf.node] = c;
-        stack.assign(1, lf.node);
-        while (!stack.empty()) {
-            int nk = stack.back();
-            stack.pop_back();
-            auto visit = [&](int src) {
-                if (src < 0) return;
-                if (mix_node[src]) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %d reads the mix bus: post-mix processing is not supported yet", nk);
-                if (comp[src] < 0) {
-                    comp[src] = c;
-                    stack.push_back(src);
-                } else {
-                    int a = find(comp[src]), b = find(c);
-                    if (a != b) uf[std::max(a, b)] = std::min(a, b);
-                }
-            };
-            for (uint32_t k = in_off[nk]; k < in_off[nk + 1]; k++) visit(in_edges[k].first);
-            for (auto &pe : par_edges[nk]) visit(std::get<1>(pe));
-        }
-    }
     // per component: leaves in order
     std::unordered_map<int, std::vector<Leaf>> comp_leaves;
     std::vector<int> comp_order;
@@ -906,6 +1001,46 @@ void HostPlan::build(const kgpu_graph_desc &d) {
             comp_order.push_back(c);
             comp_leaves[c] = {lf};
         } else it->second.push_back(lf);
+    }
+    // levels: a voice renders after every signal it reads, a signal is complete after its last contributor
+    std::unordered_map<int, int> comp_level;
+    signal_level.assign(D.n_signals, -1);
+    {
+        std::unordered_map<int, std::vector<int>> reads;    // component -> signals read
+        for (uint32_t nk = 0; nk < N; nk++) {
+            if (comp[nk] < 0) continue;
+            const int c = find(comp[nk]);
+            for (uint32_t k = in_off[nk]; k < in_off[nk + 1]; k++)
+                if (D.in_ext[k] >= 0) reads[c].push_back(D.in_ext[k]);
+            for (int e : D.par_ext[nk])
+                if (e >= 0) reads[c].push_back(e);
+        }
+        std::vector<std::vector<int>> feeders(D.n_signals);  // signal -> contributing components
+        for (auto &lf : leaves)
+            if (lf.target >= n_outputs) feeders[lf.target - n_outputs].push_back(find(comp[lf.node]));
+        std::unordered_map<int, int> state; // 1 visiting, 2 done
+        std::function<int(int)> level_of = [&](int c) -> int {
+            if (state[c] == 2) return comp_level[c];
+            if (state[c] == 1) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "a voice reads a signal it contributes to: feedback is not supported");
+            state[c] = 1;
+            int lv = 0;
+            for (int sg : reads[c]) {
+                int sl = 0;
+                for (int f : feeders[sg]) sl = std::max(sl, level_of(f));
+                signal_level[sg] = std::max(signal_level[sg], sl);
+                lv = std::max(lv, sl + 1);
+            }
+            state[c] = 2;
+            return comp_level[c] = lv;
+        };
+        max_level = 0;
+        for (int c : comp_order) max_level = std::max(max_level, level_of(c));
+        for (uint32_t sg = 0; sg < D.n_signals; sg++)
+            if (signal_level[sg] < 0) { // a signal nobody reads cannot exist; keep it well-defined anyway
+                int sl = 0;
+                for (int f : feeders[sg]) sl = std::max(sl, comp_level[f]);
+                signal_level[sg] = sl;
+            }
     }
     node_ref.assign(N, NodeRef{});
     for (uint32_t i = 0; i < N; i++) node_ref[i].n_params = (uint16_t)total_params(d.nodes[i]);
@@ -927,7 +1062,9 @@ void HostPlan::build(const kgpu_graph_desc &d) {
                 bool pushed = false;
                 while (cur < ne + np) {
                     int src = cur < ne ? in_edges[in_off[nk] + cur].first : std::get<1>(par_edges[nk][cur - ne]);
+                    const int ext = cur < ne ? D.in_ext[in_off[nk] + cur] : D.par_ext[nk][cur - ne];
                     cur++;
+                    if (ext >= 0) continue; // an internal signal: not a node of this voice
                     if (src >= 0 && local_of[src] == -1) {
                         local_of[src] = -2;
                         dstack.push_back({src, 0});
@@ -947,6 +1084,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
             }
         }
         Template t;
+        t.level = comp_level[c];
         t.nodes.resize(order.size());
         for (size_t li = 0; li < order.size(); li++) {
             uint32_t nk = order[li];
@@ -955,11 +1093,17 @@ void HostPlan::build(const kgpu_graph_desc &d) {
             tn.kind = nd.kind; tn.mode = nd.mode; tn.channels = nd.kind == KGPU_MATH ? nd.channels : 1; tn.flags = nd.flags;
             tn.n_segments = nd.kind == KGPU_ENVELOPE ? nd.n_segments : 0;
             tn.wrappers.assign(nd.wrappers, nd.wrappers + nd.n_wrappers);
-            for (uint32_t k = in_off[nk]; k < in_off[nk + 1]; k++)
-                tn.in.push_back({in_edges[k].first >= 0 ? local_of[in_edges[k].first] : -1, in_edges[k].second});
-            for (auto &pe : par_edges[nk]) tn.par.push_back({std::get<0>(pe), local_of[std::get<1>(pe)], std::get<2>(pe)});
+            for (uint32_t k = in_off[nk]; k < in_off[nk + 1]; k++) {
+                if (D.in_ext[k] >= 0) tn.in.push_back({EXT_BASE - D.in_ext[k], 0u});
+                else tn.in.push_back({in_edges[k].first >= 0 ? local_of[in_edges[k].first] : -1, in_edges[k].second});
+            }
+            for (size_t k = 0; k < par_edges[nk].size(); k++) {
+                auto &pe = par_edges[nk][k];
+                if (D.par_ext[nk][k] >= 0) tn.par.push_back({std::get<0>(pe), EXT_BASE - D.par_ext[nk][k], 0u});
+                else tn.par.push_back({std::get<0>(pe), local_of[std::get<1>(pe)], std::get<2>(pe)});
+            }
         }
-        for (auto &lf : comp_leaves[c]) t.outs.push_back({local_of[lf.node], lf.ch, lf.out_ch});
+        for (auto &lf : comp_leaves[c]) t.outs.push_back({local_of[lf.node], lf.ch, lf.target});
         uint64_t h = template_hash(t);
         int gi = -1;
         for (uint32_t cand : by_hash[h])
@@ -979,6 +1123,22 @@ void HostPlan::build(const kgpu_graph_desc &d) {
             node_ref[order[li]].voice = voice;
             node_ref[order[li]].local = (uint16_t)li;
         }
+    }
+    // groups in level order (a level's groups launch together, then its signals are reduced): stable, with node_ref remapped
+    if (max_level > 0) {
+        std::vector<uint32_t> perm(groups.size());
+        for (uint32_t i = 0; i < perm.size(); i++) perm[i] = i;
+        std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return groups[a].tpl.level < groups[b].tpl.level; });
+        std::vector<int> new_of(groups.size());
+        std::vector<Group> sorted;
+        sorted.reserve(groups.size());
+        for (uint32_t i = 0; i < perm.size(); i++) {
+            new_of[perm[i]] = (int)i;
+            sorted.push_back(std::move(groups[perm[i]]));
+        }
+        groups = std::move(sorted);
+        for (NodeRef &nr : node_ref)
+            if (nr.group >= 0) nr.group = new_of[nr.group];
     }
     // initial registers + control state: Node::init (graph.rs:462-475) of every node of every voice
     const float sr = (float)sample_rate;

@@ -107,9 +107,13 @@ struct TemplateNode {
 
 struct Template {
     std::vector<TemplateNode> nodes;                         // local topological order
-    std::vector<std::tuple<int, uint32_t, uint32_t>> outs;   // (local node, channel, graph output channel)
+    std::vector<std::tuple<int, uint32_t, uint32_t>> outs;   // (local node, channel, target): target < n_outputs = graph output
+                                                             // channel, else n_outputs + internal signal (HostPlan::signal_level)
+    int level = 0;                                           // 0: reads no internal signal; else 1 + the highest level it reads
     bool same_shape(const Template &o) const;
 };
+// an input / parameter-route source that is not a node of the same voice: internal signal s is encoded as EXT_BASE - s
+constexpr int EXT_BASE = -2;
 
 struct Group {
     Template tpl;
@@ -189,6 +193,13 @@ struct HostPlan {
     std::vector<Group> groups;
     std::vector<NodeRef> node_ref; // per graph node
     uint32_t n_mix_nodes = 0;
+    // Internal signals: what a node reads from OUTSIDE its own voice -- the sum of many voices' outputs (post-mix
+    // processing: `mix * 0.5`, a master filter; graph_edit.rs:1145-1225 over graph.rs:850-864) or a source shared by many voices
+    // (one LFO into every voice's cutoff).  Each is rendered like a graph output -- its contributors' partial rows are
+    // reduced into a buffer [signal][frame] -- one level before the voices that read it.  signal_level[s] = the level of
+    // its highest contributor; groups are sorted by level.
+    std::vector<int> signal_level;
+    int max_level = 0;
     uint64_t graph_hash = 0;       // of the whole graph description (snapshots only restore into the same graph)
     uint64_t dropped_changes = 0, ignored_delays = 0, device_events = 0;
     std::vector<RawEvent, DefaultInitAllocator<RawEvent>> pending; // not yet simulated, arrival order
