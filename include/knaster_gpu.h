@@ -133,7 +133,7 @@ typedef struct {
     uint32_t abi_version;  /* KGPU_ABI_VERSION */
     uint32_t sample_rate;
     uint32_t block_size;
-    uint32_t n_inputs;     /* must be 0: run_without_inputs() is the supported render call */
+    uint32_t n_inputs;     /* graph inputs (<= 16): rendered with kgpu_render_inputs; 0: run_without_inputs() */
     uint32_t n_outputs;    /* 1..8 */
     int32_t device;        /* CUDA device ordinal, -1 = current */
     uint32_t n_nodes;
@@ -190,6 +190,10 @@ int kgpu_render_block(kgpu_plan *plan);
 const float *kgpu_output_block(kgpu_plan *plan);
 /* Render n_blocks back to back.  host_out: [n_blocks][n_outputs][block_size] or NULL. */
 int kgpu_render(kgpu_plan *plan, uint64_t n_blocks, float *host_out);
+/* AudioProcessor::run(&[&[F]]) (processor.rs:119-141), batched: the graph's inputs for n_blocks blocks,
+ * host_in: [n_blocks][n_inputs][block_size].  A graph with inputs is rendered with this call only (kgpu_render* fail with
+ * KGPU_ERR_STATE, like run_without_inputs() asserts inputs() == 0, processor.rs:143); host_out as in kgpu_render. */
+int kgpu_render_inputs(kgpu_plan *plan, uint64_t n_blocks, const float *host_in, float *host_out);
 /* Same, leaving the result in DEVICE memory (device_out: n_blocks*n_outputs*block_size floats
  * on the plan's device) and enqueued on `cuda_stream` (a cudaStream_t, NULL = the plan's own
  * stream) without synchronising: the multi-GPU path reduces the bus from here. */

@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
     L.kgpu_output_block.argtypes = [vp]
     L.kgpu_output_block.restype = C.POINTER(C.c_float)
     L.kgpu_render.argtypes = [vp, u64, vp]
+    L.kgpu_render_inputs.argtypes = [vp, u64, vp, vp]
     L.kgpu_render_device.argtypes = [vp, u64, vp, vp]
     L.kgpu_plan_synchronize.argtypes = [vp]
     L.kgpu_plan_block_size.argtypes = [vp]

@@ -118,6 +118,8 @@ struct kgpu_plan {
     DevBuf<float> tap_out;
     // internal signals (plan.hpp HostPlan::signal_level): [signal][frames of the launch], reduced level by level
     DevBuf<float> signals;
+    DevBuf<uint32_t> in_pairs;              // device: (graph input, graph output) pairs wired without a node in between
+    PinBuf<float> in_pinned;                // the caller's input blocks of the current render call
     DevBuf<uint32_t> sig_which;             // device: the signals of level 0, then level 1, ... (sig_level_off indexes it)
     std::vector<uint32_t> sig_level_off;    // [max_level + 2]
     std::vector<uint32_t> level_rows_end;   // [max_level + 1]: partial rows of the groups up to and including that level
@@ -219,6 +221,12 @@ void layout_rows(kgpu_plan *p) {
         for (uint32_t sg = 0; sg < p->host.signal_level.size(); sg++)
             if (p->host.signal_level[sg] == l) which.push_back(sg);
         p->sig_level_off[l + 1] = (uint32_t)which.size();
+    }
+    {
+        std::vector<uint32_t> pairs;
+        for (auto &io : p->host.input_to_output) { pairs.push_back(io.first); pairs.push_back(io.second); }
+        p->in_pairs.ensure(std::max<size_t>(1, pairs.size()));
+        if (!pairs.empty()) CUDA_TRY(cudaMemcpyAsync(p->in_pairs.p, pairs.data(), pairs.size() * 4, cudaMemcpyHostToDevice, p->stream));
     }
     p->sig_which.ensure(std::max<size_t>(1, which.size()));
     if (!which.empty()) CUDA_TRY(cudaMemcpyAsync(p->sig_which.p, which.data(), which.size() * 4, cudaMemcpyHostToDevice, p->stream));
@@ -352,7 +360,8 @@ void upload_launch_events(kgpu_plan *p, size_t launch, cudaStream_t stream) {
 // runs launch by launch, one launch ahead of the device: while launch L renders, the control
 // simulation of launch L+1 runs on the host threads and its events are staged in pinned memory.
 // pinned_out: optional page-locked mirror of device_out, filled launch by launch.
-void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream_t stream, float *pinned_out = nullptr) {
+void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream_t stream, float *pinned_out = nullptr,
+                  const float *host_in = nullptr) {
     const uint32_t bs = p->host.block_size, n_out = p->host.n_outputs;
     p->rendered = true;
     const uint64_t total_frames = n_blocks * bs;
@@ -376,6 +385,12 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
 
     const bool peer = p->peer_world > 1;
     const uint32_t n_signals = (uint32_t)p->host.signal_level.size();
+    const uint32_t n_in = p->host.n_inputs;
+    if (n_in && !host_in) KGPU_THROW(KGPU_ERR_STATE, "this graph has %u inputs: render it with kgpu_render_inputs (AudioProcessor::run), not run_without_inputs", n_in);
+    if (n_in) { // the input blocks, page-locked for the strided copies below
+        p->in_pinned.ensure((size_t)n_blocks * n_in * bs);
+        std::memcpy(p->in_pinned.p, host_in, (size_t)n_blocks * n_in * bs * 4);
+    }
     if (n_signals) {
         if (peer) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "a plan with internal signals (post-mix nodes, sources shared between voices) cannot be sharded over a peer bus");
         p->signals.ensure((size_t)n_signals * std::min<uint64_t>(bpl, n_blocks) * bs);
@@ -462,6 +477,10 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb).count());
             piece = 0;
         }
+        // graph inputs: [block][input][frame] from the caller -> rows [0, n_inputs) of the signal buffer, [input][frame of the launch]
+        for (uint32_t c = 0; c < n_in; c++)
+            CUDA_TRY(cudaMemcpy2DAsync(p->signals.p + (size_t)c * nf, (size_t)bs * 4, p->in_pinned.p + ((size_t)done * n_in + c) * bs, (size_t)n_in * bs * 4,
+                                       (size_t)bs * 4, (size_t)nb, cudaMemcpyHostToDevice, stream));
         for (uint32_t gi = 0; gi < p->gd.size(); gi++, piece++) {
             Group &g = p->host.groups[gi];
             GroupDev &d = p->gd[gi];
@@ -525,6 +544,10 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             p->kernel_launches++;
         } else {
             CUDA_TRY(launch_reduce_bus(p->partials.p, p->row_mask.p, p->n_rows, nf, dst, n_out, bs, stream));
+            if (!p->host.input_to_output.empty()) {
+                CUDA_TRY(launch_add_inputs(p->signals.p, nf, dst, n_out, bs, p->in_pairs.p, (uint32_t)p->host.input_to_output.size(), stream));
+                p->kernel_launches++;
+            }
         }
         mark(1, false);
         p->kernel_launches++;
@@ -660,7 +683,7 @@ void kgpu_plan_destroy(kgpu_plan *p) {
         if (e) cudaEventDestroy(e);
     if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
     if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
-    p->scratch.release(); p->signals.release(); p->sig_which.release();
+    p->scratch.release(); p->signals.release(); p->sig_which.release(); p->in_pairs.release(); p->in_pinned.release();
     p->partials.release(); p->row_mask.release(); p->out.release(); p->sine.release(); p->tap_out.release();
     for (cudaEvent_t e : p->kev) cudaEventDestroy(e);
     for (cudaEvent_t e : p->out_ev) cudaEventDestroy(e);
@@ -694,7 +717,13 @@ int kgpu_render_device(kgpu_plan *p, uint64_t n_blocks, float *device_out, void 
     }
 }
 
-int kgpu_render(kgpu_plan *p, uint64_t n_blocks, float *host_out) {
+static int render_host(kgpu_plan *p, uint64_t n_blocks, const float *host_in, float *host_out);
+int kgpu_render(kgpu_plan *p, uint64_t n_blocks, float *host_out) { return render_host(p, n_blocks, nullptr, host_out); }
+int kgpu_render_inputs(kgpu_plan *p, uint64_t n_blocks, const float *host_in, float *host_out) {
+    if (p && p->host.n_inputs && !host_in) return fail(KGPU_ERR_INVALID, "kgpu_render_inputs: NULL input buffer");
+    return render_host(p, n_blocks, host_in, host_out);
+}
+static int render_host(kgpu_plan *p, uint64_t n_blocks, const float *host_in, float *host_out) {
     if (!p) return fail(KGPU_ERR_INVALID, "kgpu_render: NULL plan");
     if (n_blocks == 0) return KGPU_OK;
     try {
@@ -708,7 +737,7 @@ int kgpu_render(kgpu_plan *p, uint64_t n_blocks, float *host_out) {
             auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
             const auto t0 = now();
             p->out_pinned.ensure(per_block * n_blocks);
-            render_range(p, n_blocks, p->out.p, p->stream, p->out_pinned.p);
+            render_range(p, n_blocks, p->out.p, p->stream, p->out_pinned.p, host_in);
             const auto t1 = now();
             // hand the audio over piece by piece, each as soon as its download has landed (the rest still renders)
             for (size_t i = 0; i < p->out_pieces.size(); i++) {
@@ -735,7 +764,7 @@ int kgpu_render(kgpu_plan *p, uint64_t n_blocks, float *host_out) {
             if (timing && n_blocks > 100)
                 fprintf(stderr, "[kgpu timing] kgpu_render: host loop %.1f ms, device tail %.1f ms, copy out %.1f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, now()));
         } else {
-            render_range(p, n_blocks, p->out.p, p->stream);
+            render_range(p, n_blocks, p->out.p, p->stream, nullptr, host_in);
             if (!(p->peer_world > 1 && p->peer_rank != 0))
                 CUDA_TRY(cudaMemcpyAsync(p->last_block.data(), p->out.p + per_block * (n_blocks - 1), per_block * 4, cudaMemcpyDeviceToHost, p->stream));
             CUDA_TRY(cudaStreamSynchronize(p->stream));

@@ -776,6 +776,18 @@ __global__ void reduce_signals(const float *__restrict__ partials, const uint32_
     }
 }
 
+// graph inputs that reach a graph output without a node in between (graph_tests.rs:49-79): added to the reduced bus
+__global__ void add_inputs(const float *__restrict__ sig, uint32_t n_frames, float *__restrict__ out, uint32_t n_out, uint32_t block_size,
+                           const uint32_t *__restrict__ pairs, uint32_t n_pairs) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_frames) return;
+    const uint32_t blk = t / block_size, i = t % block_size;
+    for (uint32_t k = 0; k < n_pairs; k++) {
+        float *o = out + ((size_t)blk * n_out + pairs[2 * k + 1]) * block_size + i;
+        *o = *o + sig[(size_t)pairs[2 * k] * n_frames + t];
+    }
+}
+
 // ---- multi-GPU mix bus over peer memory (NVLink) ------------------------------------------------
 // Every rank's reduce_bus writes its bus straight into its slot of a buffer in rank 0's memory;
 // signal_flag then publishes "launch L of epoch E is there" with a system-scope release store, and
@@ -838,6 +850,11 @@ cudaError_t launch_reduce_bus(const float *partials, const uint32_t *row_mask, u
 cudaError_t launch_reduce_signals(const float *partials, const uint32_t *row_mask, uint32_t n_rows, uint32_t n_frames, float *sig,
                                   uint32_t first_bit, const uint32_t *which, uint32_t n_which, cudaStream_t stream) {
     reduce_signals<<<(n_frames + 127) / 128, 128, 0, stream>>>(partials, row_mask, n_rows, n_frames, sig, first_bit, which, n_which);
+    return cudaGetLastError();
+}
+cudaError_t launch_add_inputs(const float *sig, uint32_t n_frames, float *out, uint32_t n_out, uint32_t block_size, const uint32_t *pairs,
+                              uint32_t n_pairs, cudaStream_t stream) {
+    add_inputs<<<(n_frames + 127) / 128, 128, 0, stream>>>(sig, n_frames, out, n_out, block_size, pairs, n_pairs);
     return cudaGetLastError();
 }
 cudaError_t launch_signal_flag(uint32_t *flag, uint32_t value, cudaStream_t stream) {

@@ -37,6 +37,10 @@ cudaError_t launch_reduce_bus(const float *partials, const uint32_t *row_mask, u
 cudaError_t launch_reduce_signals(const float *partials, const uint32_t *row_mask, uint32_t n_rows, uint32_t n_frames, float *sig,
                                   uint32_t first_bit, const uint32_t *which, uint32_t n_which, cudaStream_t stream);
 
+// graph inputs wired straight into graph outputs: out[block][pairs[2k+1]][i] += sig[pairs[2k]][frame]
+cudaError_t launch_add_inputs(const float *sig, uint32_t n_frames, float *out, uint32_t n_out, uint32_t block_size, const uint32_t *pairs,
+                              uint32_t n_pairs, cudaStream_t stream);
+
 // multi-GPU mix bus over peer memory (kernels.cu)
 cudaError_t launch_signal_flag(uint32_t *flag, uint32_t value, cudaStream_t stream);
 cudaError_t launch_wait_flag(const uint32_t *flag, uint32_t value, uint32_t *timeout_flag, cudaStream_t stream);

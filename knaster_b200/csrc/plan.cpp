@@ -778,7 +778,9 @@ void HostPlan::build(const kgpu_graph_desc &d) {
     if (d.sample_rate == 0 || d.block_size == 0) KGPU_THROW(KGPU_ERR_INVALID, "sample_rate and block_size must be non-zero"); // processor.rs:75
     if (d.block_size > 65535) KGPU_THROW(KGPU_ERR_INVALID, "block_size must fit the u16 in-block delay (graph_gen.rs:292)");
     if (d.n_outputs < 1 || d.n_outputs > (uint32_t)MAX_BUS) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "n_outputs must be 1..%d", MAX_BUS);
-    if (d.n_inputs != 0) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "graphs with inputs are not supported: render with run_without_inputs()");
+    if (d.n_inputs > 16) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "more than 16 graph inputs");
+    n_inputs = d.n_inputs;
+    input_to_output.clear();
     if ((d.n_nodes && !d.nodes) || (d.n_edges && !d.edges) || (d.n_param_edges && !d.param_edges))
         KGPU_THROW(KGPU_ERR_INVALID, "NULL array in graph description");
     sample_rate = d.sample_rate;
@@ -814,7 +816,10 @@ void HostPlan::build(const kgpu_graph_desc &d) {
     std::vector<std::pair<int, uint32_t>> out_edges(n_outputs, {-1, 0u});
     std::vector<uint32_t> fanout(N, 0);
     auto check_src = [&](int32_t src, uint32_t ch, const char *what) {
-        if (src == KGPU_GRAPH) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "%s: graph inputs are not supported", what);
+        if (src == KGPU_GRAPH) { // NodeOrGraph::Graph as a source: a graph input
+            if (ch >= d.n_inputs) KGPU_THROW(KGPU_ERR_INVALID, "%s: GraphInputOutOfBounds(%u)", what, ch);
+            return;
+        }
         if (src < 0 || (uint32_t)src >= N) KGPU_THROW(KGPU_ERR_INVALID, "%s: source node %d not found", what, src);
         if (ch >= (uint32_t)kind_info(d.nodes[src]).n_out) KGPU_THROW(KGPU_ERR_INVALID, "%s: OutputOutOfBounds(%u)", what, ch);
     };
@@ -843,7 +848,8 @@ void HostPlan::build(const kgpu_graph_desc &d) {
     for (auto &e : out_edges)
         if (e.first >= 0) fanout[e.first]++;
     for (auto &pl : par_edges)
-        for (auto &pe : pl) fanout[std::get<1>(pe)]++;
+        for (auto &pe : pl)
+            if (std::get<1>(pe) >= 0) fanout[std::get<1>(pe)]++;
 
     // ---- mix buses, internal signals, voices ---------------------------------------------------------------------------
     // A graph output is the left fold ((v0+v1)+v2)+... of an Add chain (graph.rs:850-864): its leaves are voice outputs and
@@ -854,6 +860,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
     // consumers.  16 keeps every graph that fitted a voice before (MAX_NODES = 24) exactly as it was; if a component still
     // outgrows a voice the discovery is repeated with 2 (every fan-in / fan-out point is a cut).
     auto sum_like = [&](int node) {
+        if (node < 0) return false;
         const kgpu_node_desc &nd = d.nodes[node];
         if (nd.kind != KGPU_MATH || nd.mode != KGPU_OP_ADD || nd.channels != 1 || nd.n_wrappers != 0) return false;
         return in_edges[in_off[node]].first >= 0 && in_edges[in_off[node] + 1].first >= 0;
@@ -876,6 +883,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
         D.par_ext.resize(N);
         for (uint32_t i = 0; i < N; i++) D.par_ext[i].assign(par_edges[i].size(), -1);
         D.comp.assign(N, -1);
+        D.n_signals = n_inputs; // the graph's inputs come first
         // expands the Add chain rooted at `root` (the root itself may have any fan-out, inner Adds exactly one consumer)
         auto expand = [&](std::pair<int, uint32_t> root, uint32_t target, bool root_any_fanout, bool commit, std::vector<Leaf> &out) {
             std::vector<std::pair<int, uint32_t>> stack{root};
@@ -896,7 +904,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
             }
         };
         for (uint32_t oc = 0; oc < n_outputs; oc++) {
-            if (out_edges[oc].first < 0) continue;
+            if (out_edges[oc].first == KGPU_SOURCE_NONE) continue;
             // a large sum that feeds this output AND something else (the dry mix beside a master effect): its leaves go to the
             // output directly, whatever else reads the sum gets it as an internal signal made of the same leaves
             std::vector<Leaf> probe;
@@ -939,6 +947,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
         std::vector<int> stack;
         for (size_t li = 0; li < D.leaves.size(); li++) { // grows while signals are found
             const Leaf lf = D.leaves[li];
+            if (lf.node == KGPU_GRAPH) continue; // a graph input summed straight into an output: no voice behind it
             if (D.mix_node[lf.node]) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "node %d is both summed into a mix and read on its own", lf.node);
             if (D.comp[lf.node] >= 0) continue;
             const int c = (int)D.uf.size();
@@ -949,6 +958,10 @@ void HostPlan::build(const kgpu_graph_desc &d) {
                 const int nk = stack.back();
                 stack.pop_back();
                 auto visit = [&](int src, uint32_t ch, int &ext) {
+                    if (src == KGPU_GRAPH) {
+                        ext = (int)ch; // graph input ch = signal ch
+                        return;
+                    }
                     if (src < 0) return;
                     ext = resolve(src, ch);
                     if (ext >= 0) return; // read through the signal's buffer: no edge between the two voices
@@ -995,6 +1008,11 @@ void HostPlan::build(const kgpu_graph_desc &d) {
     std::unordered_map<int, std::vector<Leaf>> comp_leaves;
     std::vector<int> comp_order;
     for (auto &lf : leaves) {
+        if (lf.node == KGPU_GRAPH) {
+            if (lf.target >= n_outputs) KGPU_THROW(KGPU_ERR_UNSUPPORTED, "a graph input summed into an internal mix is not supported");
+            input_to_output.push_back({lf.ch, lf.target});
+            continue;
+        }
         int c = find(comp[lf.node]);
         auto it = comp_leaves.find(c);
         if (it == comp_leaves.end()) {
@@ -1017,7 +1035,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
         }
         std::vector<std::vector<int>> feeders(D.n_signals);  // signal -> contributing components
         for (auto &lf : leaves)
-            if (lf.target >= n_outputs) feeders[lf.target - n_outputs].push_back(find(comp[lf.node]));
+            if (lf.target >= n_outputs && lf.node >= 0) feeders[lf.target - n_outputs].push_back(find(comp[lf.node]));
         std::unordered_map<int, int> state; // 1 visiting, 2 done
         std::function<int(int)> level_of = [&](int c) -> int {
             if (state[c] == 2) return comp_level[c];
@@ -1025,6 +1043,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
             state[c] = 1;
             int lv = 0;
             for (int sg : reads[c]) {
+                if ((uint32_t)sg < n_inputs) continue; // a graph input: there before the first launch
                 int sl = 0;
                 for (int f : feeders[sg]) sl = std::max(sl, level_of(f));
                 signal_level[sg] = std::max(signal_level[sg], sl);
@@ -1035,7 +1054,7 @@ void HostPlan::build(const kgpu_graph_desc &d) {
         };
         max_level = 0;
         for (int c : comp_order) max_level = std::max(max_level, level_of(c));
-        for (uint32_t sg = 0; sg < D.n_signals; sg++)
+        for (uint32_t sg = n_inputs; sg < D.n_signals; sg++)
             if (signal_level[sg] < 0) { // a signal nobody reads cannot exist; keep it well-defined anyway
                 int sl = 0;
                 for (int f : feeders[sg]) sl = std::max(sl, comp_level[f]);

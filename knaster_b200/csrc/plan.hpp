@@ -198,8 +198,12 @@ struct HostPlan {
     // (one LFO into every voice's cutoff).  Each is rendered like a graph output -- its contributors' partial rows are
     // reduced into a buffer [signal][frame] -- one level before the voices that read it.  signal_level[s] = the level of
     // its highest contributor; groups are sorted by level.
+    // The graph's own inputs (AudioProcessor::run(&[&[F]]), processor.rs:119-141) are the first n_inputs signals, level -1:
+    // the caller's input block is copied into their rows before a launch.
     std::vector<int> signal_level;
     int max_level = 0;
+    uint32_t n_inputs = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> input_to_output; // graph input wired (or summed) straight into a graph output
     uint64_t graph_hash = 0;       // of the whole graph description (snapshots only restore into the same graph)
     uint64_t dropped_changes = 0, ignored_delays = 0, device_events = 0;
     std::vector<RawEvent, DefaultInitAllocator<RawEvent>> pending; // not yet simulated, arrival order

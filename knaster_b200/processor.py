@@ -108,11 +108,14 @@ class AudioProcessor:
         _ffi.check(self._lib.kgpu_render_block(self._plan))
 
     def run(self, inputs) -> None:
+        """``AudioProcessor::run(&[&[F]])`` (processor.rs:119-141): one block, one slice of block_size samples per graph input."""
         if len(inputs) != self.inputs():
             raise GraphError("wrong number of input channels")  # processor.rs:120
-        if self.inputs() != 0:
-            raise GraphError("graphs with inputs are not supported by the GPU engine")
-        self.run_without_inputs()
+        if self.inputs() == 0:
+            self.run_without_inputs()
+            return
+        blk = np.stack([np.ascontiguousarray(x, dtype=np.float32).reshape(self.block_size()) for x in inputs])[None]
+        self.render(1, inputs=blk)
 
     def output_block(self) -> np.ndarray:
         """[outputs][block_size] copy of the last rendered block (processor.rs:182-184)."""
@@ -134,14 +137,22 @@ class AudioProcessor:
         return int(self._lib.kgpu_plan_frame_clock(self._plan)) if self._plan else 0
 
     # -- batched rendering
-    def render(self, n_blocks: int, out: Optional[np.ndarray] = None) -> np.ndarray:
-        """Render n_blocks; returns host audio [n_blocks][outputs][block_size]."""
+    def render(self, n_blocks: int, out: Optional[np.ndarray] = None, inputs: Optional[np.ndarray] = None) -> np.ndarray:
+        """Render n_blocks; returns host audio [n_blocks][outputs][block_size].  inputs: [n_blocks][graph inputs][block_size]
+        for a graph with inputs (the batched form of ``run``)."""
         self._ensure_plan()
         self._push_events()
         self._started = True
         if out is None:
             out = np.empty((n_blocks, self.outputs(), self.block_size()), dtype=np.float32)
         assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and out.size == n_blocks * self.outputs() * self.block_size()
+        if inputs is not None:
+            inp = np.ascontiguousarray(inputs, dtype=np.float32)
+            if inp.shape != (n_blocks, self.inputs(), self.block_size()):
+                raise GraphError("inputs must be [n_blocks][graph inputs][block_size]")
+            _ffi.check(self._lib.kgpu_render_inputs(self._plan, n_blocks, inp.ctypes.data, out.ctypes.data))
+            self._last_render_frames = n_blocks * self.block_size()
+            return out
         _ffi.check(self._lib.kgpu_render(self._plan, n_blocks, out.ctypes.data))
         self._last_render_frames = n_blocks * self.block_size()
         return out

@@ -35,6 +35,7 @@ extern "C" {
     pub fn kgpu_render_block(plan: *mut kgpu_plan) -> c_int;
     pub fn kgpu_output_block(plan: *mut kgpu_plan) -> *const f32;
     pub fn kgpu_render(plan: *mut kgpu_plan, n_blocks: u64, host_out: *mut f32) -> c_int;
+    pub fn kgpu_render_inputs(plan: *mut kgpu_plan, n_blocks: u64, host_in: *const f32, host_out: *mut f32) -> c_int;
     pub fn kgpu_render_device(plan: *mut kgpu_plan, n_blocks: u64, device_out: *mut f32, cuda_stream: *mut c_void) -> c_int;
     pub fn kgpu_plan_prepare(plan: *mut kgpu_plan, n_blocks: u64) -> c_int;
     pub fn kgpu_plan_synchronize(plan: *mut kgpu_plan) -> c_int;

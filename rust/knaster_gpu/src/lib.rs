@@ -109,6 +109,12 @@ impl GpuProcessor {
         self.drain_events()?;
         check(unsafe { ffi::kgpu_render_block(self.plan) })
     }
+    /// AudioProcessor::run (processor.rs:119-141): one block with one slice per graph input
+    pub fn run(&mut self, inputs: &[&[f32]]) -> Result<(), GraphError> {
+        self.drain_events()?;
+        let flat: Vec<f32> = inputs.iter().flat_map(|c| c[..self.block].iter().copied()).collect();   // [inputs][block]
+        check(unsafe { ffi::kgpu_render_inputs(self.plan, 1, flat.as_ptr(), std::ptr::null_mut()) })
+    }
     /// AudioProcessor::output_block (processor.rs:182-184): [outputs][block] f32
     pub fn output_block(&mut self) -> &[f32] { unsafe { std::slice::from_raw_parts(ffi::kgpu_output_block(self.plan), self.block * self.outputs) } }
     /// Non-realtime render of n blocks: [n_blocks][outputs][block]

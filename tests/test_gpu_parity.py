@@ -375,9 +375,9 @@ def test_unsupported_graph_fails_loudly_on_gpu_too():
     graph, p = AudioProcessor.new(0, 1, AudioProcessorOptions())
     with graph.edit() as g:
         lfo = g.push(kn.SinWt(3.0))
-        f = g.push(kn.SvfFilter(kn.SvfFilterType.Low, 500.0, 1.0, 0.0).ar_params())
-        f.link("cutoff_freq", lfo * 100.0 + 500.0)   # audio-rate route into filter coefficients: not built yet
-        g.push(kn.SinWt(100.0)).to(f).to_graph_out()
+        e = g.push(kn.EnvAsr(0.01, 0.1).ar_params())
+        e.link("attack_time", lfo * 0.001 + 0.01)    # audio-rate route into an envelope time: not built
+        (g.push(kn.SinWt(100.0)) * e).to_graph_out()
     from knaster_b200._ffi import KgpuError
 
     with pytest.raises(KgpuError):

@@ -112,3 +112,70 @@ def test_post_mix_nodes_and_shared_sources(shape, jit):
     err_tap = float(np.abs(taps - ref_taps).max())
     print(f"{shape.__name__} jit={jit}: kernels {sorted(set(info['kernels']))}, bus err {err_bus:.2e}, tap err {err_tap:.2e}")
     assert err_bus <= 1e-5 and err_tap <= 1e-5
+
+
+# ---- graph inputs: AudioProcessor::run(&[&[F]]) (processor.rs:119-141) ---------------------------------------------
+def test_reference_graph_input_tests_on_gpu():
+    # knaster_graph/src/tests/graph_tests.rs:49-79: inputs straight to outputs
+    graph, p = AudioProcessor.new(3, 3, AudioProcessorOptions(block_size=16))
+    with graph.edit() as g:
+        g.from_inputs(1).to_graph_out_channels(0)
+        g.from_inputs(2).to_graph_out_channels(1)
+    p.run([np.ones(16, np.float32)] * 3)
+    out = p.output_block()
+    assert (out[0, 0], out[1, 0], out[2, 0]) == (1.0, 1.0, 0.0)
+    # graph_tests.rs:81-126: inputs through nodes, and summed with nodes on an output
+    graph, p = AudioProcessor.new(3, 3, AudioProcessorOptions(block_size=16))
+    with graph.edit() as g:
+        g.from_inputs([0, 0]).to_graph_out_channels([1, 2])
+        g0 = g.push(kn.TestInPlusParamUGen())
+        g1 = g.push(kn.TestInPlusParamUGen())
+        g0.param("number").set(0.75)
+        g1.param("number").set(0.5)
+        g0.to_graph_out_channels(2)
+        g.from_inputs(2).to(g1).to_graph_out_channels(0)
+    p.run([np.full(16, 2.0, np.float32)] * 3)
+    out = p.output_block()
+    assert (out[0, 0], out[1, 0], out[2, 0]) == (2.5, 2.0, 2.75)
+    with pytest.raises(Exception):
+        p.run_without_inputs()                     # processor.rs:143: run_without_inputs on a graph with inputs
+
+
+def test_graph_input_through_a_filter_bank_matches_the_oracle():
+    # an external signal (noise) through 24 different band filters with gain envelopes: the batched form of run()
+    n_blocks = 300
+    r = np.random.Generator(np.random.PCG64(9))
+    x = (r.standard_normal((n_blocks, 1, 64)) * 0.3).astype(np.float32)
+
+    def build(graph):
+        ids = []
+        with graph.edit() as g:
+            for i in range(24):
+                flt = g.push(kn.SvfFilter(kn.SvfFilterType.Band, 200.0 * (i + 1), 4.0, 0.0).precise_timing(4))
+                env = g.push(kn.EnvAsr(0.01, 0.1).wr_mul(1.0 / 24))
+                env.param("t_restart").trig_at(at(100 + 400 * i))
+                env.param("t_release").trig_at(at(9000 + 100 * i))
+                flt.param("cutoff_freq").set_at(250.0 * (i + 1), at(5000 + 7 * i))
+                sig = g.from_inputs(0).to(flt) * env
+                sig.out([0, 0]).to_graph_out()
+                ids.append(sig._outputs[0][0])
+        return ids
+
+    graph, proc = AudioProcessor.new(1, 2, AudioProcessorOptions())
+    ids = build(graph)
+    for i in ids:
+        proc.add_tap(i, 0)
+    out = proc.render(n_blocks, inputs=x)
+    taps = proc.read_taps()
+    g2 = Graph(1, 2, 64, SR)
+    ids2 = build(g2)
+    orc = OracleProcessor(g2, ring_buffer_size=1 << 22)
+    for i in ids2:
+        orc.add_tap(i, 0)
+    ref = np.zeros_like(out)
+    ref_taps = np.zeros_like(taps)
+    for b in range(n_blocks):                      # the oracle takes its inputs block by block, like knaster
+        orc.run([x[b, 0]])
+        ref[b] = orc.output_block()
+    assert np.abs(ref).max() > 1e-3
+    assert np.abs(out - ref).max() <= 1e-5
