@@ -1480,13 +1480,14 @@ const char *fused_recipe_name(int recipe) {
 // recipe 1: two lanes per voice while that still leaves at most one warp per SM sub-partition (148 x 4)
 bool fm_two_lanes(uint32_t n_voices) { return (n_voices + FM_VPW - 1) / FM_VPW <= 148u * 4u; }
 // recipe 0 -> 4: a bank this small leaves most schedulers without a warp under one-lane-per-voice; one warp per voice
-// with the frames of a chunk across the lanes is faster up to ~4800 voices.  Chunks of 32 frames
-// must tile the block grid, so that a render is identical however it is split into launches.
+// with the frames of a chunk across the lanes is faster up to ~1500 voices (measured, 10 s steps: 256 voices 6.7 ms against
+// 13.0, 1024 9.3 against 13.1, 2048 15.2 against 13.2).  Chunks of 32 frames must tile the block grid, so
+// that a render is identical however it is split into launches.
 bool sub_scan_applies(uint32_t n_voices, uint32_t block_size) {
     static const int force = [] { const char *e = getenv("KGPU_SUB_SCAN"); return e ? atoi(e) : -1; }(); // 0 never, 1 always (tests / measurements)
     if (block_size % SCAN_CHUNK) return false;
     if (force >= 0) return force != 0;
-    return n_voices <= 4096;
+    return n_voices <= 1024;
 }
 uint32_t fused_rows(int recipe, uint32_t n_voices, uint32_t n_ubus) {
     if (recipe == 4) return n_voices * n_ubus;                // one partial row per voice
