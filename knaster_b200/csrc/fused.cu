@@ -1258,6 +1258,18 @@ __global__ void __launch_bounds__(32, 8) render_fm2_wide(FusedArgs a) {
 // launch has both oscillators at the same frame.
 constexpr int FM_VPW = 16; // voices per warp
 
+// element k of a register array with k a loop variable of a partially unrolled loop (the exact path): a select chain, no local memory
+template <int N> KN_DEV float fm_pick(const float (&a)[N], int k) {
+    float r = a[0];
+#pragma unroll
+    for (int i = 1; i < N; i++) r = k == i ? a[i] : r;
+    return r;
+}
+template <int N> KN_DEV void fm_put(float (&a)[N], int k, float v) {
+#pragma unroll
+    for (int i = 0; i < N; i++) a[i] = k == i ? v : a[i];
+}
+
 struct FmLane {
     float ph, off, inc;   // this lane's oscillator: modulator (F_MPH..) or carrier (F_CPH..)
     float idx, fc, amp;   // carrier lanes: the Mul / Add constants of the route and the output gain
@@ -1346,73 +1358,108 @@ __global__ void __launch_bounds__(32, 8) render_fm2(FusedArgs a) {
     float *prow = a.partials + (size_t)(a.row0 + gwarp) * a.n_frames;
     const uint32_t NF = a.n_frames, NG = (NF + FM_SUB - 1) / FM_SUB;
     const uint32_t lag = s.car ? 2u * FM_SUB : 0u;       // the carriers run two groups behind the modulators
-    // Software pipeline, per iteration G:  (1) phases of this lane's group, using the modulator samples
-    // the previous iteration exchanged (mcur);  (2) this group's sines are ISSUED (sn_new);  (3) the
-    // previous iteration's sines (sn_old, complete by now) are shuffled to the carrier lanes (-> mcur of
-    // the next iteration) and, on carrier lanes, staged as output.  Nothing in an iteration waits for a
-    // sine issued in the same iteration.
-    float mcur[FM_SUB], sn_old[FM_SUB], amp_old[FM_SUB];
+    // Software pipeline, per iteration G:  (1) phases of this lane's group, from the carrier increments the previous iteration made out
+    // of the modulator samples it exchanged;  (2) this group's sines are ISSUED (sn_new);  (3) the previous iteration's sines (sn_old,
+    // complete by now) are staged as output on the carrier lanes and shuffled from the modulator lanes to the carrier lanes, which turn
+    // them into the increments of their next group.  Nothing in an iteration waits for a sine issued in the same iteration, and an
+    // event-free iteration is ONE basic block: the f64 pipe takes a warp instruction every other cycle (8 cycles latency; measured,
+    // tools/microbench/fp64_bench.cu), so the sixteen f64 operations of a sine leave sixteen issue slots that only the f32 / integer /
+    // shared-memory work of steps (1) and (3) can fill -- if it sits in the same block.
+    // The output gain of a group: event-free groups have ONE gain per lane (0 on lanes that emit nothing: a sine of an in-range argument
+    // is finite, so sine * 0 is a zero); groups that took the exact path multiply per frame as they go, zero what is not to be heard and
+    // hand over the products with gain 1 (x * 1 is exact).  The modulator lanes' staging columns are never read.
+    float mcur[FM_SUB], q[FM_SUB], sn_old[FM_SUB];
+    float amp_old = 0.f;
+    bool q_ok = false;                                   // q[] holds the carrier increments of the next group (no numerator was tiny)
 #pragma unroll
-    for (int k = 0; k < FM_SUB; k++) mcur[k] = sn_old[k] = amp_old[k] = 0.f;
+    for (int k = 0; k < FM_SUB; k++) mcur[k] = q[k] = sn_old[k] = 0.f;
     bool all_inrange = __all_sync(0xFFFFFFFFu, !active || s.inrange());
     uint32_t tile0 = 0;                                  // first frame of the staging tile the carriers are filling
+    // steps (3): staging, exchange, increments of the next group.  Part of both branches below, so that the event-free one stays whole.
+    auto hand_over = [&](uint32_t G, uint32_t gf) {
+        if (G >= 3) { // the carriers' sines of the previous iteration: frames (G - 3) * FM_SUB + k
+            float *row = st + (gf - 3u * FM_SUB - tile0) * SUB_PAD + lane;
+#pragma unroll
+            for (int k = 0; k < FM_SUB; k++) {
+                const float o = sn_old[k] * amp_old;     // MathUGen<Mul> with the gain as it was at that frame
+                row[k * SUB_PAD] = o;
+                if (TAPS) {
+                    const uint32_t fr = gf - 3u * FM_SUB + k;
+                    if (tap && emit && fr < NF) tap[fr] = o;
+                }
+            }
+        }
+        // the modulators' sines of the previous iteration (frames (G - 1) * FM_SUB + k) reach the carrier lanes, which get to those
+        // frames in the next iteration: audio_rate.rs:42-57 + osc.rs:240-242, phase_increment = F::new(v as f64) / F::new(sr as f32).
+        // The increments depend on the exchanged samples and the route's constants only, not on the phase; if a numerator is too small
+        // for div_rc's exactness argument (|v| <= 1e-20: the quotient's last bit would need the scaled form) the next group takes the
+        // exact path, as it does when an event changes the constants
+        float vmin = 1.0f;
+#pragma unroll
+        for (int k = 0; k < FM_SUB; k++) {
+            mcur[k] = __shfl_sync(0xFFFFFFFFu, sn_old[k], mod_lane);
+            const float vv = mcur[k] * s.idx + s.fc;     // MathUGen<Mul>, MathUGen<Add>
+            vmin = fminf(vmin, fabsf(vv));
+            q[k] = div_rc(vv, sr, rc_sr);
+        }
+        q_ok = !__any_sync(0xFFFFFFFFu, s.car && vmin <= 1e-20f);
+    };
 #pragma unroll 1
     for (uint32_t G = 0; G <= NG + 2; G++) {
         const uint32_t gf = G * FM_SUB;                  // the modulators' first frame in this iteration
         const uint32_t lf = gf - lag;                    // this lane's first frame (meaningful while role_on)
         const bool role_on = s.car ? (G >= 2 && G < NG + 2) : G < NG;
         const bool ev_group = __any_sync(0xFFFFFFFFu, role_on && next_frame < lf + FM_SUB);
-        float sn_new[FM_SUB], amp_new[FM_SUB];
-        if (!ev_group && all_inrange && G >= 2 && gf + FM_SUB <= NF) { // both roles have a whole group
-            float arg[FM_SUB];
+        if (!ev_group && all_inrange && q_ok && G >= 3 && gf + FM_SUB <= NF) { // both roles have a whole group
+            float arg[FM_SUB], sn_new[FM_SUB];
+            float ph = s.ph;
 #pragma unroll
             for (int k = 0; k < FM_SUB; k++) {
-                arg[k] = s.advance<true>(mcur[k], sr, rc_sr, true);
-                amp_new[k] = s.amp;
+                arg[k] = (ph + s.off) * KN_TAU;          // osc.rs:264
+                const float pn = ph + (s.car ? q[k] : s.inc);
+                ph = pn > 1.0f ? pn - 1.0f : pn;         // osc.rs:266-268
             }
+            s.ph = ph;
+            s.inc = s.car ? q[FM_SUB - 1] : s.inc;
 #pragma unroll
-            for (int k = 0; k < FM_SUB; k++) sn_new[k] = kn_sinf_glibc_inrange(arg[k]);
+            for (int k = 0; k < FM_SUB; k++) sn_new[k] = kn_sinf_glibc_lean(arg[k]);
+            hand_over(G, gf);
+#pragma unroll
+            for (int k = 0; k < FM_SUB; k++) sn_old[k] = sn_new[k];
+            amp_old = emit ? s.amp : 0.f;
         } else {
+            float sn_new[FM_SUB];
+#pragma unroll 1
+            for (int k0 = 0; k0 < FM_SUB; k0 += 4) {
 #pragma unroll
-            for (int k = 0; k < FM_SUB; k++) {
-                const uint32_t fr = lf + k;
-                const bool valid = role_on && fr < NF;
-                bool touched = false;
-                while (valid && next_frame <= fr) {
-                    const DevEvent e = a.events[cur];
-                    if (e.op == OP_SET) s.set(e.reg, e.value);
-                    cur++;
-                    next_frame = cur < end ? a.events[cur].frame : 0xFFFFFFFFu;
-                    touched = true;
+                for (int kk = 0; kk < 4; kk++) {
+                    const int k = k0 + kk;
+                    const uint32_t fr = lf + k;
+                    const bool valid = role_on && fr < NF;
+                    bool touched = false;
+                    while (valid && next_frame <= fr) {
+                        const DevEvent e = a.events[cur];
+                        if (e.op == OP_SET) s.set(e.reg, e.value);
+                        cur++;
+                        next_frame = cur < end ? a.events[cur].frame : 0xFFFFFFFFu;
+                        touched = true;
+                    }
+                    if (__any_sync(0xFFFFFFFFu, touched)) all_inrange = __all_sync(0xFFFFFFFFu, !active || s.inrange());
+                    const float sn = kn_sinf(s.advance<false>(fm_pick(mcur, k), sr, rc_sr, valid));
+                    // carriers: MathUGen<Mul> with the gain of this frame; modulators hand over the bare sample
+                    fm_put(sn_new, k, s.car ? (valid && emit ? sn * s.amp : 0.f) : sn);
                 }
-                if (__any_sync(0xFFFFFFFFu, touched)) all_inrange = __all_sync(0xFFFFFFFFu, !active || s.inrange());
-                amp_new[k] = s.amp;
-                sn_new[k] = kn_sinf(s.advance<false>(mcur[k], sr, rc_sr, valid));
             }
-        }
-        if (G >= 3) { // the carriers' sines of the previous iteration: frames (G - 3) * FM_SUB + k
+            hand_over(G, gf);
 #pragma unroll
-            for (int k = 0; k < FM_SUB; k++) {
-                const uint32_t fr = gf - 3u * FM_SUB + k;
-                const float o = sn_old[k] * amp_old[k];  // MathUGen<Mul> with the gain as it was at that frame
-                const bool ok = emit && fr < NF;
-                st[(fr - tile0) * SUB_PAD + lane] = ok ? o : 0.f;
-                if (TAPS && tap && ok) tap[fr] = o;
-            }
-        }
-        // the modulators' sines of the previous iteration (frames (G - 1) * FM_SUB + k) reach the
-        // carrier lanes, which get to those frames in the next iteration
-#pragma unroll
-        for (int k = 0; k < FM_SUB; k++) {
-            mcur[k] = __shfl_sync(0xFFFFFFFFu, sn_old[k], mod_lane);
-            sn_old[k] = sn_new[k];
-            amp_old[k] = amp_new[k];
+            for (int k = 0; k < FM_SUB; k++) sn_old[k] = sn_new[k];
+            amp_old = 1.0f;
         }
         if (G >= 3) {
             const uint32_t cend = min(gf - 2u * FM_SUB, NF); // every frame below cend is staged
             if (cend - tile0 == SUB_TILE || G == NG + 2) {
                 __syncwarp();
-                // lane = frame: sum the 16 carrier columns (the modulator columns hold zeros)
+                // lane = frame: sum the 16 carrier columns
                 float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
                 for (int j = FM_VPW; j < 32; j += 4) {

@@ -7,8 +7,10 @@
 // s_sinf.c + s_sincosf.h + s_sincosf_data.c).  This is a restatement of that published algorithm:
 // fast range reduction by pi/2 in f64 and a degree-7 sine / degree-8 cosine polynomial in f64,
 // rounded once to f32.  tests/test_host_plan.py::test_sinf_restatement_matches_libm checks it
-// bit-for-bit against the libm the oracle links, over millions of arguments in [-16, 16] (with and
-// without FMA contraction the rounded results are identical there).
+// bit-for-bit against the libm the oracle links, over millions of arguments in [-16, 16], and
+// tests/test_sinf_exhaustive.py (tools/sinf_exhaustive.cpp) over EVERY float below 120 in magnitude.
+// The fused multiply-adds are glibc's too: on a CPU with FMA its ifunc selects __sinf_fma, the same source
+// compiled with contraction (12 of the 2.2e9 results differ from the un-fused build).
 //
 // Why it matters: an FM carrier integrates its modulator's output, so 1-ulp differences between the
 // device sine and libm's would random-walk the carrier phase past the 1e-5 budget within seconds.
@@ -28,7 +30,9 @@ KN_SINF_HD double kn_fma(double a, double b, double c) {
 #if defined(__CUDA_ARCH__)
     return __fma_rn(a, b, c);
 #else
-    return a * b + c; // contraction does not change the rounded f32 (verified exhaustively on the tested range)
+    // a true fused multiply-add, as in glibc's __sinf_fma (the variant its ifunc picks on every CPU with FMA): over ALL floats
+    // |y| < 120 the un-fused form differs from it in 12 results (tools/sinf_exhaustive.cpp)
+    return __builtin_fma(a, b, c);
 #endif
 }
 
@@ -85,6 +89,58 @@ KN_SINF_HD float kn_sinf_glibc_inrange(float y) { // requires |y| < 120
     double res = odd ? rc : rs_;
     res = neg ? -res : res;
     return top < 0x398 ? y : (float)res;              // |y| < 2^-12: sin(y) = y to f32 precision
+}
+
+// The same function in the form the FM kernels use: fewer instructions on the pipes that bound render_fm2.
+//   * n comes from the "magic number" rounding of x * 2/pi (t = u + 1.5 * 2^52 leaves RN(u) in t's low word and t - 1.5 * 2^52 is n as a
+//     double): two FP64 additions instead of F2I + shift + add + I2F (two quarter-rate conversions).  glibc's n is
+//     floor((trunc(x * 2^24 * 2/pi) + 2^23) / 2^24), round-half-up of the same product for x >= 0: the two disagree for five negative
+//     floats in the whole domain (arguments a hair beyond an odd multiple of pi/4), and there both polynomials round to the same f32;
+//   * the sign is bit 1 of n for both parities ({+sin, +cos, -sin, -cos}) and is applied to the rounded f32;
+//   * no special case below 2^-12: the sine polynomial rounds to y there anyway.
+// tools/sinf_exhaustive.cpp compares it with libm's sinf for EVERY float |y| < 120 (2.2e9 arguments, 5 s on 8 cores): bit-identical
+// everywhere except sin(-0.0), which is +0.0 here (an oscillator's phase argument is never -0: x + (-x) rounds to +0).
+// Every f64 operation of the selected polynomial is still glibc's, in glibc's order.
+KN_SINF_HD float kn_sinf_glibc_lean(float y) { // requires |y| < 120
+    const double TWO_OVER_PI = 0x1.45F306DC9C883p-1, MAGIC = 0x1.8p52;
+    const double HPI = 0x1.921FB54442D18p0;
+    const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+                 C4 = 0x1.99343027bf8c3p-16;
+    const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+    double x = (double)y;
+#if defined(__CUDA_ARCH__)
+    const double t = __dadd_rn(__dmul_rn(x, TWO_OVER_PI), MAGIC); // two roundings (the product, then the sum): never contracted
+    const double nd = __dadd_rn(t, -MAGIC);
+    const uint32_t n = (uint32_t)__double2loint(t);
+#else
+    volatile double u = x * TWO_OVER_PI;               // (volatile: keeps a host compiler from fusing the product into the sum)
+    const double t = u + MAGIC;
+    const double nd = t - MAGIC;
+    uint64_t tb;
+    memcpy(&tb, &t, 8);
+    const uint32_t n = (uint32_t)tb;
+#endif
+    x = kn_fma(-nd, HPI, x);
+    const double x2 = x * x;
+    const double x3 = x * x2, s1 = kn_fma(x2, S3, S2), x7 = x3 * x2, sp = kn_fma(x3, S1, x);
+    double rs = kn_fma(x7, s1, sp);
+    const double x4 = x2 * x2, c2 = kn_fma(x2, C4, C3), c1 = kn_fma(x2, C1, C0), x6 = x4 * x2, cp = kn_fma(x4, C2, c1);
+    double rc = kn_fma(x6, c2, cp);
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+d"(rs), "+d"(rc));             // both polynomials stay unconditional (see kn_sinf_glibc_inrange)
+#endif
+    const float f = (float)((n & 1u) ? rc : rs);
+    uint32_t fb;
+#if defined(__CUDA_ARCH__)
+    fb = __float_as_uint(f) ^ ((n << 30) & 0x80000000u);
+    return __uint_as_float(fb);
+#else
+    memcpy(&fb, &f, 4);
+    fb ^= (n << 30) & 0x80000000u;
+    float o;
+    memcpy(&o, &fb, 4);
+    return o;
+#endif
 }
 
 // Returns true and the sine in *out for |y| < 120 (glibc's reduce_fast domain); false otherwise
