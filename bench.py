@@ -33,7 +33,8 @@ sys.path.insert(0, ROOT)
 SR, BLOCK = 48000, 64
 # algorithmic ops per voice-sample (Envelope: 7 f64 + cvt in place of EnvAsr's 5 + scale)
 W_FLOPS = {"subtractive": 40.0, "subtractive_seg": 42.0, "additive": 6.0, "fm": 15.0, "chain": 43.0}  # chain: + OnePoleLpf 3
-N_SM, FP32_LANES, XU_LANES, LDS_BANKS = 148, 128, 16, 32
+N_SM, FP32_LANES, FP64_LANES, LDS_BANKS = 148, 128, 64, 32
+F64_OPS_PER_SINF = 16
 DEFAULT_VOICES = {"subtractive": 16384, "subtractive_seg": 16384, "additive": 4096, "fm": 8192, "chain": 16384}
 WORKLOAD_NAMES = {
     "subtractive": "subtractive polysynth: saw -> SvfFilter lowpass -> EnvAsr -> VCA, sample-accurate note events",
@@ -378,10 +379,14 @@ def roofline_of(res, peaks, peak_src):
     rate = vs_per_launch / (avg_launch_ms / 1e3)  # voice-samples/s of the render kernel(s) alone
     kernel = res["info"]["kernels"][0]
     if wl == "fm":
-        # 2 sinf per voice-sample on the XU/SFU pipe: peak_xu = n_SM x 16 x f_SM
-        peak = N_SM * XU_LANES * sm_max * 1e6 / 1e9
-        out = {"bound": "xu", "achieved": rate * 2.0 / 1e9, "peak": peak, "unit": "G sinf/s (XU pipe, 2 per voice-sample)",
-               "peak_source": f"{N_SM} SMs x {XU_LANES} XU lanes x sm_max_mhz {sm_max:g} ({peak_src})",
+        # knaster's SinNumeric is libm's sinf (osc.rs:264): glibc evaluates it in f64 (reduction + degree-7 / degree-8 polynomial) and
+        # so must the device, bit for bit -- 16 f64 operations per sine (csrc/sinf_glibc.h::kn_sinf_glibc_lean), 2 sines per voice-sample,
+        # on a pipe that takes 16 lanes per SM sub-partition per cycle (measured: tools/microbench/fp64_bench.cu, 2.07 cycles per warp DFMA)
+        peak = N_SM * FP64_LANES * sm_max * 1e6 / 1e9
+        out = {"bound": "fp64", "achieved": rate * 2.0 * F64_OPS_PER_SINF / 1e9, "peak": peak,
+               "unit": "G f64 instr/s (FP64 pipe; 16 per sinf, 2 sinf per voice-sample)",
+               "peak_source": f"{N_SM} SMs x {FP64_LANES} FP64 lanes x sm_max_mhz {sm_max:g} ({peak_src})",
+               "sinf_per_s": rate * 2.0,
                "fp32_frac": rate * W_FLOPS[wl] / 1e9 / (N_SM * FP32_LANES * sm_max * 1e6 / 1e9)}
     elif wl == "additive":
         # one 4-byte shared-memory table lookup per voice-sample: peak_lds = n_SM x 32 banks x f_SM (conflict-free)

@@ -1108,7 +1108,7 @@ bool match_sub_seg(const DevProgram &p) {
 // template order: 0 mod, 1 Constant idx, 2 Mul, 3 Constant fc, 4 Add, 5 car, 6 Constant amp, 7 Mul
 enum : uint32_t { F_MPH = 0, F_MOFF = 1, F_MINC = 2, F_IDX = 3, F_FC = 4, F_CPH = 5, F_COFF = 6, F_CINC = 7, F_AMP = 8, FM_NREGS = 9 };
 #ifndef FM_SUB_N
-#define FM_SUB_N 16 // frames per straight-line group of render_fm2 (8 or 16: measured)
+#define FM_SUB_N 32 // frames per straight-line group of render_fm2: 8 -> 23.9 ms, 16 -> 18.7 ms, 32 -> 17.7 ms per 10 s step of configs[3] (236 registers, no spills)
 #endif
 constexpr int FM_SUB = FM_SUB_N; // independent f64 sine chains in flight per lane
 
@@ -1421,8 +1421,12 @@ __global__ void __launch_bounds__(32, 8) render_fm2(FusedArgs a) {
             }
             s.ph = ph;
             s.inc = s.car ? q[FM_SUB - 1] : s.inc;
+#ifdef FM_STAGED
+            kn_sinf_glibc_lean_n(arg, sn_new);
+#else
 #pragma unroll
             for (int k = 0; k < FM_SUB; k++) sn_new[k] = kn_sinf_glibc_lean(arg[k]);
+#endif
             hand_over(G, gf);
 #pragma unroll
             for (int k = 0; k < FM_SUB; k++) sn_old[k] = sn_new[k];

@@ -143,6 +143,61 @@ KN_SINF_HD float kn_sinf_glibc_lean(float y) { // requires |y| < 120
 #endif
 }
 
+#if defined(__CUDACC__)
+// N independent sines, written stage by stage (every stage over all N arguments before the next one): the order a software-pipelined
+// schedule wants; the operations per argument are kn_sinf_glibc_lean's.
+template <int N> __device__ __forceinline__ void kn_sinf_glibc_lean_n(const float (&y)[N], float (&o)[N]) {
+    const double TWO_OVER_PI = 0x1.45F306DC9C883p-1, MAGIC = 0x1.8p52;
+    const double HPI = 0x1.921FB54442D18p0;
+    const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+                 C4 = 0x1.99343027bf8c3p-16;
+    const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+    double x[N], t[N], x2[N], a[N], b[N], c[N], d[N];
+    uint32_t n[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = (double)y[i];
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = __dmul_rn(x[i], TWO_OVER_PI);
+#pragma unroll
+    for (int i = 0; i < N; i++) t[i] = __dadd_rn(t[i], MAGIC);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        n[i] = (uint32_t)__double2loint(t[i]);
+        t[i] = __dadd_rn(t[i], -MAGIC);
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) x[i] = __fma_rn(-t[i], HPI, x[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) x2[i] = __dmul_rn(x[i], x[i]);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        a[i] = __dmul_rn(x[i], x2[i]);            // x3
+        b[i] = __fma_rn(x2[i], S3, S2);           // s1
+        c[i] = __dmul_rn(x2[i], x2[i]);           // x4
+        d[i] = __fma_rn(x2[i], C4, C3);           // c2
+        t[i] = __fma_rn(x2[i], C1, C0);           // c1
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        x[i] = __fma_rn(a[i], S1, x[i]);          // sp
+        a[i] = __dmul_rn(a[i], x2[i]);            // x7
+        t[i] = __fma_rn(c[i], C2, t[i]);          // cp
+        c[i] = __dmul_rn(c[i], x2[i]);            // x6
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        a[i] = __fma_rn(a[i], b[i], x[i]);        // rs
+        c[i] = __fma_rn(c[i], d[i], t[i]);        // rc
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        asm volatile("" : "+d"(a[i]), "+d"(c[i]));
+        const float f = (float)((n[i] & 1u) ? c[i] : a[i]);
+        o[i] = __uint_as_float(__float_as_uint(f) ^ ((n[i] << 30) & 0x80000000u));
+    }
+}
+#endif
+
 // Returns true and the sine in *out for |y| < 120 (glibc's reduce_fast domain); false otherwise
 // (the large-argument reduction is not restated).
 KN_SINF_HD bool kn_sinf_glibc(float y, float *out) {

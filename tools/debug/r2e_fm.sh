@@ -3,9 +3,9 @@
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 O=gpurun_out/r2m; mkdir -p $O
 Q="--no-parity --no-other-workloads --no-cpu-baseline"
-python -m pytest tests -m gpu -x -q -k "fm or FM or fuzz or golden or pan2 or noise" > $O/pytest_fm.log 2>&1; echo "rc=$?" >> $O/pytest_fm.log
-python -m pytest tests/test_gpu_full_size.py -x -q -k "fm" > $O/pytest_full_fm.log 2>&1; echo "rc=$?" >> $O/pytest_full_fm.log
-for rep in 1 2; do for v in _build; do
+#python -m pytest tests -m gpu -x -q -k "fm or FM or fuzz or golden or pan2 or noise" > $O/pytest_fm.log 2>&1; echo "rc=$?" >> $O/pytest_fm.log
+#python -m pytest tests/test_gpu_full_size.py -x -q -k "fm" > $O/pytest_full_fm.log 2>&1; echo "rc=$?" >> $O/pytest_full_fm.log
+for rep in 1 2; do for v in _build _build_F32 _build_ST; do
   KNASTER_GPU_LIB=knaster_b200/csrc/$v/libknaster_gpu.so python bench.py --workload fm $Q --steps 5 > $O/bench_fm${v}_$rep.json 2>$O/bench_fm${v}_$rep.err
 done; done
 tail -3 $O/pytest_fm.log $O/pytest_full_fm.log; cat $O/bench_fm*.json | python -c "
