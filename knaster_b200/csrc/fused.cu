@@ -1566,6 +1566,14 @@ cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream) {
     if (recipe == 4) {
         // KGPU_SCAN_PIPE=0: the unpipelined form (pre-pass, then the frame-parallel half), kept for measurements
         static const bool pipe = [] { const char *e = getenv("KGPU_SCAN_PIPE"); return !(e && *e == '0'); }();
+        // KGPU_SCAN_WARPS=2: two warps per voice (render_sub_scan2), kept as a measured negative result: 6.3 ms per 10 s step of 256
+        // voices against 5.8 ms for the one-warp kernel (fused_scan.cuh)
+        static const bool two_warps = [] { const char *e = getenv("KGPU_SCAN_WARPS"); return e && *e == '2'; }();
+        if (two_warps) {
+            if (a.n_taps) render_sub_scan2<true><<<a.n_voices, 64, 0, stream>>>(a);
+            else render_sub_scan2<false><<<a.n_voices, 64, 0, stream>>>(a);
+            return cudaGetLastError();
+        }
         if (pipe) {
             if (a.n_taps) render_sub_scan<true, true><<<a.n_voices, 32, 0, stream>>>(a);
             else render_sub_scan<false, true><<<a.n_voices, 32, 0, stream>>>(a);
