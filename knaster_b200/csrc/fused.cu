@@ -1566,12 +1566,25 @@ cudaError_t launch_fused(int recipe, const FusedArgs &a, cudaStream_t stream) {
     if (recipe == 4) {
         // KGPU_SCAN_PIPE=0: the unpipelined form (pre-pass, then the frame-parallel half), kept for measurements
         static const bool pipe = [] { const char *e = getenv("KGPU_SCAN_PIPE"); return !(e && *e == '0'); }();
-        // KGPU_SCAN_WARPS=2: two warps per voice (render_sub_scan2), kept as a measured negative result: 6.3 ms per 10 s step of 256
-        // voices against 5.8 ms for the one-warp kernel (fused_scan.cuh)
-        static const bool two_warps = [] { const char *e = getenv("KGPU_SCAN_WARPS"); return e && *e == '2'; }();
+        // Default: two warps per voice (render_sub_scan2, 64-frame chunks): 4.3 ms per 10 s step of 256 voices.  KGPU_SCAN_WARPS=1
+        // selects the one-warp kernels, kept for measurements: render_sub_scan_n (KGPU_SCAN_FPL=2, 5.0 ms) and render_sub_scan
+        // (KGPU_SCAN_FPL=1, 5.8 ms)
+        static const bool two_warps = [] { const char *e = getenv("KGPU_SCAN_WARPS"); return !(e && *e == '1'); }();
+        // KGPU_SCAN_FPL: frames per lane of render_sub_scan_n (2 or 4; 1 = render_sub_scan below)
+        static const int fpl = [] { const char *e = getenv("KGPU_SCAN_FPL"); return e && *e ? atoi(e) : 2; }();
+        if (!two_warps && fpl == 2) {
+            if (a.n_taps) render_sub_scan_n<true, 2><<<a.n_voices, 32, 0, stream>>>(a);
+            else render_sub_scan_n<false, 2><<<a.n_voices, 32, 0, stream>>>(a);
+            return cudaGetLastError();
+        }
+        if (!two_warps && fpl == 4) {
+            if (a.n_taps) render_sub_scan_n<true, 4><<<a.n_voices, 32, 0, stream>>>(a);
+            else render_sub_scan_n<false, 4><<<a.n_voices, 32, 0, stream>>>(a);
+            return cudaGetLastError();
+        }
         if (two_warps) {
-            if (a.n_taps) render_sub_scan2<true><<<a.n_voices, 64, 0, stream>>>(a);
-            else render_sub_scan2<false><<<a.n_voices, 64, 0, stream>>>(a);
+            if (a.n_taps) render_sub_scan2<true, 2><<<a.n_voices, 64, 0, stream>>>(a);
+            else render_sub_scan2<false, 2><<<a.n_voices, 64, 0, stream>>>(a);
             return cudaGetLastError();
         }
         if (pipe) {

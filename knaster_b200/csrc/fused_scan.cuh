@@ -243,20 +243,351 @@ __global__ void __launch_bounds__(32, 16) render_sub_scan(FusedArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
-// "render_sub_scan2": the same chunks on TWO warps per voice.  In render_sub_scan one warp carries both halves of a chunk and
-// its time is the sum of two latency-bound paths that the compiler overlaps only in part.  Here the halves are roles:
-//   warp 0 (phase warp)  runs the sequential f32 recurrences and nothing else -- 8 cycles per frame (wrap_threshold) -- and
-//       leaves (t_k, et_k) of every frame in a ring of chunks in shared memory; it also owns the decision "scan or exact";
-//   warp 1 (filter warp) takes the chunks from the ring: saw + blep, envelope, the SvfFilter scan, output -- two chunks per
-//       trip when both are there, so that the shuffle rounds of one scan fill the stalls of the other.
-// Warps of a CTA sit on different SM sub-partitions, so the two chains run side by side: a bank of V voices is V CTAs of 64.
-// Hand-over: named barriers, the producer / consumer pattern of the PTX manual (st.shared; bar.arrive -- bar.sync; ld.shared): per ring
-// slot one barrier "full" (phase warp arrives, filter warp waits) and one "empty" (the reverse), plus one for the return of an
-// exact chunk.  (A first version used sequence counters behind __threadfence_block(): the fence also waits for the filter warp's
-// global stores, 7.9 ms per step against 6.1 for the one-warp kernel.)  An EXACT chunk (parameter event, envelope transition,
-// outside the straight-line domain) is rendered by the filter warp in reference order, as in render_sub_scan; the phase warp
-// hands it (t, et), waits, and takes the voice's registers back.
-constexpr int SCAN2_RING = 4;     // chunks between the two warps
+// "render_sub_scan_n": FPL frames per lane.  In render_sub_scan a chunk is 32 frames and its critical path is the scan itself:
+// five rounds of shuffle + two dependent FFMAs (~30 cycles each) behind the oscillator, ~350 cycles, against 256 for the phase
+// chain.  Here a lane owns FPL CONSECUTIVE frames: it folds them locally (the filter's own recurrence, one step per frame), the
+// warp scans the 32 lane totals with the powers A^(FPL 2^r), and every lane replays its FPL frames from the state before its
+// first one -- in the reference's arithmetic (svf.rs:272-278), so only the state at every FPL-th frame carries re-associated
+// sums.  The five rounds now serve 32 * FPL frames; the phase chain (8 cycles per frame, nothing to amortise) becomes the bound.
+template <int FPL> struct ScanKN {
+    float a[4];        // A, row-major
+    float b[2];
+    float pw[5][4];    // A^(FPL 2^r), r = 0..4
+    float pn[4];       // A^(32 FPL)
+    float pk[4];       // A^(FPL lane)
+    KN_DEV void build(float a1, float a2, float a3, uint32_t lane) {
+        double A[4] = {2.0 * (double)a1 - 1.0, -2.0 * (double)a2, 2.0 * (double)a2, 1.0 - 2.0 * (double)a3};
+        b[0] = 2.0f * a2;
+        b[1] = 2.0f * a3;
+        double P[4] = {A[0], A[1], A[2], A[3]};
+#pragma unroll
+        for (int i = 1; i < FPL; i <<= 1) ScanK::mul(P, P, P);   // A^FPL (FPL a power of two)
+        double K[4] = {1.0, 0.0, 0.0, 1.0};
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) pw[r][i] = (float)P[i];
+            if ((lane >> r) & 1u) ScanK::mul(P, K, K);
+            ScanK::mul(P, P, P);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            a[i] = (float)A[i];
+            pn[i] = (float)P[i];
+            pk[i] = (float)K[i];
+        }
+    }
+};
+
+template <bool TAPS, int FPL>
+__global__ void __launch_bounds__(32, 16) render_sub_scan_n(FusedArgs a) {
+    static_assert(FPL == 1 || FPL == 2 || FPL == 4, "frames per lane");
+    constexpr int CH = SCAN_CHUNK * FPL;                  // frames per chunk
+    __shared__ __align__(16) float pre_t[2][CH];
+    __shared__ __align__(16) float pre_e[2][CH];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t v = blockIdx.x;
+    const uint32_t V = a.n_voices;
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+    SubVoice<AsrEnv> s; // the voice's registers, identical on every lane
+    {
+        uint32_t r[R_EST];
+#pragma unroll
+        for (int i = 0; i < R_EST; i++) r[i] = a.regs[(size_t)i * V + v];
+#pragma unroll
+        for (int i = 0; i < R_EST; i++) s.set_core(i, r[i]);
+        s.e.load(a, v);
+    }
+    uint32_t cur = 0, end = 0, next_frame = 0xFFFFFFFFu;
+    if (a.events) {
+        cur = a.ev_off[v];
+        end = a.ev_off[v + 1];
+        if (cur < end) next_frame = __ldg(&a.events[cur].frame);
+    }
+    float *tap = nullptr;
+    if (TAPS)
+        for (uint32_t i = 0; i < a.n_taps; i++)
+            if (a.taps[i].voice == v) tap = a.tap_out + (size_t)a.taps[i].tap * a.tap_stride + a.tap_frame0;
+    float *prow = a.partials + (size_t)(a.row0 + v) * a.n_frames;
+
+    ScanKN<FPL> K;
+    K.build(s.a1, s.a2, s.a3, lane);
+    float omd = 1.0f - s.dt, rc = div_prep(s.dt), tflag = wrap_flag_const(wrap_threshold(s.dt));
+    AsrEnv::D d;
+    s.e.derive(d);
+    const uint32_t NF = a.n_frames;
+
+    // the pre-pass of one chunk: the two f32 recurrences, sequentially, in the reference's rounding order.  Every lane runs the
+    // same chain; lane 0 leaves (t_k, et_k) in shared memory, four frames per store.
+    auto prepass = [&](uint32_t buf) {
+        float t = s.t, et = s.e.et;
+        float4 *dt4 = reinterpret_cast<float4 *>(pre_t[buf]), *de4 = reinterpret_cast<float4 *>(pre_e[buf]);
+#pragma unroll
+        for (int k = 0; k < CH; k += 4) {
+            float tt[4], ee[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                tt[j] = t;
+                ee[j] = et;
+                t = (t + s.dt) - wrap_flag(t, tflag);     // inc(), polyblep.rs:232-235: wrap01(t + dt), see wrap_threshold
+                et = et + d.delta;                        // envelopes.rs:58-66 with the state fixed over the chunk
+            }
+            if (lane == 0) {
+                dt4[k / 4] = make_float4(tt[0], tt[1], tt[2], tt[3]);
+                de4[k / 4] = make_float4(ee[0], ee[1], ee[2], ee[3]);
+            }
+        }
+        s.t = t;
+        s.e.et = (d.att || d.rel) ? et : s.e.et;
+    };
+    // whether the chunk starting at f0 can take the scan path, given the state at its first frame
+    auto chunk_fast = [&](uint32_t f0) {
+        return f0 + CH <= NF && next_frame >= f0 + CH && sub_lane_fast(s) && s.e.safe_frames() >= (uint32_t)CH;
+    };
+    // the frame-parallel half of a chunk: lane k renders frames f0 + FPL k .. + FPL - 1
+    auto parallel = [&](uint32_t buf, uint32_t f0) {
+        const bool ramp = d.att || d.rel;
+        float x[FPL], env[FPL];
+#pragma unroll
+        for (int j = 0; j < FPL; j++) {
+            const float t = pre_t[buf][FPL * lane + j], et = pre_e[buf][FPL * lane + j];
+            x[j] = saw_eval(t, s.dt, omd, rc);                      // saw + blep, polyblep.rs:490-498
+            const float tl = ramp ? et : d.cval;
+            const float u = d.rel ? et : 1.0f;
+            env[j] = (((tl * u) * u) * d.sc2) * s.e.gain;           // EnvAsr::next_sample, then WrMul
+        }
+        // the lane's own frames folded from a zero state: c = sum_j A^(FPL-1-j) b x_j
+        float c1 = K.b[0] * x[0], c2 = K.b[1] * x[0];
+#pragma unroll
+        for (int j = 1; j < FPL; j++) {
+            const float n1 = __fmaf_rn(K.a[0], c1, __fmaf_rn(K.a[1], c2, K.b[0] * x[j]));
+            const float n2 = __fmaf_rn(K.a[2], c1, __fmaf_rn(K.a[3], c2, K.b[1] * x[j]));
+            c1 = n1;
+            c2 = n2;
+        }
+        // inclusive scan of the lane totals: c_L = sum_{j<=L} (A^FPL)^(L-j) c_j
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const float u1 = __shfl_up_sync(FULL, c1, 1u << r), u2 = __shfl_up_sync(FULL, c2, 1u << r);
+            if (lane >= (1u << r)) {
+                c1 = __fmaf_rn(K.pw[r][0], u1, __fmaf_rn(K.pw[r][1], u2, c1));
+                c2 = __fmaf_rn(K.pw[r][2], u1, __fmaf_rn(K.pw[r][3], u2, c2));
+            }
+        }
+        float e1 = __shfl_up_sync(FULL, c1, 1), e2 = __shfl_up_sync(FULL, c2, 1);
+        if (lane == 0) e1 = e2 = 0.0f;
+        const float l1 = __shfl_sync(FULL, c1, 31), l2 = __shfl_sync(FULL, c2, 31);
+        // the state before this lane's first frame: s = A^(FPL lane) s_0 + c_(lane-1); then its frames as the filter runs them
+        float ic1 = __fmaf_rn(K.pk[0], s.ic1, __fmaf_rn(K.pk[1], s.ic2, e1));
+        float ic2 = __fmaf_rn(K.pk[2], s.ic1, __fmaf_rn(K.pk[3], s.ic2, e2));
+        const float n1 = __fmaf_rn(K.pn[0], s.ic1, __fmaf_rn(K.pn[1], s.ic2, l1));
+        const float n2 = __fmaf_rn(K.pn[2], s.ic1, __fmaf_rn(K.pn[3], s.ic2, l2));
+        s.ic1 = n1;
+        s.ic2 = n2;
+        float out[FPL];
+#pragma unroll
+        for (int j = 0; j < FPL; j++) {
+            const float v3 = x[j] - ic2;                            // svf.rs:272-278
+            const float v1 = s.a1 * ic1 + s.a2 * v3;
+            const float v2 = (ic2 + s.a2 * ic1) + s.a3 * v3;
+            ic1 = 2.0f * v1 - ic1;
+            ic2 = 2.0f * v2 - ic2;
+            const float y = (s.m0 * x[j] + s.m1 * v1) + s.m2 * v2;
+            out[j] = y * env[j];                                    // MathUGen<Mul>, math.rs:45-47
+        }
+        float *dst = prow + f0 + FPL * lane;
+        if (FPL == 1) dst[0] = out[0];
+        else if (FPL == 2) *reinterpret_cast<float2 *>(dst) = make_float2(out[0], out[FPL > 1 ? 1 : 0]);
+        else *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[FPL > 1 ? 1 : 0], out[FPL > 2 ? 2 : 0], out[FPL > 3 ? 3 : 0]);
+        if (TAPS && tap) {
+#pragma unroll
+            for (int j = 0; j < FPL; j++) tap[f0 + FPL * lane + j] = out[j];
+        }
+    };
+
+    // Both halves of the steady state in ONE hand-interleaved instruction stream: the pre-pass of the NEXT chunk (a latency-bound
+    // chain, ~9 cycles per frame) cut into eight segments, and between them the stages of THIS chunk's frame-parallel half
+    // (oscillator, local fold, the five scan rounds, the replay): each stage's shuffle latencies sit inside a chain segment.
+    // ptxas keeps the order it is given (measured: written one after the other, the two halves ran one after the other,
+    // 820 + 470 cycles per chunk).
+    auto fused_chunk = [&](uint32_t buf, uint32_t f0) {
+        float t = s.t, et = s.e.et;
+        float4 *dt4 = reinterpret_cast<float4 *>(pre_t[buf ^ 1]), *de4 = reinterpret_cast<float4 *>(pre_e[buf ^ 1]);
+        auto seg = [&](auto seg_c) {
+            constexpr int S = decltype(seg_c)::value;
+            constexpr int N = CH / 8;                      // frames per segment
+#pragma unroll
+            for (int k = S * N; k < (S + 1) * N; k += 4) {
+                float tt[4], ee[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    tt[j] = t;
+                    ee[j] = et;
+                    t = (t + s.dt) - wrap_flag(t, tflag);
+                    et = et + d.delta;
+                }
+                if (lane == 0) {
+                    dt4[k / 4] = make_float4(tt[0], tt[1], tt[2], tt[3]);
+                    de4[k / 4] = make_float4(ee[0], ee[1], ee[2], ee[3]);
+                }
+            }
+        };
+        const bool ramp = d.att || d.rel;
+        float x[FPL], env[FPL], c1, c2;
+        seg(std::integral_constant<int, 0>{});
+#pragma unroll
+        for (int j = 0; j < FPL; j++) {
+            const float tj = pre_t[buf][FPL * lane + j], ej = pre_e[buf][FPL * lane + j];
+            x[j] = saw_eval(tj, s.dt, omd, rc);
+            const float tl = ramp ? ej : d.cval;
+            const float u = d.rel ? ej : 1.0f;
+            env[j] = (((tl * u) * u) * d.sc2) * s.e.gain;
+        }
+        seg(std::integral_constant<int, 1>{});
+        c1 = K.b[0] * x[0], c2 = K.b[1] * x[0];
+#pragma unroll
+        for (int j = 1; j < FPL; j++) {
+            const float n1 = __fmaf_rn(K.a[0], c1, __fmaf_rn(K.a[1], c2, K.b[0] * x[j]));
+            const float n2 = __fmaf_rn(K.a[2], c1, __fmaf_rn(K.a[3], c2, K.b[1] * x[j]));
+            c1 = n1;
+            c2 = n2;
+        }
+        auto round = [&](auto r_c) {
+            constexpr int r = decltype(r_c)::value;
+            const float u1 = __shfl_up_sync(FULL, c1, 1u << r), u2 = __shfl_up_sync(FULL, c2, 1u << r);
+            if (lane >= (1u << r)) {
+                c1 = __fmaf_rn(K.pw[r][0], u1, __fmaf_rn(K.pw[r][1], u2, c1));
+                c2 = __fmaf_rn(K.pw[r][2], u1, __fmaf_rn(K.pw[r][3], u2, c2));
+            }
+        };
+        round(std::integral_constant<int, 0>{});
+        seg(std::integral_constant<int, 2>{});
+        round(std::integral_constant<int, 1>{});
+        seg(std::integral_constant<int, 3>{});
+        round(std::integral_constant<int, 2>{});
+        seg(std::integral_constant<int, 4>{});
+        round(std::integral_constant<int, 3>{});
+        seg(std::integral_constant<int, 5>{});
+        round(std::integral_constant<int, 4>{});
+        seg(std::integral_constant<int, 6>{});
+        float e1 = __shfl_up_sync(FULL, c1, 1), e2 = __shfl_up_sync(FULL, c2, 1);
+        if (lane == 0) e1 = e2 = 0.0f;
+        const float l1 = __shfl_sync(FULL, c1, 31), l2 = __shfl_sync(FULL, c2, 31);
+        seg(std::integral_constant<int, 7>{});
+        s.t = t;
+        s.e.et = ramp ? et : s.e.et;
+        float ic1 = __fmaf_rn(K.pk[0], s.ic1, __fmaf_rn(K.pk[1], s.ic2, e1));
+        float ic2 = __fmaf_rn(K.pk[2], s.ic1, __fmaf_rn(K.pk[3], s.ic2, e2));
+        const float n1 = __fmaf_rn(K.pn[0], s.ic1, __fmaf_rn(K.pn[1], s.ic2, l1));
+        const float n2 = __fmaf_rn(K.pn[2], s.ic1, __fmaf_rn(K.pn[3], s.ic2, l2));
+        s.ic1 = n1;
+        s.ic2 = n2;
+        float out[FPL];
+#pragma unroll
+        for (int j = 0; j < FPL; j++) {
+            const float v3 = x[j] - ic2;                            // svf.rs:272-278
+            const float v1 = s.a1 * ic1 + s.a2 * v3;
+            const float v2 = (ic2 + s.a2 * ic1) + s.a3 * v3;
+            ic1 = 2.0f * v1 - ic1;
+            ic2 = 2.0f * v2 - ic2;
+            const float y = (s.m0 * x[j] + s.m1 * v1) + s.m2 * v2;
+            out[j] = y * env[j];
+        }
+        float *dst = prow + f0 + FPL * lane;
+        if (FPL == 1) dst[0] = out[0];
+        else if (FPL == 2) *reinterpret_cast<float2 *>(dst) = make_float2(out[0], out[FPL > 1 ? 1 : 0]);
+        else *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[FPL > 1 ? 1 : 0], out[FPL > 2 ? 2 : 0], out[FPL > 3 ? 3 : 0]);
+        if (TAPS && tap) {
+#pragma unroll
+            for (int j = 0; j < FPL; j++) tap[f0 + FPL * lane + j] = out[j];
+        }
+    };
+
+    bool have = false;   // the pre-pass of the chunk at f0 is already in pre[buf]
+    uint32_t buf = 0;
+    uint32_t f0 = 0;
+#pragma unroll 1
+    while (f0 < NF) {
+        if (have || chunk_fast(f0)) {
+            if (!have) {
+                prepass(buf);
+                __syncwarp();
+            }
+            // the NEXT chunk's pre-pass (a latency-bound chain) is issued in the same basic block as this chunk's frame-parallel
+            // half (shuffle latencies): each fills the other's stalls
+            if (chunk_fast(f0 + CH)) {
+                fused_chunk(buf, f0);
+                have = true;
+            } else {
+                parallel(buf, f0);
+                have = false;
+            }
+            __syncwarp();
+            buf ^= 1;
+            f0 += CH;
+        } else {
+            // ---- exact chunk: events applied at their frames, every frame in reference order, all lanes in step (32 frames at a
+            // time: lane k keeps frame k).  The WHOLE chunk, so that the chunk grid stays where it is: which frames are scanned must
+            // not depend on how the render is cut into launches (multiples of 64 frames).
+            bool touched = false;
+            const uint32_t fe = min(f0 + (uint32_t)CH, NF);
+#pragma unroll 1
+            for (; f0 < fe; f0 += SCAN_CHUNK) {
+                float out = 0.0f;
+                const uint32_t nf = min((uint32_t)SCAN_CHUNK, fe - f0);
+#pragma unroll 1
+                for (uint32_t k = 0; k < nf; k++) {
+                    while (next_frame <= f0 + k) { // sorted by (frame, node, arrival)
+                        const DevEvent e = ldg_event(a.events + cur);
+                        if (e.op == OP_SET) s.set(e.reg, e.value);
+                        else s.e.op(e);
+                        cur++;
+                        next_frame = cur < end ? __ldg(&a.events[cur].frame) : 0xFFFFFFFFu;
+                        touched = true;
+                    }
+                    const float o = s.tick();
+                    if (lane == k) out = o;
+                }
+                if (lane < nf) {
+                    prow[f0 + lane] = out;
+                    if (TAPS && tap) tap[f0 + lane] = out;
+                }
+            }
+            if (touched) {
+                K.build(s.a1, s.a2, s.a3, lane);
+                omd = 1.0f - s.dt;
+                rc = div_prep(s.dt);
+                tflag = wrap_flag_const(wrap_threshold(s.dt));
+            }
+            s.e.derive(d);
+        }
+    }
+    if (lane == 0) {
+        const uint32_t regs_out[R_EST] = {__float_as_uint(s.t), __float_as_uint(s.dt), s.use_sin, __float_as_uint(s.pw), s.wf,
+                                           __float_as_uint(s.ic1), __float_as_uint(s.ic2), __float_as_uint(s.a1), __float_as_uint(s.a2),
+                                           __float_as_uint(s.a3), __float_as_uint(s.m0), __float_as_uint(s.m1), __float_as_uint(s.m2)};
+#pragma unroll
+        for (int i = 0; i < R_EST; i++) a.regs[(size_t)i * V + v] = regs_out[i];
+        s.e.store(a, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// "render_sub_scan2": the same chunks on TWO warps per voice.  One warp issues in order: when the chain and the scan share a warp,
+// every stall of one (a shuffle not back yet) also holds the other (measured on render_sub_scan_n: 1070 cycles per 64-frame chunk
+// where the chain alone needs 592).  Here the halves are roles, on two SM sub-partitions (warps of a CTA are spread over them):
+//   warp 0 (phase warp)  runs the sequential f32 recurrences and nothing else and leaves (t_k, et_k) of every frame in a ring of
+//       chunks in shared memory; it also owns the decision "scan or exact";
+//   warp 1 (filter warp) takes the chunks from the ring: saw + blep, envelope, the SvfFilter scan (FPL frames per lane), output.
+// Hand-over: named barriers, the producer / consumer pattern of the PTX manual (st.shared; bar.arrive -- bar.sync; ld.shared): per
+// ring slot one barrier "full" (phase warp arrives, filter warp waits) and one "empty" (the reverse), plus one for the return of
+// an exact chunk.  Barrier ids are immediates and the loop is unrolled over the ring's slots: a barrier named by a register costs a
+// warp-synchronising prologue of ~100 cycles per use, and a first version with sequence counters behind __threadfence_block()
+// also waited for the filter warp's global stores.  An EXACT chunk (parameter event, envelope transition, outside the
+// straight-line domain) is rendered by the filter warp in reference order, as in render_sub_scan; the phase warp hands it
+// (t, et), waits, and takes the voice's registers back.
+constexpr int SCAN2_RING = 2;     // chunks between the two warps
 constexpr int SCAN2_WORDS = 19;   // the voice's registers: 13 core + 6 envelope
 
 KN_DEV void scan2_pack(const SubVoice<AsrEnv> &s, uint32_t *w) {
@@ -272,35 +603,22 @@ KN_DEV void scan2_unpack(SubVoice<AsrEnv> &s, const uint32_t *w) {
 #pragma unroll
     for (int i = 0; i < 6; i++) s.e.set(R_EST + i, w[R_EST + i]);
 }
-// barrier ids (0 is __syncthreads'): full[slot] = 1 + slot, empty[slot] = 1 + RING + slot, returned = 1 + 2 * RING; 64 threads each.
-// Immediate ids: a barrier named by a register costs a warp-synchronising prologue of ~100 cycles per use (measured, ncu r2c).
+// four floats to a shared-memory address given as such (a generic pointer makes the compiler rebuild the shared window's base --
+// S2R + LEA -- in front of every store)
+KN_DEV void scan2_sts4(uint32_t addr, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+// barrier ids (0 is __syncthreads'): full[slot] = 1 + slot, empty[slot] = 1 + RING + slot, returned = 1 + 2 * RING; 64 threads each
 template <int ID> KN_DEV void scan2_sync() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
 template <int ID> KN_DEV void scan2_arrive() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
 constexpr int SCAN2_FULL = 1, SCAN2_EMPTY = 1 + SCAN2_RING, SCAN2_RETURNED = 1 + 2 * SCAN2_RING;
-// ... and ONE copy of everything else (the kernel has to stay inside the instruction cache: two warps of a CTA run different code):
-// the slot is a run-time value, only the barrier instruction itself is picked by a (warp-uniform) switch
-template <int BASE> KN_DEV void scan2_sync_slot(uint32_t slot) {
-    static_assert(SCAN2_RING == 4, "one case per ring slot");
-    switch (slot) {
-    case 0: scan2_sync<BASE + 0>(); break;
-    case 1: scan2_sync<BASE + 1>(); break;
-    case 2: scan2_sync<BASE + 2>(); break;
-    default: scan2_sync<BASE + 3>(); break;
-    }
-}
-template <int BASE> KN_DEV void scan2_arrive_slot(uint32_t slot) {
-    switch (slot) {
-    case 0: scan2_arrive<BASE + 0>(); break;
-    case 1: scan2_arrive<BASE + 1>(); break;
-    case 2: scan2_arrive<BASE + 2>(); break;
-    default: scan2_arrive<BASE + 3>(); break;
-    }
-}
 
-template <bool TAPS>
+template <bool TAPS, int FPL>
 __global__ void __launch_bounds__(64, 8) render_sub_scan2(FusedArgs a) {
-    __shared__ __align__(16) float ring_t[SCAN2_RING][SCAN_CHUNK];   // the phase before every frame of the chunk ([0]: at an exact chunk's start)
-    __shared__ __align__(16) float ring_et[SCAN2_RING][SCAN_CHUNK];  // the envelope ramp likewise (written while the envelope ramps)
+    static_assert(SCAN2_RING == 2, "the loops below are unrolled over two slots");
+    constexpr int CH = SCAN_CHUNK * FPL;                                 // frames per chunk
+    __shared__ __align__(16) float ring_t[SCAN2_RING][CH];               // the phase before every frame ([0]: at an exact chunk's start)
+    __shared__ __align__(16) float ring_et[SCAN2_RING][CH];              // the envelope ramp likewise
     __shared__ uint32_t ring_exact[SCAN2_RING];
     __shared__ uint32_t hand[SCAN2_WORDS];
     const uint32_t lane = threadIdx.x & 31u;
@@ -324,83 +642,96 @@ __global__ void __launch_bounds__(64, 8) render_sub_scan2(FusedArgs a) {
         end = a.ev_off[v + 1];
         if (cur < end) next_frame = __ldg(&a.events[cur].frame);
     }
-    const uint32_t NF = a.n_frames, NC = (NF + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    const uint32_t NF = a.n_frames, NC = (NF + CH - 1) / CH;
     AsrEnv::D d;
     s.e.derive(d);
 
     if (phase_warp) {
-        float tstar = wrap_flag_const(wrap_threshold(s.dt));
+        float tthr = wrap_threshold(s.dt), tflag = wrap_flag_const(tthr);
         // Whether a chunk takes the scan path is a function of the state at ITS first frame only (so that a render does not depend on
         // how it is cut into launches): no event inside, the straight-line domain, no envelope transition possible inside.
         bool lane_fast = sub_lane_fast(s);                 // the voice's parameters: they only change in exact chunks
-#pragma unroll 1
-        for (uint32_t c = 0; c < NC; c++) {
-            const uint32_t SLOT = c % SCAN2_RING;
-            const uint32_t f0 = c * SCAN_CHUNK;
-            if (c >= SCAN2_RING) scan2_sync_slot<SCAN2_EMPTY>(SLOT);              // the slot is free again
-            const bool fast = lane_fast && f0 + SCAN_CHUNK <= min(next_frame, NF) &&
-                              (!(d.att || d.rel) || s.e.safe_frames() >= (uint32_t)SCAN_CHUNK);
+        uint32_t ring_t_sa = (uint32_t)__cvta_generic_to_shared(&ring_t[0][0]);
+        uint32_t ring_et_sa = (uint32_t)__cvta_generic_to_shared(&ring_et[0][0]);
+        asm volatile("" : "+r"(ring_t_sa), "+r"(ring_et_sa)); // opaque: kept in registers instead of being rebuilt before every store
+        auto chunk = [&](auto slot_c, uint32_t c) {
+            constexpr int SLOT = decltype(slot_c)::value;
+            const uint32_t f0 = c * CH;
+            if (c >= SCAN2_RING) scan2_sync<SCAN2_EMPTY + SLOT>();                // the slot is free again
+            const bool fast = lane_fast && f0 + CH <= min(next_frame, NF) && (!(d.att || d.rel) || s.e.safe_frames() >= (uint32_t)CH);
             if (fast) {
                 // the f32 recurrences of the chunk, sequentially, in the reference's rounding order (every lane the same chain;
                 // lane 0 leaves the values before each frame in the ring)
-                float t = s.t;
-                float4 *dt4 = reinterpret_cast<float4 *>(ring_t[SLOT]);
-                if (d.att || d.rel) {
-                    float et = s.e.et;
-                    float4 *de4 = reinterpret_cast<float4 *>(ring_et[SLOT]);
+                float t = s.t, et = s.e.et;
+                // A chunk that provably does not wrap skips the flag: t_k <= t_0 + k (dt + 2^-24) (every sum below 1 rounds by at
+                // most 2^-25), so if that stays below the threshold T for the whole chunk the chain is one FADD per frame (4 cycles
+                // instead of 9).  One decision per chunk: a branch per group of frames cost more than it saved (6.8 ms against 4.4).
+                const bool calm = __fmaf_rn((float)CH, s.dt + 5.9604644775390625e-8f, t) < tthr;
+                if (calm) {
 #pragma unroll
-                    for (int k = 0; k < SCAN_CHUNK; k += 4) {
+                    for (int k = 0; k < CH; k += 4) {
                         float tt[4], ee[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             tt[j] = t;
                             ee[j] = et;
-                            t = (t + s.dt) - wrap_flag(t, tstar);                 // inc(), polyblep.rs:232-235 (wrap_threshold)
-                            et = et + d.delta;                                    // envelopes.rs:58-66, state fixed over the chunk
+                            t = t + s.dt;                                         // no wrap here: (t + dt) - 0
+                            et = et + d.delta;
                         }
                         if (lane == 0) {
-                            dt4[k / 4] = make_float4(tt[0], tt[1], tt[2], tt[3]);
-                            de4[k / 4] = make_float4(ee[0], ee[1], ee[2], ee[3]);
+                            scan2_sts4(ring_t_sa + (SLOT * CH + k) * 4, tt[0], tt[1], tt[2], tt[3]);
+                            scan2_sts4(ring_et_sa + (SLOT * CH + k) * 4, ee[0], ee[1], ee[2], ee[3]);
                         }
                     }
-                    s.e.et = et;
                 } else {
 #pragma unroll
-                    for (int k = 0; k < SCAN_CHUNK; k += 4) {
-                        float tt[4];
+                    for (int k = 0; k < CH; k += 4) {
+                        float tt[4], ee[4];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             tt[j] = t;
-                            t = (t + s.dt) - wrap_flag(t, tstar);
+                            ee[j] = et;
+                            t = (t + s.dt) - wrap_flag(t, tflag);                 // inc(), polyblep.rs:232-235 (wrap_threshold)
+                            et = et + d.delta;                                    // envelopes.rs:58-66, state fixed over the chunk
                         }
-                        if (lane == 0) dt4[k / 4] = make_float4(tt[0], tt[1], tt[2], tt[3]);
+                        if (lane == 0) {
+                            scan2_sts4(ring_t_sa + (SLOT * CH + k) * 4, tt[0], tt[1], tt[2], tt[3]);
+                            scan2_sts4(ring_et_sa + (SLOT * CH + k) * 4, ee[0], ee[1], ee[2], ee[3]);
+                        }
                     }
                 }
                 s.t = t;
+                s.e.et = (d.att || d.rel) ? et : s.e.et;
                 if (lane == 0) ring_exact[SLOT] = 0u;
-                scan2_arrive_slot<SCAN2_FULL>(SLOT);
+                scan2_arrive<SCAN2_FULL + SLOT>();
             } else {
                 if (lane == 0) {
                     ring_t[SLOT][0] = s.t;
                     ring_et[SLOT][0] = s.e.et;
                     ring_exact[SLOT] = 1u;
                 }
-                scan2_arrive_slot<SCAN2_FULL>(SLOT);
+                scan2_arrive<SCAN2_FULL + SLOT>();
                 // the filter warp renders this chunk in reference order and returns the voice
                 scan2_sync<SCAN2_RETURNED>();
                 uint32_t w[SCAN2_WORDS];
 #pragma unroll
                 for (int i = 0; i < SCAN2_WORDS; i++) w[i] = hand[i];
                 scan2_unpack(s, w);
-                const uint32_t fe = min(f0 + SCAN_CHUNK, NF);
+                const uint32_t fe = min(f0 + (uint32_t)CH, NF);
                 while (next_frame < fe) { // the events of the chunk are applied (by the filter warp): step over them
                     cur++;
                     next_frame = cur < end ? __ldg(&a.events[cur].frame) : 0xFFFFFFFFu;
                 }
                 s.e.derive(d);
-                tstar = wrap_flag_const(wrap_threshold(s.dt));
+                tthr = wrap_threshold(s.dt);
+                tflag = wrap_flag_const(tthr);
                 lane_fast = sub_lane_fast(s);
             }
+        };
+#pragma unroll 1
+        for (uint32_t c = 0; c < NC; c += SCAN2_RING) {
+            chunk(std::integral_constant<int, 0>{}, c);
+            if (c + 1 < NC) chunk(std::integral_constant<int, 1>{}, c + 1);
         }
         // the phase warp's share of the state: the phase and the envelope
         if (lane == 0) {
@@ -416,66 +747,89 @@ __global__ void __launch_bounds__(64, 8) render_sub_scan2(FusedArgs a) {
         for (uint32_t i = 0; i < a.n_taps; i++)
             if (a.taps[i].voice == v) tap = a.tap_out + (size_t)a.taps[i].tap * a.tap_stride + a.tap_frame0;
     float *prow = a.partials + (size_t)(a.row0 + v) * a.n_frames;
-    ScanK K;
+    ScanKN<FPL> K;
     K.build(s.a1, s.a2, s.a3, lane);
     float omd = 1.0f - s.dt, rc = div_prep(s.dt);
 
-    // the scan of one chunk up to the inclusive prefix (c1, c2) and the input x: no dependence on the filter's state
-    auto scan = [&](float t, float et, float &x, float &env, float &c1, float &c2) {
-        const bool ramp = d.att || d.rel;
-        x = saw_eval(t, s.dt, omd, rc);                            // saw + blep, polyblep.rs:490-498
-        const float tl = ramp ? et : d.cval;
-        const float u = d.rel ? et : 1.0f;
-        env = (((tl * u) * u) * d.sc2) * s.e.gain;                 // EnvAsr::next_sample, then WrMul
-        c1 = K.b[0] * x, c2 = K.b[1] * x;
+    auto chunk = [&](auto slot_c, uint32_t c) {
+        constexpr int SLOT = decltype(slot_c)::value;
+        uint32_t f0 = c * CH;
+        scan2_sync<SCAN2_FULL + SLOT>();
+        const bool exact = __shfl_sync(FULL, ring_exact[SLOT], 0) != 0u; // (one lane's reading: the branches hold barriers)
+        if (!exact) {
+            float tq[FPL], eq[FPL];
 #pragma unroll
-        for (int r = 0; r < 5; r++) {
-            const float u1 = __shfl_up_sync(FULL, c1, 1u << r), u2 = __shfl_up_sync(FULL, c2, 1u << r);
-            if (lane >= (1u << r)) {
-                c1 = __fmaf_rn(K.pw[r][0], u1, __fmaf_rn(K.pw[r][1], u2, c1));
-                c2 = __fmaf_rn(K.pw[r][2], u1, __fmaf_rn(K.pw[r][3], u2, c2));
+            for (int j = 0; j < FPL; j++) {
+                tq[j] = ring_t[SLOT][FPL * lane + j];
+                eq[j] = ring_et[SLOT][FPL * lane + j];
             }
+            // the slot is handed back as soon as it has been read -- except the last RING chunks, whose "empty" nobody waits for
+            if (c + SCAN2_RING < NC) scan2_arrive<SCAN2_EMPTY + SLOT>();
+            const bool ramp = d.att || d.rel;
+            float x[FPL], env[FPL];
+#pragma unroll
+            for (int j = 0; j < FPL; j++) {
+                x[j] = saw_eval(tq[j], s.dt, omd, rc);                  // saw + blep, polyblep.rs:490-498
+                const float tl = ramp ? eq[j] : d.cval;
+                const float u = d.rel ? eq[j] : 1.0f;
+                env[j] = (((tl * u) * u) * d.sc2) * s.e.gain;           // EnvAsr::next_sample, then WrMul
+            }
+            // the lane's own frames folded from a zero state, then the inclusive scan of the lane totals (render_sub_scan_n)
+            float c1 = K.b[0] * x[0], c2 = K.b[1] * x[0];
+#pragma unroll
+            for (int j = 1; j < FPL; j++) {
+                const float n1 = __fmaf_rn(K.a[0], c1, __fmaf_rn(K.a[1], c2, K.b[0] * x[j]));
+                const float n2 = __fmaf_rn(K.a[2], c1, __fmaf_rn(K.a[3], c2, K.b[1] * x[j]));
+                c1 = n1;
+                c2 = n2;
+            }
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const float u1 = __shfl_up_sync(FULL, c1, 1u << r), u2 = __shfl_up_sync(FULL, c2, 1u << r);
+                if (lane >= (1u << r)) {
+                    c1 = __fmaf_rn(K.pw[r][0], u1, __fmaf_rn(K.pw[r][1], u2, c1));
+                    c2 = __fmaf_rn(K.pw[r][2], u1, __fmaf_rn(K.pw[r][3], u2, c2));
+                }
+            }
+            float e1 = __shfl_up_sync(FULL, c1, 1), e2 = __shfl_up_sync(FULL, c2, 1);
+            if (lane == 0) e1 = e2 = 0.0f;
+            const float l1 = __shfl_sync(FULL, c1, 31), l2 = __shfl_sync(FULL, c2, 31);
+            float ic1 = __fmaf_rn(K.pk[0], s.ic1, __fmaf_rn(K.pk[1], s.ic2, e1));
+            float ic2 = __fmaf_rn(K.pk[2], s.ic1, __fmaf_rn(K.pk[3], s.ic2, e2));
+            const float n1 = __fmaf_rn(K.pn[0], s.ic1, __fmaf_rn(K.pn[1], s.ic2, l1));
+            const float n2 = __fmaf_rn(K.pn[2], s.ic1, __fmaf_rn(K.pn[3], s.ic2, l2));
+            s.ic1 = n1;
+            s.ic2 = n2;
+            float out[FPL];
+#pragma unroll
+            for (int j = 0; j < FPL; j++) {
+                const float v3 = x[j] - ic2;                            // svf.rs:272-278
+                const float v1 = s.a1 * ic1 + s.a2 * v3;
+                const float v2 = (ic2 + s.a2 * ic1) + s.a3 * v3;
+                ic1 = 2.0f * v1 - ic1;
+                ic2 = 2.0f * v2 - ic2;
+                const float y = (s.m0 * x[j] + s.m1 * v1) + s.m2 * v2;
+                out[j] = y * env[j];                                    // MathUGen<Mul>, math.rs:45-47
+            }
+            float *dst = prow + f0 + FPL * lane;
+            if (FPL == 1) dst[0] = out[0];
+            else if (FPL == 2) *reinterpret_cast<float2 *>(dst) = make_float2(out[0], out[FPL > 1 ? 1 : 0]);
+            else *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[FPL > 1 ? 1 : 0], out[FPL > 2 ? 2 : 0], out[FPL > 3 ? 3 : 0]);
+            if (TAPS && tap) {
+#pragma unroll
+                for (int j = 0; j < FPL; j++) tap[f0 + FPL * lane + j] = out[j];
+            }
+            return;
         }
-    };
-    // the state-dependent rest: every lane's pre-update state, its frame's output, the state after the chunk
-    auto finish = [&](float x, float env, float c1, float c2, uint32_t f0) {
-        float e1 = __shfl_up_sync(FULL, c1, 1), e2 = __shfl_up_sync(FULL, c2, 1);
-        if (lane == 0) e1 = e2 = 0.0f;
-        const float l1 = __shfl_sync(FULL, c1, 31), l2 = __shfl_sync(FULL, c2, 31);
-        const float ic1 = __fmaf_rn(K.pk[0], s.ic1, __fmaf_rn(K.pk[1], s.ic2, e1));
-        const float ic2 = __fmaf_rn(K.pk[2], s.ic1, __fmaf_rn(K.pk[3], s.ic2, e2));
-        const float n1 = __fmaf_rn(K.p32[0], s.ic1, __fmaf_rn(K.p32[1], s.ic2, l1));
-        const float n2 = __fmaf_rn(K.p32[2], s.ic1, __fmaf_rn(K.p32[3], s.ic2, l2));
-        s.ic1 = n1;
-        s.ic2 = n2;
-        const float v3 = x - ic2;                                   // svf.rs:272-278 from the pre-update state
-        const float v1 = s.a1 * ic1 + s.a2 * v3;
-        const float v2 = (ic2 + s.a2 * ic1) + s.a3 * v3;
-        const float y = (s.m0 * x + s.m1 * v1) + s.m2 * v2;
-        const float out = y * env;                                  // MathUGen<Mul>, math.rs:45-47
-        prow[f0 + lane] = out;
-        if (TAPS && tap) tap[f0 + lane] = out;
-    };
-    // a slot is handed back as soon as it has been read -- except the last RING chunks, whose "empty" nobody would wait for
-    auto release = [&](uint32_t c) {
-        if (c + SCAN2_RING < NC) scan2_arrive_slot<SCAN2_EMPTY>(c % SCAN2_RING);
-    };
-    // Two chunks per trip when both are scan chunks: the two scans run side by side.  (The second chunk's barrier is only waited on
-    // when the first is a scan chunk: behind an exact chunk the phase warp is itself waiting for this warp.)
-    uint32_t c = 0;
-    bool synced = false; // chunk c's "full" barrier has been passed already
+        // ---- exact chunk: events applied at their frames, every frame in reference order, all lanes in step (32 frames at a time)
+        s.t = ring_t[SLOT][0];
+        s.e.et = ring_et[SLOT][0];
+        bool touched = false;
+        const uint32_t fe = min(f0 + (uint32_t)CH, NF);
 #pragma unroll 1
-    while (c < NC) {
-        const uint32_t S0 = c % SCAN2_RING, S1 = (c + 1) % SCAN2_RING, f0 = c * SCAN_CHUNK;
-        if (!synced) scan2_sync_slot<SCAN2_FULL>(S0);
-        synced = false;
-        if (__shfl_sync(FULL, ring_exact[S0], 0) != 0u) { // (one lane's reading: the branches hold barriers)
-            // ---- exact chunk: events applied at their frames, every frame in reference order, all lanes in step
-            s.t = ring_t[S0][0];
-            s.e.et = ring_et[S0][0];
+        for (; f0 < fe; f0 += SCAN_CHUNK) {
             float out = 0.0f;
-            bool touched = false;
-            const uint32_t nf = min((uint32_t)SCAN_CHUNK, NF - f0);
+            const uint32_t nf = min((uint32_t)SCAN_CHUNK, fe - f0);
 #pragma unroll 1
             for (uint32_t k = 0; k < nf; k++) {
                 while (next_frame <= f0 + k) { // sorted by (frame, node, arrival)
@@ -489,51 +843,30 @@ __global__ void __launch_bounds__(64, 8) render_sub_scan2(FusedArgs a) {
                 const float o = s.tick();
                 if (lane == k) out = o;
             }
-            if (touched) {
-                K.build(s.a1, s.a2, s.a3, lane);
-                omd = 1.0f - s.dt;
-                rc = div_prep(s.dt);
-            }
-            s.e.derive(d);
-            if (f0 + lane < NF) {
+            if (lane < nf) {
                 prow[f0 + lane] = out;
                 if (TAPS && tap) tap[f0 + lane] = out;
             }
-            if (lane == 0) {
-                uint32_t w[SCAN2_WORDS];
-                scan2_pack(s, w);
+        }
+        if (touched) {
+            K.build(s.a1, s.a2, s.a3, lane);
+            omd = 1.0f - s.dt;
+            rc = div_prep(s.dt);
+        }
+        s.e.derive(d);
+        if (lane == 0) {
+            uint32_t w[SCAN2_WORDS];
+            scan2_pack(s, w);
 #pragma unroll
-                for (int i = 0; i < SCAN2_WORDS; i++) hand[i] = w[i];
-            }
-            release(c);
-            scan2_arrive<SCAN2_RETURNED>();
-            c += 1;
-            continue;
+            for (int i = 0; i < SCAN2_WORDS; i++) hand[i] = w[i];
         }
-        bool two = false;
-        if (c + 1 < NC) {
-            scan2_sync_slot<SCAN2_FULL>(S1);
-            two = __shfl_sync(FULL, ring_exact[S1], 0) == 0u;
-            synced = !two;
-        }
-        if (two) {
-            const float ta = ring_t[S0][lane], ea = ring_et[S0][lane], tb = ring_t[S1][lane], eb = ring_et[S1][lane];
-            release(c);
-            release(c + 1);
-            float xa, va, a1, a2, xb, vb, b1, b2;
-            scan(ta, ea, xa, va, a1, a2);
-            scan(tb, eb, xb, vb, b1, b2);
-            finish(xa, va, a1, a2, f0);
-            finish(xb, vb, b1, b2, f0 + SCAN_CHUNK);
-            c += 2;
-        } else {
-            const float ta = ring_t[S0][lane], ea = ring_et[S0][lane];
-            release(c);
-            float xa, va, a1, a2;
-            scan(ta, ea, xa, va, a1, a2);
-            finish(xa, va, a1, a2, f0);
-            c += 1;
-        }
+        if (c + SCAN2_RING < NC) scan2_arrive<SCAN2_EMPTY + SLOT>();
+        scan2_arrive<SCAN2_RETURNED>();
+    };
+#pragma unroll 1
+    for (uint32_t c = 0; c < NC; c += SCAN2_RING) {
+        chunk(std::integral_constant<int, 0>{}, c);
+        if (c + 1 < NC) chunk(std::integral_constant<int, 1>{}, c + 1);
     }
     // the filter warp's share of the state: everything but the phase and the envelope
     if (lane == 0) {

@@ -140,4 +140,4 @@ def test_small_bank_is_faster_on_the_scan_kernel():
 
     t_scan, t_lane = run(False), run(True)
     print(f"256 voices x 10 s: render_sub_scan {t_scan:.2f} ms, render_sub_asr {t_lane:.2f} ms ({t_lane / t_scan:.1f}x)")
-    assert t_scan * 1.4 < t_lane
+    assert t_scan * 2.5 < t_lane
