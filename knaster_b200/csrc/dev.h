@@ -53,6 +53,9 @@ enum ArCode : uint8_t {
     AR_SVF_Q = 9,         // q = v; set_coeffs                 svf.rs:91-99
     AR_SVF_GAIN = 10,     // gain_db = v; set_coeffs           svf.rs:101-109
     AR_ONEPOLE_CUTOFF = 11, // b1 = exp(-2 pi v / sr), a0 = 1 - b1   onepole.rs:35-46,135-139
+    // routes into an EnvAsr / EnvAr time: the rate is remade from the sample (idempotent, so the reference's "if changed" guard drops out)
+    AR_ENV_ATTACK = 12,   // attack_rate = v == 0 ? 1 : 1 / (v * sr)    envelopes.rs:84-97,246-259
+    AR_ENV_RELEASE = 13,  // release_rate likewise                       envelopes.rs:98-111,260-273
     AR_POST = 32,         // AR_POST + k: value of arithmetic wrapper k = v (wr_mul)   math.rs:92-98
 };
 

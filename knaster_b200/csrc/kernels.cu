@@ -384,7 +384,8 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                 float t, ar, rr, sc;
 #define ENV_LOAD (st = sreg[rb * 32], t = __uint_as_float(sreg[(rb + 1) * 32]), ar = __uint_as_float(sreg[(rb + 2) * 32]), \
                   rr = __uint_as_float(sreg[(rb + 3) * 32]), sc = __uint_as_float(sreg[(rb + 4) * 32]))
-#define ENV_STORE (sreg[rb * 32] = st, sreg[(rb + 1) * 32] = __float_as_uint(t), sreg[(rb + 4) * 32] = __float_as_uint(sc))
+#define ENV_STORE (sreg[rb * 32] = st, sreg[(rb + 1) * 32] = __float_as_uint(t), sreg[(rb + 2) * 32] = __float_as_uint(ar), \
+                   sreg[(rb + 3) * 32] = __float_as_uint(rr), sreg[(rb + 4) * 32] = __float_as_uint(sc))
                 ENV_LOAD;
                 const bool asr = dn.kind == DK_ENVASR;
                 FOR_GROUPS {
@@ -396,6 +397,10 @@ __global__ void __launch_bounds__(32) render_interp(InterpArgs a) {
                     for (uint32_t f = g0_; f < fe_; f++) {
                     EVENTS_AT(f, ENV_STORE, ENV_LOAD)
                     AR_POST_ROUTES(f)
+                    for (int ai = 0; ai < dn.n_ar; ai++) { // envelopes.rs:84-111: F::ONE / (seconds * sample_rate), 1 for 0 s
+                        if (dn.ar_code[ai] == AR_ENV_ATTACK) ar = env_rate_dev(RDV(dn.ar_slot[ai], f), sr);
+                        else if (dn.ar_code[ai] == AR_ENV_RELEASE) rr = env_rate_dev(RDV(dn.ar_slot[ai], f), sr);
+                    }
                     float y = asr ? envasr_tick(st, t, ar, rr, sc) : envar_tick(st, t, ar, rr, sc);
                     EMIT(f, 0, y)
                 }

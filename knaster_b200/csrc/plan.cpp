@@ -627,6 +627,10 @@ uint8_t ar_code_for(const TemplateNode &tn, uint32_t param, int ar_level) {
         if (param == 2) return AR_SVF_GAIN;
         break;
     case KGPU_ONEPOLE_LPF: case KGPU_ONEPOLE_HPF: if (param == 0) return AR_ONEPOLE_CUTOFF; break;
+    case KGPU_ENV_ASR: case KGPU_ENV_AR:
+        if (param == 0) return AR_ENV_ATTACK;
+        if (param == 1) return AR_ENV_RELEASE;
+        break; // the triggers are not floats: WrArParams would hand them a Float (a type error in knaster too)
     default: break;
     }
     KGPU_THROW(KGPU_ERR_UNSUPPORTED, "audio-rate route to parameter %u of ugen kind %u is not supported yet", param, tn.kind);

@@ -48,7 +48,21 @@ def lfo_q_and_onepole(g, i):
     return (saw >> svf >> lp) * (1.0 / 12)
 
 
-@pytest.mark.parametrize("voice", [lfo_cutoff, env_cutoff, lfo_q_and_onepole])
+def lfo_envelope_times(g, i):
+    """envelopes.rs:84-111 under WrArParams: attack_time / release_time re-set every frame from an LFO"""
+    saw = g.push(kn.PolyBlep(kn.Waveform.Sawtooth, 70.0 + 29.0 * i))
+    lfo = g.push(kn.SinWt(1.5 + 0.5 * i))
+    env = g.push((kn.EnvAsr(0.05, 0.2) if i % 2 == 0 else kn.EnvAr(0.05, 0.2)).ar_params())
+    env.link("attack_time", lfo * 0.02 + 0.03)
+    env.link("release_time", lfo * 0.1 + 0.25)
+    for k in range(8):
+        env.param("t_restart").trig_at(at(1000 + 60000 * k + 17 * i))
+        if i % 2 == 0:
+            env.param("t_release").trig_at(at(1000 + 60000 * k + 20000))
+    return (saw * env) * (1.0 / 12)
+
+
+@pytest.mark.parametrize("voice", [lfo_cutoff, env_cutoff, lfo_q_and_onepole, lfo_envelope_times])
 @pytest.mark.parametrize("jit", [False, True])
 def test_audio_rate_routes_into_filter_parameters(voice, jit):
     n_blocks = 7500                                  # 10 s

@@ -376,7 +376,7 @@ def test_unsupported_graph_fails_loudly_on_gpu_too():
     with graph.edit() as g:
         lfo = g.push(kn.SinWt(3.0))
         e = g.push(kn.EnvAsr(0.01, 0.1).ar_params())
-        e.link("attack_time", lfo * 0.001 + 0.01)    # audio-rate route into an envelope time: not built
+        e.link("t_restart", lfo * 0.001 + 0.01)      # audio-rate route into a trigger: rejected (a type error in knaster too)
         (g.push(kn.SinWt(100.0)) * e).to_graph_out()
     from knaster_b200._ffi import KgpuError
 

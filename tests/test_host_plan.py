@@ -278,9 +278,18 @@ def test_unsupported_shapes_are_rejected_not_faked():
     with g.edit() as e:
         lfo = e.push(kn.SinWt(3.0))
         env = e.push(kn.EnvAsr(0.01, 0.1).ar_params())
+        env.link("t_restart", lfo * 0.001 + 0.01)
+        (e.push(kn.SinWt(100.0)) * env).to_graph_out()
+    expect_error(g, _ffi.KGPU_ERR_UNSUPPORTED)          # audio-rate route into a trigger (a type error in knaster too): rejected
+
+    g = Graph(0, 1, 64, SR)                             # ... into an envelope TIME it compiles (round 2)
+    with g.edit() as e:
+        lfo = e.push(kn.SinWt(3.0))
+        env = e.push(kn.EnvAsr(0.01, 0.1).ar_params())
         env.link("attack_time", lfo * 0.001 + 0.01)
         (e.push(kn.SinWt(100.0)) * env).to_graph_out()
-    expect_error(g, _ffi.KGPU_ERR_UNSUPPORTED)          # audio-rate route into an envelope time: not built
+    _evs, _nodes, info = _ffi.debug_simulate(g, g.take_events(), 2)
+    assert info["n_voices"] == 1
 
     g = Graph(0, 1, 64, SR)                             # ... into filter parameters it is (round 2): the plan compiles
     with g.edit() as e:
