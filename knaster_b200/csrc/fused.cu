@@ -94,6 +94,16 @@ template <class ENV> struct SubVoice {
 #ifndef SUB_ROT
 #define SUB_ROT 1     // rotated main loop: filter(group g) beside oscillator + envelope(group g + 1), see sub_produce / sub_consume
 #endif
+#ifndef SUB_F32X2
+#define SUB_F32X2 0   // (measured: no gain) the frame-parallel half of a group (saw + blep, the envelope's products, the VCA) on packed f32x2
+                      // instructions, two frames per instruction (nodes.cuh::saw_eval2): bit-identical, the 8-frame loop shrinks from 317 to 254
+                      // instructions -- and takes 13.60 ms per step against 13.40 (16-frame groups: 13.43): a packed instruction holds the FMA pipe
+                      // for two cycles, so the pipe sees the same 248 cycles per group either way; issue slots were not what the loop waits for
+#endif
+#ifndef SUB_SAT_RELEASE
+#define SUB_SAT_RELEASE 1 // EnvAsr's Releasing -> Stopped transition inside the straight-line groups (saturating ramp steps, FADD.SAT: no extra
+                          // instruction): one limit frame fewer per note, 13.60 -> 13.40 ms per step
+#endif
 #ifndef SUB_COMPACT
 #define SUB_COMPACT 0 // (measured: slower, 14.7 ms against 14.1 -- an exact frame costs more than a 4- / 1-frame group) the frames between the last whole group and the limit frame run through ONE rolled exact-frame loop
                       // instead of 4- and 1-frame straight-line groups: a limit costs ~1900 cycles of mostly instruction
@@ -173,24 +183,68 @@ struct AsrEnv {
         const float n = __fdividef(dist, rate) - 1.0f;
         return n >= 1.0f ? (uint32_t)fminf(n, 1073741824.0f) : 0u; // NaN -> 0: always the exact path
     }
+    // The same bound for callers that render with group(): the end of a release needs no limit there -- group() steps both
+    // ramps with a saturating add, so a ramp that reaches <= 0 stays at +0, exactly what Stopped produces (t = 0, output 0;
+    // envelopes.rs:71-76), and settle() names the state before it is stored.  Attack -> Sustaining keeps its limit: t
+    // stays at its first value >= 1 there (t_restart resumes from it, envelopes.rs:131-133), which a clamp would lose.
+    KN_DEV uint32_t safe_frames_group() const {
+#if SUB_SAT_RELEASE
+        if (est == ASR_RELEASING) return 0x40000000u;
+#endif
+        return safe_frames();
+    }
     // EnvAsr::next_sample (envelopes.rs:52-81) with the state fixed over the group
-    template <int N> KN_DEV void group(const D &d, float (&env)[N]) {
+    template <int N, bool SAT = true> KN_DEV void group(const D &d, float (&env)[N]) {
         const bool ramp = d.att || d.rel;
         float tl = ramp ? et : d.cval;
         float u = d.rel ? et : 1.0f;
+#if SUB_F32X2
+        if constexpr (N % 2 == 0) { // the two ramps stay scalar chains; the four products of a frame pair are packed
+#pragma unroll
+            for (int k = 0; k < N; k += 2) {
+                const float tl1 = asr_step<SAT>(tl, d.delta), u1 = asr_step<SAT>(u, d.du);
+                const float2 t2 = make_float2(tl, tl1), u2 = make_float2(u, u1);
+                const float2 e2 = mul2(mul2(mul2(mul2(t2, u2), u2), dup2(d.sc2)), dup2(gain));
+                env[k] = e2.x;
+                env[k + 1] = e2.y;
+                tl = asr_step<SAT>(tl1, d.delta);
+                u = asr_step<SAT>(u1, d.du);
+            }
+            et = ramp ? tl : et;
+            return;
+        }
+#endif
 #pragma unroll
         for (int k = 0; k < N; k++) {
             const float o = ((tl * u) * u) * d.sc2;
-            tl = tl + d.delta;
-            u = u + d.du;
+            tl = asr_step<SAT>(tl, d.delta);
+            u = asr_step<SAT>(u, d.du);
             env[k] = o * gain;      // WrMul, wrappers_core/math.rs:63-67
         }
         et = ramp ? tl : et;
     }
+    // A ramp step of a straight-line group.  Inside a group every ramp value lies in [0, 1] (an attack's limit frame comes
+    // before its sum can reach 1), so FADD.SAT only ever acts on a release that crosses 0: it leaves +0 where the
+    // reference's Stopped state sets t = 0, and 0 - rate stays there.
+    template <bool SAT> static KN_DEV float asr_step(float x, float dx) {
+#if SUB_SAT_RELEASE
+        if (SAT) return __saturatef(x + dx);
+#endif
+        return x + dx;
+    }
+    // Releasing with t at 0 is Stopped (a group may have carried the ramp through its end, see safe_frames)
+    KN_DEV void settle() {
+#if SUB_SAT_RELEASE
+        if (est == ASR_RELEASING && et <= 0.0f) {
+            est = ASR_STOPPED;
+            et = 0.0f;
+        }
+#endif
+    }
     // one frame, then EnvAsr's transitions (envelopes.rs:60-77): they only change what FOLLOWING frames do
     KN_DEV float exact1(const D &d) {
         float env[1];
-        group<1>(d, env);
+        group<1, false>(d, env); // not saturating: an attack keeps its first t >= 1 (see safe_frames_group)
         if (d.att && et >= 1.0f) est = ASR_SUSTAINING;
         if (d.rel && et <= 0.0f) {
             est = ASR_STOPPED;
@@ -332,6 +386,8 @@ struct SegEnv {
         const float n = __fdividef((float)__dsub_rn(dur, time), (float)step) * 0.999999f - 1.0f;
         return n >= 1.0f ? (uint32_t)fminf(n, 1073741824.0f) : 0u;
     }
+    KN_DEV uint32_t safe_frames_group() const { return safe_frames(); }
+    KN_DEV void settle() {}
     template <int N> KN_DEV void group(const D &d, float (&env)[N]) {
         double tl = d.run ? time : 0.0;
 #pragma unroll
@@ -467,6 +523,17 @@ KN_DEV void sub_produce(SubVoice<ENV> &s, const typename ENV::D &d, float omd, f
         s.t = wrap01(s.t + s.dt); // inc(), polyblep.rs:232-235
     }
     s.e.template group<N>(d, env);
+#if SUB_F32X2
+    if constexpr (N % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k += 2) {
+            const float2 y = saw_eval2(make_float2(ph[k], ph[k + 1]), s.dt, omd, rc);
+            x[k] = y.x;
+            x[k + 1] = y.y;
+        }
+        return;
+    }
+#endif
 #pragma unroll
     for (int k = 0; k < N; k++) x[k] = saw_eval(ph[k], s.dt, omd, rc);
 }
@@ -485,6 +552,7 @@ KN_DEV void sub_consume(SubVoice<ENV> &s, const float (&x)[N], const float (&env
         tot = h + __shfl_xor_sync(0xFFFFFFFFu, h, 16);
     }
     if (sum_store) *sum_dst = tot;
+    float yy[N];
 #pragma unroll
     for (int k = 0; k < N; k++) {
         const float v0 = x[k];
@@ -499,6 +567,16 @@ KN_DEV void sub_consume(SubVoice<ENV> &s, const float (&x)[N], const float (&env
         } else {
             y = svf_tick(v0, s.ic1, s.ic2, s.a1, s.a2, s.a3, s.m0, s.m1, s.m2);
         }
+        yy[k] = y;
+#if SUB_F32X2
+        if (N % 2 == 0 && (k & 1)) { // the VCA of a frame pair as one packed multiplication
+            const float2 o2 = mul2(make_float2(yy[k - 1], y), make_float2(env[k - 1], env[k]));
+            strow[(k - 1) * SUBW_PAD] = o2.x;
+            strow[k * SUBW_PAD] = o2.y;
+            if (TAPS && tap) { tap[k - 1] = o2.x; tap[k] = o2.y; }
+        }
+        if (N % 2 == 0) continue;
+#endif
         const float o = y * env[k];
         strow[k * SUBW_PAD] = o;
         if (TAPS && tap) tap[k] = o;
@@ -552,7 +630,7 @@ KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
     // envelope may change state, or its parameters are outside the fast domain).  Warp-uniform.
     auto lane_limit = [&](uint32_t f) -> uint32_t {
         if (!lane_fast) return 0u;
-        const uint32_t safe = f + s.e.safe_frames();
+        const uint32_t safe = f + s.e.safe_frames_group();
         return min(ec.next_frame, safe);
     };
     uint32_t limit = __reduce_min_sync(0xFFFFFFFFu, lane_limit(0));
@@ -708,6 +786,7 @@ KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
         a.regs[(size_t)R_M0 * V + v] = __float_as_uint(s.m0);
         a.regs[(size_t)R_M1 * V + v] = __float_as_uint(s.m1);
         a.regs[(size_t)R_M2 * V + v] = __float_as_uint(s.m2);
+        s.e.settle();
         s.e.store(a, v);
     }
 }

@@ -11,3 +11,4 @@ for rep in 1 2 3; do for v in $V; do
 import json;d=json.loads(open('$O/ab${v}_$rep.json').read().strip().splitlines()[-1]);print('$v',$rep,round(d['ms_per_step'],3),round(d['e2e']['ms_per_step'],3))"
 done; done
 if [ -n "$TESTS" ]; then timeout 600 python -m pytest $TESTS -x -q 2>&1 | tail -3; fi
+if [ -n "$TESTS2" ]; then KNASTER_GPU_LIB=knaster_b200/csrc/${TESTLIB2:-_build_A}/libknaster_gpu.so timeout 600 python -m pytest $TESTS2 -x -q 2>&1 | tail -3; fi
