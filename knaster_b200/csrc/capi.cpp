@@ -173,6 +173,11 @@ struct kgpu_plan {
     uint64_t peer_slot_floats = 0;
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t peer_ev[2] = {nullptr, nullptr};
+    // the mix-bus reduction of launch L runs on its own stream beside the rendering of launch L+1 (the partial rows
+    // ping-pong between two buffers): part_ready[b] = the render kernels have filled buffer b, part_free[b] = its
+    // reduction has read it
+    cudaStream_t red_stream = nullptr;
+    cudaEvent_t part_ready[2] = {nullptr, nullptr}, part_free[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -378,7 +383,22 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
     const uint64_t bpl = was_prepared ? p->prepared_bpl : blocks_per_launch(p);
     p->prepared = false;
     if (!was_prepared) p->last_h2d_bytes = 0;
-    p->partials.ensure((size_t)std::max(1u, p->n_rows) * std::min<uint64_t>(bpl, n_blocks) * bs);
+    // Streaming path with more than one launch: launch L's mix-bus reduction runs beside launch L+1's rendering, on two
+    // partial-row buffers (device span of a 10 s step 14.48 -> 14.20 ms).  Prepared renders keep the kernels back to back on
+    // one stream -- their launches are few and large, and the concurrent reduction costs the render kernel 1.2 % for 0.8 % of
+    // the step (measured; KGPU_REDUCE_OVERLAP=1 / 0 forces either).
+    static const char *ov_env = getenv("KGPU_REDUCE_OVERLAP");
+    const bool overlap = n_blocks > bpl && (ov_env ? *ov_env == '1' : !was_prepared);
+    const size_t part_stride = (size_t)std::max(1u, p->n_rows) * std::min<uint64_t>(bpl, n_blocks) * bs;
+    p->partials.ensure(part_stride * (overlap ? 2 : 1));
+    if (overlap && !p->red_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&p->red_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(cudaEventCreateWithFlags(&p->part_ready[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&p->part_free[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t rs = overlap ? p->red_stream : stream; // the stream the reduction (and what follows it) runs on
     const uint64_t t_begin = p->frame_clock, t_end = t_begin + total_frames;
     std::vector<uint32_t> chunks;
     for (GroupDev &d : p->gd) chunks.push_back(d.chunk);
@@ -421,13 +441,13 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
     };
     p->kev_used = 0;
     p->kev_class.clear();
-    auto mark = [&](int cls, bool begin) {
+    auto mark = [&](int cls, bool begin, cudaStream_t on = nullptr) {
         if (p->kev_used == p->kev.size()) {
             cudaEvent_t e;
             CUDA_TRY(cudaEventCreate(&e));
             p->kev.push_back(e);
         }
-        CUDA_TRY(cudaEventRecord(p->kev[p->kev_used++], stream));
+        CUDA_TRY(cudaEventRecord(p->kev[p->kev_used++], on ? on : stream));
         if (begin) p->kev_class.push_back((uint8_t)cls);
     };
     struct StreamGuard { // stream_begin is always paired with stream_end, also when a launch throws
@@ -465,6 +485,9 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
     for (size_t launch = 0; launch < sizes.size(); done += sizes[launch], launch++) {
         const uint64_t nb = sizes[launch];
         const uint32_t nf = (uint32_t)(nb * bs);
+        const int pb = overlap ? (int)(launch & 1) : 0;
+        float *part = p->partials.p + (size_t)pb * part_stride;
+        if (overlap && launch >= 2) CUDA_TRY(cudaStreamWaitEvent(stream, p->part_free[pb], 0)); // launch - 2's reduction has read this buffer
         if (!was_prepared) {
             static const bool timing = getenv("KGPU_TIMING") != nullptr;
             const auto ta = std::chrono::steady_clock::now();
@@ -490,7 +513,7 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
                 const uint32_t w0 = p->sig_level_off[lv], w1 = p->sig_level_off[lv + 1];
                 if (w1 > w0) {
                     mark(1, true);
-                    CUDA_TRY(launch_reduce_signals(p->partials.p, p->row_mask.p, p->level_rows_end[lv], nf, p->signals.p, n_out, p->sig_which.p + w0, w1 - w0, stream));
+                    CUDA_TRY(launch_reduce_signals(part, p->row_mask.p, p->level_rows_end[lv], nf, p->signals.p, n_out, p->sig_which.p + w0, w1 - w0, stream));
                     mark(1, false);
                     p->kernel_launches++;
                 }
@@ -504,7 +527,7 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             if (d.recipe >= 0) {
                 FusedArgs a{};
                 a.prog = d.prog.p; a.regs = d.regs.p; a.n_voices = g.n_voices; a.events = d_ev; a.ev_off = d_off;
-                a.n_frames = nf; a.partials = p->partials.p; a.row0 = d.row0;
+                a.n_frames = nf; a.partials = part; a.row0 = d.row0;
                 a.taps = d.taps.p; a.n_taps = (uint32_t)d.host_taps.size(); a.tap_out = p->tap_out.p;
                 a.tap_stride = total_frames; a.tap_frame0 = done * bs; a.sine_table = p->sine.p;
                 a.host_prog = &g.prog; a.block_size = bs;
@@ -522,7 +545,7 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             } else {
                 InterpArgs a{};
                 a.prog = d.prog.p; a.regs = d.regs.p; a.n_voices = g.n_voices; a.events = d_ev; a.ev_off = d_off;
-                a.n_frames = nf; a.chunk = d.chunk; a.partials = p->partials.p; a.row0 = d.row0;
+                a.n_frames = nf; a.chunk = d.chunk; a.partials = part; a.row0 = d.row0;
                 a.taps = d.taps.p; a.n_taps = (uint32_t)d.host_taps.size(); a.tap_out = p->tap_out.p;
                 a.tap_stride = total_frames; a.tap_frame0 = done * bs; a.sine_table = p->sine.p;
                 a.ext = n_signals ? p->signals.p : nullptr; a.ext_stride = nf;
@@ -535,25 +558,30 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             CUDA_TRY(cudaEventRecord(p->kern_done[launch & 1], stream));
             p->kern_recorded[launch & 1] = true;
         }
-        mark(1, true);
+        if (overlap) {
+            CUDA_TRY(cudaEventRecord(p->part_ready[pb], stream));
+            CUDA_TRY(cudaStreamWaitEvent(rs, p->part_ready[pb], 0));
+        }
+        mark(1, true, rs);
         float *dst = device_out + (size_t)done * n_out * bs;
         if (peer) { // reduce straight into this rank's slot in rank 0's memory (NVLink stores), then publish the launch
             float *slot = p->peer_slots + (size_t)p->peer_rank * p->peer_slot_floats + (size_t)done * n_out * bs;
-            CUDA_TRY(launch_reduce_bus(p->partials.p, p->row_mask.p, p->n_rows, nf, slot, n_out, bs, stream));
-            CUDA_TRY(launch_signal_flag(p->peer_flags + (size_t)p->peer_rank * KGPU_PEER_MAX_LAUNCHES + launch, p->peer_epoch, stream));
+            CUDA_TRY(launch_reduce_bus(part, p->row_mask.p, p->n_rows, nf, slot, n_out, bs, rs));
+            CUDA_TRY(launch_signal_flag(p->peer_flags + (size_t)p->peer_rank * KGPU_PEER_MAX_LAUNCHES + launch, p->peer_epoch, rs));
             p->kernel_launches++;
         } else {
-            CUDA_TRY(launch_reduce_bus(p->partials.p, p->row_mask.p, p->n_rows, nf, dst, n_out, bs, stream));
+            CUDA_TRY(launch_reduce_bus(part, p->row_mask.p, p->n_rows, nf, dst, n_out, bs, rs));
             if (!p->host.input_to_output.empty()) {
-                CUDA_TRY(launch_add_inputs(p->signals.p, nf, dst, n_out, bs, p->in_pairs.p, (uint32_t)p->host.input_to_output.size(), stream));
+                CUDA_TRY(launch_add_inputs(p->signals.p, nf, dst, n_out, bs, p->in_pairs.p, (uint32_t)p->host.input_to_output.size(), rs));
                 p->kernel_launches++;
             }
         }
-        mark(1, false);
+        mark(1, false, rs);
+        if (overlap) CUDA_TRY(cudaEventRecord(p->part_free[pb], rs));
         p->kernel_launches++;
         if (peer) {
             if (p->peer_rank == 0) { // fold the slots beside the next launch's rendering
-                CUDA_TRY(cudaEventRecord(p->peer_ev[launch & 1], stream));
+                CUDA_TRY(cudaEventRecord(p->peer_ev[launch & 1], rs));
                 CUDA_TRY(cudaStreamWaitEvent(p->aux_stream, p->peer_ev[launch & 1], 0));
                 CUDA_TRY(launch_sum_slots(p->peer_slots + (size_t)done * n_out * bs, p->peer_slot_floats, p->peer_world, p->peer_flags + launch,
                                           KGPU_PEER_MAX_LAUNCHES, p->peer_epoch, dst, (size_t)nf * n_out, p->peer_timeout, p->aux_stream));
@@ -564,13 +592,19 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
                 }
             }
         } else if (pinned_out) {
-            cudaStream_t cs = was_prepared ? stream : p->d2h_stream;
-            if (!was_prepared) {
-                CUDA_TRY(cudaEventRecord(p->red_done[launch & 1], stream));
+            // the bus of a launch comes down behind its reduction: on the reduction's own stream when that runs beside the
+            // rendering, else (one launch per call) on the copy stream of the streaming path
+            cudaStream_t cs = overlap || was_prepared ? rs : p->d2h_stream;
+            if (cs != rs) {
+                CUDA_TRY(cudaEventRecord(p->red_done[launch & 1], rs));
                 CUDA_TRY(cudaStreamWaitEvent(cs, p->red_done[launch & 1], 0));
             }
             CUDA_TRY(cudaMemcpyAsync(pinned_out + (size_t)done * n_out * bs, dst, (size_t)nf * n_out * 4, cudaMemcpyDeviceToHost, cs));
             piece_landed((size_t)done * n_out * bs, (size_t)nf * n_out, cs);
+            if (cs != rs && launch + 1 == sizes.size()) { // `stream` ends after the last download
+                CUDA_TRY(cudaEventRecord(p->red_done[0], cs));
+                CUDA_TRY(cudaStreamWaitEvent(stream, p->red_done[0], 0));
+            }
         }
     }
     if (peer) {
@@ -579,9 +613,10 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
             CUDA_TRY(cudaEventRecord(p->peer_ev[0], p->aux_stream));
             CUDA_TRY(cudaStreamWaitEvent(stream, p->peer_ev[0], 0));
         }
-    } else if (pinned_out && !was_prepared) { // `stream` ends after the last download
-        CUDA_TRY(cudaEventRecord(p->red_done[0], p->d2h_stream));
-        CUDA_TRY(cudaStreamWaitEvent(stream, p->red_done[0], 0));
+    }
+    if (overlap) { // `stream` ends after the last reduction (and its download)
+        CUDA_TRY(cudaEventRecord(p->part_ready[0], rs));
+        CUDA_TRY(cudaStreamWaitEvent(stream, p->part_ready[0], 0));
     }
     if (guard.h) {
         guard.h = nullptr;
@@ -679,6 +714,11 @@ void kgpu_plan_destroy(kgpu_plan *p) {
         if (p->red_done[i]) cudaEventDestroy(p->red_done[i]);
     }
     if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
+    if (p->red_stream) cudaStreamDestroy(p->red_stream);
+    for (int i = 0; i < 2; i++) {
+        if (p->part_ready[i]) cudaEventDestroy(p->part_ready[i]);
+        if (p->part_free[i]) cudaEventDestroy(p->part_free[i]);
+    }
     for (cudaEvent_t e : p->peer_ev)
         if (e) cudaEventDestroy(e);
     if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
