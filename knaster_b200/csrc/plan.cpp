@@ -1550,7 +1550,8 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
         r.due_frame = due < frame_clock ? frame_clock : due;    // late: saturating_sub -> delay 0
         return true;
     };
-    const unsigned T = n >= 32768 ? std::min<unsigned>(workers().size(), (unsigned)(n / 8192)) : 1u;
+    // (one chunk more than the pool has threads: WorkPool::run lets the calling thread take one as well)
+    const unsigned T = n >= 32768 ? std::min<unsigned>(workers().size() + 1, (unsigned)(n / 8192)) : 1u;
     std::vector<size_t> dropped(T, 0);
     std::vector<Error> errs(T, Error{0, ""});
     const size_t base = pending.size();
@@ -1758,6 +1759,8 @@ struct StreamState {
     bool any_work = false;
     bool identity = false;                       // the ready events are `pending` itself, already grouped by voice: vorder unused
     unsigned n_threads = 0;                      // contexts of this call: th[0..n_threads)
+    int driver_ctx = -1;                         // >= 0: th[driver_ctx] (the last slice) is simulated by the calling thread, launch by launch
+    size_t driver_done = 0;                      // launches of that slice already simulated
     std::vector<std::unique_ptr<ThreadCtx>> th;
     std::vector<std::vector<uint32_t>> hist;     // bucketing scratch
     bool pooled = false; // workers run on HostPlan::pool
@@ -1880,25 +1883,28 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     pg.cnt[L][v - pg.v_begin] = (uint32_t)(out.size() - out0);
 }
 
+// one slice of the voices, one launch window
+void stream_worker_step(HostPlan &P, StreamState &S, StreamState::ThreadCtx &tc, size_t L) {
+    for (uint32_t gi = 0; gi < P.groups.size(); gi++) {
+        StreamState::PerGroup &pg = tc.g[gi];
+        // calls without active ramps (block-by-block rendering, banks without smoothing): a voice without a
+        // ready event has nothing to do -- skip it on two loads instead of entering the simulation
+        const bool quick = P.n_active_ramps == 0 && tc.ramp_delta == 0;
+        const uint64_t t1 = S.bounds[L + 1];
+        const uint64_t *nd = pg.next_due.data();
+        for (uint32_t v = pg.v_begin; v < pg.v_end; v++) {
+            if (quick && nd[v - pg.v_begin] >= t1) continue; // nothing of this voice becomes ready in this window
+            simulate_voice_window(P, S, tc, gi, v, L);
+        }
+    }
+}
+
 void stream_worker(HostPlan &P, StreamState &S, unsigned ti) {
     StreamState::ThreadCtx &tc = *S.th[ti];
     static const bool timing = getenv("KGPU_TIMING") != nullptr;
     try {
         for (size_t L = 0; L < S.n_launch; L++) {
-            for (uint32_t gi = 0; gi < P.groups.size(); gi++) {
-                StreamState::PerGroup &pg = tc.g[gi];
-                // calls without active ramps (block-by-block rendering, banks without smoothing): a voice without a
-                // ready event has nothing to do -- skip it on two loads instead of entering the simulation
-                const bool quick = P.n_active_ramps == 0 && tc.ramp_delta == 0;
-                const uint32_t *vc = P.vcount.data() + P.voice_base[gi];
-                const uint64_t t1 = S.bounds[L + 1];
-                const uint64_t *nd = pg.next_due.data();
-                (void)vc;
-                for (uint32_t v = pg.v_begin; v < pg.v_end; v++) {
-                    if (quick && nd[v - pg.v_begin] >= t1) continue; // nothing of this voice becomes ready in this window
-                    simulate_voice_window(P, S, tc, gi, v, L);
-                }
-            }
+            stream_worker_step(P, S, tc, L);
             tc.done.store((uint32_t)L + 1, std::memory_order_release);
             if (timing && L < 2 && ti < 3 && S.n_launch > 2)
                 fprintf(stderr, "[kgpu timing]     worker %u finished launch %zu at +%.2f ms\n", ti, L,
@@ -2074,6 +2080,8 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
     S->identity = identity;
     S->pooled = false;
     S->n_threads = 0;
+    S->driver_ctx = -1;
+    S->driver_done = 0;
     stream_active = true;
     if (!any_work) return;
     // bucket by global voice (arrival order inside a voice)
@@ -2095,28 +2103,39 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
     const size_t work = n_ready + n_active_ramps;
     unsigned T = work > 20000 ? workers().size() : 1u;
     T = std::min<unsigned>(T, std::max<unsigned>(1u, (unsigned)(NV / 64)));
-    S->n_threads = T;
-    while (S->th.size() < T) S->th.emplace_back(new StreamState::ThreadCtx());
+    // With few workers (several GPUs sharing one box's cores) the control simulation, not the device, paces the call, and the
+    // calling thread would only wait for them: it takes a slice of the voices of its own -- half a worker's, it also merges,
+    // uploads and launches -- and simulates it launch by launch inside stream_launch.  Slices are weighted 2 : ... : 2 : 1.
+    // Measured on the bench configuration (one B200, 16 host cores): 3 workers 15.35 -> 15.07 ms per step end to end; 7 workers
+    // 14.48 -> 14.53 ms (the device paces that call, nothing to gain), so the slice is taken with up to 4 workers only.
+    static const char *drv_env = getenv("KGPU_DRIVER_SLICE"); // 0 = never, 1 = whenever workers run (default: up to 4 workers)
+    const bool driver_slice = T > 1 && (drv_env ? atoi(drv_env) != 0 : T <= 4) && NV >= 64u * (T + 1);
+    const unsigned NT = T + (driver_slice ? 1u : 0u), WT = driver_slice ? 2 * T + 1 : T;
+    S->n_threads = NT;
+    S->driver_ctx = driver_slice ? (int)T : -1;
+    while (S->th.size() < NT) S->th.emplace_back(new StreamState::ThreadCtx());
     // every worker lays out its own context (per-launch event lists and counts, per-voice cursors) before it starts on
     // launch 0: in parallel, 0.3 ms of the call's start-up when the driver thread did it for all of them
-    for (unsigned ti = 0; ti < T; ti++) { // what the driver thread polls (stream_launch) is reset before any worker runs
+    for (unsigned ti = 0; ti < NT; ti++) { // what the driver thread polls (stream_launch) is reset before any worker runs
         StreamState::ThreadCtx &tc = *S->th[ti];
         tc.done.store(0, std::memory_order_relaxed);
         tc.error.clear();
         tc.error_code = 0;
     }
     const uint32_t *vo_all = identity ? nullptr : vorder.data();
-    auto init_ctx = [this, S, n_groups, n_launch, T, identity, vo_all](unsigned ti) {
+    auto init_ctx = [this, S, n_groups, n_launch, T, WT, driver_slice, identity, vo_all](unsigned ti) {
         const uint32_t *vo = vo_all;
         StreamState::ThreadCtx &tc = *S->th[ti];
         tc.g.resize(n_groups);
         tc.ramp_delta = 0;
         tc.sink.dropped = tc.sink.ignored = tc.sink.devev = 0;
+        const unsigned w0 = driver_slice ? 2 * ti : ti, w1 = driver_slice ? std::min(2 * ti + 2, WT) : ti + 1;
+        (void)T;
         for (size_t gi = 0; gi < n_groups; gi++) {
             StreamState::PerGroup &pg = tc.g[gi];
             const uint32_t V = groups[gi].n_voices;
-            pg.v_begin = (uint32_t)((uint64_t)V * ti / T);
-            pg.v_end = (uint32_t)((uint64_t)V * (ti + 1) / T);
+            pg.v_begin = (uint32_t)((uint64_t)V * w0 / WT);
+            pg.v_end = (uint32_t)((uint64_t)V * w1 / WT);
             const uint32_t nv = pg.v_end - pg.v_begin;
             if (pg.ev.size() < n_launch) pg.ev.resize(n_launch);
             if (pg.cnt.size() < n_launch) pg.cnt.resize(n_launch);
@@ -2145,6 +2164,26 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
             init_ctx(ti);
             stream_worker(*this, *S, ti);
         });
+        if (driver_slice) init_ctx(T);
+    }
+}
+
+// The calling thread's own slice (StreamState::driver_ctx), up to and including launch L
+void HostPlan::driver_slice_through(size_t L) {
+    StreamState *S = stream;
+    if (S->driver_ctx < 0) return;
+    StreamState::ThreadCtx &tc = *S->th[S->driver_ctx];
+    while (S->driver_done <= L && S->driver_done < S->n_launch) {
+        if (!tc.error_code) {
+            try {
+                stream_worker_step(*this, *S, tc, S->driver_done);
+            } catch (const Error &e) {
+                tc.error = e.msg;
+                tc.error_code = e.code;
+            }
+        }
+        S->driver_done++;
+        tc.done.store((uint32_t)S->driver_done, std::memory_order_release);
     }
 }
 
@@ -2161,6 +2200,8 @@ void HostPlan::stream_launch(size_t L, CompiledEvents &out) {
     out.piece_any.assign(n_groups, 0);
     if (!S->any_work) return;
     PhaseTimer pt("stream_launch");
+    driver_slice_through(L);
+    pt.lap("own slice");
     for (unsigned ti = 0; ti < S->n_threads; ti++) {
         StreamState::ThreadCtx *tc = S->th[ti].get();
         // The driver thread has a core of its own (the pool leaves one free), and what it waits for is short: spin on the
@@ -2220,6 +2261,7 @@ void HostPlan::consume_ready(uint64_t b1) {
 void HostPlan::stream_end() {
     StreamState *S = stream;
     if (!S || !stream_active) return;
+    if (S->any_work) driver_slice_through(S->n_launch); // a call that ended early: the slice's state still advances over the whole range, like the workers'
     if (S->pooled) workers().wait();
 #ifdef KGPU_PROFILE_HOST
     {

@@ -242,6 +242,7 @@ struct HostPlan {
     // (pieces indexed by group).  Always pair stream_begin with stream_end.
     void stream_begin(const std::vector<uint64_t> &bounds, const std::vector<uint32_t> &chunk_of_group);
     void stream_launch(size_t launch, CompiledEvents &out);
+    void driver_slice_through(size_t launch);
     void stream_end();
     void consume_ready(uint64_t b1);
     // what HostPlan::push learns about a large batch while converting it (see push / stream_begin)

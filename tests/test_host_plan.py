@@ -403,3 +403,28 @@ def test_event_calendar_does_not_change_what_the_device_sees():
     assert a.keys() == b.keys()
     for k in a:
         assert a[k] == b[k], f"voice {k}: device events differ between one call and block-by-block calls"
+
+
+def test_driver_slice_leaves_the_event_stream_unchanged(monkeypatch):
+    """With few worker threads the calling thread simulates a slice of the voices itself (HostPlan::driver_slice_through).
+    The device event stream -- per voice and in order -- must not depend on how the voices are split over threads:
+    1 thread (inline), 3 workers + the caller's half slice, 9 workers (no slice of its own), for two launch splits,
+    on a bank with smoothing ramps (additive) and one with sample-accurate events (subtractive)."""
+    from knaster_b200 import banks
+
+    for wl, nv, secs in (("subtractive", 1536, 2.0), ("additive", 4608, 2.0)):
+        n_blocks = int(secs * 48000) // 64
+        ref = None
+        for threads in ("1", "3", "9"):
+            monkeypatch.setenv("KGPU_THREADS", threads)
+            for bpc in (0, 400):
+                g = Graph(0, 2, 64, 48000)
+                banks.bank_builder(wl, secs)(g, nv, 0, nv)
+                ev = g.take_events()
+                assert len(ev) > 20000  # large enough for the pooled path
+                evs, _, info = _ffi.debug_simulate(g, ev, n_blocks, bpc, cap=1 << 21)
+                key = (sorted(evs, key=lambda e: (e[0], e[1])), info["device_events"], info["dropped_changes"], info["ignored_delays"])
+                if ref is None:
+                    ref = key
+                assert key[1:] == ref[1:], (wl, threads, bpc)
+                assert key[0] == ref[0], (wl, threads, bpc)
