@@ -104,6 +104,11 @@ template <class ENV> struct SubVoice {
 #define SUB_SAT_RELEASE 1 // EnvAsr's Releasing -> Stopped transition inside the straight-line groups (saturating ramp steps, FADD.SAT: no extra
                           // instruction): one limit frame fewer per note, 13.60 -> 13.40 ms per step
 #endif
+#ifndef SUB_SAT_ATTACK
+#define SUB_SAT_ATTACK 1  // EnvAsr's Attacking -> Sustaining transition inside the straight-line groups as well: the saturating ramp step leaves
+                          // 1.0 where Sustaining outputs 1, and the first t >= 1 (which Sustaining keeps and t_restart resumes from) is replayed
+                          // from a per-group checkpoint of the last ramp value below 1 when the next limit frame / the launch's end needs it
+#endif
 #ifndef SUB_COMPACT
 #define SUB_COMPACT 0 // (measured: slower, 14.7 ms against 14.1 -- an exact frame costs more than a 4- / 1-frame group) the frames between the last whole group and the limit frame run through ONE rolled exact-frame loop
                       // instead of 4- and 1-frame straight-line groups: a limit costs ~1900 cycles of mostly instruction
@@ -125,6 +130,7 @@ constexpr int SUBW_TILE = 2 * SUB_SUB; // render_sub_asr staging tile: two halve
 struct AsrEnv {
     uint32_t est;
     float et, ar, rr, sc, gain;
+    float tck; // SUB_SAT_ATTACK: the attack ramp's last group-end value below 1 (see group_ck / settle)
     // What a straight-line group needs, fixed while the state machine does not move.  The group is
     // select-free: every lane evaluates ((tl * u) * u) * sc2 with
     //   Releasing  tl = u = t (both step by -release_rate, so they stay equal), sc2 = release_scale:
@@ -145,8 +151,9 @@ struct AsrEnv {
         for (int i = 0; i < 6; i++) r[i] = a.regs[(size_t)(R_EST + i) * V + v];
 #pragma unroll
         for (int i = 0; i < 6; i++) set(R_EST + i, r[i]);
+        tck = et;
     }
-    KN_DEV void idle() { est = ASR_STOPPED; et = 0.f; ar = rr = 1.f; sc = 0.f; gain = 0.f; }
+    KN_DEV void idle() { est = ASR_STOPPED; et = 0.f; ar = rr = 1.f; sc = 0.f; gain = 0.f; tck = 0.f; }
     KN_DEV void set(uint32_t reg, uint32_t bits) {
         const float f = __uint_as_float(bits);
         switch (reg) {
@@ -162,13 +169,16 @@ struct AsrEnv {
     KN_DEV void op(const DevEvent &e) {
         if (e.op == OP_ASR_RELEASE) envasr_release(est, et, sc);
     }
-    KN_DEV void derive(D &d) const {
+    KN_DEV void derive(D &d) {
         d.att = est == ASR_ATTACKING;
         d.rel = est == ASR_RELEASING;
         d.delta = d.att ? ar : (d.rel ? -rr : 0.0f);
         d.du = d.rel ? -rr : 0.0f;
         d.sc2 = d.rel ? sc : 1.0f;
         d.cval = est == ASR_SUSTAINING ? 1.0f : 0.0f;
+#if SUB_SAT_ATTACK
+        tck = et;
+#endif
     }
     // Number of coming frames in which the envelope state machine provably cannot change state.
     // Attacking: t_n = t + n*ar + err with |err| <= n*2^-25 (one rounding of a value below 2 per add),
@@ -183,15 +193,28 @@ struct AsrEnv {
         const float n = __fdividef(dist, rate) - 1.0f;
         return n >= 1.0f ? (uint32_t)fminf(n, 1073741824.0f) : 0u; // NaN -> 0: always the exact path
     }
-    // The same bound for callers that render with group(): the end of a release needs no limit there -- group() steps both
+    // The same bound for callers that render with group_ck(): the end of a release needs no limit there -- the groups step both
     // ramps with a saturating add, so a ramp that reaches <= 0 stays at +0, exactly what Stopped produces (t = 0, output 0;
-    // envelopes.rs:71-76), and settle() names the state before it is stored.  Attack -> Sustaining keeps its limit: t
-    // stays at its first value >= 1 there (t_restart resumes from it, envelopes.rs:131-133), which a clamp would lose.
+    // envelopes.rs:71-76), and settle() names the state before it is read or stored.  Attack -> Sustaining (SUB_SAT_ATTACK): the
+    // saturated ramp stays at 1.0, which is what Sustaining outputs; Sustaining keeps t at its first value >= 1 (t_restart
+    // resumes from it, envelopes.rs:131-133), which settle() recomputes from the checkpoint group_ck() keeps.
     KN_DEV uint32_t safe_frames_group() const {
 #if SUB_SAT_RELEASE
         if (est == ASR_RELEASING) return 0x40000000u;
 #endif
+#if SUB_SAT_ATTACK && SUB_SAT_RELEASE
+        // an attack that has not reached 1 yet and does move towards it: group_ck() carries it through its end (ar > 0 is false for NaN)
+        if (est == ASR_ATTACKING && et < 1.0f && ar > 0.0f) return 0x40000000u;
+#endif
         return safe_frames();
+    }
+    // group() for the kernels that let an attack run through its end (render_sub_body): the ramp's value at the end of the group is
+    // remembered while it is below 1, so that settle() finds the first value >= 1 within N additions
+    template <int N> KN_DEV void group_ck(const D &d, float (&env)[N]) {
+        group<N>(d, env);
+#if SUB_SAT_ATTACK && SUB_SAT_RELEASE
+        tck = et < 1.0f ? et : tck;
+#endif
     }
     // EnvAsr::next_sample (envelopes.rs:52-81) with the state fixed over the group
     template <int N, bool SAT = true> KN_DEV void group(const D &d, float (&env)[N]) {
@@ -233,13 +256,30 @@ struct AsrEnv {
         return x + dx;
     }
     // Releasing with t at 0 is Stopped (a group may have carried the ramp through its end, see safe_frames)
-    KN_DEV void settle() {
+    // ... and Attacking with t at 1 (the saturated ramp; a real attack leaves Attacking with its first t >= 1) is Sustaining with the
+    // value the unsaturated ramp reaches first: at most SUB_SUB additions from the checkpoint.  Called where no event has been applied
+    // since the last group, so Attacking with t >= 1 can only be the saturated ramp (t_restart on a sustaining envelope makes the same
+    // pair, but the exact frame that follows the event resolves it at once).
+    KN_DEV bool settle() { // true: the state's name changed, what derive() made of it is stale
+        bool changed = false;
 #if SUB_SAT_RELEASE
         if (est == ASR_RELEASING && et <= 0.0f) {
             est = ASR_STOPPED;
             et = 0.0f;
+            changed = true;
+        }
+#if SUB_SAT_ATTACK
+        if (est == ASR_ATTACKING && et >= 1.0f) {
+            float t = tck;
+#pragma unroll 1
+            for (int i = 0; i < 32 && t < 1.0f; i++) t = t + ar;
+            et = t;
+            est = ASR_SUSTAINING;
+            changed = true;
         }
 #endif
+#endif
+        return changed;
     }
     // one frame, then EnvAsr's transitions (envelopes.rs:60-77): they only change what FOLLOWING frames do
     KN_DEV float exact1(const D &d) {
@@ -387,7 +427,8 @@ struct SegEnv {
         return n >= 1.0f ? (uint32_t)fminf(n, 1073741824.0f) : 0u;
     }
     KN_DEV uint32_t safe_frames_group() const { return safe_frames(); }
-    KN_DEV void settle() {}
+    KN_DEV bool settle() { return false; }
+    template <int N> KN_DEV void group_ck(const D &d, float (&env)[N]) { group<N>(d, env); }
     template <int N> KN_DEV void group(const D &d, float (&env)[N]) {
         double tl = d.run ? time : 0.0;
 #pragma unroll
@@ -487,7 +528,7 @@ KN_DEV void sub_group_fast(SubVoice<ENV> &s, const typename ENV::D &d, float omd
         s.t = wrap01(s.t + s.dt); // inc(), polyblep.rs:232-235
     }
     if constexpr (EXACT) env[0] = s.e.exact1(d); // N == 1: the envelope's whole state machine
-    else s.e.template group<N>(d, env);           // envelope * WrMul gain with the state fixed over the group
+    else s.e.template group_ck<N>(d, env);        // envelope * WrMul gain with the state fixed over the group
 #pragma unroll
     for (int k = 0; k < N; k++) {
         const float v0 = saw_eval(ph[k], s.dt, omd, rc);
@@ -522,7 +563,7 @@ KN_DEV void sub_produce(SubVoice<ENV> &s, const typename ENV::D &d, float omd, f
         ph[k] = s.t;
         s.t = wrap01(s.t + s.dt); // inc(), polyblep.rs:232-235
     }
-    s.e.template group<N>(d, env);
+    s.e.template group_ck<N>(d, env);
 #if SUB_F32X2
     if constexpr (N % 2 == 0) {
 #pragma unroll
@@ -724,6 +765,7 @@ KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
         // frames between the last whole group and `limit` come through here as well -- nothing is due in them and the
         // envelope cannot move, the exact frame is simply the general one -- and keep `limit` as it is.)
         const bool at_limit = f >= limit;
+        if (s.e.settle()) s.e.derive(d); // a ramp the groups carried through its end gets its state's name (and an attack its exact t) before anything reads it
         if (f >= next_ev) {
             bool touched = false;
             while (ec.next_frame <= f) { // events are sorted by (frame, node, arrival)

@@ -17,9 +17,9 @@ pytestmark = pytest.mark.gpu
 SR = 48000
 
 
-def both(build, n_blocks, outputs=2, block_size=64, taps=True, force_interpreter=False):
+def both(build, n_blocks, outputs=2, block_size=64, taps=True, force_interpreter=False, no_scan=False):
     """Run `build(graph) -> tap node ids` through the GPU engine and the oracle."""
-    opts = AudioProcessorOptions(block_size=block_size, sample_rate=SR, force_interpreter=force_interpreter)
+    opts = AudioProcessorOptions(block_size=block_size, sample_rate=SR, force_interpreter=force_interpreter, no_scan=no_scan)
     graph, proc = AudioProcessor.new(0, outputs, opts)
     ids = build(graph)
     ev = graph.take_events()
@@ -217,6 +217,68 @@ def test_envelope_choreography_in_the_fused_voice_shape():
     assert np.abs(gpu - ref).max() <= 1e-5
     _, _, gi, _, _ = both(build, 200, force_interpreter=True)
     assert np.array_equal(gt, gi)
+
+
+def test_envasr_choreography_in_the_fused_voice_shape():
+    # EnvAsr state machine edge cases inside the render_sub_asr voice shape (the straight-line groups carry an attack and a
+    # release through their ends, fused.cu SUB_SAT_ATTACK / SUB_SAT_RELEASE): t_restart while sustaining (one frame of the
+    # kept first t >= 1), while attacking and while releasing, t_release during the attack, attack_time / release_time
+    # changed in the middle of a ramp, a zero-length attack, a release that is never started, several launches per render
+    def build(graph):
+        ids = []
+        with graph.edit() as g:
+            for i in range(48):
+                att = [0.0, 0.0005, 0.003, 0.011, 0.03][i % 5]
+                rel = [0.002, 0.02, 0.07][i % 3]
+                saw = g.push(kn.PolyBlep(kn.Waveform.Sawtooth, 82.0 * (1 + i % 11)).precise_timing(8))
+                svf = g.push(kn.SvfFilter(kn.SvfFilterType.Low, 500.0 + 120.0 * i, 1.5, 0.0).precise_timing(8))
+                env = g.push(kn.EnvAsr(att, rel).wr_mul(0.04).precise_timing(8))
+                sig = (saw >> svf) * env
+                sig.out([0, 0]).to_graph_out()
+                at = lambda n: kn.Seconds.from_samples(n, SR)
+                env.param("t_restart").trig_at(at(90 + 17 * i))
+                if i % 4 == 0:      # restart while sustaining, twice
+                    env.param("t_restart").trig_at(at(3000 + i))
+                    env.param("t_restart").trig_at(at(3001 + i))
+                if i % 4 == 1:      # restart in the middle of the attack, release during the next attack
+                    env.param("t_restart").trig_at(at(120 + 17 * i))
+                    env.param("t_release").trig_at(at(4000 + i))
+                    env.param("t_restart").trig_at(at(4100 + i))
+                    env.param("t_release").trig_at(at(4130 + i))
+                if i % 4 == 2:      # attack_time changed during the attack, release_time during the release
+                    env.param("attack_time").set_at(0.05, at(100 + 17 * i))
+                    env.param("attack_time").set_at(0.001, at(400 + 17 * i))
+                    env.param("t_release").trig_at(at(5000))
+                    env.param("release_time").set_at(0.3, at(5040 + i))
+                    env.param("t_restart").trig_at(at(5600 + i))     # restart while releasing
+                if i % 4 == 3:      # release at the frame the attack ends, and one frame around it
+                    n_att = int(att * SR)
+                    env.param("t_release").trig_at(at(90 + 17 * i + n_att + (i % 3) - 1))
+                    env.param("t_restart").trig_at(at(6000 + i))     # restart after Stopped, never released again
+                env.param("wr_mul").set_at(0.02, at(7000 + i))
+                ids.append(sig._outputs[0][0])
+        return ids
+
+    gpu, ref, gt, rt, proc = both(build, 160, no_scan=True)
+    assert proc.info()["kernels"] == ["render_sub_asr"]
+    assert np.abs(rt).max() > 1e-3
+    assert np.abs(gt - rt).max() <= 1e-4
+    assert np.abs(gpu - ref).max() <= 1e-5
+    _, _, gi, _, _ = both(build, 160, force_interpreter=True)
+    assert np.array_equal(gt, gi)
+    # the small-bank scan kernel renders the chunks that hold these events in reference order
+    gs, _, gst, _, ps = both(build, 160)
+    assert ps.info()["kernels"][0].startswith("render_sub_scan")
+    assert np.abs(gst - rt).max() <= 1e-4 and np.abs(gs - ref).max() <= 1e-5
+    # block-by-block calls (every call stores and reloads the envelope state) render the same samples
+    opts = AudioProcessorOptions(block_size=64, sample_rate=SR, no_scan=True)
+    graph, p2 = AudioProcessor.new(0, 2, opts)
+    build(graph)
+    blocks = []
+    for _ in range(160):
+        p2.run_without_inputs()
+        blocks.append(p2.output_block())
+    assert np.array_equal(np.stack(blocks), gpu)
 
 
 def test_subtractive_intermediate_nodes_match():
