@@ -325,39 +325,56 @@ void ensure_stream_objects(kgpu_plan *p) {
 // Uploads the events of ONE launch (the only launch in p->ce): pinned staging buffer -> device
 // buffer (launch & 1) on h2d_stream, which first waits until the kernels of launch - 2 (the last
 // readers of that buffer) are done.  `stream` then waits for the copy.
+// The staging buffer the next launch's events go through: stream_launch lays them out in it directly when they fit
+// (HostPlan::CompiledEvents::ext_*), so the merge of the workers' lists is the only host copy before the upload.
+void offer_staging(kgpu_plan *p) {
+    Staging &sg = p->staging[p->staging_next];
+    if (sg.in_flight && sg.copied) {
+        CUDA_TRY(cudaEventSynchronize(sg.copied));
+        sg.in_flight = false;
+    }
+    p->ce.ext_ev = sg.ev.p;
+    p->ce.ext_ev_cap = sg.ev.cap;
+    p->ce.ext_off = sg.off.p;
+    p->ce.ext_off_cap = sg.off.cap;
+}
 void upload_launch_events(kgpu_plan *p, size_t launch, cudaStream_t stream) {
-    if (p->ce.events.empty()) return;
+    const size_t n_ev = p->ce.n_events(), n_off = p->ce.n_offsets();
+    if (!n_ev) return;
     const int pp = (int)(launch & 1);
     Staging &sg = p->staging[p->staging_next];
     p->staging_next = (p->staging_next + 1) % 3;
     if (!sg.copied) CUDA_TRY(cudaEventCreateWithFlags(&sg.copied, cudaEventDisableTiming));
-    if (sg.in_flight) CUDA_TRY(cudaEventSynchronize(sg.copied));
-    if (p->ce.events.size() > sg.ev.cap || p->ce.offsets.size() > sg.off.cap) {
-        // grow all three staging buffers together (with headroom): page-locked allocation is slow
-        // and synchronises, so it should happen in the first render call only
-        for (Staging &o : p->staging) {
-            if (o.in_flight && o.copied) CUDA_TRY(cudaEventSynchronize(o.copied));
-            o.ev.ensure(p->ce.events.size() + p->ce.events.size() / 2);
-            o.off.ensure(p->ce.offsets.size() + p->ce.offsets.size() / 2);
+    if (!p->ce.ext_used) {
+        if (sg.in_flight) CUDA_TRY(cudaEventSynchronize(sg.copied));
+        if (n_ev > sg.ev.cap || n_off > sg.off.cap) {
+            // grow all three staging buffers together (with headroom): page-locked allocation is slow
+            // and synchronises, so it should happen in the first render call only
+            for (Staging &o : p->staging) {
+                if (o.in_flight && o.copied) CUDA_TRY(cudaEventSynchronize(o.copied));
+                o.in_flight = false;
+                o.ev.ensure(n_ev + n_ev / 2);
+                o.off.ensure(n_off + n_off / 2);
+            }
         }
+        std::memcpy(sg.ev.p, p->ce.events.data(), n_ev * sizeof(DevEvent));
+        std::memcpy(sg.off.p, p->ce.offsets.data(), n_off * 4);
     }
-    std::memcpy(sg.ev.p, p->ce.events.data(), p->ce.events.size() * sizeof(DevEvent));
-    std::memcpy(sg.off.p, p->ce.offsets.data(), p->ce.offsets.size() * 4);
-    if (p->ce.events.size() > p->d_events_pp[pp].cap || p->ce.offsets.size() > p->d_off_pp[pp].cap) {
+    if (n_ev > p->d_events_pp[pp].cap || n_off > p->d_off_pp[pp].cap) {
         CUDA_TRY(cudaStreamSynchronize(stream)); // cudaFree of a buffer a queued kernel still reads: first render call only
         for (int i = 0; i < 2; i++) {
-            p->d_events_pp[i].ensure(p->ce.events.size() + p->ce.events.size() / 2);
-            p->d_off_pp[i].ensure(p->ce.offsets.size() + p->ce.offsets.size() / 2);
+            p->d_events_pp[i].ensure(n_ev + n_ev / 2);
+            p->d_off_pp[i].ensure(n_off + n_off / 2);
         }
     }
     if (p->kern_recorded[pp]) CUDA_TRY(cudaStreamWaitEvent(p->h2d_stream, p->kern_done[pp], 0));
-    CUDA_TRY(cudaMemcpyAsync(p->d_events_pp[pp].p, sg.ev.p, p->ce.events.size() * sizeof(DevEvent), cudaMemcpyHostToDevice, p->h2d_stream));
-    CUDA_TRY(cudaMemcpyAsync(p->d_off_pp[pp].p, sg.off.p, p->ce.offsets.size() * 4, cudaMemcpyHostToDevice, p->h2d_stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_events_pp[pp].p, sg.ev.p, n_ev * sizeof(DevEvent), cudaMemcpyHostToDevice, p->h2d_stream));
+    CUDA_TRY(cudaMemcpyAsync(p->d_off_pp[pp].p, sg.off.p, n_off * 4, cudaMemcpyHostToDevice, p->h2d_stream));
     CUDA_TRY(cudaEventRecord(sg.copied, p->h2d_stream));
     CUDA_TRY(cudaEventRecord(p->h2d_done[pp], p->h2d_stream));
     CUDA_TRY(cudaStreamWaitEvent(stream, p->h2d_done[pp], 0));
     sg.in_flight = true;
-    p->last_h2d_bytes += p->ce.events.size() * sizeof(DevEvent) + p->ce.offsets.size() * 4;
+    p->last_h2d_bytes += n_ev * sizeof(DevEvent) + n_off * 4;
 }
 
 // Renders n_blocks blocks into device_out.  If the range was prepared (kgpu_plan_prepare) the
@@ -491,6 +508,7 @@ void render_range(kgpu_plan *p, uint64_t n_blocks, float *device_out, cudaStream
         if (!was_prepared) {
             static const bool timing = getenv("KGPU_TIMING") != nullptr;
             const auto ta = std::chrono::steady_clock::now();
+            offer_staging(p);
             p->host.stream_launch(launch, p->ce);
             const auto tb = std::chrono::steady_clock::now();
             upload_launch_events(p, launch, stream);

@@ -1841,7 +1841,7 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
         for (uint32_t li = 0; li < nn; li++) {
             const NodeStatic &ns = g.nstat[li];
             HostNode &hn = g.host[(size_t)v * nn + li];
-            if (!((mask >> li) & 1u) && !hn.ramp_active) continue;
+            if (!((mask >> li) & 1u) && (ns.fast || !hn.ramp_active)) continue; // (a fast node never ramps: its state is not even touched)
             Sim s{P, sk, li, hn};
             if (ns.fast) {
                 fast_node_block(s, ns, evp.data(), evp.size(), li, block_start);
@@ -1883,6 +1883,9 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     pg.cnt[L][v - pg.v_begin] = (uint32_t)(out.size() - out0);
 }
 
+#ifndef KGPU_HOST_PREFETCH
+#define KGPU_HOST_PREFETCH 6 // voices of look-ahead in the control simulation's walk (0: none)
+#endif
 // one slice of the voices, one launch window
 void stream_worker_step(HostPlan &P, StreamState &S, StreamState::ThreadCtx &tc, size_t L) {
     for (uint32_t gi = 0; gi < P.groups.size(); gi++) {
@@ -1892,7 +1895,23 @@ void stream_worker_step(HostPlan &P, StreamState &S, StreamState::ThreadCtx &tc,
         const bool quick = P.n_active_ramps == 0 && tc.ramp_delta == 0;
         const uint64_t t1 = S.bounds[L + 1];
         const uint64_t *nd = pg.next_due.data();
+        // The walk is latency-bound: a voice's control-side nodes and its next events were last touched a launch ago (megabytes
+        // of other voices in between).  They are fetched KGPU_PF voices ahead of their use.
+        Group &g = P.groups[gi];
+        const size_t nn = g.tpl.nodes.size(), node_bytes = nn * sizeof(HostNode);
+        const char *hosts = reinterpret_cast<const char *>(g.host.data());
+        const uint32_t *cur = pg.cursor.data();
+        const uint32_t *vo = S.identity ? nullptr : P.vorder.data();
+        const RawEvent *pend = P.pending.data();
+        constexpr uint32_t KGPU_PF = KGPU_HOST_PREFETCH;
         for (uint32_t v = pg.v_begin; v < pg.v_end; v++) {
+            const uint32_t vp = v + KGPU_PF;
+            if (KGPU_PF && vp < pg.v_end && !(quick && nd[vp - pg.v_begin] >= t1)) {
+                const char *h = hosts + (size_t)vp * node_bytes;
+                for (size_t o = 0; o < node_bytes; o += 64) __builtin_prefetch(h + o, 1, 1);
+                const uint32_t c = cur[vp - pg.v_begin];
+                if (c < P.vcount[P.voice_base[gi] + vp + 1]) __builtin_prefetch(pend + (vo ? vo[c] : c), 0, 1);
+            }
             if (quick && nd[v - pg.v_begin] >= t1) continue; // nothing of this voice becomes ready in this window
             simulate_voice_window(P, S, tc, gi, v, L);
         }
@@ -2105,12 +2124,18 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
     T = std::min<unsigned>(T, std::max<unsigned>(1u, (unsigned)(NV / 64)));
     // With few workers (several GPUs sharing one box's cores) the control simulation, not the device, paces the call, and the
     // calling thread would only wait for them: it takes a slice of the voices of its own -- half a worker's, it also merges,
-    // uploads and launches -- and simulates it launch by launch inside stream_launch.  Slices are weighted 2 : ... : 2 : 1.
+    // uploads and launches -- and simulates it launch by launch inside stream_launch.
     // Measured on the bench configuration (one B200, 16 host cores): 3 workers 15.35 -> 15.07 ms per step end to end; 7 workers
     // 14.48 -> 14.53 ms (the device paces that call, nothing to gain), so the slice is taken with up to 4 workers only.
     static const char *drv_env = getenv("KGPU_DRIVER_SLICE"); // 0 = never, 1 = whenever workers run (default: up to 4 workers)
     const bool driver_slice = T > 1 && (drv_env ? atoi(drv_env) != 0 : T <= 4) && NV >= 64u * (T + 1);
-    const unsigned NT = T + (driver_slice ? 1u : 0u), WT = driver_slice ? 2 * T + 1 : T;
+    // slice weights: a worker 100, the calling thread KGPU_DRIVER_WEIGHT (default 50: it also merges, uploads and launches)
+    static const unsigned drv_weight = [] {
+        const char *e = getenv("KGPU_DRIVER_WEIGHT");
+        const int w = e ? atoi(e) : 50;
+        return (unsigned)std::min(100, std::max(5, w));
+    }();
+    const unsigned NT = T + (driver_slice ? 1u : 0u), WT = driver_slice ? 100 * T + drv_weight : T;
     S->n_threads = NT;
     S->driver_ctx = driver_slice ? (int)T : -1;
     while (S->th.size() < NT) S->th.emplace_back(new StreamState::ThreadCtx());
@@ -2129,7 +2154,7 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
         tc.g.resize(n_groups);
         tc.ramp_delta = 0;
         tc.sink.dropped = tc.sink.ignored = tc.sink.devev = 0;
-        const unsigned w0 = driver_slice ? 2 * ti : ti, w1 = driver_slice ? std::min(2 * ti + 2, WT) : ti + 1;
+        const unsigned w0 = driver_slice ? 100 * ti : ti, w1 = driver_slice ? std::min(100 * ti + 100, WT) : ti + 1;
         (void)T;
         for (size_t gi = 0; gi < n_groups; gi++) {
             StreamState::PerGroup &pg = tc.g[gi];
@@ -2195,6 +2220,8 @@ void HostPlan::stream_launch(size_t L, CompiledEvents &out) {
     const size_t n_groups = groups.size();
     out.events.clear();
     out.offsets.clear();
+    out.ext_used = false;
+    out.ext_n_ev = out.ext_n_off = 0;
     out.piece_ev.assign(n_groups, 0);
     out.piece_off.assign(n_groups, 0);
     out.piece_any.assign(n_groups, 0);
@@ -2221,27 +2248,47 @@ void HostPlan::stream_launch(size_t L, CompiledEvents &out) {
         if (tc->error_code) throw Error{tc->error_code, tc->error};
     }
     pt.lap("wait");
+    // sizes first: the caller's buffers are used when the whole launch fits
+    size_t all_ev = 0, all_off = 0;
     for (size_t gi = 0; gi < n_groups; gi++) {
         size_t total = 0;
         for (unsigned ti = 0; ti < S->n_threads; ti++) total += S->th[ti]->g[gi].ev[L].size();
-        out.piece_ev[gi] = out.events.size();
+        if (!total) continue;
+        all_ev += total;
+        all_off += groups[gi].n_voices + 1;
+    }
+    const bool ext = out.ext_ev && out.ext_off && all_ev <= out.ext_ev_cap && all_off <= out.ext_off_cap;
+    if (ext) {
+        out.ext_used = true;
+        out.ext_n_ev = all_ev;
+        out.ext_n_off = all_off;
+    } else {
+        out.events.resize(all_ev);
+        out.offsets.resize(all_off);
+    }
+    DevEvent *ev_dst = ext ? out.ext_ev : out.events.data();
+    uint32_t *off_dst = ext ? out.ext_off : out.offsets.data();
+    size_t ev0 = 0, off0 = 0;
+    for (size_t gi = 0; gi < n_groups; gi++) {
+        size_t total = 0;
+        for (unsigned ti = 0; ti < S->n_threads; ti++) total += S->th[ti]->g[gi].ev[L].size();
+        out.piece_ev[gi] = ev0;
         if (!total) continue;
         out.piece_any[gi] = 1;
-        out.piece_off[gi] = out.offsets.size();
-        const size_t ev0 = out.events.size(), off0 = out.offsets.size();
-        out.events.resize(ev0 + total);
-        out.offsets.resize(off0 + groups[gi].n_voices + 1);
+        out.piece_off[gi] = off0;
         uint32_t run_off = 0;
-        uint32_t *off = out.offsets.data() + off0;
+        uint32_t *off = off_dst + off0;
         for (unsigned ti = 0; ti < S->n_threads; ti++) {
             StreamState::PerGroup &pg = S->th[ti]->g[gi];
-            if (!pg.ev[L].empty()) std::memcpy(out.events.data() + ev0 + run_off, pg.ev[L].data(), pg.ev[L].size() * sizeof(DevEvent));
+            if (!pg.ev[L].empty()) std::memcpy(ev_dst + ev0 + run_off, pg.ev[L].data(), pg.ev[L].size() * sizeof(DevEvent));
             for (uint32_t c : pg.cnt[L]) {
                 *off++ = run_off;
                 run_off += c;
             }
         }
         *off = run_off;
+        ev0 += total;
+        off0 += groups[gi].n_voices + 1;
     }
 }
 
@@ -2292,6 +2339,9 @@ void HostPlan::compile_events(const std::vector<uint64_t> &bounds, const std::ve
     const size_t n_launch = bounds.size() - 1, n_groups = groups.size();
     out.events.clear();
     out.offsets.clear();
+    out.ext_used = false;
+    out.ext_ev = nullptr;
+    out.ext_off = nullptr;
     out.piece_ev.assign(n_launch * n_groups, 0);
     out.piece_off.assign(n_launch * n_groups, 0);
     out.piece_any.assign(n_launch * n_groups, 0);

@@ -229,6 +229,17 @@ struct HostPlan {
         std::vector<uint32_t, DefaultInitAllocator<uint32_t>> offsets;  // concatenated CSR offset arrays (n_voices+1 each)
         std::vector<uint64_t> piece_ev, piece_off; // [launch * n_groups + group]
         std::vector<uint8_t> piece_any;
+        // stream_launch only: where the caller wants the launch's events and offsets laid out (page-locked staging memory,
+        // so that the merge of the workers' lists is the only copy before the upload).  Used when both fit; `ext_used` says so,
+        // `events` / `offsets` stay empty then.
+        DevEvent *ext_ev = nullptr;
+        uint32_t *ext_off = nullptr;
+        size_t ext_ev_cap = 0, ext_off_cap = 0, ext_n_ev = 0, ext_n_off = 0;
+        bool ext_used = false;
+        size_t n_events() const { return ext_used ? ext_n_ev : events.size(); }
+        size_t n_offsets() const { return ext_used ? ext_n_off : offsets.size(); }
+        const DevEvent *events_data() const { return ext_used ? ext_ev : events.data(); }
+        const uint32_t *offsets_data() const { return ext_used ? ext_off : offsets.data(); }
     };
 
     void build(const kgpu_graph_desc &d);
