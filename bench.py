@@ -417,7 +417,7 @@ def roofline_of(res, peaks, peak_src):
         if tj["voices"] == voices:
             out["traffic"] = tj["traffic_bytes_per_launch"] * frames_per_launch / tj["frames_per_launch"]
             out["traffic_source"] = f"{tj['source']} (ncu --set full capture of one launch, scaled by frames per launch; NOT measured in this run)"
-    except (OSError, KeyError, ValueError):
+    except (OSError, KeyError, ValueError, TypeError, ZeroDivisionError):  # a malformed record must not take the bench line down
         pass
     return out
 

@@ -113,7 +113,11 @@ __global__ void add_wt_params(FusedArgs a, uint32_t gain_reg, WtParam *__restric
 constexpr uint32_t WT_VCHUNK = 128;     // voices staged in shared memory at a time
 constexpr uint32_t WT_MAX_TILE_BLOCKS = WT_THREADS / 32; // a 256-frame tile touches at most 8 blocks (block_size >= 32)
 
-template <bool TAPS>
+// FPT = frames per thread.  FPT = 2 (block sizes that are multiples of 64): a thread renders frames k and k + 32 of ONE block, so the
+// voice's record (a broadcast LDS.128) is loaded once per two samples.  Measured: 1.73 -> 1.70 ms per 10 s step of the 4096-partial
+// bank -- the record load was not what keeps the shared-memory path 89 % busy (r2j capture); the table lookups are (1.34 wavefronts
+// each: consecutive frames of a high partial stride through the 64 KiB table).
+template <bool TAPS, int FPT>
 __global__ void __launch_bounds__(WT_THREADS) add_wt_render(FusedArgs a, const WtParam *__restrict__ table, uint32_t n_slices, uint32_t n_tiles) {
     extern __shared__ __align__(16) float tab[]; // the sine table (wavetable.rs:130-139), then the staged voice records
     uint4 *stage = reinterpret_cast<uint4 *>(tab + SINE_TABLE_SIZE); // [tile block][WT_VCHUNK]
@@ -122,19 +126,22 @@ __global__ void __launch_bounds__(WT_THREADS) add_wt_render(FusedArgs a, const W
         float4 *dst = reinterpret_cast<float4 *>(tab);
         for (uint32_t i = threadIdx.x; i < SINE_TABLE_SIZE / 4; i += WT_THREADS) dst[i] = src[i];
     }
+    constexpr uint32_t TILE = WT_THREADS * FPT;
     const uint32_t V = a.n_voices, bs = a.block_size;
     const uint32_t slice = blockIdx.y;
     const uint32_t v0 = (uint32_t)((uint64_t)V * slice / n_slices), v1 = (uint32_t)((uint64_t)V * (slice + 1) / n_slices);
     float *prow = a.partials + (size_t)(a.row0 + slice) * a.n_frames;
     for (uint32_t tile = blockIdx.x * WT_TILES_PER_CTA; tile < min(n_tiles, (blockIdx.x + 1) * WT_TILES_PER_CTA); tile++) {
-        const uint32_t f_tile = tile * WT_THREADS;
-        const uint32_t f = f_tile + threadIdx.x;
+        const uint32_t f_tile = tile * TILE;
+        // FPT = 2: warp w renders frames [64 w, 64 w + 64) of the tile, lane l the frames 64 w + l and 64 w + 32 + l (one block: bs % 64 == 0)
+        const uint32_t f = FPT == 1 ? f_tile + threadIdx.x : f_tile + (threadIdx.x >> 5) * 64u + (threadIdx.x & 31u);
         const bool on = f < a.n_frames;
+        const bool on2 = FPT == 2 && f + 32u < a.n_frames;
         const uint32_t b_first = f_tile / bs;
-        const uint32_t b_last = (min(a.n_frames, f_tile + WT_THREADS) - 1) / bs;
+        const uint32_t b_last = (min(a.n_frames, f_tile + TILE) - 1) / bs;
         const uint32_t nb = b_last - b_first + 1;
-        const uint32_t b = on ? f / bs : b_first, k = f - b * bs;
-        float acc = 0.f;
+        const uint32_t b = on ? f / bs : b_first, k = f - b * bs, k2 = k + 32u;
+        float acc = 0.f, acc2 = 0.f;
         for (uint32_t vc = v0; vc < v1; vc += WT_VCHUNK) {
             const uint32_t nv = min(WT_VCHUNK, v1 - vc);
             __syncthreads(); // the previous chunk's readers are done (and the sine table is in place)
@@ -148,11 +155,19 @@ __global__ void __launch_bounds__(WT_THREADS) add_wt_render(FusedArgs a, const W
             if (!TAPS) {
                 for (; vi + 4 <= nv; vi += 4) {
                     const uint4 p0 = row[vi], p1 = row[vi + 1], p2 = row[vi + 2], p3 = row[vi + 3];
-                    const float s0 = tab[((p0.x + k * p0.y + p0.z) >> 16) & 0x3FFFu] * __uint_as_float(p0.w); // WrMul, wrappers_core/math.rs:63-67
-                    const float s1 = tab[((p1.x + k * p1.y + p1.z) >> 16) & 0x3FFFu] * __uint_as_float(p1.w);
-                    const float s2 = tab[((p2.x + k * p2.y + p2.z) >> 16) & 0x3FFFu] * __uint_as_float(p2.w);
-                    const float s3 = tab[((p3.x + k * p3.y + p3.z) >> 16) & 0x3FFFu] * __uint_as_float(p3.w);
+                    const uint32_t q0 = p0.x + p0.z, q1 = p1.x + p1.z, q2 = p2.x + p2.z, q3 = p3.x + p3.z; // (phase + k inc) + off, mod 2^32: any order
+                    const float s0 = tab[((q0 + k * p0.y) >> 16) & 0x3FFFu] * __uint_as_float(p0.w); // WrMul, wrappers_core/math.rs:63-67
+                    const float s1 = tab[((q1 + k * p1.y) >> 16) & 0x3FFFu] * __uint_as_float(p1.w);
+                    const float s2 = tab[((q2 + k * p2.y) >> 16) & 0x3FFFu] * __uint_as_float(p2.w);
+                    const float s3 = tab[((q3 + k * p3.y) >> 16) & 0x3FFFu] * __uint_as_float(p3.w);
                     acc = (((acc + s0) + s1) + s2) + s3;
+                    if (FPT == 2) {
+                        const float t0 = tab[((q0 + k2 * p0.y) >> 16) & 0x3FFFu] * __uint_as_float(p0.w);
+                        const float t1 = tab[((q1 + k2 * p1.y) >> 16) & 0x3FFFu] * __uint_as_float(p1.w);
+                        const float t2 = tab[((q2 + k2 * p2.y) >> 16) & 0x3FFFu] * __uint_as_float(p2.w);
+                        const float t3 = tab[((q3 + k2 * p3.y) >> 16) & 0x3FFFu] * __uint_as_float(p3.w);
+                        acc2 = (((acc2 + t0) + t1) + t2) + t3;
+                    }
                 }
             }
             for (; vi < nv; vi++) {
@@ -162,9 +177,11 @@ __global__ void __launch_bounds__(WT_THREADS) add_wt_render(FusedArgs a, const W
                     for (uint32_t i = 0; i < a.n_taps; i++)
                         if (a.taps[i].voice == vc + vi) a.tap_out[(size_t)a.taps[i].tap * a.tap_stride + a.tap_frame0 + f] = s;
                 acc = acc + s;
+                if (FPT == 2) acc2 = acc2 + tab[((p.x + k2 * p.y + p.z) >> 16) & 0x3FFFu] * __uint_as_float(p.w);
             }
         }
         if (on) prow[f] = acc;
+        if (on2) prow[f + 32u] = acc2;
     }
 }
 
@@ -217,7 +234,10 @@ cudaError_t launch_add_wt(const FusedArgs &a, cudaStream_t stream) {
     ce = cudaMemcpyAsync(a.regs, ap.regs_out, (size_t)a.host_prog->n_regs * a.n_voices * 4, cudaMemcpyDeviceToDevice, stream);
     if (ce != cudaSuccess) return ce;
     const uint32_t n_slices = add_wt_slices(a.n_voices);
-    const uint32_t n_tiles = (a.n_frames + WT_THREADS - 1) / WT_THREADS;
+    // two frames per thread where a block holds both of a lane's frames (and no taps: the tapped form is test-only)
+    const bool two = !a.n_taps && a.block_size % 64 == 0;
+    const uint32_t tile_frames = WT_THREADS * (two ? 2u : 1u);
+    const uint32_t n_tiles = (a.n_frames + tile_frames - 1) / tile_frames;
     const dim3 grid((n_tiles + WT_TILES_PER_CTA - 1) / WT_TILES_PER_CTA, n_slices);
     const size_t smem = SINE_TABLE_SIZE * sizeof(float) + (size_t)WT_MAX_TILE_BLOCKS * WT_VCHUNK * sizeof(uint4);
     // the opt-in above 48 KB of dynamic shared memory is a PER-DEVICE function attribute: one flag per device, so
@@ -227,13 +247,15 @@ cudaError_t launch_add_wt(const FusedArgs &a, cudaStream_t stream) {
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
-        e = cudaFuncSetAttribute(add_wt_render<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(add_wt_render<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(add_wt_render<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(add_wt_render<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(add_wt_render<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
-    if (a.n_taps) add_wt_render<true><<<grid, WT_THREADS, smem, stream>>>(a, table, n_slices, n_tiles);
-    else add_wt_render<false><<<grid, WT_THREADS, smem, stream>>>(a, table, n_slices, n_tiles);
+    if (a.n_taps) add_wt_render<true, 1><<<grid, WT_THREADS, smem, stream>>>(a, table, n_slices, n_tiles);
+    else if (two) add_wt_render<false, 2><<<grid, WT_THREADS, smem, stream>>>(a, table, n_slices, n_tiles);
+    else add_wt_render<false, 1><<<grid, WT_THREADS, smem, stream>>>(a, table, n_slices, n_tiles);
     return cudaGetLastError();
 }
 

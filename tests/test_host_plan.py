@@ -428,3 +428,20 @@ def test_driver_slice_leaves_the_event_stream_unchanged(monkeypatch):
                     ref = key
                 assert key[1:] == ref[1:], (wl, threads, bpc)
                 assert key[0] == ref[0], (wl, threads, bpc)
+
+
+def test_traffic_records_are_well_formed():
+    """profiles/traffic.json feeds `roofline.traffic` of every bench line (bench.py roofline_of): numbers where numbers are read."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")) as f:
+        tj = json.load(f)
+    assert {"render_sub_asr", "render_sub_seg", "render_fm2", "render_add_wt", "render_jit"} <= set(tj)
+    for name, rec in tj.items():
+        assert isinstance(rec["source"], str), name
+        for key in ("frames_per_launch", "voices"):
+            assert isinstance(rec[key], int) and rec[key] > 0, (name, key)
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum", "traffic_bytes_per_launch"):
+            assert isinstance(rec[key], (int, float)) and rec[key] >= 0, (name, key)
+        assert abs(rec["traffic_bytes_per_launch"] - rec["dram__bytes_read.sum"] - rec["dram__bytes_write.sum"]) < 1.0, name
