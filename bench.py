@@ -401,6 +401,11 @@ def roofline_of(res, peaks, peak_src):
                "peak_source": f"{N_SM} SMs x {FP32_LANES} FP32 lanes x sm_max_mhz {sm_max:g} ({peak_src}); no tensor/HBM bound: "
                               "nothing here is a dense contraction and intermediates never touch HBM"}
     out["frac"] = out["achieved"] / out["peak"]
+    if kernel == "render_sub_asr" and voices == 16384:
+        # measured, not derived: profiles/r2_microbench_issue_mix.txt (tools/microbench/issue_mix.cu)
+        out["formulation_ceiling"] = {"frac": 0.865 * 0.914, "why": "one lane per voice: 512 warps on 592 schedulers (0.865) x the issue rate of ONE warp "
+                                      "on this kernel's FADD / FMUL / FFMA / FSET mix as independent chains (1.094 cycles per instruction, 0.914)",
+                                      "frac_of_ceiling": out["frac"] / (0.865 * 0.914)}
     out.update({"kernel": kernel, "avg_launch_ms": avg_launch_ms, "launches": res["kern_launches"],
                 "kernel_share_of_step": res["kern_ms"] / max(1e-9, res["step_ms_sum"]), "reduce_bus_ms_per_step": res["red_ms"] / res["steps"]})
     # HBM side: algorithmic bytes per launch (state in + out, events, per-warp partial rows) against the measured copy peak
