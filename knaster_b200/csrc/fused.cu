@@ -109,6 +109,12 @@ template <class ENV> struct SubVoice {
                           // 1.0 where Sustaining outputs 1, and the first t >= 1 (which Sustaining keeps and t_restart resumes from) is replayed
                           // from a per-group checkpoint of the last ramp value below 1 when the next limit frame / the launch's end needs it
 #endif
+#ifndef SUB_PTRS
+#define SUB_PTRS 0   // (measured: much slower, 15.86 ms per step against 13.33) rotated loop: staging / partial-row addresses carried as running values
+                     // instead of rebuilt from `half` and `f` -- 314-316 instead of 319 instructions per group, still one basic block, but ptxas
+                     // schedules the group differently (the previous group's staged rows are loaded and summed at the loop's head, the
+                     // filter chain starts behind them): the instruction count is not what this loop is short of
+#endif
 #ifndef SUB_COMPACT
 #define SUB_COMPACT 0 // (measured: slower, 14.7 ms against 14.1 -- an exact frame costs more than a 4- / 1-frame group) the frames between the last whole group and the limit frame run through ONE rolled exact-frame loop
                       // instead of 4- and 1-frame straight-line groups: a limit costs ~1900 cycles of mostly instruction
@@ -592,7 +598,12 @@ KN_DEV void sub_consume(SubVoice<ENV> &s, const float (&x)[N], const float (&env
         const float h = q + __shfl_xor_sync(0xFFFFFFFFu, q, 8);
         tot = h + __shfl_xor_sync(0xFFFFFFFFu, h, 16);
     }
+#if SUB_PTRS
+    // a predicated store, spelled out (no branch whatever ptxas makes of the running destination pointer)
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.global.f32 [%0], %1; }" ::"l"(sum_dst), "f"(tot), "r"((uint32_t)sum_store));
+#else
     if (sum_store) *sum_dst = tot;
+#endif
     float yy[N];
 #pragma unroll
     for (int k = 0; k < N; k++) {
@@ -718,7 +729,33 @@ KN_DEV void render_sub_body(const FusedArgs &a, float *st) {
             bool pending = false;
             // lane = (staged frame r, voice group c of 32 / (32 / SUB_SUB) voices)
             const uint32_t r = lane & (SUB_SUB - 1u), c = lane / SUB_SUB, cw = SUB_SUB == 32 ? 32u : (SUB_SUB == 16 ? 16u : 8u);
-#if SUB_ROT
+#if SUB_ROT && SUB_PTRS
+            // the staging addresses as running values: the write column and the read row swap halves by "sum minus itself" (one
+            // integer addition each), the destination of the sums advances by a group -- the loop spent 14 instructions per
+            // iteration rebuilding the three from `half` and `f`
+            constexpr uint32_t TOG = SUB_SUB * SUBW_PAD;
+            const uint32_t ro0 = r * SUBW_PAD + c * cw;
+            uint32_t wo = lane, ro = TOG + ro0;
+            const uint32_t wsum = 2u * lane + TOG, rsum = 2u * ro0 + TOG;
+            float *pd = prow + ((ptrdiff_t)f - (ptrdiff_t)SUB_SUB + (ptrdiff_t)r); // never stored to before a group is pending
+            float gx[SUB_SUB], ge[SUB_SUB];
+            sub_produce<ENV, SUB_SUB>(s, d, omd, rc, gx, ge);      // the group at f; the oscillator / envelope state is now at f + SUB_SUB
+#pragma unroll 1
+            while (f + 2 * SUB_SUB <= lim) {
+                __syncwarp();
+                sub_consume<ENV, LP, SUB_SUB, TAPS>(s, gx, ge, st + wo, TAPS && tap ? tap + f : nullptr, st + ro, pd, pending && c == 0);
+                sub_produce<ENV, SUB_SUB>(s, d, omd, rc, gx, ge);
+                pending = true;
+                wo = wsum - wo;
+                ro = rsum - ro;
+                pd += SUB_SUB;
+                f += SUB_SUB;
+            }
+            __syncwarp();
+            sub_consume<ENV, LP, SUB_SUB, TAPS>(s, gx, ge, st + wo, TAPS && tap ? tap + f : nullptr, st + ro, pd, pending && c == 0);
+            half = wo >= TOG ? 0u : 1u; // as if toggled after the last group: the group just staged sits in half ^ 1
+            f += SUB_SUB;
+#elif SUB_ROT
             float gx[SUB_SUB], ge[SUB_SUB];
             sub_produce<ENV, SUB_SUB>(s, d, omd, rc, gx, ge);      // the group at f; the oscillator / envelope state is now at f + SUB_SUB
 #pragma unroll 1
