@@ -240,7 +240,7 @@ void svf_coeffs(uint32_t ty, float cutoff, float q, float gain_db, float sr, flo
 // per-thread sink of the control simulation: the device events of the block being simulated, in emission order
 // (node-major; inside a node by frame, then arrival), frames relative to the launch window's first frame
 struct Sink {
-    std::vector<DevEvent> blk;
+    std::vector<DevEvent> *dst = nullptr; // the launch's event list of the worker's slice: events are written in place, field by field
     uint64_t t0 = 0;
     uint64_t dropped = 0, ignored = 0, devev = 0;
 };
@@ -250,14 +250,14 @@ struct Sim {
     uint32_t local;
     HostNode &hn;
     void emit(uint64_t frame, uint16_t op, uint32_t reg, uint32_t value) {
-        DevEvent d;
+        // (built in place: a DevEvent assembled in a local and copied as 16 bytes reads narrow stores back with one wide load,
+        // which the store buffer cannot forward -- that copy was the hottest line of the whole simulation)
+        DevEvent &d = out.dst->emplace_back();
         d.frame = (uint32_t)(frame - out.t0);
         d.node = (uint16_t)local;
         d.op = op;
         d.reg = reg;
         d.value = value;
-        out.blk.push_back(d);
-        out.devev++;
     }
     void set_f(uint64_t frame, uint32_t reg, float v) { emit(frame, OP_SET, reg, fbits(v)); }
     void set_u(uint64_t frame, uint32_t reg, uint32_t v) { emit(frame, OP_SET, reg, v); }
@@ -1758,6 +1758,7 @@ struct StreamState {
     uint64_t b0 = 0;
     bool any_work = false;
     bool identity = false;                       // the ready events are `pending` itself, already grouped by voice: vorder unused
+    bool all_ready = false;                      // every queued event is consumed by this call (known from push's bucketing): the queue is simply cleared
     unsigned n_threads = 0;                      // contexts of this call: th[0..n_threads)
     int driver_ctx = -1;                         // >= 0: th[driver_ctx] (the last slice) is simulated by the calling thread, launch by launch
     size_t driver_done = 0;                      // launches of that slice already simulated
@@ -1819,6 +1820,7 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
     Sink &sk = tc.sink;
     sk.t0 = t0;
     std::vector<DevEvent> &out = pg.ev[L];
+    sk.dst = &out;
     const size_t out0 = out.size();
     auto ready_block = [&](uint32_t k) { return std::max(P.block_of(ev_at(k).due_frame), wb0); };
     uint32_t ei = e0;
@@ -1835,7 +1837,7 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
             evp.push_back(&r);
             mask |= 1u << r.local;
         }
-        sk.blk.clear();
+        const size_t blk0 = out.size(); // this block's device events: out[blk0 ..)
         PROF_T(q1);
         PROF_ADD(1, q0, q1);
         for (uint32_t li = 0; li < nn; li++) {
@@ -1857,22 +1859,25 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
         }
         // device order inside the block: (frame / chunk, node, frame, arrival).  Emission order is (node, frame, arrival),
         // so a stable sort by chunk is all that is left (insertion sort: a block holds a handful of events)
-        const size_t nb = sk.blk.size();
+        const size_t nb = out.size() - blk0;
         PROF_T(q2);
         PROF_ADD(2, q1, q2);
         if (nb) {
-            DevEvent *be = sk.blk.data();
-            for (size_t i = 1; i < nb; i++) {
-                const DevEvent x = be[i];
-                const uint32_t kx = x.frame >> chunk_shift;
-                size_t j = i;
-                while (j > 0 && (be[j - 1].frame >> chunk_shift) > kx) {
-                    be[j] = be[j - 1];
-                    j--;
+            sk.devev += nb;
+            DevEvent *be = out.data() + blk0;
+            bool sorted = true; // the usual block: a handful of events that share a frame, or come in frame order
+            for (size_t i = 1; i < nb && sorted; i++) sorted = (be[i - 1].frame >> chunk_shift) <= (be[i].frame >> chunk_shift);
+            if (!sorted)
+                for (size_t i = 1; i < nb; i++) {
+                    const DevEvent x = be[i];
+                    const uint32_t kx = x.frame >> chunk_shift;
+                    size_t j = i;
+                    while (j > 0 && (be[j - 1].frame >> chunk_shift) > kx) {
+                        be[j] = be[j - 1];
+                        j--;
+                    }
+                    be[j] = x;
                 }
-                be[j] = x;
-            }
-            out.insert(out.end(), be, be + nb);
         }
         PROF_T(q3);
         PROF_ADD(3, q2, q3);
@@ -1884,7 +1889,7 @@ void simulate_voice_window(HostPlan &P, StreamState &S, StreamState::ThreadCtx &
 }
 
 #ifndef KGPU_HOST_PREFETCH
-#define KGPU_HOST_PREFETCH 6 // voices of look-ahead in the control simulation's walk (0: none)
+#define KGPU_HOST_PREFETCH 8 // voices of look-ahead in the control simulation's walk (0: none)
 #endif
 // one slice of the voices, one launch window
 void stream_worker_step(HostPlan &P, StreamState &S, StreamState::ThreadCtx &tc, size_t L) {
@@ -1908,9 +1913,13 @@ void stream_worker_step(HostPlan &P, StreamState &S, StreamState::ThreadCtx &tc,
             const uint32_t vp = v + KGPU_PF;
             if (KGPU_PF && vp < pg.v_end && !(quick && nd[vp - pg.v_begin] >= t1)) {
                 const char *h = hosts + (size_t)vp * node_bytes;
-                for (size_t o = 0; o < node_bytes; o += 64) __builtin_prefetch(h + o, 1, 1);
+                for (size_t o = 0; o < node_bytes; o += 64) __builtin_prefetch(h + o, 0, 3);
                 const uint32_t c = cur[vp - pg.v_begin];
-                if (c < P.vcount[P.voice_base[gi] + vp + 1]) __builtin_prefetch(pend + (vo ? vo[c] : c), 0, 1);
+                if (c < P.vcount[P.voice_base[gi] + vp + 1]) {
+                    const char *e = reinterpret_cast<const char *>(pend + (vo ? vo[c] : c));
+                    __builtin_prefetch(e, 0, 3);
+                    __builtin_prefetch(e + 64, 0, 3); // a window holds two to four of the voice's events on average
+                }
             }
             if (quick && nd[v - pg.v_begin] >= t1) continue; // nothing of this voice becomes ready in this window
             simulate_voice_window(P, S, tc, gi, v, L);
@@ -2022,6 +2031,7 @@ void HostPlan::stream_begin(const std::vector<uint64_t> &bounds, const std::vect
     if (prepped)
         for (unsigned c = 0; c < bp.T; c++) prepped &= bp.max_due[c] < t_ready; // every queued event is ready
     bp.valid = false; // one use: the queue changes below / at the end of the call
+    S->all_ready = prepped;
     const unsigned TB = prepped ? bp.T : (NP >= 65536 ? workers().size() : 1u);
     std::vector<std::vector<uint32_t>> &hist = prepped ? bp.hist : S->hist;
     hist.resize(std::max<size_t>(hist.size(), TB));
@@ -2296,8 +2306,9 @@ void HostPlan::stream_launch(size_t L, CompiledEvents &out) {
 void HostPlan::consume_ready(uint64_t b1) {
     const uint64_t bs = block_size;
     size_t w = 0;
+    const uint64_t t_keep = b1 * bs; // due block >= b1, without a division per event
     for (size_t i = 0; i < pending.size(); i++)
-        if (pending[i].due_frame / bs >= b1) {
+        if (pending[i].due_frame >= t_keep) {
             if (w != i) pending[w] = pending[i];
             w++;
         }
@@ -2329,7 +2340,8 @@ void HostPlan::stream_end() {
         n_active_ramps = (uint64_t)((int64_t)n_active_ramps + tc->ramp_delta);
         if (tc->error_code && !err.code) err = Error{tc->error_code, tc->error};
     }
-    consume_ready(S->bounds.back() / block_size);
+    if (S->all_ready && far_horizon == UINT64_MAX) pending.clear(); // nothing to keep: no pass over the queue
+    else consume_ready(S->bounds.back() / block_size);
     if (err.code) throw err;
 }
 

@@ -5,6 +5,7 @@
 #include <functional>
 #include <memory>
 #include <string>
+#include <cstddef>
 #include <vector>
 
 #include "../../include/knaster_gpu.h"
@@ -55,27 +56,32 @@ struct WrapSim {
 };
 
 // control-side state of one node of one voice: the fields knaster's setters read/write
-struct HostNode {
+// One cache line of what the control simulation reads and writes per parameter change, then the rest: the walk over the voices
+// is latency-bound (megabytes of other voices between two visits of a voice), so a node costs one line, fetched ahead of its use.
+struct alignas(64) HostNode {
+    // ---- hot: the fast path of a parameter change (ugen_param_apply, fast_node_block)
     uint8_t kind = 0;        // kgpu_ugen_kind
     uint8_t dev_kind = 0;
-    uint32_t mode = 0;       // waveform / filter type
-    uint16_t reg = 0;        // register base inside the voice
-    uint16_t n_seg = 0;
-    uint32_t base_params = 0;
-    // SinWt.freq, PolyBlep.freq_in_hz; Svf cutoff,q,gain; EnvAsr attack_seconds,release_seconds
-    float f0 = 0.f, f1 = 0.f, f2 = 0.f;
-    double d0 = 0.0;         // Envelope start_value
-    float svf_coef[6] = {0, 0, 0, 0, 0, 0};
-    std::vector<WrapSim> wr; // innermost first
-    bool has_smooth = false, has_precise = false;
-    int8_t smooth_level = -1, precise_level = -1;
     bool ramp_active = false;
     bool ar_regs = false;    // SvfFilter with an audio-rate route into cutoff / q / gain: the parameters live on the device too
-    uint32_t ramp_list_pos = 0;
+    uint16_t reg = 0;        // register base inside the voice
+    uint16_t n_seg = 0;
+    uint32_t mode = 0;       // waveform / filter type
+    // SinWt.freq, PolyBlep.freq_in_hz; Svf cutoff,q,gain; EnvAsr attack_seconds,release_seconds
+    float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+    float svf_coef[6] = {0, 0, 0, 0, 0, 0};
     // WrPreciseTiming::next_delay of a node on the fast path (NodeStatic::fast): sticky, App. B1.  Such a node keeps
     // no WrapSim at all -- everything else about its wrapper stack is static and lives in the template's NodeStatic.
     uint16_t nd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // ---- the second line: nodes with WrSmoothParams / Envelope / Phasor, plan-time data
+    double d0 = 0.0;         // Envelope start_value
+    uint32_t base_params = 0;
+    uint32_t ramp_list_pos = 0;
+    bool has_smooth = false, has_precise = false;
+    int8_t smooth_level = -1, precise_level = -1;
+    std::vector<WrapSim> wr; // innermost first
 };
+static_assert(sizeof(HostNode) == 128 && offsetof(HostNode, d0) == 64, "HostNode: the hot fields fill exactly the first cache line");
 
 // What the control simulation needs to know about one node of a voice TEMPLATE (the same for every voice of the
 // group): its wrapper stack, innermost first.  A node without WrSmoothParams takes the fast path: parameter changes
