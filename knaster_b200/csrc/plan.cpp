@@ -1913,7 +1913,7 @@ void stream_worker_step(HostPlan &P, StreamState &S, StreamState::ThreadCtx &tc,
             const uint32_t vp = v + KGPU_PF;
             if (KGPU_PF && vp < pg.v_end && !(quick && nd[vp - pg.v_begin] >= t1)) {
                 const char *h = hosts + (size_t)vp * node_bytes;
-                for (size_t o = 0; o < node_bytes; o += 64) __builtin_prefetch(h + o, 0, 3);
+                for (size_t o = 0; o < node_bytes; o += sizeof(HostNode)) __builtin_prefetch(h + o, 0, 3); // the hot line of every node (plan.hpp)
                 const uint32_t c = cur[vp - pg.v_begin];
                 if (c < P.vcount[P.voice_base[gi] + vp + 1]) {
                     const char *e = reinterpret_cast<const char *>(pend + (vo ? vo[c] : c));
