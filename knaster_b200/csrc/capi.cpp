@@ -994,7 +994,7 @@ int kgpu_plan_set_blocks_per_launch(kgpu_plan *p, uint64_t blocks) {
 // far), the simulated events that lie beyond the last render's end, the frame clock and the counters.
 struct kgpu_snapshot {
     std::vector<std::vector<uint32_t>> regs;       // per group: [n_regs][n_voices]
-    std::vector<std::vector<HostNode>> host;       // per group
+    std::vector<std::vector<HostNode, HugeAllocator<HostNode>>> host; // per group
     decltype(HostPlan::pending) pending, pending_far;
     uint64_t far_horizon = UINT64_MAX;
     size_t pending_clean = 0;

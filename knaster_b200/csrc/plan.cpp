@@ -26,9 +26,13 @@
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
+#include <new>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 #include <thread>
 #include <tuple>
 #include <unordered_map>
@@ -1415,6 +1419,20 @@ void HostPlan::finish_build() {
     }
     for (NodeRef &nr : node_ref)
         if (nr.group >= 0) nr.rule_base = base[nr.group][nr.local];
+}
+
+void *kgpu_big_alloc(size_t bytes, size_t align) {
+    constexpr size_t HUGE = size_t(2) << 20;
+    if (bytes == 0) bytes = 1;
+    const bool big = bytes >= HUGE;
+    const size_t a = big ? HUGE : std::max<size_t>(align, 16);
+    const size_t rounded = (bytes + a - 1) / a * a;
+    void *p = aligned_alloc(a, rounded);
+    if (!p) throw std::bad_alloc();
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    if (big) madvise(p, rounded, MADV_HUGEPAGE); // a hint; failure changes nothing
+#endif
+    return p;
 }
 
 // ---- WorkPool -----------------------------------------------------------------------------------

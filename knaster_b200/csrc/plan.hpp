@@ -6,6 +6,7 @@
 #include <memory>
 #include <string>
 #include <cstddef>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/knaster_gpu.h"
@@ -56,6 +57,31 @@ struct WrapSim {
 };
 
 // control-side state of one node of one voice: the fields knaster's setters read/write
+// Allocator of the host path's big arrays (the event queue, the control-side nodes): allocations of 2 MiB and more are aligned
+// to 2 MiB and advised as huge pages -- the control simulation walks them with a stride of a voice, and with 4 KiB pages the
+// tens of megabytes one plan touches are far beyond the TLB's reach (every first touch of a voice's events was a page walk on top
+// of the cache miss).  The advice is a hint: where transparent huge pages are off nothing changes.
+void *kgpu_big_alloc(size_t bytes, size_t align);
+template <class T> struct HugeAllocator {
+    using value_type = T;
+    HugeAllocator() = default;
+    template <class U> HugeAllocator(const HugeAllocator<U> &) noexcept {}
+    template <class U> struct rebind { using other = HugeAllocator<U>; };
+    T *allocate(size_t n) { return static_cast<T *>(kgpu_big_alloc(n * sizeof(T), alignof(T))); }
+    void deallocate(T *p, size_t) noexcept { free(p); }
+    template <class U> bool operator==(const HugeAllocator<U> &) const noexcept { return true; }
+    template <class U> bool operator!=(const HugeAllocator<U> &) const noexcept { return false; }
+};
+// ... whose value-less construct() default-initialises: vector::resize() of a POD then leaves
+// the new elements uninitialised instead of zero-filling them (HostPlan::push fills them in parallel)
+template <class T> struct DefaultInitAllocator : HugeAllocator<T> {
+    DefaultInitAllocator() = default;
+    template <class U> DefaultInitAllocator(const DefaultInitAllocator<U> &) noexcept {}
+    template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+    template <class U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+
 // One cache line of what the control simulation reads and writes per parameter change, then the rest: the walk over the voices
 // is latency-bound (megabytes of other voices between two visits of a voice), so a node costs one line, fetched ahead of its use.
 struct alignas(64) HostNode {
@@ -127,7 +153,7 @@ struct Group {
     std::vector<std::vector<uint32_t>> voice_nodes; // [voice][local] -> graph node index
     uint32_t n_voices = 0;
     std::vector<uint32_t> init_regs;                // [reg][voice]
-    std::vector<HostNode> host;                     // [voice * n_nodes + local]
+    std::vector<HostNode, HugeAllocator<HostNode>> host; // [voice * n_nodes + local]
     std::vector<NodeStatic> nstat;                  // [local]
     std::vector<std::vector<uint16_t>> slot_of;     // [local][channel] -> value slot
     int fused_recipe = -1;                          // index into the fused-kernel table, -1 = interpreter
@@ -140,14 +166,6 @@ struct NodeRef { // 16 bytes
     uint16_t local = 0;
     uint16_t n_params = 0;
     uint32_t rule_base = 0; // first validation rule of this node's parameters in HostPlan::rules
-};
-
-// std::allocator whose value-less construct() default-initialises: vector::resize() of a POD then leaves
-// the new elements uninitialised instead of zero-filling them (HostPlan::push fills them in parallel)
-template <class T> struct DefaultInitAllocator : std::allocator<T> {
-    template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
-    template <class U> void construct(U *p) noexcept { ::new (static_cast<void *>(p)) U; }
-    template <class U, class... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
 };
 
 struct RawEvent { // 32 bytes
