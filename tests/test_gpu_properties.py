@@ -1,10 +1,10 @@
 """GPU property and edge-case tests for the fused voice-bank path (through the C ABI).
 
-The parity tests in test_gpu_parity.py compare against the CPU oracle at sizes the oracle renders
-in seconds.  At BASELINE.json's full size (16 384 voices) the oracle is too slow, so the full-size
-cases here use properties that do not depend on it: invariance under the way a render is split
-into launches, exact scaling by a power of two, silence without notes, determinism, and
-bus == sum of the voices.  The edge cases (ragged voice counts, odd block sizes and frame counts,
+The parity tests in test_gpu_parity.py compare against the CPU oracle at small sizes, and
+test_gpu_full_size.py at BASELINE.json's full sizes (16 384 voices x 10 s against the threaded oracle).
+The full-size cases here add the properties that do not depend on an oracle: invariance under the
+way a render is split into launches, exact scaling by a power of two, silence without notes,
+determinism, and bus == sum of the voices.  The edge cases (ragged voice counts, odd block sizes and frame counts,
 event collisions, dense event streams, events on the first and last frame, parameters outside the
 straight-line domain) are small and are checked against the oracle."""
 import os
