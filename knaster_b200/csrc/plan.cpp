@@ -1413,7 +1413,8 @@ void HostPlan::finish_build() {
             base[gi][li] = (uint32_t)rules.size();
             for (uint32_t p = 0; p < g.nstat[li].total_params; p++) {
                 ParamRule pr = param_rule(g.tpl.nodes[li], g.nstat[li].base_params, p);
-                rules.push_back({pr.want, (uint8_t)pr.smooth_ok, (uint8_t)pr.polyblep_wave, (uint8_t)pr.svf_type});
+                const uint8_t ok_kinds = pr.want == 't' ? 0x1Eu : (pr.want == 'f' ? 1u << 1 : (pr.want == 'i' ? 1u << 3 : (pr.want == 'b' ? 1u << 4 : 0u)));
+                rules.push_back({pr.want, (uint8_t)pr.smooth_ok, (uint8_t)pr.polyblep_wave, (uint8_t)pr.svf_type, ok_kinds});
             }
         }
     }
@@ -1545,8 +1546,7 @@ void HostPlan::push(const kgpu_event *evs, size_t n, uint64_t frame_clock) {
             KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: smoothing sent to node %u param %u which has no WrSmoothParams around it "
                        "(knaster would panic: parameter value is expected to be a float)", i, e.node, e.param);
         if (e.value_kind != 0) {
-            const char want = ru.want;
-            const bool ok = want == 't' || (want == 'f' && e.value_kind == 1) || (want == 'i' && e.value_kind == 3) || (want == 'b' && e.value_kind == 4);
+            const bool ok = (ru.ok_kinds >> e.value_kind) & 1u; // value_kind <= 4 (checked above)
             if (!ok) KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: wrong value type for node %u param %u", i, e.node, e.param);
             if (ru.polyblep_wave && ((int64_t)e.value < 0 || (int64_t)e.value > 13))
                 KGPU_THROW(KGPU_ERR_PARAMETER, "event %zu: bad PolyBlep Waveform %lld", i, (long long)e.value);

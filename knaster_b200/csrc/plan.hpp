@@ -240,7 +240,8 @@ struct HostPlan {
     void calendar_update(uint64_t b0, uint64_t b1);
 
     // caches / scratch of the hot host path (push / compile_events)
-    struct Rule { char want; uint8_t smooth_ok, polyblep_wave, svf_type; };
+    struct Rule { // ok_kinds: bit k set = an event of value_kind k is accepted ('t' any, 'f' float, 'i' integer, 'b' bool): one shift instead of a branch chain per event
+        char want; uint8_t smooth_ok, polyblep_wave, svf_type, ok_kinds; };
     std::vector<Rule> rules;                             // flat: NodeRef::rule_base + param
     uint64_t n_active_ramps = 0;
     std::vector<uint64_t> voice_base;                    // prefix sum of voices per group
